@@ -1,0 +1,143 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+Writes tests/golden/rambo_n{3,4,5,8}.npz, tests/golden/rqs_*.npz, tests/golden/known_answers.json.
+
+Phase space: imports memflow.phasespace from /root/reference as-is (only the unused
+`particle` import is stubbed). Two variants are stored:
+  *_lit   : the literal reference (float32 volume / incoming rows, rambo_generator.py:132,:533)
+  *_clean : same files with `.to(torch.float)` / `.float()` neutralised by patching
+            torch.Tensor.float / torch.Tensor.to for the duration of the call ("fp64-clean").
+Spline: zuko is not available; the fixture comes from oracle/rqs_torch.py (op-for-op torch
+restatement of upstream zuko) -> "parity unpinned" for the spline.
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("MEMFLOW_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    torch.set_default_dtype(torch.float64)  # BEFORE importing memflow.phasespace
+    stub = types.ModuleType("particle")
+    stub.Particle = type("Particle", (), {})
+    sys.modules.setdefault("particle", stub)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from memflow.phasespace import phasespace, rambo_generator, utils  # noqa
+    return phasespace, rambo_generator, utils
+
+
+@contextlib.contextmanager
+def fp64_clean():
+    """Neutralise the two float32 casts of the reference without touching its files."""
+    orig_float, orig_to = torch.Tensor.float, torch.Tensor.to
+
+    def to(self, *a, **k):
+        if len(a) == 1 and a[0] in (torch.float, torch.float32) and not k:
+            return self
+        return orig_to(self, *a, **k)
+
+    torch.Tensor.float = lambda self: self
+    torch.Tensor.to = to
+    try:
+        yield
+    finally:
+        torch.Tensor.float, torch.Tensor.to = orig_float, orig_to
+
+
+CASES = {
+    3: [125.25, 172.5, 172.5],
+    4: [125.25, 172.5, 172.5, 1e-5],
+    5: [125.25, 172.5, 172.5, 1e-5, 1e-5],
+    8: [4.7, 4.7, 4.7, 4.7, 0.1, 0.0, 0.3, 0.3],
+}
+E_CM = 13000.0
+N = 384
+
+
+def make_u(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand(N, 3 * n - 2, dtype=torch.float64, generator=g)
+    # a band of edge-of-cube points: tiny / near-one mass variables and angles
+    u[0:8, : n - 2] = 1e-9
+    u[8:16, : n - 2] = 1 - 1e-9
+    u[16:24, n - 2:3 * n - 4] = torch.tensor([1e-10, 0.5, 1 - 1e-10, 0.25, 0.75, 1e-7, 0.5 + 1e-9, 0.5 - 1e-9]
+                                             ).unsqueeze(1)
+    return u.clamp(1e-10, 1 - 1e-10)
+
+
+def main():
+    phasespace, rambo_generator, utils = import_reference()
+    known = {"get_flatWeights(13000,3)": rambo_generator.FlatInvertiblePhasespace.get_flatWeights(13000, 3)}
+    for n, masses in CASES.items():
+        m = torch.tensor(masses, dtype=torch.float64)
+        ps = phasespace.PhaseSpace(E_CM, [21, 21], list(range(n)), final_masses=m, dev=torch.device("cpu"))
+        u = make_u(n, 1000 + n)
+        out = {"u": u.numpy(), "masses": m.numpy(), "e_cm": np.float64(E_CM)}
+        for tag, ctx in (("lit", contextlib.nullcontext()), ("clean", fp64_clean())):
+            with ctx:
+                mom, w, x1, x2 = ps.get_momenta_from_ps(u)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    psb, prob = ps.generator.getPSpoint_batch(mom[:, 2:], x1, x2, order=list(range(n)))
+            out["mom_" + tag] = mom.numpy()
+            out["w_" + tag] = w.numpy()
+            out["x1_" + tag] = x1.numpy()
+            out["x2_" + tag] = x2.numpy()
+            out["inv_ps_" + tag] = psb.double().numpy()
+            out["inv_prob_" + tag] = prob.double().numpy()
+        # cuts (literal only): pT > 20, dR > 0.4, |eta| < 5
+        mom, w, x1, x2 = ps.get_momenta_from_ps(u, pT_mincut=20.0, delR_mincut=0.4, rap_maxcut=5.0)
+        out["w_cuts_lit"] = w.numpy()
+        # permuted inverse with off-shell per-event masses (ensure_onShell=False)
+        perm = list(reversed(range(n)))
+        with fp64_clean(), contextlib.redirect_stdout(io.StringIO()):
+            mom_c = torch.from_numpy(out["mom_clean"])
+            x1c, x2c = torch.from_numpy(out["x1_clean"]), torch.from_numpy(out["x2_clean"])
+            psb, prob = ps.generator.getPSpoint_batch(mom_c[:, 2:], x1c, x2c, order=perm)
+            out["inv_ps_perm_clean"] = psb.numpy()
+            out["inv_prob_perm_clean"] = prob.numpy()
+            out["perm"] = np.array(perm, dtype=np.int32)
+            tm = (m[perm] * 1.001).unsqueeze(0)  # [1, n]: the only shape the reference handles (it sums over ALL dims, :660)
+            psb, prob = ps.generator.getPSpoint_batch(mom_c[:, 2:], x1c, x2c, order=perm, target_mass=tm,
+                                                      ensure_onShell=False)
+            out["inv_ps_offshell_clean"] = psb.numpy()
+            out["inv_prob_offshell_clean"] = prob.numpy()
+            out["target_mass"] = tm.numpy()
+        np.savez_compressed(os.path.join(HERE, "rambo_n%d.npz" % n), **out)
+        print("n=%d written; max|w_lit/w_clean-1| = %.3g" % (
+            n, np.nanmax(np.abs(out["w_lit"] / out["w_clean"] - 1))))
+
+    # ---- spline fixture from the torch restatement (parity unpinned) ----
+    sys.path.insert(0, ROOT)
+    from oracle import rqs_torch
+    for tag, dt, F, K, bound in (("f64_F7K10", torch.float64, 7, 10, 1.0), ("f32_F20K64", torch.float32, 20, 64, 1.1),
+                                 ("f64_F10K40", torch.float64, 10, 40, 1.1)):
+        g = torch.Generator().manual_seed(7)
+        B = 128 if K <= 16 else 40
+        phi = torch.randn(B, F, 3 * K - 1, generator=g, dtype=torch.float64).to(dt)
+        x = ((torch.rand(B, F, generator=g, dtype=torch.float64) * 2.6 - 1.3) * bound / 1.0).to(dt)
+        t = rqs_torch.MonotonicRQSTransform(phi[..., :K], phi[..., K:2 * K], phi[..., 2 * K:], bound=bound)
+        y, ladj = t.call_and_ladj(x)
+        xi = t._inverse(x)
+        np.savez_compressed(os.path.join(HERE, "rqs_%s.npz" % tag), phi=phi.numpy(), x=x.numpy(), y=y.numpy(),
+                            ladj=ladj.numpy(), x_inv=xi.numpy(), bound=np.float64(bound),
+                            bin_fwd=(t.searchsorted(t.horizontal, x) - 1).numpy().astype(np.int64),
+                            bin_inv=(t.searchsorted(t.vertical, x) - 1).numpy().astype(np.int64))
+    with open(os.path.join(HERE, "known_answers.json"), "w") as f:
+        json.dump(known, f, indent=1)
+    print(known)
+
+
+if __name__ == "__main__":
+    main()
