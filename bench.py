@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the phase-space / importance-sampling hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3], "Full importance-sampling chain ... on 1 GPU", sharded as configs[4] for
+N > 1): one STEP = one chunk of 2^22 ttH points through the fused chain
+    Philox base sample -> 2 RQ-spline inverses (F=7, K=10, per-event parameters streamed from HBM)
+    -> PhaseSpace map u -> momenta (n=3: H, t, tbar at sqrt(s) = 13 TeV, fp64) + Jacobian
+    -> weight w = jac / (2 x1 x2 s) / q(u) -> (sum w, sum w^2, n_valid),
+one kernel launch per step (memflow_b200/csrc/is_chain.cu), one all-reduce of the 3 accumulators at the end.
+Metric: phase-space points/sec (map + Jacobian + weights), whole job.
+
+Prints ONE JSON line (rank 0). Keys follow the driver's contract; see DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "phase-space points/sec (map+Jacobian+weights)"
+UNIT = "points/s"
+E_CM = 13000.0
+MASSES = [125.25, 172.5, 172.5]
+N_FINAL, T_FLOW, K_BINS, F_DIM = 3, 2, 10, 7
+PW = 3 * K_BINS - 1
+CHUNK = 1 << 22
+BYTES_PER_EVENT = T_FLOW * F_DIM * PW * 4  # algorithmic: only the spline parameters touch HBM
+CONFIG = {"workload": "is_chain_ttH: philox -> 2x RQS inverse (F=7,K=10,fp32) -> RAMBO n=3 fp64 -> weight -> sum w, sum w^2",
+          "chunk_events": CHUNK, "n_final": N_FINAL, "flow": {"T": T_FLOW, "F": F_DIM, "K": K_BINS, "bound": 1.0},
+          "sqrt_s": E_CM, "masses": MASSES, "me2": 1, "pdf": 1,
+          "l2_policy": "inputs larger than L2 (6.8 GB of parameters per step)", "parallelism": "events sharded, 1 allreduce"}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                out["sm_max_mhz"] = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def cpu_chain(O, OP, phi, seed, event_offset):
+    """The chain on the host with the oracle port (the reference's algorithm restated in C, oracle/)."""
+    import numpy as np
+    n = phi.shape[1]
+    z = OP.base_sample(n, F_DIM, 1.0, seed, event_offset)
+    lsum = np.zeros(n)
+    for t in range(T_FLOW - 1, -1, -1):
+        z, l, _ = O.rqs_inverse(phi[t], z, bound=1.0)
+        lsum += l.astype(np.float64).sum(1)
+    u = (z.astype(np.float64) + 1.0) / 2.0
+    mom, w, x1, x2 = O.rambo_forward(u, MASSES, E_CM)
+    tgt = 1.0 / (2 * E_CM * E_CM) / (x1 * x2)
+    return O.is_reduce(tgt, w, lsum)
+
+
+def cpu_leg(steps, warmup, budget_s):
+    """Times the CPU port on a bounded sample; returns (points/s, cores, sample description, ms/step)."""
+    import numpy as np
+    from oracle import oracle as O, philox as OP
+    O.build()
+    cores = O.max_threads()
+    O.set_threads(cores)
+    rng = np.random.default_rng(0)
+    probe = 1 << 13
+    phi = rng.standard_normal((T_FLOW, probe, F_DIM, PW)).astype(np.float32)
+    cpu_chain(O, OP, phi, 1, 0)
+    t0 = time.perf_counter()
+    cpu_chain(O, OP, phi, 1, 0)
+    per_ev = (time.perf_counter() - t0) / probe
+    n = int(budget_s / max(steps + warmup, 1) / per_ev)
+    n = max(1 << 12, min(n, 1 << 20))
+    phi = rng.standard_normal((T_FLOW, n, F_DIM, PW)).astype(np.float32)
+    for i in range(warmup):
+        cpu_chain(O, OP, phi, 1, i * n)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        cpu_chain(O, OP, phi, 1, (warmup + i) * n)
+    dt = time.perf_counter() - t0
+    return steps * n / dt, cores, "%d steps x %d points of the same chain (oracle port: C, pthreads)" % (steps, n), dt / steps * 1e3
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; the Python reference cannot
+    travel to the GPU box). Rank 0 only."""
+    if rank != 0:
+        return
+    v, cores, sample, ms = cpu_leg(args.steps, args.warmup, budget_s=100.0)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": CONFIG,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def extras(torch, dev, hbm_peak):
+    """Per-kernel rates for the other BASELINE configs (device-resident, CUDA events): K1, K2, K3, K4."""
+    from memflow_b200.phasespace.phasespace import PhaseSpace
+    from memflow_b200 import transforms as TR
+
+    def timeit(f, n=5, warm=2):
+        for _ in range(warm):
+            f()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            f()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n * 1e-3
+
+    out = {}
+    try:
+        N = 1 << 24
+        ps3 = PhaseSpace(E_CM, [21, 21], [25, 6, -6], final_masses=torch.tensor(MASSES, dtype=torch.float64), dev=dev)
+        u = torch.rand(N, 7, dtype=torch.float64, device=dev).clamp_(1e-10, 1 - 1e-10)
+        t = timeit(lambda: ps3.get_momenta_from_ps(u))
+        out["K1_forward_n3_f64_16M"] = {"points_per_s": N / t, "GBps": 240 * N / t / 1e9, "frac_hbm": 240 * N / t / 1e9 / hbm_peak}
+        del u
+        m8 = [4.7, 4.7, 4.7, 4.7, 0.1, 0.0, 0.3, 0.3]
+        ps8 = PhaseSpace(E_CM, [21, 21], list(range(8)), final_masses=torch.tensor(m8, dtype=torch.float64), dev=dev)
+        u = torch.rand(N, 22, dtype=torch.float64, device=dev).clamp_(1e-10, 1 - 1e-10)
+        tf = timeit(lambda: ps8.get_momenta_from_ps(u))
+        mom, w, x1, x2 = ps8.get_momenta_from_ps(u)
+        ti = timeit(lambda: ps8.generator.getPSpoint_batch(mom[:, 2:], x1, x2))
+        out["K1_forward_n8_f64_16M"] = {"points_per_s": N / tf, "GBps": 520 * N / tf / 1e9, "frac_hbm": 520 * N / tf / 1e9 / hbm_peak}
+        out["K2_inverse_n8_f64_16M"] = {"points_per_s": N / ti, "GBps": 456 * N / ti / 1e9, "frac_hbm": 456 * N / ti / 1e9 / hbm_peak}
+        out["config2_round_trip_n8_16M"] = {"points_per_s": N / (tf + ti), "GBps": 976 * N / (tf + ti) / 1e9,
+                                            "frac_hbm": 976 * N / (tf + ti) / 1e9 / hbm_peak}
+        del u, mom, w, x1, x2
+        B, F, K = 1 << 20, 20, 64
+        phi = torch.randn(B, F, 3 * K - 1, device=dev, dtype=torch.float32)
+        x = (torch.rand(B, F, device=dev) * 2.6 - 1.3) * 1.1
+        by = (F * (3 * K - 1) + 2 * F + 1) * 4
+        tf = timeit(lambda: TR.rqs_forward(phi, x, bound=1.1))
+        ti = timeit(lambda: TR.rqs_inverse(phi, x, bound=1.1))
+        out["K3_rqs_forward_F20_K64_f32_1M"] = {"points_per_s": B / tf, "GBps": by * B / tf / 1e9, "frac_hbm": by * B / tf / 1e9 / hbm_peak}
+        out["K4_rqs_inverse_F20_K64_f32_1M"] = {"points_per_s": B / ti, "GBps": by * B / ti / 1e9, "frac_hbm": by * B / ti / 1e9 / hbm_peak}
+        out["note"] = "wrapper-level timings (include the output allocations of the Python API)"
+    except Exception as e:  # extras must never break the headline line
+        out["error"] = repr(e)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: memflow_b200 has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    from memflow_b200 import estimator as ES
+    from memflow_b200.distributed import allreduce_accumulators
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, peak_src = load_peaks()
+    K, W = args.steps, max(args.warmup, 0)
+
+    # resident synthetic parameters for one chunk: [T, CHUNK, F, 3K-1] fp32 = 6.8 GB (> L2)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    phi = torch.randn(T_FLOW, CHUNK, F_DIM, PW, device=dev, dtype=torch.float32, generator=g)
+    smp = ES.ImportanceSampler(MASSES, E_CM, bound=1.0, seed=2026, device=dev)
+    acc = ES.new_accumulator(dev)
+    per_rank_events = (W + K) * CHUNK
+    base = rank * per_rank_events  # disjoint global event ranges per rank (Philox counter = global index)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        smp.run_chunk(phi, event_offset=base + i * CHUNK, acc=acc)
+    barrier()
+    acc.zero_()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    t_wall = time.perf_counter()
+    evs[0].record()
+    for i in range(K):
+        smp.run_chunk(phi, event_offset=base + (W + i) * CHUNK, acc=acc)
+        evs[i + 1].record()
+    allreduce_accumulators(acc)       # the path's only collective: 3 doubles, once
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if sampler else None
+    t_dev = evs[0].elapsed_time(end) * 1e-3
+    kern_ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(K))
+    t = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_max = float(t.item())
+    total_events = world * K * CHUNK
+    value = total_events / t_max
+    acc_host = acc.cpu().tolist()
+    I, sigma, nvalid = ES.mc_estimate(acc_host, total_events)
+
+    # ---- e2e: host parameters in pinned memory -> H2D -> chain -> D2H accumulators, every step ----
+    e2e_chunk = 1 << 20
+    e2e_steps = max(3, min(K, 12))
+    host = torch.empty((T_FLOW, e2e_chunk, F_DIM, PW), dtype=torch.float32).pin_memory()
+    host.copy_(phi[:, :e2e_chunk].cpu())
+    res_host = torch.empty(3, dtype=torch.float64).pin_memory()
+    bufs = [torch.empty_like(host, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    acc2 = ES.new_accumulator(dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_pass(nsteps, off0):
+        for i in range(nsteps):
+            b = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])
+                bufs[b].copy_(host, non_blocking=True)
+                copied[b].record(copy_stream)
+            main_stream.wait_event(copied[b])
+            smp.run_chunk(bufs[b], event_offset=off0 + i * e2e_chunk, acc=acc2)
+            consumed[b].record(main_stream)
+            res_host.copy_(acc2, non_blocking=True)   # the step's result goes back to the host
+        torch.cuda.synchronize()
+
+    for b in range(2):
+        consumed[b].record(main_stream)
+    e2e_pass(2, 0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_pass(e2e_steps, 2 * e2e_chunk)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps * e2e_chunk / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    med_kernel_s = kern_ms[len(kern_ms) // 2] * 1e-3
+    avg_kernel_s = sum(kern_ms) / len(kern_ms) * 1e-3
+    achieved = BYTES_PER_EVENT * CHUNK / avg_kernel_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("is_chain_kernel_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_max / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": CONFIG,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": 24,
+                "steps": e2e_steps, "chunk_events": e2e_chunk,
+                "note": "spline parameters start in pinned host memory; H2D double-buffered against the kernel"},
+        "gpu_launches": K * world,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic, "kernel": "is_chain_kernel<3>", "peak_source": peak_src,
+                     "algorithmic_bytes_per_event": BYTES_PER_EVENT, "events_per_launch": CHUNK,
+                     "kernel_ms_avg": avg_kernel_s * 1e3, "kernel_ms_median": med_kernel_s * 1e3,
+                     "note": "kernel is FP32/FP64-issue bound, not HBM bound: see DESIGN.md and profiles/"},
+        "clocks": clocks,
+        "estimate": {"I": I, "sigma": sigma, "n_valid": nvalid, "n_total": total_events},
+        "wall_s_timed_region": t_wall,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, sample, _ = cpu_leg(3, 1, budget_s=20.0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    if world == 1 and not args.no_extras:
+        del phi, bufs
+        torch.cuda.empty_cache()
+        line["extra"] = extras(torch, dev, hbm_peak)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

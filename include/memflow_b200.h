@@ -1,0 +1,165 @@
+/*
+ * memflow_b200.h -- C ABI of the B200-native (sm_100a) MEMFlow phase-space hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types. Every entry point
+ * replaces one reference interface, cited as file:line relative to valsdav/MEMFlow.
+ * The Python host layer (memflow_b200/) binds these with ctypes and mirrors the reference's
+ * classes; INTEGRATION.md shows the stub a MEMFlow maintainer would add.
+ *
+ * Conventions
+ *   - All array pointers are DEVICE pointers unless the comment says "host".
+ *   - Row-major, contiguous. Momenta are AoS [event][particle][E,px,py,pz] exactly as the
+ *     reference returns them (rambo_generator.py:327-331).
+ *   - Kernels are enqueued on `stream` (a cudaStream_t); nothing synchronises. Re-entrant:
+ *     no global mutable state, masses / constants travel with each launch.
+ *   - Return value: 0 = MF_OK, >0 = MF_E_* argument errors detected on the host before any
+ *     launch, <0 = -(cudaError_t) from the launch. No exceptions cross this boundary.
+ *   - Data-dependent failures of the reference (NaN scan rambo_generator.py:191-199, CM check
+ *     :630-635) are reported through the optional device word `status` (bit-or of MF_ST_*),
+ *     never by a host sync.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MEMFLOW_B200_H
+#define MEMFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mf_stream_t; /* == cudaStream_t */
+
+#define MF_ABI_VERSION 1
+#define MF_MAX_FINAL 8 /* n_final supported: 3..8 (the reference itself fails for n=2, :402-403,455) */
+#define MF_MIN_FINAL 3
+
+/* return codes */
+#define MF_OK 0
+#define MF_E_BADARG 1   /* null pointer / negative size */
+#define MF_E_NFINAL 2   /* n_final outside [MF_MIN_FINAL, MF_MAX_FINAL] */
+#define MF_E_ALIGN 3    /* pointer not aligned for the vector width used (32 B f64 / 16 B f32 momenta rows) */
+#define MF_E_SHAPE 4    /* spline K/F out of range, bad order permutation ... */
+#define MF_E_NODEVICE 5 /* no CUDA device / wrong architecture (needs sm_100) */
+
+/* flags (bit-or) */
+#define MF_FLAG_REF_FP32_QUIRKS 1u /* reproduce the reference's float32 volume/weight chain and float32 \
+                                      incoming rows (rambo_generator.py:132,489-507,533); default = clean fp64 */
+#define MF_FLAG_LAB_FRAME 2u       /* forward: return momenta boosted to the lab frame (utils.py:180-202) */
+#define MF_FLAG_CUTS 4u            /* forward: apply cuts[3] = {pT_min, dR_min, |eta|_max} (:350-393) */
+#define MF_FLAG_X1X2_DIRECT 8u     /* uniform_x1x2=False: last two columns ARE x1,x2, no Jacobian (:229-234) */
+#define MF_FLAG_NO_CM_CHECK 16u    /* inverse: ensure_CM=False (:630) */
+
+/* status bits written with atomicOr into *status (device int32, may be NULL) */
+#define MF_ST_NAN_INPUT 1 /* forward: a random variable was NaN (:191-199 raises) */
+#define MF_ST_NOT_CM 2    /* inverse: |sum p|^2 >= 1e-3 for some event (:634-635 raises) */
+
+int mf_abi_version(void);
+const char* mf_error_string(int code);
+/* device probe: fills SM count and compute capability of the current device */
+int mf_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  rambo_forward : unit hypercube -> CM-frame 4-momenta + Jacobian weight
+ * replaces FlatInvertiblePhasespace.generateKinematics_batch, rambo_generator.py:168-398
+ * (with get_x1x2_from_uniform utils.py:260-284, bisect_vec_batch :400-446 -> closed form /
+ * Halley root solve, generateIntermediatesMassive_batch :475-509, setInitialStateMomenta_batch
+ * :511-551, boost_t utils.py:88-118).
+ *   u        [N, 3n-2]    3n-4 RAMBO variables, then (u_x1, u_x2)
+ *   masses   host [n]     final-state masses
+ *   cuts     host [3]     or NULL (only read with MF_FLAG_CUTS)
+ *   momenta  [N, n+2, 4]  rows in1, in2, final_0..final_{n-1}    (32 B-aligned f64 / 16 B f32)
+ *   weight   [N]          |det J(u->p)| * x1x2 Jacobian * cut mask
+ *   logweight[N] or NULL  ln(weight) (new; avoids the reference's float32 overflow for n>=7)
+ *   x1, x2   [N]
+ * ---------------------------------------------------------------------------------------- */
+int mf_rambo_forward_f64(const double* u, int64_t N, int n_final, const double* masses, double e_collider,
+                         const double* cuts, uint32_t flags, double* momenta, double* weight,
+                         double* logweight, double* x1, double* x2, int32_t* status, mf_stream_t stream);
+int mf_rambo_forward_f32(const float* u, int64_t N, int n_final, const float* masses, float e_collider,
+                         const float* cuts, uint32_t flags, float* momenta, float* weight, float* logweight,
+                         float* x1, float* x2, int32_t* status, mf_stream_t stream);
+
+/* Mass-variable root solve alone: u[i, j] solves v = u^e ((e+1) - e u), e = n_final-2-j.
+ * replaces FlatInvertiblePhasespace.bisect_vec_batch, rambo_generator.py:400-446. v, u: [N, n_final-2]. */
+int mf_massvar_solve_f64(const double* v, int64_t N, int n_final, double* u, mf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  rambo_inverse : CM-frame final-state momenta -> unit hypercube + 1/weight
+ * replaces FlatInvertiblePhasespace.getPSpoint_batch, rambo_generator.py:615-736
+ * (with get_uniform_from_x1x2 utils.py:287-309).
+ *   momenta      final-state rows only; event e, particle k at momenta + e*event_stride + 4k
+ *                (event_stride in ELEMENTS, multiple of 4; pass 4n for a packed [N,n,4], or
+ *                4(n+2) with momenta pointing at row 2 of a forward output -- no copy needed)
+ *   order        host [n] permutation (:624-625)
+ *   masses       host [n] generator masses
+ *   target_mass  host [n] or NULL. NULL = ensure_onShell=True (masses[order], :649-650); otherwise
+ *                used as given, unpermuted (ensure_onShell=False, :651-652; the reference only
+ *                handles a [1,n] tensor there)
+ *   ps [N, 3n-2], prob [N] = jac_x1x2 / rambo_jac (:732-734), logprob [N] or NULL
+ * ---------------------------------------------------------------------------------------- */
+int mf_rambo_inverse_f64(const double* momenta, int64_t event_stride, const double* x1, const double* x2,
+                         int64_t N, int n_final, const int32_t* order, const double* masses,
+                         const double* target_mass, double e_collider, uint32_t flags, double* ps,
+                         double* prob, double* logprob, int32_t* status, mf_stream_t stream);
+int mf_rambo_inverse_f32(const float* momenta, int64_t event_stride, const float* x1, const float* x2,
+                         int64_t N, int n_final, const int32_t* order, const float* masses,
+                         const float* target_mass, float e_collider, uint32_t flags, float* ps, float* prob,
+                         float* logprob, int32_t* status, mf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 / K4  monotonic rational-quadratic spline, zuko.transforms.MonotonicRQSTransform
+ * (third-party; constructed at memflow/unfolding_flow/unfolding_flow.py:88-97 and
+ * memflow/unfolding_flow/custom_spline_flow_ps.py:16-33).
+ *   phi  [B, F, 3K-1]  per (event, feature): widths[K] | heights[K] | derivatives[K-1], unconstrained
+ *   in   [B, F]        x (forward) or y (inverse)
+ *   out  [B, F]
+ *   ladj [B, F] or NULL    forward: log|dy/dx| at x;  inverse: the same FORWARD log|dy/dx| evaluated
+ *                          at the recovered x (so sample + log q need one pass)
+ *   ladj_sum [B] or NULL   sum over F (what AutoregressiveTransform.call_and_ladj returns)
+ *   bin  [B, F] or NULL    searchsorted(knots, v) - 1 (int32; -1 / K = identity tails)
+ *   slope <= 0 disables the soft clip (zuko <= 0.1). 1 <= K <= 128.
+ * ---------------------------------------------------------------------------------------- */
+int mf_rqs_forward_f32(const float* phi, const float* x, int64_t B, int F, int K, float bound, float slope,
+                       float* y, float* ladj, float* ladj_sum, int32_t* bin, mf_stream_t stream);
+int mf_rqs_forward_f64(const double* phi, const double* x, int64_t B, int F, int K, double bound, double slope,
+                       double* y, double* ladj, double* ladj_sum, int32_t* bin, mf_stream_t stream);
+int mf_rqs_inverse_f32(const float* phi, const float* y, int64_t B, int F, int K, float bound, float slope,
+                       float* x, float* ladj, float* ladj_sum, int32_t* bin, mf_stream_t stream);
+int mf_rqs_inverse_f64(const double* phi, const double* y, int64_t B, int F, int K, double bound, double slope,
+                       double* x, double* ladj, double* ladj_sum, int32_t* bin, mf_stream_t stream);
+/* bin search alone, knots given: idx = torch.searchsorted(knots[b,f,:], v[b,f], right=False) (bit-exact) */
+int mf_searchsorted_f32(const float* knots, const float* v, int64_t BF, int len, int32_t* idx, mf_stream_t stream);
+int mf_searchsorted_f64(const double* knots, const double* v, int64_t BF, int len, int32_t* idx, mf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  importance-sampling weight + Monte-Carlo estimator reduction
+ * replaces notebooks/TestFlows_ImportanceSampling.ipynb cells [50-54] (mask of cells [35,43]):
+ *   w_i = target_i * jac_i / exp(logq_i);  valid_i = target_i > 0 and jac_i is not NaN
+ *   acc[0] += sum w, acc[1] += sum w^2, acc[2] += n_valid      (acc: device double[3])
+ * target may be NULL (== 1). Deterministic: fixed grid, per-block Kahan partials, the last block
+ * folds them in index order. workspace: device, mf_is_reduce_workspace_bytes() bytes, zeroed once
+ * by the caller before first use (the kernel leaves it zeroed).
+ * ---------------------------------------------------------------------------------------- */
+int64_t mf_is_reduce_workspace_bytes(void);
+int mf_is_reduce_f64(const double* target, const double* jac, const double* logq, int64_t N, double* acc,
+                     void* workspace, mf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused importance-sampling chain (TestFlows_ImportanceSampling.ipynb [45,50-54] in one launch):
+ *   Philox4x32-10 base sample z ~ U[-bound,bound]^F (counter = global event index, key = seed)
+ *   -> T spline inverses (K4, parameters phi[t] given)  -> u = (x + bound) / (2 bound)
+ *   -> K1 (n_final bodies, F = 3n-2)  -> w = jac / (2 x1 x2 s) / q(u)  -> K5 accumulation.
+ *   phi      [T, N, F, 3K-1] float32 (one contiguous [N, F, 3K-1] block per transform)
+ *   acc/workspace as K5. Optional outputs (NULL to skip): u_out [N,F] f64, logq [N] f64,
+ *   momenta [N,n+2,4], weight [N] (RAMBO weight), x1, x2.
+ * ---------------------------------------------------------------------------------------- */
+int mf_is_chain_f64(const float* phi, int64_t N, int n_final, int T, int K, float bound, float slope,
+                    uint64_t seed, uint64_t event_offset, const double* masses, double e_collider,
+                    uint32_t flags, double* acc, void* workspace, double* u_out, double* logq,
+                    double* momenta, double* weight, double* x1, double* x2, mf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEMFLOW_B200_H */

@@ -1,0 +1,91 @@
+"""ctypes binding of the C ABI (include/memflow_b200.h) -> memflow_b200/lib/libmemflow_b200.so.
+
+There is NO CPU fallback: if the library is missing, or a tensor is not on a CUDA device, the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmemflow_b200.so")
+
+#: every symbol include/memflow_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = (
+    "mf_abi_version", "mf_error_string", "mf_device_info",
+    "mf_rambo_forward_f64", "mf_rambo_forward_f32", "mf_massvar_solve_f64", "mf_rambo_inverse_f64", "mf_rambo_inverse_f32",
+    "mf_rqs_forward_f32", "mf_rqs_forward_f64", "mf_rqs_inverse_f32", "mf_rqs_inverse_f64",
+    "mf_searchsorted_f32", "mf_searchsorted_f64",
+    "mf_is_reduce_workspace_bytes", "mf_is_reduce_f64", "mf_is_chain_f64",
+)
+
+
+class MemflowB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once). Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MemflowB200Error(
+                "memflow_b200: %s not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C memflow_b200/csrc`. There is no CPU / PyTorch fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.mf_error_string.restype = ctypes.c_char_p
+        L.mf_error_string.argtypes = [ctypes.c_int]
+        L.mf_is_reduce_workspace_bytes.restype = ctypes.c_int64
+        for s in SYMBOLS:
+            if s not in ("mf_error_string", "mf_is_reduce_workspace_bytes"):
+                getattr(L, s).restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise MemflowB200Error("%s failed: %s (code %d)" % (what, lib().mf_error_string(rc).decode(), rc))
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not t.is_cuda:
+        raise MemflowB200Error("memflow_b200 kernels need CUDA tensors (got device %s); there is no CPU fallback"
+                               % t.device)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def host_array(values, ctype):
+    vals = [float(v) for v in values] if ctype in (ctypes.c_double, ctypes.c_float) else [int(v) for v in values]
+    return (ctype * len(vals))(*vals)
+
+
+def require_cuda(t, name):
+    if not torch.is_tensor(t) or not t.is_cuda:
+        raise MemflowB200Error(
+            "memflow_b200: `%s` must be a CUDA tensor (device is %s). This package has no CPU fallback."
+            % (name, getattr(t, "device", type(t))))
+
+
+_workspaces = {}
+
+
+def reduce_workspace(device):
+    """Zero-initialised per-(device, stream) workspace for the estimator reductions."""
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        n = int(lib().mf_is_reduce_workspace_bytes())
+        ws = torch.zeros(n, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws

@@ -1,0 +1,134 @@
+// common.cuh -- shared device helpers for the sm_100a kernels of memflow_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/memflow_b200.h"
+
+namespace mf {
+
+#define MF_HD __host__ __device__ __forceinline__
+#define MF_D __device__ __forceinline__
+
+// ---------------------------------------------------------------------------------------------
+// Non-contractible arithmetic. nvcc fuses a*b+c into FMA by default; the reference (torch CPU/GPU
+// elementwise kernels) rounds every product. These wrappers are used ONLY in the ill-conditioned
+// expressions (1 - c*c, M^2 - (N+m)^2, 1 - beta^2, E^2 - p^2) where one extra/missing rounding is
+// amplified by cancellation. Everything else may contract.
+// ---------------------------------------------------------------------------------------------
+MF_D double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+MF_D float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+MF_D double add_rn(double a, double b) { return __dadd_rn(a, b); }
+MF_D float add_rn(float a, float b) { return __fadd_rn(a, b); }
+MF_D double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+MF_D float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+
+MF_D double sqrt_(double x) { return sqrt(x); }
+MF_D float sqrt_(float x) { return sqrtf(x); }
+MF_D double exp_(double x) { return exp(x); }
+MF_D float exp_(float x) { return expf(x); }
+MF_D double log_(double x) { return log(x); }
+MF_D float log_(float x) { return logf(x); }
+MF_D double cos_(double x) { return cos(x); }
+MF_D float cos_(float x) { return cosf(x); }
+MF_D double atan_(double x) { return atan(x); }
+MF_D float atan_(float x) { return atanf(x); }
+MF_D double atan2_(double y, double x) { return atan2(y, x); }
+MF_D float atan2_(float y, float x) { return atan2f(y, x); }
+MF_D double acos_(double x) { return acos(x); }
+MF_D float acos_(float x) { return acosf(x); }
+MF_D double tan_(double x) { return tan(x); }
+MF_D float tan_(float x) { return tanf(x); }
+MF_D double fabs_(double x) { return fabs(x); }
+MF_D float fabs_(float x) { return fabsf(x); }
+MF_D double fmax_(double a, double b) { return fmax(a, b); }
+MF_D float fmax_(float a, float b) { return fmaxf(a, b); }
+MF_D double pow_(double a, double b) { return pow(a, b); }
+MF_D float pow_(float a, float b) { return powf(a, b); }
+
+template <typename T> struct Limits;
+template <> struct Limits<double> {
+    static MF_HD double huge() { return 1.7976931348623157e308; }
+    static MF_HD double sqrt_eps() { return 1.4901161193847656e-08; }  // np.finfo(float).eps ** 0.5
+    static MF_HD double tiny_u() { return 6.525304467998525e-55; }     // 2^-180, bisection floor (see rambo.cuh)
+};
+template <> struct Limits<float> {
+    static MF_HD float huge() { return 3.4028234663852886e38f; }
+    static MF_HD float sqrt_eps() { return 1.4901161193847656e-08f; }
+    static MF_HD float tiny_u() { return 1e-30f; }
+};
+
+// integer power by repeated multiplication, compile-time exponent
+template <int E, typename T> MF_D T ipow(T x) {
+    if constexpr (E == 0) return (T)1;
+    else if constexpr (E == 1) return x;
+    else if constexpr (E % 2 == 0) { T h = ipow<E / 2>(x); return h * h; }
+    else return ipow<E - 1>(x) * x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vector global memory access. A 4-momentum row is 32 B in fp64 = exactly one DRAM sector, moved
+// with one 256-bit LDG/STG (sm_100 only); 16 B in fp32.
+// ---------------------------------------------------------------------------------------------
+MF_D void st4(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+MF_D void st4(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+MF_D void ld4(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+MF_D void ld4(const float* p, float& a, float& b, float& c, float& d) {
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "l"(p));
+}
+MF_D void ld2(const double* p, double& a, double& b) {
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+}
+MF_D void ld2(const float* p, float& a, float& b) {
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(a), "=f"(b) : "l"(p));
+}
+MF_D double ld1(const double* p) { return __ldg(p); }
+MF_D float ld1(const float* p) { return __ldg(p); }
+
+// Load one row of W elements (AoS row of the reference's `points[N, W]`). The row start is only
+// guaranteed sizeof(T)*gcd-aligned, so the widest vector that divides the row pitch is used.
+template <int W, typename T> MF_D void load_row(const T* __restrict__ p, T (&r)[W]) {
+    if constexpr ((W % 4 == 0) && sizeof(T) * 4 <= 32) {
+#pragma unroll
+        for (int i = 0; i < W; i += 4) ld4(p + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
+    } else if constexpr (W % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < W; i += 2) ld2(p + i, r[i], r[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) r[i] = ld1(p + i);
+    }
+}
+MF_D void st2(double* p, double a, double b) {
+    asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+MF_D void st2(float* p, float a, float b) {
+    asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+template <int W, typename T> MF_D void store_row(T* __restrict__ p, const T (&r)[W]) {
+    if constexpr ((W % 4 == 0) && sizeof(T) * 4 <= 32) {
+#pragma unroll
+        for (int i = 0; i < W; i += 4) st4(p + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
+    } else if constexpr (W % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < W; i += 2) st2(p + i, r[i], r[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) p[i] = r[i];
+    }
+}
+
+inline int launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MF_OK : -(int)e;
+}
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+}  // namespace mf

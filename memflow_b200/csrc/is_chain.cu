@@ -1,0 +1,202 @@
+// is_chain.cu -- fused importance-sampling chain, one launch per chunk of events:
+//   Philox base sample z ~ U[-B,B]^F  ->  T spline inverses (K4)  ->  u = (x+B)/2B  ->  RAMBO forward (K1)
+//   ->  w = jac / (2 x1 x2 s) / q(u)  ->  estimator accumulators (K5).
+// Replaces the notebook sequence flow().sample / flow().log_prob / rambo.get_momenta_from_ps / weight /
+// sums (notebooks/TestFlows_ImportanceSampling.ipynb cells [45,50-54]); squared matrix element and PDF
+// are external to the reference's hot path and set to 1.
+//
+// Mapping: a CTA of 256 threads owns a tile of E events. Spline phase: one thread per (event, feature)
+// row (rows of one transform are independent once the parameters are given), parameters staged by a
+// double-buffered 1-D TMA bulk copy per (tile, transform). Phase-space phase: the first E threads, one
+// event each, fp64, registers only. Nothing but the 3 accumulators is written to HBM unless the
+// optional debug outputs are requested. Algorithmic bytes per event: T F (3K-1) 4.
+#include "philox.cuh"
+#include "rambo.cuh"
+#include "reduce.cuh"
+#include "rqs.cuh"
+
+namespace mf {
+
+constexpr int kChainThreads = 256;
+
+template <int NF>
+__global__ void __launch_bounds__(kChainThreads)
+is_chain_kernel(const float* __restrict__ phi, int64_t N, int T, int K, RqsConst<float> C, int E /*events per tile*/,
+                int bulk_ok, uint64_t seed, uint64_t event_offset, const __grid_constant__ RamboParams<double, NF> P,
+                double inv_2s, double* __restrict__ acc, void* workspace, double* __restrict__ u_out,
+                double* __restrict__ logq_out, double* __restrict__ momenta, double* __restrict__ weight,
+                double* __restrict__ x1o, double* __restrict__ x2o) {
+    constexpr int F = 3 * NF - 2, NP = NF + 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int PW = 3 * K - 1;
+    const int rows = E * F;
+    const size_t tile_elems = (size_t)rows * PW;
+    const size_t tile_bytes_al = (tile_elems * sizeof(float) + 127) / 128 * 128;
+    float* stage_base[2] = {reinterpret_cast<float*>(smem_raw), reinterpret_cast<float*>(smem_raw + tile_bytes_al)};
+    unsigned char* tail = smem_raw + 2 * tile_bytes_al;
+    float* val = reinterpret_cast<float*>(tail);                // [kChainThreads] current x per row
+    float* lsum = val + kChainThreads;                          // [kChainThreads] sum_t ladj per row
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lsum + kChainThreads);
+
+    const int tid = threadIdx.x;
+    const int64_t num_tiles = (N + E - 1) / E;
+    const size_t transform_pitch = (size_t)N * F * PW;  // elements between phi[t] and phi[t+1]
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    __syncthreads();
+
+    // work items are (tile, transform) pairs in order; item j of this CTA -> stage j & 1
+    auto tile_is_bulk = [&](int64_t tile) { return bulk_ok && (tile + 1) * (int64_t)E <= N; };
+    auto issue = [&](int64_t tile, int t, int st) {
+        if (tid == 0 && tile < num_tiles && tile_is_bulk(tile)) {
+            const uint32_t bytes = (uint32_t)(tile_elems * sizeof(float));
+            mbar_expect_tx(&bars[st], bytes);
+            bulk_g2s(stage_base[st], phi + (size_t)t * transform_pitch + (size_t)tile * tile_elems, bytes, &bars[st]);
+        }
+    };
+
+    Kahan k1, k2;
+    double cnt = 0.0;
+    uint32_t parity[2] = {0u, 0u};
+    int item = 0;
+    int64_t tile = blockIdx.x;
+    issue(tile, T - 1, 0);  // sampling applies the transforms in reverse order: f_T^-1 first
+    for (; tile < num_tiles; tile += gridDim.x) {
+        const int64_t ev0 = tile * E;
+        const int nev = (int)((N - ev0) < E ? (N - ev0) : E);
+        const int nrows = nev * F;
+        const int e = tid / F, f = tid - e * F;
+        const bool row_active = tid < nrows;
+        float x = 0.0f, ladj_acc = 0.0f;
+        if (row_active) {  // base sample: Philox counter = (global event index, feature block), key = seed
+            const uint64_t gev = event_offset + (uint64_t)(ev0 + e);
+            Philox4 r4 = philox4x32_10((uint32_t)gev, (uint32_t)(gev >> 32), (uint32_t)(f >> 2), 0u, (uint32_t)seed,
+                                       (uint32_t)(seed >> 32));
+            const uint32_t bits = (f & 3) == 0 ? r4.x : ((f & 3) == 1 ? r4.y : ((f & 3) == 2 ? r4.z : r4.w));
+            x = C.bound * (2.0f * u01_from_bits(bits) - 1.0f);
+        }
+        for (int tt = 0; tt < T; ++tt, ++item) {
+            const int t = T - 1 - tt;
+            const int st = item & 1;
+            // prefetch the next (tile, transform) item into the other stage
+            if (tt + 1 < T) issue(tile, t - 1, st ^ 1); else issue(tile + gridDim.x, T - 1, st ^ 1);
+            float* sm = stage_base[st];
+            if (tile_is_bulk(tile)) {
+                mbar_wait(&bars[st], parity[st]);
+                parity[st] ^= 1u;
+            } else {
+                const float* src = phi + (size_t)t * transform_pitch + (size_t)tile * tile_elems;
+                const size_t ne = (size_t)nrows * PW;
+                for (size_t i = tid; i < ne; i += kChainThreads) sm[i] = __ldg(src + i);
+                __syncthreads();
+            }
+            if (row_active) {
+                float out, ladj;
+                int bin;
+                rqs_row_1lane<float, true>(sm + (size_t)tid * PW, K, C, x, out, ladj, bin);
+                x = out;
+                ladj_acc += ladj;
+            }
+            fence_proxy_async();
+            __syncthreads();
+        }
+        val[tid] = x;
+        lsum[tid] = ladj_acc;
+        __syncthreads();
+        if (tid < nev) {  // phase-space phase: one event per thread, fp64
+            double r[F];
+            double logq = 0.0;
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                r[j] = ((double)val[tid * F + j] + (double)C.bound) / (2.0 * (double)C.bound);
+                logq += (double)lsum[tid * F + j];
+            }
+            double out[NP][4], jac, x1, x2;
+            rambo_forward_event<double, NF>(r, P, out, jac, x1, x2);
+            const double target = inv_2s / (x1 * x2);  // 1 / (2 x1 x2 s): ME = pdf = 1
+            const double w = target * jac / exp(logq);
+            if (target > 0.0 && jac == jac) { k1.add(w); k2.add(w * w); cnt += 1.0; }
+            const int64_t ge = ev0 + tid;
+            if (u_out) {
+#pragma unroll
+                for (int j = 0; j < F; ++j) u_out[ge * F + j] = r[j];
+            }
+            if (logq_out) logq_out[ge] = logq;
+            if (momenta) {
+#pragma unroll
+                for (int k = 0; k < NP; ++k) st4(momenta + ge * (NP * 4) + 4 * k, out[k][0], out[k][1], out[k][2], out[k][3]);
+            }
+            if (weight) weight[ge] = jac;
+            if (x1o) x1o[ge] = x1;
+            if (x2o) x2o[ge] = x2;
+        }
+        __syncthreads();  // val/lsum reused by the next tile
+    }
+    grid_accumulate<kChainThreads>(k1.value(), k2.value(), cnt, acc, workspace);
+}
+
+template <int NF>
+static int chain_launch(const float* phi, int64_t N, int T, int K, float bound, float slope, uint64_t seed,
+                        uint64_t event_offset, const double* masses, double e_collider, uint32_t flags, double* acc,
+                        void* workspace, double* u_out, double* logq, double* momenta, double* weight, double* x1,
+                        double* x2, cudaStream_t stream) {
+    constexpr int F = 3 * NF - 2;
+    const int PW = 3 * K - 1;
+    int dev = 0, sms = 148, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    int E = kChainThreads / F;
+    if (E >= 32) E = E / 32 * 32;  // whole warps in the phase-space phase
+    const size_t extra = 2 * kChainThreads * sizeof(float) + 2 * sizeof(uint64_t) + 256;
+    auto need = [&](int e) { return (((size_t)e * F * PW * sizeof(float) + 127) / 128 * 128) * 2 + extra; };
+    while (E > 1 && need(E) > (size_t)smem_max / 2) --E;  // aim for >= 2 CTAs per SM
+    while (E > 1 && need(E) > (size_t)smem_max) --E;
+    if (need(E) > (size_t)smem_max) return MF_E_SHAPE;
+    int bulk_ok = aligned(phi, 16) && (((size_t)N * F * PW * sizeof(float)) % 16 == 0 || T == 1) ? 1 : 0;
+    if (bulk_ok) {
+        int e = E;
+        while (e > 0 && ((size_t)e * F * PW * sizeof(float)) % 16 != 0) --e;
+        if (e > 0) E = e; else bulk_ok = 0;
+    }
+    const size_t smem = need(E);
+    RqsConst<float> C;
+    C.bound = bound;
+    C.clip = slope > 0.0f ? 1 : 0;
+    const double L = C.clip ? std::log((double)slope) : 1.0;
+    C.two_over_L = C.clip ? (float)(2.0 / L) : 0.0f;
+    C.one_over_L = C.clip ? (float)(1.0 / L) : 0.0f;
+    const RamboParams<double, NF> P = make_forward_params<double, NF>(masses, e_collider, nullptr, flags & ~MF_FLAG_CUTS);
+    const double inv_2s = 1.0 / (2.0 * e_collider * e_collider);
+    const int64_t num_tiles = (N + E - 1) / E;
+    int ctas_per_sm = (int)((size_t)smem_max / smem);
+    if (ctas_per_sm > 8) ctas_per_sm = 8;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    int64_t grid = (int64_t)sms * ctas_per_sm;
+    if (grid > num_tiles) grid = num_tiles;
+    if (grid > kReduceMaxBlocks) grid = kReduceMaxBlocks;
+    auto kern = is_chain_kernel<NF>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)grid, kChainThreads, smem, stream>>>(phi, N, T, K, C, E, bulk_ok, seed, event_offset, P, inv_2s, acc,
+                                                          workspace, u_out, logq, momenta, weight, x1, x2);
+    return launch_status();
+}
+
+}  // namespace mf
+
+extern "C" int mf_is_chain_f64(const float* phi, int64_t N, int n_final, int T, int K, float bound, float slope,
+                               uint64_t seed, uint64_t event_offset, const double* masses, double e_collider,
+                               uint32_t flags, double* acc, void* workspace, double* u_out, double* logq,
+                               double* momenta, double* weight, double* x1, double* x2, mf_stream_t stream) {
+    if (N < 0 || T < 1 || !masses || !acc || !workspace || (N > 0 && !phi)) return MF_E_BADARG;
+    if (K < 1 || K > 128) return MF_E_SHAPE;
+    if (n_final < MF_MIN_FINAL || n_final > MF_MAX_FINAL) return MF_E_NFINAL;
+    if (momenta && !mf::aligned(momenta, 32)) return MF_E_ALIGN;
+    if (N == 0) return MF_OK;
+    switch (n_final) {
+#define MF_CASE(NF) \
+    case NF: return mf::chain_launch<NF>(phi, N, T, K, bound, slope, seed, event_offset, masses, e_collider, flags, acc, workspace, u_out, logq, momenta, weight, x1, x2, (cudaStream_t)stream);
+        MF_CASE(3) MF_CASE(4) MF_CASE(5) MF_CASE(6) MF_CASE(7) MF_CASE(8)
+#undef MF_CASE
+    }
+    return MF_E_NFINAL;
+}

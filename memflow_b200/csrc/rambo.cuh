@@ -1,0 +1,369 @@
+// rambo.cuh -- per-event device math of the RAMBO-on-diet map (Platzer, arXiv:1308.2922, massive
+// variant) as MEMFlow implements it: memflow/phasespace/rambo_generator.py, memflow/phasespace/utils.py.
+// One event per thread; all per-particle state lives in registers (loops over particles are fully
+// unrolled on the compile-time multiplicity NF).
+#pragma once
+#include <cmath>
+#include <utility>
+
+#include "common.cuh"
+
+namespace mf {
+
+// Launch-constant parameters, passed by value (kernel parameter space / constant bank).
+template <typename T, int NF> struct RamboParams {
+    T m[NF];      // final-state masses (already permuted / target masses for the inverse)
+    T msum_rev[NF];  // forward: flip(cumsum(flip(m))) (:484-486).  inverse: sum(m[j:]) forward order (:660)
+    T msum;       // torch.sum(masses_t)
+    T q, A;       // x1x2 map constants, utils.py:266-269
+    T t1, t1sq, neg_inv_A;
+    T e_collider;
+    T flat_c, flat_ff;  // get_flatWeights: c = (2pi)^(4-3n) (pi/2)^(n-1), ff = (n-1)!(n-2)!
+    float flat_c32, flat_ff32;
+    T cut_pt, cut_dr, cut_eta;
+    int order[NF];
+    uint32_t flags;
+};
+
+// rambo_generator.py:145-149 rho(M,N,m) = sqrt((M^2-(N+m)^2)(M^2-(N-m)^2)) / (8 M^2)
+template <typename T> MF_D T rho_f(T M, T N, T m) {
+    T Msqr = mul_rn(M, M);
+    T a = N + m, b = N - m;
+    T t = mul_rn(sub_rn(Msqr, mul_rn(a, a)), sub_rn(Msqr, mul_rn(b, b)));
+    return sqrt_(t) / ((T)8 * Msqr);
+}
+
+template <typename T> MF_D T rho2_3(T x, T y, T z) { return (x * x + y * y) + z * z; }
+
+// utils.py:88-118 boost_t: general Lorentz boost by velocity bv
+template <typename T> MF_D void boost(const T (&p)[4], T bx, T by, T bz, T (&o)[4]) {
+    T b2 = add_rn(add_rn(mul_rn(bx, bx), mul_rn(by, by)), mul_rn(bz, bz));
+    T gamma = (T)1 / sqrt_(sub_rn((T)1, b2));
+    T bp = (p[1] * bx + p[2] * by) + p[3] * bz;
+    T gamma2 = (b2 > (T)0) ? (gamma - (T)1) / b2 : (T)0;
+    T factor = gamma2 * bp + gamma * p[0];
+    o[1] = p[1] + factor * bx;
+    o[2] = p[2] + factor * by;
+    o[3] = p[3] + factor * bz;
+    o[0] = gamma * (p[0] + bp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mass-variable root solve: v = u^E ((E+1) - E u), u in [0,1]  (rambo_generator.py:142-143).
+// The reference finds u by up to 180 levels of dyadic bisection over the whole batch
+// (bisect_vec_batch, :400-446: 2 pow per level -> ~360 pow per root). Here:
+//   E == 1 : closed form u = v / (1 + sqrt(1 - v)).
+//   E >= 2 : v is the CDF of Beta(E,2). Work in the well-conditioned variable: x = u and
+//            target t = v when v < 0.65, else x = 1-u and t = 1-v with
+//            1 - v = x^2 P_E(x)  (polynomial, no cancellation). fp32 asymptotic start + 2 fp32
+//            Newton steps (MUFU log2/exp2), then 2 fp64 Halley steps (cubic): converged to <= 2 ulp of
+//            the exact root for all v in (1e-30, 1), tests/test_massvar_solver.py.
+// Edge semantics follow the bisection: v <= 0 -> 2^-180 (its floor after 180 levels), v >= 1 -> 1.
+// ---------------------------------------------------------------------------------------------
+MF_HD constexpr double binom(int n, int k) {
+    if (k < 0 || k > n) return 0.0;
+    double r = 1.0;
+    for (int i = 1; i <= k; ++i) r = r * (double)(n - k + i) / (double)i;
+    return r;
+}
+// coefficient of x^k (k = 2..E+1) in 1 - (1-x)^E (1 + E x)
+MF_HD constexpr double tail_coef(int E, int k) {
+    double s = (k % 2 == 0) ? 1.0 : -1.0;
+    return -s * (binom(E, k) - (double)E * binom(E, k - 1));
+}
+template <int E, int K, typename T> MF_D T tail_horner(T x, T acc) {
+    if constexpr (K < 2) return acc;
+    else return tail_horner<E, K - 1>(x, acc * x + (T)tail_coef(E, K));
+}
+// P_E(x) with 1 - g(1-x) = x^2 P_E(x)
+template <int E, typename T> MF_D T tail_poly(T x) { return tail_horner<E, E>(x, (T)tail_coef(E, E + 1)); }
+
+template <int E, typename T> struct MassVarFn {
+    // F(x) - t, F'(x), F''(x) in the chosen variable
+    static MF_D void eval(bool small, T x, T t, T& f, T& d1, T& d2) {
+        const T ee1 = (T)(E * (E + 1));
+        if (small) {
+            T xm2 = ipow<E - 2>(x);
+            T xm1 = xm2 * x;
+            f = xm1 * x * ((T)(E + 1) - (T)E * x) - t;
+            d1 = ee1 * xm1 * ((T)1 - x);
+            d2 = ee1 * xm2 * ((T)(E - 1) - (T)E * x);
+        } else {
+            T om = (T)1 - x;
+            T omm2 = ipow<E - 2>(om);
+            T omm1 = omm2 * om;
+            f = x * x * tail_poly<E>(x) - t;
+            d1 = ee1 * x * omm1;
+            d2 = ee1 * omm2 * ((T)1 - (T)E * x);
+        }
+    }
+};
+
+template <int E> MF_D float massvar_start_f32(bool small, float tf) {
+    float x;
+    if (small) {
+        const float ie = 1.0f / (float)E;
+        x = exp2f(__log2f(tf * (1.0f / (float)(E + 1))) * ie);
+        x = exp2f(__log2f(__fdividef(tf, (float)(E + 1) - (float)E * x)) * ie);
+    } else {
+        float d0 = sqrtf((2.0f / (float)(E * (E + 1))) * tf);
+        x = d0 * (1.0f + ((float)(E - 1) / 3.0f) * d0);
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        float f, d1, d2;
+        MassVarFn<E, float>::eval(small, x, tf, f, d1, d2);
+        float xn = x - __fdividef(f, d1);
+        x = (xn > 0.0f && xn < 1.0f) ? xn : x;  // also rejects NaN/inf steps
+    }
+    return x;
+}
+
+template <int E> MF_D double solve_massvar(double v) {
+    if constexpr (E == 1) {
+        double u = v / (1.0 + sqrt(1.0 - v));
+        return (v <= 0.0) ? Limits<double>::tiny_u() : ((v >= 1.0) ? 1.0 : u);
+    } else {
+        const bool small = v < 0.65;
+        const double t = small ? v : 1.0 - v;
+        double x;
+        if (t > 1e-30) {
+            x = (double)massvar_start_f32<E>(small, (float)t);
+        } else if (t > 0.0) {  // outside fp32 range: fp64 asymptotic start (never taken for u in [1e-10, 1-1e-10])
+            x = small ? pow(t / (double)(E + 1), 1.0 / (double)E) : sqrt(2.0 * t / (double)(E * (E + 1)));
+        } else {
+            x = (t == 0.0 || t < 0.0) ? 0.0 : t;  // t <= 0 -> 0, NaN -> NaN
+        }
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            double f, d1, d2;
+            MassVarFn<E, double>::eval(small, x, t, f, d1, d2);
+            double xn = x - (2.0 * f * d1) / (2.0 * d1 * d1 - f * d2);
+            x = (xn > 0.0 && xn < 1.0) ? xn : x;
+        }
+        double u = small ? x : 1.0 - x;
+        return (u < Limits<double>::tiny_u()) ? Limits<double>::tiny_u() : u;  // NaN stays NaN
+    }
+}
+template <int E> MF_D float solve_massvar(float v) {
+    if constexpr (E == 1) {
+        float u = v / (1.0f + sqrtf(1.0f - v));
+        return (v <= 0.0f) ? Limits<float>::tiny_u() : ((v >= 1.0f) ? 1.0f : u);
+    } else {
+        const bool small = v < 0.65f;
+        const float t = small ? v : 1.0f - v;
+        float x = (t > 0.0f) ? massvar_start_f32<E>(small, t) : ((t <= 0.0f) ? 0.0f : t);
+        float f, d1, d2;
+        MassVarFn<E, float>::eval(small, x, t, f, d1, d2);
+        float xn = x - f / d1;
+        x = (xn > 0.0f && xn < 1.0f) ? xn : x;
+        float u = small ? x : 1.0f - x;
+        return (u < Limits<float>::tiny_u()) ? Limits<float>::tiny_u() : u;
+    }
+}
+
+// get_flatWeights (:111-140) * massive correction (:489-507), from K_i, M_i. quirks reproduces the
+// reference's float32 in-place chain.
+template <typename T, int NF>
+MF_D T rambo_weight(const RamboParams<T, NF>& P, T E_cm, const T (&K)[NF], const T (&M)[NF], bool quirks) {
+    T f8 = (T)8 * rho_f(M[NF - 2], P.m[NF - 1], P.m[NF - 2]);
+    T pr = (T)1;
+#pragma unroll
+    for (int i = 0; i <= NF - 3; ++i)
+        pr *= (rho_f(M[i], M[i + 1], P.m[i]) / rho_f(K[i], K[i + 1], (T)0)) * (M[i + 1] / K[i + 1]);
+    T pw = ipow<2 * NF - 4>(K[0] / M[0]);
+    if (!quirks) {
+        T w = P.flat_c * (ipow<NF - 2>(E_cm * E_cm) / P.flat_ff);
+        w *= f8;
+        w *= pr;
+        w *= pw;
+        return w;
+    } else {
+        float e = (float)E_cm;
+        float e2 = __fmul_rn(e, e);
+        float wf = __fmul_rn(P.flat_c32, __fdiv_rn(ipow<NF - 2>(e2), P.flat_ff32));
+        wf = (float)((double)wf * (double)f8);
+        wf = (float)((double)wf * (double)pr);
+        wf = (float)((double)wf * (double)pw);
+        return (T)wf;
+    }
+}
+
+template <typename T> MF_D T pseudo_rap(const T (&p)[4]) {  // utils.py:205-215
+    T pt = sqrt_(p[1] * p[1] + p[2] * p[2]);
+    T th = atan2_(pt, p[3]);
+    if (pt < Limits<T>::sqrt_eps() && fabs_(p[3]) < Limits<T>::sqrt_eps()) return Limits<T>::huge();
+    return -log_(tan_(th / (T)2));
+}
+template <typename T> MF_D T delphi(const T (&a)[4], const T (&b)[4]) {  // utils.py:231-249
+    T pt1 = sqrt_(a[1] * a[1] + a[2] * a[2]);
+    T pt2 = sqrt_(b[1] * b[1] + b[2] * b[2]);
+    T tmp = (a[1] * b[1] + a[2] * b[2]) / (pt1 * pt2);
+    T r = (fabs_(tmp) > (T)1) ? acos_(tmp / fabs_(tmp)) : acos_(tmp);
+    if (pt1 == (T)0 || pt2 == (T)0) r = Limits<T>::huge();
+    return r;
+}
+
+// One event of generateKinematics_batch (rambo_generator.py:168-398): r = the event's 3NF-2 uniforms.
+template <typename T, int NF>
+MF_D void rambo_forward_event(const T (&r)[3 * NF - 2], const RamboParams<T, NF>& P, T (&out)[NF + 2][4], T& wgt,
+                              T& x1, T& x2) {
+    constexpr int D = 3 * NF - 4, NE = NF - 2, NP = NF + 2;
+    // ---- x1, x2 from the last two uniforms: utils.py:260-284 (same operation order) ----
+    T wx;
+    if (P.flags & MF_FLAG_X1X2_DIRECT) {  // uniform_x1x2=False, rambo_generator.py:229-234
+        x1 = r[D]; x2 = r[D + 1]; wx = (T)1;
+    } else {
+        T ml1 = (P.t1 + sqrt_(P.t1sq + ((T)-2 * r[D]) / P.A)) / P.neg_inv_A;
+        T ml2 = (P.q - ml1) * r[D + 1];
+        x1 = exp_(-ml1);
+        x2 = exp_(-ml2);
+        wx = (T)1 / ((T)1 / ((P.A * x1) * x2));
+    }
+    const T E_cm = sqrt_(x1 * x2) * P.e_collider;  // :226
+
+    // ---- intermediate masses: :448-509. K_i = K_0 * prod_{j<i} t_j, M_i = K_i + sum_{j>=i} m_j ----
+    T K[NF], M[NF];
+    {
+        const T K0 = E_cm - P.msum;
+        T prod = (T)1;
+        K[0] = K0;
+        // exponent of column i is NF-2-i (:405-407); unrolled so each solve has a compile-time exponent
+        [&]<int... I>(std::integer_sequence<int, I...>) {
+            ((prod *= solve_massvar<NF - 2 - I>(r[I]), K[I + 1] = K0 * prod), ...);
+        }(std::make_integer_sequence<int, NE>{});
+#pragma unroll
+        for (int i = 0; i <= NF - 2; ++i) M[i] = K[i] + P.msum_rev[i];
+        M[NF - 1] = P.m[NF - 1];
+        K[NF - 1] = (T)0;  // unused
+    }
+    const bool quirks = (P.flags & MF_FLAG_REF_FP32_QUIRKS) != 0;
+    wgt = wx * rambo_weight<T, NF>(P, E_cm, K, M, quirks);
+
+    // ---- sequential two-body decays: :294-345 ----
+    T Q[4] = {M[0], (T)0, (T)0, (T)0};
+#pragma unroll
+    for (int k = 0; k <= NF - 2; ++k) {
+        const T qk = (T)4 * M[k] * rho_f(M[k], M[k + 1], P.m[k]);
+        const T ct = (T)2 * r[NE + 2 * k] - (T)1;
+        const T st = sqrt_(sub_rn((T)1, mul_rn(ct, ct)));
+        const T phi = (T)6.283185307179586 * r[NE + 2 * k + 1];
+        const T cp = cos_(phi);
+        const T sq = sqrt_(sub_rn((T)1, mul_rn(cp, cp)));
+        const T sp = (phi > (T)3.141592653589793) ? -sq : sq;
+        T p2[4], pb[4];
+        p2[1] = (qk * st) * cp;
+        p2[2] = (qk * st) * sp;
+        p2[3] = qk * ct;
+        const T m2 = P.m[k] * P.m[k];
+        p2[0] = sqrt_(rho2_3(p2[1], p2[2], p2[3]) + m2);
+        boost(p2, Q[1] / Q[0], Q[2] / Q[0], Q[3] / Q[0], pb);
+        pb[0] = sqrt_(rho2_3(pb[1], pb[2], pb[3]) + m2);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) out[2 + k][c] = pb[c];
+        Q[1] -= pb[1]; Q[2] -= pb[2]; Q[3] -= pb[3];
+        Q[0] = sqrt_(rho2_3(Q[1], Q[2], Q[3]) + M[k + 1] * M[k + 1]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[NP - 1][c] = Q[c];
+    {   // incoming partons :511-551
+        T h = quirks ? (T)((float)E_cm / 2.0f) : E_cm / (T)2;
+        out[0][0] = h; out[0][1] = (T)0; out[0][2] = (T)0; out[0][3] = h;
+        out[1][0] = h; out[1][1] = (T)0; out[1][2] = (T)0; out[1][3] = -h;
+    }
+
+    // ---- lab frame (utils.py:180-202) for the cuts (:350-393) and/or as the requested output ----
+    if (P.flags & (MF_FLAG_CUTS | MF_FLAG_LAB_FRAME)) {
+        T lab[NP][4];
+        if (x1 != (T)1 || x2 != (T)1) {
+            T ref0 = out[0][0] * x1 + out[1][0] * x2;
+            T ref3 = out[0][3] * x1 + out[1][3] * x2;
+            T bz = ref3 / ref0;
+#pragma unroll
+            for (int k = 0; k < NP; ++k) boost(out[k], (T)0 / ref0, (T)0 / ref0, bz, lab[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NP; ++k)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) lab[k][c] = out[k][c];
+        }
+        if (P.flags & MF_FLAG_CUTS) {
+            T ptmin = Limits<T>::huge();
+            bool ptnan = false;
+#pragma unroll
+            for (int k = 2; k < NP; ++k) {
+                T pt = sqrt_(lab[k][1] * lab[k][1] + lab[k][2] * lab[k][2]);
+                ptnan |= (pt != pt);
+                ptmin = pt < ptmin ? pt : ptmin;
+            }
+            T f2 = (!ptnan && ptmin < P.cut_pt) ? (T)0 : (T)1;
+            T eta[NF];
+#pragma unroll
+            for (int k = 0; k < NF; ++k) eta[k] = pseudo_rap(lab[k + 2]);
+#pragma unroll
+            for (int i = 0; i < NF; ++i)
+#pragma unroll
+                for (int j = 0; j < i; ++j) {
+                    T de = eta[i] - eta[j];
+                    T dp = delphi(lab[i + 2], lab[j + 2]);
+                    T dr = sqrt_(de * de + dp * dp);
+                    f2 *= (fabs_(dr) < P.cut_dr) ? (T)0 : (T)1;
+                }
+            if (P.cut_eta > (T)0) {
+                T emax = -Limits<T>::huge();
+                bool en = false;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) { en |= (eta[k] != eta[k]); emax = eta[k] > emax ? eta[k] : emax; }
+                f2 *= (!en && P.cut_eta < fabs_(emax)) ? (T)0 : (T)1;
+            }
+            wgt *= f2;
+        }
+        if (P.flags & MF_FLAG_LAB_FRAME) {
+#pragma unroll
+            for (int k = 0; k < NP; ++k)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) out[k][c] = lab[k][c];
+        }
+    }
+
+}
+
+// Host: fill the launch constants exactly as the reference's 0-dim tensors are computed.
+template <typename T, int NF>
+static RamboParams<T, NF> make_forward_params(const T* masses, T e_collider, const T* cuts, uint32_t flags) {
+    RamboParams<T, NF> P{};
+    for (int i = 0; i < NF; ++i) { P.m[i] = masses[i]; P.order[i] = i; }
+    {
+        T acc = (T)0;
+        for (int i = NF - 1; i >= 0; --i) { acc += masses[i]; P.msum_rev[i] = acc; }
+        T s = (T)0;
+        for (int i = 0; i < NF; ++i) s += masses[i];
+        P.msum = s;
+    }
+    {   // utils.py:266-269, evaluated in T like the reference's 0-dim tensors
+        T ratio = P.msum / e_collider;
+        T logtau = (T)std::log((double)(ratio * ratio));
+        if (sizeof(T) == 4) logtau = (T)logf((float)(ratio * ratio));
+        P.q = -logtau;
+        P.A = (T)(-0.5) * (P.q * P.q) + (P.q * P.q);
+        P.t1 = (-P.q) / P.A;
+        P.t1sq = P.t1 * P.t1;
+        P.neg_inv_A = (T)-1 * ((T)1 / P.A);
+    }
+    P.e_collider = e_collider;
+    {
+        const double pi = 3.141592653589793;
+        double c = std::pow(2.0 * pi, 4 - 3 * NF) * std::pow(pi / 2.0, NF - 1);
+        double ff = 1.0;
+        for (int i = 2; i <= NF - 1; ++i) ff *= i;
+        for (int i = 2; i <= NF - 2; ++i) ff *= i;
+        P.flat_c = (T)c; P.flat_ff = (T)ff;
+        P.flat_c32 = (float)c; P.flat_ff32 = (float)ff;
+    }
+    if (cuts != nullptr && (flags & MF_FLAG_CUTS)) { P.cut_pt = cuts[0]; P.cut_dr = cuts[1]; P.cut_eta = cuts[2]; }
+    else { P.cut_pt = (T)-1; P.cut_dr = (T)-1; P.cut_eta = (T)-1; flags &= ~MF_FLAG_CUTS; }
+    P.flags = flags;
+    return P;
+}
+
+}  // namespace mf

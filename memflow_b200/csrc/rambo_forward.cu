@@ -1,0 +1,117 @@
+// rambo_forward.cu -- K1: unit hypercube -> CM-frame momenta + Jacobian weight, one event per thread.
+// Replaces FlatInvertiblePhasespace.generateKinematics_batch (memflow/phasespace/rambo_generator.py:168-398),
+// which runs ~250-600 torch elementwise launches plus a 180-level batch bisection per call.
+//
+// HBM layout: the reference's AoS tensors are kept as they are.
+//   in : u[N][3n-2]            read once, row per thread, widest vector the row pitch allows; the rows of
+//                              a warp are contiguous so every DRAM sector is fetched once (L1 absorbs
+//                              the per-thread stride).
+//   out: momenta[N][n+2][4]    one 4-momentum = 32 B (fp64) = one DRAM sector = one 256-bit STG.
+//        weight/x1/x2/logw[N]  coalesced scalar stores.
+// Algorithmic bytes per event: (3n-2 + 4(n+2) + 3) * sizeof(T) (+ sizeof(T) with logweight).
+#include "rambo.cuh"
+
+namespace mf {
+
+template <typename T, int NF>
+__global__ void __launch_bounds__(256)
+rambo_forward_kernel(const T* __restrict__ u, int64_t N, const __grid_constant__ RamboParams<T, NF> P,
+                     T* __restrict__ momenta, T* __restrict__ weight, T* __restrict__ logweight,
+                     T* __restrict__ x1o, T* __restrict__ x2o, int32_t* __restrict__ status) {
+    constexpr int W = 3 * NF - 2, NP = NF + 2;
+    const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ev >= N) return;
+
+    T r[W];
+    load_row<W>(u + ev * W, r);
+
+    if (status != nullptr) {
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < W; ++i) bad |= (r[i] != r[i]);
+        if (bad) atomicOr(status, MF_ST_NAN_INPUT);
+    }
+
+    T out[NP][4], wgt, x1, x2;
+    rambo_forward_event<T, NF>(r, P, out, wgt, x1, x2);
+
+    // ---- stores ----
+    T* mo = momenta + ev * (NP * 4);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) st4(mo + 4 * k, out[k][0], out[k][1], out[k][2], out[k][3]);
+    weight[ev] = wgt;
+    x1o[ev] = x1;
+    x2o[ev] = x2;
+    if (logweight != nullptr) logweight[ev] = log_(wgt);
+}
+
+template <typename T, int NF>
+static int launch_forward(const T* u, int64_t N, const T* masses, T e_collider, const T* cuts, uint32_t flags,
+                          T* momenta, T* weight, T* logweight, T* x1, T* x2, int32_t* status, cudaStream_t stream) {
+    const RamboParams<T, NF> P = make_forward_params<T, NF>(masses, e_collider, cuts, flags);
+    if (N == 0) return MF_OK;
+    const int threads = 256;
+    const int64_t blocks = (N + threads - 1) / threads;
+    rambo_forward_kernel<T, NF><<<(unsigned)blocks, threads, 0, stream>>>(u, N, P, momenta, weight, logweight,
+                                                                          x1, x2, status);
+    return launch_status();
+}
+
+template <typename T>
+static int forward_dispatch(const T* u, int64_t N, int n, const T* masses, T e_collider, const T* cuts,
+                            uint32_t flags, T* momenta, T* weight, T* logweight, T* x1, T* x2, int32_t* status,
+                            cudaStream_t stream) {
+    if (N < 0 || masses == nullptr) return MF_E_BADARG;
+    if (n < MF_MIN_FINAL || n > MF_MAX_FINAL) return MF_E_NFINAL;
+    if (N > 0 && (!u || !momenta || !weight || !x1 || !x2)) return MF_E_BADARG;
+    if ((flags & MF_FLAG_CUTS) && cuts == nullptr) return MF_E_BADARG;
+    const int W = 3 * n - 2;
+    const size_t row_align = (W % 4 == 0) ? 4 * sizeof(T) : ((W % 2 == 0) ? 2 * sizeof(T) : sizeof(T));
+    if (!aligned(u, row_align) || !aligned(momenta, 4 * sizeof(T))) return MF_E_ALIGN;
+    if (N > (int64_t)0x7fffffff * 256) return MF_E_BADARG;
+    switch (n) {
+#define MF_CASE(NF) \
+    case NF: return launch_forward<T, NF>(u, N, masses, e_collider, cuts, flags, momenta, weight, logweight, x1, x2, status, stream);
+        MF_CASE(3) MF_CASE(4) MF_CASE(5) MF_CASE(6) MF_CASE(7) MF_CASE(8)
+#undef MF_CASE
+    }
+    return MF_E_NFINAL;
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256) massvar_kernel(const double* __restrict__ v, int64_t N, double* __restrict__ u) {
+    constexpr int NE = NF - 2;
+    const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ev >= N) return;
+    [&]<int... I>(std::integer_sequence<int, I...>) {
+        ((u[ev * NE + I] = solve_massvar<NF - 2 - I>(v[ev * NE + I])), ...);
+    }(std::make_integer_sequence<int, NE>{});
+}
+
+}  // namespace mf
+
+extern "C" int mf_massvar_solve_f64(const double* v, int64_t N, int n_final, double* u, mf_stream_t stream) {
+    if (N < 0 || (N > 0 && (!v || !u))) return MF_E_BADARG;
+    if (n_final < MF_MIN_FINAL || n_final > MF_MAX_FINAL) return MF_E_NFINAL;
+    if (N == 0) return MF_OK;
+    const unsigned blocks = (unsigned)((N + 255) / 256);
+    switch (n_final) {
+#define MF_CASE(NF) case NF: mf::massvar_kernel<NF><<<blocks, 256, 0, (cudaStream_t)stream>>>(v, N, u); break;
+        MF_CASE(3) MF_CASE(4) MF_CASE(5) MF_CASE(6) MF_CASE(7) MF_CASE(8)
+#undef MF_CASE
+    }
+    return mf::launch_status();
+}
+
+extern "C" int mf_rambo_forward_f64(const double* u, int64_t N, int n_final, const double* masses, double e_collider,
+                                    const double* cuts, uint32_t flags, double* momenta, double* weight,
+                                    double* logweight, double* x1, double* x2, int32_t* status, mf_stream_t stream) {
+    return mf::forward_dispatch<double>(u, N, n_final, masses, e_collider, cuts, flags, momenta, weight, logweight,
+                                        x1, x2, status, (cudaStream_t)stream);
+}
+extern "C" int mf_rambo_forward_f32(const float* u, int64_t N, int n_final, const float* masses, float e_collider,
+                                    const float* cuts, uint32_t flags, float* momenta, float* weight,
+                                    float* logweight, float* x1, float* x2, int32_t* status, mf_stream_t stream) {
+    return mf::forward_dispatch<float>(u, N, n_final, masses, e_collider, cuts, flags, momenta, weight, logweight,
+                                       x1, x2, status, (cudaStream_t)stream);
+}

@@ -1,0 +1,186 @@
+// rambo_inverse.cu -- K2: CM-frame final-state momenta -> unit hypercube + inverse weight.
+// Replaces FlatInvertiblePhasespace.getPSpoint_batch (memflow/phasespace/rambo_generator.py:615-736)
+// and get_uniform_from_x1x2 (memflow/phasespace/utils.py:287-309). One event per thread.
+//
+// HBM layout: momenta rows are read with one 256-bit LDG each (32 B = one sector, fp64); the
+// event pitch is a parameter so that the `momenta[:, 2:]` slice of a forward output is read in
+// place (the reference clones it, :628, and again per particle, :680).
+// Algorithmic bytes per event: (4n + 2 + 3n-2 + 1) * sizeof(T).
+#include "rambo.cuh"
+
+namespace mf {
+
+template <typename T, int NF>
+__global__ void __launch_bounds__(256)
+rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const T* __restrict__ x1a,
+                     const T* __restrict__ x2a, int64_t N, const __grid_constant__ RamboParams<T, NF> P,
+                     T* __restrict__ ps, T* __restrict__ prob, T* __restrict__ logprob,
+                     int32_t* __restrict__ status) {
+    constexpr int D = 3 * NF - 4, W = D + 2;
+    const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ev >= N) return;
+
+    T Pm[NF][4];
+    {
+        const T* base = momenta + ev * event_stride;
+#pragma unroll
+        for (int k = 0; k < NF; ++k) ld4(base + 4 * P.order[k], Pm[k][0], Pm[k][1], Pm[k][2], Pm[k][3]);
+    }
+    const T x1 = x1a[ev], x2 = x2a[ev];
+
+    if (!(P.flags & MF_FLAG_NO_CM_CHECK) && status != nullptr) {  // :630-635
+        T s1 = (T)0, s2 = (T)0, s3 = (T)0;
+#pragma unroll
+        for (int k = 0; k < NF; ++k) { s1 += Pm[k][1]; s2 += Pm[k][2]; s3 += Pm[k][3]; }
+        T r2 = (s1 * s1 + s2 * s2) + s3 * s3;
+        if (!(r2 < (T)1e-3)) atomicOr(status, MF_ST_NOT_CM);
+    }
+
+    // M_j = sqrt((sum_{k>=j} P_k)^2), K_j = M_j - sum_{k>=j} m_k   (:656-660; sums in the reference's order)
+    T M[NF], K[NF];
+#pragma unroll
+    for (int j = NF - 1; j >= 0; --j) {
+        T s[4] = {(T)0, (T)0, (T)0, (T)0};
+#pragma unroll
+        for (int k = j; k < NF; ++k)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[c] += Pm[k][c];
+        T sq = sub_rn(sub_rn(sub_rn(mul_rn(s[0], s[0]), mul_rn(s[1], s[1])), mul_rn(s[2], s[2])), mul_rn(s[3], s[3]));
+        M[j] = sqrt_(sq);
+        K[j] = M[j] - P.msum_rev[j];
+    }
+
+    T r[W];
+    T Q[4] = {Pm[NF - 1][0], Pm[NF - 1][1], Pm[NF - 1][2], Pm[NF - 1][3]};
+    // i = NF .. 2 (j = i-1): mass variable r[j-1], angles r[NF-5+2i-1], r[NF-4+2i-1]   (:665-696)
+    [&]<int... I>(std::integer_sequence<int, I...>) {
+        ((void)[&] {
+            constexpr int i = NF - I;  // NF, NF-1, ..., 2
+            constexpr int j = i - 1;
+            const T uu = K[j] / K[j - 1];
+            if constexpr (i < NF)  // i == NF writes r[NF-2] = 1, overwritten by the i == 2 angle (:672,:681)
+                r[j - 1] = (T)(NF + 1 - i) * ipow<NF - i>(uu) - (T)(NF - i) * ipow<NF + 1 - i>(uu);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Q[c] = Q[c] + Pm[j - 1][c];
+            T pb[4];
+            boost(Pm[j - 1], (T)-1 * (Q[1] / Q[0]), (T)-1 * (Q[2] / Q[0]), (T)-1 * (Q[3] / Q[0]), pb);
+            r[NF - 5 + 2 * i - 1] = ((pb[3] / sqrt_(rho2_3(pb[1], pb[2], pb[3]))) + (T)1) / (T)2;
+            T phi = atan_(pb[2] / pb[1]);
+            T dphi = (pb[2] < (T)0 && pb[1] > (T)0) ? (T)6.283185307179586 : (T)0;
+            dphi += (pb[1] < (T)0) ? (T)3.141592653589793 : (T)0;
+            phi += dphi;
+            r[NF - 4 + 2 * i - 1] = phi / (T)6.283185307179586;
+        }(), ...);
+    }(std::make_integer_sequence<int, NF - 1>{});
+
+    // x1,x2 -> uniforms (utils.py:287-309)
+    T jacinv;
+    if (P.flags & MF_FLAG_X1X2_DIRECT) {
+        r[D] = x1; r[D + 1] = x2; jacinv = (T)1;
+    } else {
+        const T ml1 = -log_(x1), ml2 = -log_(x2);
+        r[D] = ((T)(-0.5) * (ml1 * ml1) + P.q * ml1) / P.A;
+        r[D + 1] = ml2 / (P.q - ml1);
+        jacinv = (T)1 / ((P.A * x1) * x2);
+    }
+    const T E_cm = sqrt_(x1 * x2) * P.e_collider;
+    const bool quirks = (P.flags & MF_FLAG_REF_FP32_QUIRKS) != 0;
+    const T jac = rambo_weight<T, NF>(P, E_cm, K, M, quirks);
+    T pr;
+    if (!quirks) {
+        pr = ((T)1 / jac) * jacinv;
+    } else {
+        float pf = __fdiv_rn(1.0f, (float)jac);
+        pr = (T)(float)((double)pf * (double)jacinv);
+    }
+    store_row<W>(ps + ev * W, r);
+    prob[ev] = pr;
+    if (logprob != nullptr) logprob[ev] = log_(pr);
+}
+
+template <typename T, int NF>
+static int launch_inverse(const T* momenta, int64_t event_stride, const T* x1, const T* x2, int64_t N,
+                          const int32_t* order, const T* masses, const T* target_mass, T e_collider,
+                          uint32_t flags, T* ps, T* prob, T* logprob, int32_t* status, cudaStream_t stream) {
+    RamboParams<T, NF> P{};
+    bool seen[NF] = {};
+    for (int i = 0; i < NF; ++i) {
+        int o = order ? order[i] : i;
+        if (o < 0 || o >= NF || seen[o]) return MF_E_SHAPE;
+        seen[o] = true;
+        P.order[i] = o;
+        P.m[i] = target_mass ? target_mass[i] : masses[o];  // :649-652
+    }
+    for (int j = 0; j < NF; ++j) {  // torch.sum(masses_t[:, j:]) in forward order (:660)
+        T s = (T)0;
+        for (int k = j; k < NF; ++k) s += P.m[k];
+        P.msum_rev[j] = s;
+    }
+    {
+        T s = (T)0;
+        for (int i = 0; i < NF; ++i) s += masses[i];  // self.tot_final_state_masses
+        P.msum = s;
+        T ratio = P.msum / e_collider;
+        T logtau = (sizeof(T) == 4) ? (T)logf((float)(ratio * ratio)) : (T)std::log((double)(ratio * ratio));
+        P.q = -logtau;
+        P.A = (T)(-0.5) * (P.q * P.q) + (P.q * P.q);
+        P.t1 = (-P.q) / P.A;
+        P.t1sq = P.t1 * P.t1;
+        P.neg_inv_A = (T)-1 * ((T)1 / P.A);
+    }
+    P.e_collider = e_collider;
+    {
+        const double pi = 3.141592653589793;
+        double c = std::pow(2.0 * pi, 4 - 3 * NF) * std::pow(pi / 2.0, NF - 1);
+        double ff = 1.0;
+        for (int i = 2; i <= NF - 1; ++i) ff *= i;
+        for (int i = 2; i <= NF - 2; ++i) ff *= i;
+        P.flat_c = (T)c; P.flat_ff = (T)ff;
+        P.flat_c32 = (float)c; P.flat_ff32 = (float)ff;
+    }
+    P.flags = flags;
+    if (N == 0) return MF_OK;
+    const int threads = 256;
+    const int64_t blocks = (N + threads - 1) / threads;
+    rambo_inverse_kernel<T, NF><<<(unsigned)blocks, threads, 0, stream>>>(momenta, event_stride, x1, x2, N, P, ps,
+                                                                          prob, logprob, status);
+    return launch_status();
+}
+
+template <typename T>
+static int inverse_dispatch(const T* momenta, int64_t event_stride, const T* x1, const T* x2, int64_t N, int n,
+                            const int32_t* order, const T* masses, const T* target_mass, T e_collider,
+                            uint32_t flags, T* ps, T* prob, T* logprob, int32_t* status, cudaStream_t stream) {
+    if (N < 0 || masses == nullptr) return MF_E_BADARG;
+    if (n < MF_MIN_FINAL || n > MF_MAX_FINAL) return MF_E_NFINAL;
+    if (N > 0 && (!momenta || !x1 || !x2 || !ps || !prob)) return MF_E_BADARG;
+    if (event_stride < 4 * n || event_stride % 4 != 0) return MF_E_SHAPE;
+    const int W = 3 * n - 2;
+    const size_t row_align = (W % 4 == 0) ? 4 * sizeof(T) : ((W % 2 == 0) ? 2 * sizeof(T) : sizeof(T));
+    if (!aligned(momenta, 4 * sizeof(T)) || !aligned(ps, row_align)) return MF_E_ALIGN;
+    if (N > (int64_t)0x7fffffff * 256) return MF_E_BADARG;
+    switch (n) {
+#define MF_CASE(NF) \
+    case NF: return launch_inverse<T, NF>(momenta, event_stride, x1, x2, N, order, masses, target_mass, e_collider, flags, ps, prob, logprob, status, stream);
+        MF_CASE(3) MF_CASE(4) MF_CASE(5) MF_CASE(6) MF_CASE(7) MF_CASE(8)
+#undef MF_CASE
+    }
+    return MF_E_NFINAL;
+}
+
+}  // namespace mf
+
+extern "C" int mf_rambo_inverse_f64(const double* momenta, int64_t event_stride, const double* x1, const double* x2,
+                                    int64_t N, int n_final, const int32_t* order, const double* masses,
+                                    const double* target_mass, double e_collider, uint32_t flags, double* ps,
+                                    double* prob, double* logprob, int32_t* status, mf_stream_t stream) {
+    return mf::inverse_dispatch<double>(momenta, event_stride, x1, x2, N, n_final, order, masses, target_mass,
+                                        e_collider, flags, ps, prob, logprob, status, (cudaStream_t)stream);
+}
+extern "C" int mf_rambo_inverse_f32(const float* momenta, int64_t event_stride, const float* x1, const float* x2,
+                                    int64_t N, int n_final, const int32_t* order, const float* masses,
+                                    const float* target_mass, float e_collider, uint32_t flags, float* ps,
+                                    float* prob, float* logprob, int32_t* status, mf_stream_t stream) {
+    return mf::inverse_dispatch<float>(momenta, event_stride, x1, x2, N, n_final, order, masses, target_mass,
+                                       e_collider, flags, ps, prob, logprob, status, (cudaStream_t)stream);
+}

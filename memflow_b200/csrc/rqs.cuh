@@ -1,0 +1,156 @@
+// rqs.cuh -- device math of zuko's MonotonicRQSTransform (monotonic rational-quadratic spline) on one
+// parameter row [w(K) | h(K) | d(K-1)] staged in shared memory. Used by rqs.cu (K3/K4) and by the fused
+// importance-sampling chain (is_chain.cu).
+//
+// zuko (third party, un-vendored): soft clip -> softmax -> pad -> cumsum -> knots
+// X_j = B(2 c_j - 1) -> searchsorted(right=False) -> gather -> rational quadratic / its inverse.
+// Here the row is processed IN PLACE in shared memory by LANES (1 or 2) threads:
+//   pass 1  e_k = exp(clip(w_k)) (lane 0: widths, lane 1: heights), sequential sum S
+//   pass 2  knots in place: arr[k] <- B(2 * cumsum_{i<=k}(e_i / S) - 1), counting knots < v on the fly
+//   epilogue (one lane)  gather the 4 knots + 2 derivatives of the selected bin, evaluate.
+// Only the two derivatives of the selected bin are exponentiated (the reference exponentiates all K-1).
+#pragma once
+#include "common.cuh"
+
+namespace mf {
+
+template <typename T> struct FastMath;
+template <> struct FastMath<float> {
+    // softmax inputs are bounded by |log slope|/2 after the soft clip, so ex2.approx on x*log2(e)
+    // (rel. error <= ~3e-7 there) and rcp.approx are within the fp32 parity budget (1e-5).
+    static MF_D float exp(float x) {
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+        return r;
+    }
+    static MF_D float rcp(float x) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    static MF_D float log(float x) { return logf(x); }
+};
+template <> struct FastMath<double> {
+    static MF_D double exp(double x) { return ::exp(x); }
+    static MF_D double rcp(double x) { return 1.0 / x; }
+    static MF_D double log(double x) { return ::log(x); }
+};
+
+template <typename T> struct RqsConst {
+    T bound;
+    T two_over_L;  // 2 / log(slope)   (soft clip of widths/heights), 0 when clip disabled
+    T one_over_L;  // 1 / log(slope)   (soft clip of derivatives)
+    int clip;      // slope > 0
+};
+
+MF_D double soft_clip(double a, double c) { return a / (1.0 + fabs(a * c)); }
+MF_D float soft_clip(float a, float c) { return a * FastMath<float>::rcp(1.0f + fabsf(a * c)); }
+
+// One thread transforms one of the two softmax arrays of a row into knots, in place.
+// Returns the number of knots (including X_0 = -B) strictly below v  == torch.searchsorted(knots, v).
+template <typename T>
+MF_D int rqs_knots_inplace(T* __restrict__ arr, int K, const RqsConst<T>& C, T v) {
+    T S = (T)0;
+    if (C.clip) {
+        for (int k = 0; k < K; ++k) {
+            T a = arr[k];
+            a = soft_clip(a, C.two_over_L);
+            T e = FastMath<T>::exp(a);
+            S += e;
+            arr[k] = e;
+        }
+    } else {
+        T mx = arr[0];
+        for (int k = 1; k < K; ++k) mx = fmax_(mx, arr[k]);
+        for (int k = 0; k < K; ++k) {
+            T e = FastMath<T>::exp(arr[k] - mx);
+            S += e;
+            arr[k] = e;
+        }
+    }
+    const T inv = FastMath<T>::rcp(S);
+    T c = (T)0;
+    int cnt = ((T)-C.bound < v) ? 1 : 0;  // X_0 = B(2*0 - 1)
+    for (int k = 0; k < K; ++k) {
+        c += arr[k] * inv;
+        T x = C.bound * ((T)2 * c - (T)1);
+        arr[k] = x;
+        cnt += (x < v) ? 1 : 0;
+    }
+    return cnt;
+}
+
+// Epilogue, knots already in place: Xk[j-1] = X_j (j = 1..K), X_0 = -B. bin = searchsorted - 1.
+// INV == false: v = x -> y, ladj = log|dy/dx|.  INV == true: v = y -> x, ladj = log|dy/dx| at that x.
+template <typename T, bool INV>
+MF_D void rqs_eval(const T* __restrict__ Xk, const T* __restrict__ Yk, const T* __restrict__ d, int K,
+                   const RqsConst<T>& C, int bin, T v, T& out, T& ladj) {
+    if (bin < 0 || bin >= K) { out = v; ladj = (T)0; return; }  // identity tails: mask == False
+    const T x0 = bin == 0 ? -C.bound : Xk[bin - 1], x1 = Xk[bin];
+    const T y0 = bin == 0 ? -C.bound : Yk[bin - 1], y1 = Yk[bin];
+    T d0 = (T)1, d1 = (T)1;  // D_0 = D_K = exp(0)
+    if (bin > 0) { T t = d[bin - 1]; if (C.clip) t = soft_clip(t, C.one_over_L); d0 = exp_(t); }
+    if (bin < K - 1) { T t = d[bin]; if (C.clip) t = soft_clip(t, C.one_over_L); d1 = exp_(t); }
+    const T dx = x1 - x0, dy = y1 - y0;
+    const T s = dy / dx;
+    const T dd = d0 + d1 - (T)2 * s;
+    T z;
+    if constexpr (!INV) {
+        z = (v - x0) / dx;
+        const T zz = z * ((T)1 - z);
+        const T den = s + dd * zz;
+        out = y0 + dy * (s * (z * z) + d0 * zz) / den;
+    } else {
+        const T y_ = v - y0;
+        const T a = dy * (s - d0) + y_ * dd;
+        const T b = dy * d0 - y_ * dd;
+        const T c = -s * y_;
+        z = (T)2 * c / (-b - sqrt_(b * b - (T)4 * a * c));
+        out = x0 + z * dx;
+    }
+    const T zz = z * ((T)1 - z);
+    const T den = s + dd * zz;
+    const T omz = (T)1 - z;
+    const T jac = (s * s) * ((T)2 * s * zz + d0 * (omz * omz) + d1 * (z * z)) / (den * den);
+    ladj = log_(jac);
+}
+
+// Whole row by ONE thread (used when rows are small: the fused chain, K <= ~16).
+template <typename T, bool INV>
+MF_D void rqs_row_1lane(T* __restrict__ row, int K, const RqsConst<T>& C, T v, T& out, T& ladj, int& bin) {
+    const T big = Limits<T>::huge();
+    int cx = rqs_knots_inplace(row, K, C, INV ? big : v);
+    int cy = rqs_knots_inplace(row + K, K, C, INV ? v : big);
+    bin = (INV ? cy : cx) - 1;
+    rqs_eval<T, INV>(row, row + K, row + 2 * K, K, C, bin, v, out, ladj);
+}
+
+// Bulk async copy (TMA, 1-D) global -> shared with mbarrier completion.
+MF_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+MF_D void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+MF_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+MF_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MF_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MF_DONE;\n"
+        "bra MF_WAIT;\n"
+        "MF_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+MF_D void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+MF_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+MF_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+}  // namespace mf

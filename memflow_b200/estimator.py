@@ -1,0 +1,94 @@
+"""Importance-sampling weight, Monte-Carlo estimator and the fused sampling chain (K5 + chain kernel).
+
+Reference: notebooks/TestFlows_ImportanceSampling.ipynb cells [50-54] (weights, I, sigma), mask of cells
+[35,43]; notebooks/TestMadgraphChain.ipynb [19-24]. The reference has no module for this -- only notebook
+cells -- so the function names here are ours; the arithmetic is the notebook's.
+"""
+import ctypes
+import math
+
+import torch
+
+from ._lib import check, host_array, lib, ptr, reduce_workspace, require_cuda, stream_ptr
+
+
+def new_accumulator(device):
+    """Device double[3] = (sum w, sum w^2, n_valid)."""
+    return torch.zeros(3, dtype=torch.float64, device=device)
+
+
+def accumulate_weights(target, rambo_jac, logq, acc=None):
+    """acc += (sum w, sum w^2, n_valid) with w = target * rambo_jac / exp(logq); valid = target > 0 and
+    rambo_jac not NaN. `target=None` means 1. Returns acc (device tensor; no host sync)."""
+    require_cuda(rambo_jac, "rambo_jac")
+    dev = rambo_jac.device
+    jac = rambo_jac.detach().double().contiguous()
+    lq = logq.detach().double().contiguous()
+    tg = None if target is None else target.detach().double().contiguous()
+    if acc is None:
+        acc = new_accumulator(dev)
+    ws = reduce_workspace(dev)
+    with torch.cuda.device(dev):
+        check(lib().mf_is_reduce_f64(ptr(tg), ptr(jac), ptr(lq), ctypes.c_int64(jac.shape[0]), ptr(acc), ptr(ws),
+                                     stream_ptr(dev)), "mf_is_reduce_f64")
+    return acc
+
+
+def mc_estimate(acc, n_total, variant="N+1"):
+    """I = sum w / N, sigma = sqrt((sum w^2 / N - I^2) / (N + 1))  (cell [54]; variant "N-1" = cell [35]).
+    `acc` may be a device tensor (one host sync here) or a sequence of 3 floats."""
+    a = acc.detach().cpu().tolist() if torch.is_tensor(acc) else list(acc)
+    n = float(n_total)
+    I = a[0] / n
+    den = n + 1.0 if variant == "N+1" else n - 1.0
+    return I, math.sqrt(max(a[1] / n - I * I, 0.0) / den), int(a[2])
+
+
+class ImportanceSampler:
+    """Fused chain: Philox base sample -> T spline inverses -> PhaseSpace map -> weight -> accumulators,
+    one kernel launch per chunk (TestFlows_ImportanceSampling.ipynb [45,50-54]; ME = pdf = 1).
+
+    phi: float32 [T, N, F, 3K-1] spline parameters (the hyper-network output, given), F = 3 n_final - 2.
+    """
+
+    def __init__(self, final_masses, collider_energy, bound=1.0, slope=1e-3, seed=0, device=None):
+        self.masses = [float(m) for m in torch.as_tensor(final_masses).double().cpu().tolist()]
+        self.n_final = len(self.masses)
+        self.collider_energy = float(collider_energy)
+        self.bound = float(bound)
+        self.slope = slope
+        self.seed = int(seed)
+        self.device = torch.device(device if device is not None else "cuda:0")
+
+    def run_chunk(self, phi, event_offset=0, acc=None, debug_outputs=False):
+        require_cuda(phi, "phi")
+        if phi.dtype != torch.float32 or phi.dim() != 4:
+            raise AssertionError("phi must be float32 [T, N, F, 3K-1]")
+        T, N, F, PW = phi.shape
+        n = self.n_final
+        if F != 3 * n - 2 or (PW + 1) % 3 != 0:
+            raise AssertionError("phi shape does not match n_final (F must be 3n-2, last dim 3K-1)")
+        K = (PW + 1) // 3
+        phi = phi.contiguous()
+        dev = phi.device
+        if acc is None:
+            acc = new_accumulator(dev)
+        ws = reduce_workspace(dev)
+        out = {}
+        if debug_outputs:
+            out = dict(u=torch.empty((N, F), dtype=torch.float64, device=dev),
+                       logq=torch.empty(N, dtype=torch.float64, device=dev),
+                       momenta=torch.empty((N, n + 2, 4), dtype=torch.float64, device=dev),
+                       weight=torch.empty(N, dtype=torch.float64, device=dev),
+                       x1=torch.empty(N, dtype=torch.float64, device=dev),
+                       x2=torch.empty(N, dtype=torch.float64, device=dev))
+        with torch.cuda.device(dev):
+            rc = lib().mf_is_chain_f64(
+                ptr(phi), ctypes.c_int64(N), ctypes.c_int(n), ctypes.c_int(T), ctypes.c_int(K),
+                ctypes.c_float(self.bound), ctypes.c_float(self.slope if self.slope is not None else 0.0),
+                ctypes.c_uint64(self.seed), ctypes.c_uint64(int(event_offset)),
+                host_array(self.masses, ctypes.c_double), ctypes.c_double(self.collider_energy), ctypes.c_uint32(0),
+                ptr(acc), ptr(ws), ptr(out.get("u")), ptr(out.get("logq")), ptr(out.get("momenta")),
+                ptr(out.get("weight")), ptr(out.get("x1")), ptr(out.get("x2")), stream_ptr(dev))
+        check(rc, "mf_is_chain_f64")
+        return (acc, out) if debug_outputs else acc

@@ -1,0 +1,262 @@
+"""Host mirror of memflow/phasespace/rambo_generator.py: same class / method names, argument meaning
+and return values, every batch method backed by ONE hand-written sm_100a kernel through the C ABI
+(include/memflow_b200.h). The reference is adapted from NGoetz/TorchPS and follows S. Platzer,
+arXiv:1308.2922 ("RAMBO on diet"), massive variant.
+
+Deviations from the reference, all deliberate (DESIGN.md "Reference quirks"):
+  * weights and incoming rows are computed in clean fp64. Set `ref_fp32_quirks=True` on the generator to
+    reproduce the reference's float32 volume / weight chain / incoming rows (rambo_generator.py:132,489-507,533).
+  * data-dependent raises (NaN scan :191-199, CM check :630-635) cost host syncs in the reference. Here
+    they set bits in `generator.last_status` (device int32); `sync_errors=True` restores the raises.
+  * CUDA tensors only: there is no CPU fallback.
+"""
+import ctypes
+import math
+
+import torch
+
+from .. import _lib
+from .._lib import MemflowB200Error, check, host_array, lib, ptr, require_cuda, stream_ptr
+
+M_HIGGS = 125.25
+M_TOP = 172.5
+M_GLUON = 0.0  # rambo_generator.py:14 (phasespace.py:31 uses 1e-5)
+
+MF_FLAG_REF_FP32_QUIRKS = 1
+MF_FLAG_LAB_FRAME = 2
+MF_FLAG_CUTS = 4
+MF_FLAG_X1X2_DIRECT = 8
+MF_FLAG_NO_CM_CHECK = 16
+MF_ST_NAN_INPUT = 1
+MF_ST_NOT_CM = 2
+
+
+class PhaseSpaceGeneratorError(Exception):
+    pass
+
+
+class VirtualPhaseSpaceGenerator(object):
+    """rambo_generator.py:29-83."""
+
+    def __init__(self, initial_masses, final_masses, collider_energy, pdf=None, pdf_active=False,
+                 uniform_x1x2=True, lhapdf_dir=None, dev=None):
+        if dev is None:
+            dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
+        self.dev = torch.device(dev)
+        self.initial_masses = initial_masses
+        self.masses_t = torch.as_tensor(final_masses).clone().to(self.dev)
+        self.tot_final_state_masses = torch.sum(self.masses_t)
+        self.n_initial = len(initial_masses)
+        self.n_final = len(final_masses)
+        self.collider_energy = collider_energy
+        self.pdf = pdf
+        self.pdf_active = pdf_active
+        self.uniform_x1x2 = uniform_x1x2
+        # host copy of the masses: travels with every launch (kernel parameter space), never re-read from HBM
+        self._masses_host = [float(m) for m in self.masses_t.detach().cpu().double().tolist()]
+
+    def generateKinematics(self, E_cm, random_variables):
+        raise NotImplementedError
+
+    @property
+    def nDimPhaseSpace(self):
+        if self.n_final == 1:
+            return 0
+        return 3 * self.n_final - 4
+
+
+class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
+    """rambo_generator.py:86-736, B200-native."""
+
+    epsilon_border = 1e-10
+    absolute_Ecm_min = 1.0
+
+    def __init__(self, *args, **opts):
+        self.ref_fp32_quirks = bool(opts.pop("ref_fp32_quirks", False))
+        self.sync_errors = bool(opts.pop("sync_errors", False))
+        self.compute_dtype = opts.pop("compute_dtype", torch.float64)
+        super().__init__(*args, **opts)
+        if self.n_initial == 1:
+            raise PhaseSpaceGeneratorError("This basic generator does not support decay topologies.")
+        if self.n_initial > 2:
+            raise PhaseSpaceGeneratorError("This basic generator does not support more than 2 incoming particles.")
+        self.last_status = None
+
+    # ------------------------------------------------------------------ small closed-form helpers
+    @staticmethod
+    def get_flatWeights(E_cm, n):
+        """Massless n-body volume (2pi)^(4-3n) (pi/2)^(n-1) E^(2n-4) / ((n-1)!(n-2)!)  (:111-140).
+        Tensor inputs stay in their own dtype (the reference silently casts them to float32, :132)."""
+        if n == 1:
+            return 1.0
+        c = math.pow(2 * math.pi, 4 - 3 * n) * math.pow(math.pi / 2.0, n - 1) \
+            / (math.factorial(n - 1) * math.factorial(n - 2))
+        if not torch.is_tensor(E_cm):
+            return (math.pow(2 * math.pi, 4 - 3 * n) * math.pow((math.pi / 2.0), n - 1)
+                    * (math.pow((E_cm ** 2), n - 2) / (math.factorial(n - 1) * math.factorial(n - 2))))
+        return c * (E_cm ** 2) ** (n - 2)
+
+    def massless_map(self, x, exp):
+        """:142-143."""
+        return (x ** exp) * ((exp + 1) - exp * x)
+
+    @staticmethod
+    def rho(M, N, m):
+        """:145-149."""
+        Msqr = M ** 2
+        return ((Msqr - (N + m) ** 2) * (Msqr - (N - m) ** 2)) ** 0.5 / (8.0 * Msqr)
+
+    def bisect_vec_batch(self, v_t, target=1.0e-16, maxLevel=600):
+        """Solve v = u^e ((e+1) - e u), e = n-2-column, for u (:400-446). The reference bisects the whole
+        batch for up to 180 levels; the kernel uses a closed form (e=1) / fp32-seeded Halley iteration.
+        `target` / `maxLevel` are accepted for signature compatibility and ignored."""
+        if v_t.size(1) == 0:
+            return None
+        require_cuda(v_t, "v_t")
+        if v_t.shape[1] != self.n_final - 2:
+            raise AssertionError("bisect_vec_batch expects [N, n_final-2]")
+        v = v_t.detach().to(torch.float64).contiguous()
+        u = torch.empty_like(v)
+        with torch.cuda.device(v.device):
+            check(lib().mf_massvar_solve_f64(ptr(v), ctypes.c_int64(v.shape[0]), ctypes.c_int(self.n_final), ptr(u),
+                                             stream_ptr(v.device)), "mf_massvar_solve_f64")
+        return u
+
+    # ------------------------------------------------------------------ K1
+    def generateKinematics_batch(self, random_variables_full, pT_mincut=-1, delR_mincut=-1, rap_maxcut=-1,
+                                 pdgs=[0, 0], requires_grad=False, lab_frame=False, return_logweight=False):
+        """u [N, 3n-2] -> (momenta [N, n+2, 4] in the partonic CM frame, weight [N], x1 [N], x2 [N]), all
+        float64 on the input's device (:168-398). Extras: `lab_frame=True` returns lab-frame momenta
+        (utils.py:180-202 fused in), `return_logweight=True` appends ln(weight)."""
+        if not self.pdf_active:
+            # reference: E_cm is never assigned on this branch (:264-266) -> NameError
+            raise PhaseSpaceGeneratorError("pdf_active=False is not supported (it is broken in the reference too)")
+        require_cuda(random_variables_full, "random_variables_full")
+        if requires_grad or random_variables_full.requires_grad:
+            if torch.is_grad_enabled() and random_variables_full.requires_grad:
+                raise MemflowB200Error("autograd through the CUDA phase-space map is not implemented yet "
+                                       "(SURVEY 8f-4); call under torch.no_grad() or detach the input")
+        assert random_variables_full.shape[1] - 2 == self.nDimPhaseSpace
+        dev = random_variables_full.device
+        dt = self.compute_dtype
+        u = random_variables_full.detach().to(dt).contiguous()
+        N, n = u.shape[0], self.n_final
+        momenta = torch.empty((N, n + 2, 4), dtype=dt, device=dev)
+        weight = torch.empty(N, dtype=dt, device=dev)
+        x1 = torch.empty(N, dtype=dt, device=dev)
+        x2 = torch.empty(N, dtype=dt, device=dev)
+        logw = torch.empty(N, dtype=dt, device=dev) if return_logweight else None
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        flags = 0
+        if self.ref_fp32_quirks:
+            flags |= MF_FLAG_REF_FP32_QUIRKS
+        if not self.uniform_x1x2:
+            flags |= MF_FLAG_X1X2_DIRECT
+        if lab_frame:
+            flags |= MF_FLAG_LAB_FRAME
+        # the reference evaluates the cuts always; with the default -1 thresholds they cannot fire
+        cuts_on = (pT_mincut > 0) or (delR_mincut > 0) or (rap_maxcut > 0)
+        if cuts_on:
+            flags |= MF_FLAG_CUTS
+        if dt == torch.float64:
+            fn, ct = lib().mf_rambo_forward_f64, ctypes.c_double
+        elif dt == torch.float32:
+            fn, ct = lib().mf_rambo_forward_f32, ctypes.c_float
+        else:
+            raise MemflowB200Error("compute_dtype must be torch.float64 or torch.float32")
+        masses = host_array(self._masses_host, ct)
+        cuts = host_array([pT_mincut, delR_mincut, rap_maxcut], ct) if cuts_on else None
+        with torch.cuda.device(dev):
+            rc = fn(ptr(u), ctypes.c_int64(N), ctypes.c_int(n), masses, ct(float(self.collider_energy)), cuts,
+                    ctypes.c_uint32(flags), ptr(momenta), ptr(weight), ptr(logw), ptr(x1), ptr(x2), ptr(status),
+                    stream_ptr(dev))
+        check(rc, "mf_rambo_forward")
+        self.last_status = status
+        if self.sync_errors and int(status.item()) & MF_ST_NAN_INPUT:
+            raise PhaseSpaceGeneratorError("Some of the random variables passed to the phase-space generator are NaN")
+        if dt != torch.float64:  # reference contract: outputs are float64
+            momenta, weight, x1, x2 = momenta.double(), weight.double(), x1.double(), x2.double()
+            logw = logw.double() if logw is not None else None
+        if return_logweight:
+            return momenta, weight, x1, x2, logw
+        return momenta, weight, x1, x2
+
+    # ------------------------------------------------------------------ K2
+    def getPSpoint_batch(self, momenta_batch, x1, x2, order=None, target_mass=None, ensure_CM=True,
+                         ensure_onShell=True, return_logprob=False):
+        """Final-state momenta [N, n, 4] (CM frame) + x1, x2 -> (ps [N, 3n-2], prob [N]) (:615-736).
+        `order=None` means the identity permutation for any n (the reference's default [0,1,2,3] only
+        fits n=4). `target_mass` ([n] or [1,n]) is used when ensure_onShell=False (:649-652)."""
+        require_cuda(momenta_batch, "momenta_batch")
+        dev = momenta_batch.device
+        n = self.n_final
+        if momenta_batch.dim() != 3 or momenta_batch.shape[1] != n or momenta_batch.shape[2] != 4:
+            raise AssertionError("momenta_batch must be [N, %d, 4]" % n)
+        dt = self.compute_dtype
+        mom = momenta_batch.detach()
+        if mom.dtype != dt:
+            mom = mom.to(dt)
+        # read a [:, 2:] slice of a forward output in place when its strides allow it
+        esz = mom.element_size()
+        if not (mom.stride(2) == 1 and mom.stride(1) == 4 and mom.stride(0) % 4 == 0 and mom.stride(0) >= 4 * n
+                and mom.data_ptr() % (4 * esz) == 0):
+            mom = mom.contiguous()
+        N = mom.shape[0]
+        x1c = x1.detach().to(dt).contiguous()
+        x2c = x2.detach().to(dt).contiguous()
+        ps = torch.empty((N, 3 * n - 2), dtype=dt, device=dev)
+        prob = torch.empty(N, dtype=dt, device=dev)
+        logp = torch.empty(N, dtype=dt, device=dev) if return_logprob else None
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        order = list(range(n)) if order is None else [int(o) for o in order]
+        if len(order) != n:
+            raise AssertionError("order must have n_final=%d entries" % n)
+        flags = 0
+        if self.ref_fp32_quirks:
+            flags |= MF_FLAG_REF_FP32_QUIRKS
+        if not self.uniform_x1x2:
+            flags |= MF_FLAG_X1X2_DIRECT
+        if not ensure_CM:
+            flags |= MF_FLAG_NO_CM_CHECK
+        if dt == torch.float64:
+            fn, ct = lib().mf_rambo_inverse_f64, ctypes.c_double
+        else:
+            fn, ct = lib().mf_rambo_inverse_f32, ctypes.c_float
+        masses = host_array(self._masses_host, ct)
+        tm = None
+        if not ensure_onShell:
+            if target_mass is None:
+                raise AssertionError("ensure_onShell=False needs target_mass")
+            tmv = torch.as_tensor(target_mass).detach().cpu().double().reshape(-1).tolist()
+            if len(tmv) != n:
+                raise AssertionError("target_mass must hold n_final=%d masses ([n] or [1,n])" % n)
+            tm = host_array(tmv, ct)
+        with torch.cuda.device(dev):
+            rc = fn(ptr(mom), ctypes.c_int64(mom.stride(0)), ptr(x1c), ptr(x2c), ctypes.c_int64(N), ctypes.c_int(n),
+                    host_array(order, ctypes.c_int32), masses, tm, ct(float(self.collider_energy)),
+                    ctypes.c_uint32(flags), ptr(ps), ptr(prob), ptr(logp), ptr(status), stream_ptr(dev))
+        check(rc, "mf_rambo_inverse")
+        self.last_status = status
+        if ensure_CM and self.sync_errors and int(status.item()) & MF_ST_NOT_CM:
+            raise Exception("Momenta batch not in the CM, failing to convert back to PS point")
+        if dt != torch.float64:
+            ps, prob = ps.double(), prob.double()
+            logp = logp.double() if logp is not None else None
+        if return_logprob:
+            return ps, prob, logp
+        return ps, prob
+
+    def setInitialStateMomenta_batch(self, output_momenta, E_cm):
+        """Rows 0,1 <- (E/2, 0, 0, +-E/2) for massless beams (:511-551); in place, like the reference."""
+        if self.n_initial != 2:
+            raise PhaseSpaceGeneratorError("This PS generator only supports 2 initial states")
+        if not (self.initial_masses[0] == 0.0 or self.initial_masses[1] == 0.0):
+            raise PhaseSpaceGeneratorError("massive beams are unreachable from PhaseSpace and not supported")
+        h = (E_cm if torch.is_tensor(E_cm) else torch.as_tensor(E_cm, dtype=output_momenta.dtype,
+                                                                device=output_momenta.device)) / 2
+        output_momenta[:, 0, :] = 0
+        output_momenta[:, 1, :] = 0
+        output_momenta[:, 0, 0] = h
+        output_momenta[:, 0, 3] = h
+        output_momenta[:, 1, 0] = h
+        output_momenta[:, 1, 3] = -h

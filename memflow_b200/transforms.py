@@ -1,0 +1,161 @@
+"""zuko-style monotonic rational-quadratic spline transform backed by the K3/K4 CUDA kernels.
+
+`MonotonicRQSTransform(widths, heights, derivatives, bound=5.0, slope=1e-3)` has the constructor and the
+`torch.distributions.Transform` surface of `zuko.transforms.MonotonicRQSTransform` (third-party dependency
+of the reference, constructed at memflow/unfolding_flow/unfolding_flow.py:88-97 and
+memflow/unfolding_flow/custom_spline_flow_ps.py:16-33): `t(x)`, `t.inv(y)`, `t.call_and_ladj(x)`,
+`t.log_abs_det_jacobian(x, y)`. The functional forms `rqs_forward / rqs_inverse` take the hyper-network
+output row `phi[B, F, 3K-1]` directly and also return the per-event sum of log-dets.
+
+Inference only (no autograd yet). CUDA tensors only.
+"""
+import ctypes
+
+import torch
+from torch.distributions import Transform, constraints
+
+from ._lib import MemflowB200Error, check, lib, ptr, require_cuda, stream_ptr
+
+
+def _fn(direction, dtype):
+    if dtype == torch.float32:
+        return getattr(lib(), "mf_rqs_%s_f32" % direction), ctypes.c_float
+    if dtype == torch.float64:
+        return getattr(lib(), "mf_rqs_%s_f64" % direction), ctypes.c_double
+    raise MemflowB200Error("spline kernels support float32 / float64, got %s" % dtype)
+
+
+def _run(direction, phi, v, bound, slope, want_ladj=True, want_sum=False, want_bin=False):
+    require_cuda(phi, "phi")
+    require_cuda(v, "x")
+    if phi.dim() != 3:
+        raise AssertionError("phi must be [B, F, 3K-1]")
+    B, F, PW = phi.shape
+    if (PW + 1) % 3 != 0:
+        raise AssertionError("last dim of phi must be 3K-1")
+    K = (PW + 1) // 3
+    if v.shape != (B, F):
+        raise AssertionError("x must be [B, F] = %s, got %s" % ((B, F), tuple(v.shape)))
+    phi = phi.detach().contiguous()
+    v = v.detach().to(phi.dtype).contiguous()
+    fn, ct = _fn(direction, phi.dtype)
+    out = torch.empty_like(v)
+    ladj = torch.empty_like(v) if want_ladj else None
+    lsum = torch.empty(B, dtype=phi.dtype, device=phi.device) if want_sum else None
+    bins = torch.empty((B, F), dtype=torch.int32, device=phi.device) if want_bin else None
+    with torch.cuda.device(phi.device):
+        rc = fn(ptr(phi), ptr(v), ctypes.c_int64(B), ctypes.c_int(F), ctypes.c_int(K), ct(float(bound)),
+                ct(float(slope) if slope is not None else 0.0), ptr(out), ptr(ladj), ptr(lsum), ptr(bins),
+                stream_ptr(phi.device))
+    check(rc, "mf_rqs_%s" % direction)
+    return out, ladj, lsum, bins
+
+
+def rqs_forward(phi, x, bound=5.0, slope=1e-3, return_bins=False):
+    """y, ladj [B,F], ladj_sum [B] = spline(x) with parameters phi[B, F, 3K-1] = [widths|heights|derivatives]."""
+    y, ladj, lsum, bins = _run("forward", phi, x, bound, slope, True, True, return_bins)
+    return (y, ladj, lsum, bins) if return_bins else (y, ladj, lsum)
+
+
+def rqs_inverse(phi, y, bound=5.0, slope=1e-3, return_bins=False):
+    """x, ladj [B,F], ladj_sum [B]: x = spline^-1(y); ladj is the FORWARD log|dy/dx| at x (sample + log q in one pass)."""
+    x, ladj, lsum, bins = _run("inverse", phi, y, bound, slope, True, True, return_bins)
+    return (x, ladj, lsum, bins) if return_bins else (x, ladj, lsum)
+
+
+def searchsorted(knots, v):
+    """torch.searchsorted(knots[..., :], v[..., None], right=False) on the GPU kernel's bin search (bit-exact)."""
+    require_cuda(knots, "knots")
+    knots = knots.detach().contiguous()
+    v = v.detach().to(knots.dtype).contiguous()
+    length = knots.shape[-1]
+    BF = v.numel()
+    idx = torch.empty(v.shape, dtype=torch.int32, device=knots.device)
+    fn = lib().mf_searchsorted_f32 if knots.dtype == torch.float32 else lib().mf_searchsorted_f64
+    with torch.cuda.device(knots.device):
+        check(fn(ptr(knots), ptr(v), ctypes.c_int64(BF), ctypes.c_int(length), ptr(idx), stream_ptr(knots.device)),
+              "mf_searchsorted")
+    return idx
+
+
+def _pack(widths, heights, derivatives):
+    """Return phi[rows, 1, 3K-1]. Zero-copy when the three tensors are the split views of one hyper-network
+    output row (what zuko's MAF passes); otherwise one torch.cat."""
+    K = widths.shape[-1]
+    if heights.shape[-1] != K or derivatives.shape[-1] != K - 1:
+        raise AssertionError("shapes must be widths[*,K], heights[*,K], derivatives[*,K-1]")
+    lead = torch.broadcast_shapes(widths.shape[:-1], heights.shape[:-1], derivatives.shape[:-1])
+    PW = 3 * K - 1
+    es = widths.element_size()
+    same = (widths.dtype == heights.dtype == derivatives.dtype and widths.shape[:-1] == lead
+            and heights.shape[:-1] == lead and derivatives.shape[:-1] == lead
+            and widths.stride() == heights.stride() == derivatives.stride()
+            and widths.stride(-1) == 1
+            and heights.data_ptr() == widths.data_ptr() + K * es
+            and derivatives.data_ptr() == widths.data_ptr() + 2 * K * es)
+    if same:
+        # contiguous rows of pitch PW?
+        exp, ok = PW, True
+        for size, stride in zip(reversed(lead), reversed(widths.stride()[:-1])):
+            if size != 1 and stride != exp:
+                ok = False
+                break
+            exp *= size
+        if ok:
+            rows = 1
+            for s in lead:
+                rows *= s
+            return torch.as_strided(widths, (rows, 1, PW), (PW, PW, 1)), lead
+    w = widths.expand(*lead, K)
+    h = heights.expand(*lead, K)
+    d = derivatives.expand(*lead, K - 1)
+    return torch.cat((w, h, d), dim=-1).reshape(-1, 1, PW), lead
+
+
+class MonotonicRQSTransform(Transform):
+    r"""Monotonic rational-quadratic spline (Durkan et al. 2019) on [-bound, bound], identity outside."""
+
+    domain = constraints.real
+    codomain = constraints.real
+    bijective = True
+    sign = +1
+
+    def __init__(self, widths, heights, derivatives, bound=5.0, slope=1e-3, **kwargs):
+        super().__init__(**kwargs)
+        self.bound = float(bound)
+        self.slope = slope
+        self.phi, self.lead = _pack(widths, heights, derivatives)
+
+    @property
+    def bins(self):
+        return (self.phi.shape[-1] + 1) // 3
+
+    def _rows(self, x):
+        shape = torch.broadcast_shapes(self.lead, x.shape)
+        if tuple(shape) != tuple(self.lead):
+            raise MemflowB200Error("parameters must broadcast to the shape of x (per-element parameters)")
+        return x.expand(shape).reshape(-1, 1), shape
+
+    def _call(self, x):
+        v, shape = self._rows(x)
+        y, _, _, _ = _run("forward", self.phi, v, self.bound, self.slope, want_ladj=False)
+        return y.reshape(shape).to(x.dtype)
+
+    def _inverse(self, y):
+        v, shape = self._rows(y)
+        x, _, _, _ = _run("inverse", self.phi, v, self.bound, self.slope, want_ladj=False)
+        return x.reshape(shape).to(y.dtype)
+
+    def call_and_ladj(self, x):
+        v, shape = self._rows(x)
+        y, ladj, _, _ = _run("forward", self.phi, v, self.bound, self.slope)
+        return y.reshape(shape).to(x.dtype), ladj.reshape(shape).to(x.dtype)
+
+    def inverse_and_ladj(self, y):
+        """(x, forward ladj at x): lets a sampler get log q without a second pass."""
+        v, shape = self._rows(y)
+        x, ladj, _, _ = _run("inverse", self.phi, v, self.bound, self.slope)
+        return x.reshape(shape).to(y.dtype), ladj.reshape(shape).to(y.dtype)
+
+    def log_abs_det_jacobian(self, x, y=None):
+        return self.call_and_ladj(x)[1]

@@ -1,0 +1,50 @@
+"""Parity metrics, stated once and used by every test.
+
+The reference's own formulas are ill-conditioned in three places, and any last-ulp difference between two
+correct implementations (libm vs Sleef vs libdevice cos/exp/log) is amplified there:
+  * sin(phi) = +-sqrt(1 - cos(phi)^2)      (rambo_generator.py:321-322): factor ~ 1/|sin phi|
+  * boosts with gamma >> 1                  (utils.py:99: gamma = 1/sqrt(1 - b^2)):  factor ~ gamma^2
+  * mass-variable roots with u -> 1         (bisection on a function with f'(1) = 0): factor ~ 1/(1-u)^2 on the
+                                             weight and 1/(1-u) on the momenta
+So the bound for an event is  tol * kappa(event)  with kappa >= 1 computed from the ORACLE's own outputs.
+`kappa == 1` for a well-conditioned event, where the plain tolerance (1e-12 fp64 / 1e-5 fp32) applies.
+"""
+import numpy as np
+
+
+def momenta_error(mom, mom_ref, x1_ref, x2_ref, e_collider):
+    """max over particles/components of |p - p_ref| / E_cm(event)."""
+    ecm = np.sqrt(x1_ref * x2_ref) * e_collider
+    return np.abs(mom - mom_ref).reshape(mom.shape[0], -1).max(axis=1) / ecm
+
+
+def conditioning(u, mom_ref, n):
+    """kappa per event from the oracle's momenta (final rows 2..) and the input point u."""
+    N = u.shape[0]
+    fin = mom_ref[:, 2:, :]
+    # gamma of every intermediate system Q_k = sum_{j>=k} p_j, in the frame the decay is boosted from
+    q = np.cumsum(fin[:, ::-1, :], axis=1)[:, ::-1, :]
+    m2 = q[..., 0] ** 2 - (q[..., 1:] ** 2).sum(-1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gamma2 = np.where(m2 > 0, q[..., 0] ** 2 / m2, np.inf)
+    g2 = np.nanmax(gamma2[:, : n - 1], axis=1)
+    ne = n - 2
+    phi = 2 * np.pi * u[:, ne + 1: 3 * n - 4: 2]
+    sinphi = np.abs(np.sin(phi)).min(axis=1)
+    ct = 2 * u[:, ne: 3 * n - 4: 2] - 1
+    sinth = np.sqrt(np.maximum(1 - ct * ct, 0)).min(axis=1)
+    k_angle = 1.0 + 1e-3 / np.maximum(np.minimum(sinphi, sinth), 1e-300)
+    if ne > 0:
+        uv = u[:, :ne]
+        k_mass = (1.0 / np.maximum(np.minimum(uv, 1 - uv), 1e-300) ** 2).max(axis=1) * 1e-2 + 1.0
+    else:
+        k_mass = np.ones(N)
+    return np.maximum(g2, 1.0) * k_angle * k_mass
+
+
+def summarize(err, tol, kappa=None):
+    out = {"max": float(np.nanmax(err)), "p50": float(np.nanquantile(err, 0.5)),
+           "p99": float(np.nanquantile(err, 0.99)), "frac_gt_tol": float((err > tol).mean())}
+    if kappa is not None:
+        out["max_over_kappa"] = float(np.nanmax(err / kappa))
+    return out

@@ -1,0 +1,171 @@
+"""CPU: pin the C oracle against the golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py) and against the reference's own known answers."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+NS = (3, 4, 5, 8)
+EDGE = 24  # first rows of every fixture are edge-of-cube points (make_golden.make_u)
+
+
+def load(golden_dir, n):
+    return np.load(os.path.join(golden_dir, "rambo_n%d.npz" % n))
+
+
+def test_known_answer_flat_volume(golden_dir):
+    """notebooks/RamboTest.ipynb [18]: get_flatWeights(13000, 3) = 21291.052028166854."""
+    from memflow_b200.phasespace.rambo_generator import FlatInvertiblePhasespace
+    ka = json.load(open(os.path.join(golden_dir, "known_answers.json")))
+    assert ka["get_flatWeights(13000,3)"] == 21291.052028166854
+    assert FlatInvertiblePhasespace.get_flatWeights(13000, 3) == 21291.052028166854
+
+
+@pytest.mark.parametrize("n", NS)
+@pytest.mark.parametrize("tag,quirks", [("clean", False), ("lit", True)])
+def test_forward_matches_reference(oracle, golden_dir, n, tag, quirks):
+    g = load(golden_dir, n)
+    mom, w, x1, x2 = oracle.rambo_forward(g["u"], g["masses"], float(g["e_cm"]), fp32_quirks=quirks)
+    ecm = np.sqrt(g["x1_" + tag] * g["x2_" + tag]) * float(g["e_cm"])
+    dm = np.abs(mom - g["mom_" + tag]).max(axis=(1, 2)) / ecm
+    assert dm[EDGE:].max() < 1e-12, dm.max()          # bulk: libm vs Sleef last-ulp differences only
+    assert dm.max() < 1e-11
+    np.testing.assert_allclose(x1, g["x1_" + tag], rtol=0, atol=5e-15)
+    np.testing.assert_allclose(x2, g["x2_" + tag], rtol=0, atol=5e-15)
+    ref_w = g["w_" + tag]
+    assert np.array_equal(np.isinf(w), np.isinf(ref_w))        # float32 overflow pattern of the literal n=8 case
+    fin = np.isfinite(ref_w) & (ref_w > 0)
+    dl = np.abs(np.log(w[fin]) - np.log(ref_w[fin]))
+    tol = 5e-7 if quirks else 1e-11                            # literal: float32 ulps (powf differs by 1 ulp)
+    assert np.nanmax(dl[EDGE:]) < tol
+    assert np.nanmax(dl) < max(tol, 1e-9)                      # edge rows: conditioning of the mass variables
+
+
+@pytest.mark.parametrize("n", NS)
+@pytest.mark.parametrize("tag,quirks", [("clean", False), ("lit", True)])
+def test_inverse_matches_reference(oracle, golden_dir, n, tag, quirks):
+    g = load(golden_dir, n)
+    ps, prob, rc = oracle.rambo_inverse(g["mom_" + tag][:, 2:], g["x1_" + tag], g["x2_" + tag], g["masses"],
+                                        float(g["e_cm"]), fp32_quirks=quirks)
+    assert rc == 0
+    ref = g["inv_ps_" + tag]
+    assert np.array_equal(np.isnan(ps), np.isnan(ref))
+    assert np.nanmax(np.abs(ps - ref)) < 1e-12
+    refp = g["inv_prob_" + tag]
+    fin = np.isfinite(refp) & (refp > 0)
+    assert np.array_equal(prob == 0, refp == 0)               # 1/inf of the literal float32 volume
+    dl = np.abs(np.log(prob[fin]) - np.log(refp[fin]))
+    assert np.nanmax(dl[EDGE:][np.isfinite(dl[EDGE:])]) < (5e-7 if quirks else 1e-11)
+
+
+@pytest.mark.parametrize("n", NS)
+def test_inverse_permuted_and_offshell(oracle, golden_dir, n):
+    g = load(golden_dir, n)
+    E = float(g["e_cm"])
+    a = (g["mom_clean"][:, 2:], g["x1_clean"], g["x2_clean"], g["masses"], E)
+    ps, prob, _ = oracle.rambo_inverse(*a, order=g["perm"])
+    assert np.nanmax(np.abs(ps - g["inv_ps_perm_clean"])[EDGE:]) < 1e-12
+    ps, prob, _ = oracle.rambo_inverse(*a, order=g["perm"], target_mass=g["target_mass"])
+    ref = g["inv_ps_offshell_clean"]
+    assert np.array_equal(np.isnan(ps), np.isnan(ref))
+    assert np.nanmax(np.abs(ps - ref)[EDGE:]) < 1e-12
+
+
+@pytest.mark.parametrize("n", NS)
+def test_cuts_match_reference(oracle, golden_dir, n):
+    g = load(golden_dir, n)
+    _, w, _, _ = oracle.rambo_forward(g["u"], g["masses"], float(g["e_cm"]), fp32_quirks=True, pT_mincut=20.0,
+                                      delR_mincut=0.4, rap_maxcut=5.0)
+    assert np.array_equal(w == 0, g["w_cuts_lit"] == 0)
+    assert 0 < (w == 0).mean() < 1
+
+
+def test_round_trip_property(oracle):
+    """notebooks/RamboTest.ipynb [41-46]: u -> p -> u is the identity (n=3 residual ~4e-16 there)."""
+    rng = np.random.default_rng(5)
+    masses = [125.25, 172.5, 172.5]
+    u = rng.random((2000, 7)).clip(1e-10, 1 - 1e-10)
+    mom, w, x1, x2 = oracle.rambo_forward(u, masses, 13000.0)
+    ps, prob, rc = oracle.rambo_inverse(mom[:, 2:], x1, x2, masses, 13000.0)
+    assert rc == 0
+    assert np.abs(ps - u).max() < 1e-9
+    assert np.median(np.abs(ps - u)) < 1e-14
+    np.testing.assert_allclose(prob * w, 1.0, rtol=1e-9)
+    # momentum conservation and mass shells
+    tot = mom[:, 2:].sum(axis=1)
+    ecm = np.sqrt(x1 * x2) * 13000.0
+    assert np.abs(tot[:, 0] - ecm).max() / 13000.0 < 1e-13 and np.abs(tot[:, 1:]).max() < 1e-9
+
+
+def test_not_cm_is_reported(oracle):
+    mom = np.zeros((3, 3, 4)); mom[:, :, 0] = 200.0; mom[:, 0, 1] = 5.0
+    _, _, rc = oracle.rambo_inverse(mom, np.full(3, 0.1), np.full(3, 0.1), [125.25, 172.5, 172.5], 13000.0)
+    assert rc == 2
+
+
+def test_nan_input_raises(oracle):
+    u = np.full((2, 7), 0.5); u[1, 3] = np.nan
+    with pytest.raises(ValueError):
+        oracle.rambo_forward(u, [125.25, 172.5, 172.5], 13000.0)
+
+
+@pytest.mark.parametrize("tag", ["f64_F7K10", "f32_F20K64", "f64_F10K40"])
+def test_spline_oracle_matches_torch_restatement(oracle, golden_dir, tag):
+    """The spline is 'parity unpinned' (zuko absent): the C oracle is checked against the op-for-op torch
+    restatement (oracle/rqs_torch.py), bins exactly and values to dtype precision."""
+    g = np.load(os.path.join(golden_dir, "rqs_%s.npz" % tag))
+    bound = float(g["bound"])
+    y, ladj, bins = oracle.rqs_forward(g["phi"], g["x"], bound=bound)
+    f32 = g["phi"].dtype == np.float32
+    same = bins == g["bin_fwd"]
+    assert same.mean() > (0.999 if f32 else 1.0 - 1e-12)
+    tol_y, tol_l = (2e-5, 5e-3) if f32 else (1e-13, 1e-11)
+    assert np.abs(y - g["y"])[same].max() < tol_y
+    assert np.abs(ladj - g["ladj"])[same].max() < tol_l
+    x, _, bins_i = oracle.rqs_inverse(g["phi"], g["x"], bound=bound)
+    same = bins_i == g["bin_inv"]
+    assert same.mean() > (0.999 if f32 else 1.0 - 1e-12)
+    assert np.abs(x - g["x_inv"])[same].max() < (1e-4 if f32 else 1e-12)
+    # identity tails: |x| > bound untouched, ladj exactly 0
+    out = np.abs(g["x"]) > bound * 1.0001
+    assert out.any() and np.array_equal(y[out], g["x"][out]) and np.all(ladj[out] == 0)
+
+
+def test_spline_self_consistency(oracle):
+    """inverse(forward(x)) = x and ladj = log of the numerical derivative (fp64)."""
+    rng = np.random.default_rng(3)
+    phi = rng.standard_normal((500, 5, 3 * 12 - 1))
+    x = rng.uniform(-0.95, 0.95, (500, 5))
+    y, ladj, _ = oracle.rqs_forward(phi, x, bound=1.0)
+    xb, ladj_b, _ = oracle.rqs_inverse(phi, y, bound=1.0)
+    assert np.abs(xb - x).max() < 1e-12
+    assert np.abs(ladj_b - ladj).max() < 1e-10
+    h = 1e-6
+    yp, _, bp = oracle.rqs_forward(phi, x + h, bound=1.0)
+    ym, _, bm = oracle.rqs_forward(phi, x - h, bound=1.0)
+    ok = bp == bm
+    assert np.abs(np.log((yp - ym) / (2 * h)) - ladj)[ok].max() < 1e-5
+
+
+def test_estimator_oracle():
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    t = rng.random(1000); t[::10] = -1
+    j = rng.random(1000) * 5; j[3] = np.nan
+    lq = rng.standard_normal(1000)
+    acc = O.is_reduce(t, j, lq)
+    ok = (t > 0) & ~np.isnan(j)
+    w = (t * j / np.exp(lq))[ok]
+    np.testing.assert_allclose(acc, [w.sum(), (w * w).sum(), ok.sum()], rtol=1e-13)
+    I, s = O.estimator(acc, 1000)
+    assert s > 0 and np.isclose(I, w.sum() / 1000)
+
+
+def test_philox_known_answer():
+    """Random123 known-answer test for Philox4x32-10: counter = key = 0 and all-ones."""
+    from oracle import philox as P
+    r = P.philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(v[0]) for v in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    r = P.philox4x32_10([0xffffffff], [0xffffffff], [0xffffffff], [0xffffffff], 0xffffffff, 0xffffffff)
+    assert [int(v[0]) for v in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]

@@ -1,0 +1,240 @@
+"""GPU parity of K1 (rambo_forward) and K2 (rambo_inverse) against the oracle and the committed golden
+vectors, through the reference-shaped Python API (which calls the C ABI). Tolerances: tests/parity.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+E = 13000.0
+MASSES = {3: [125.25, 172.5, 172.5], 4: [125.25, 172.5, 172.5, 1e-5], 5: [125.25, 172.5, 172.5, 1e-5, 1e-5],
+          6: [125.25, 172.5, 172.5, 4.7, 4.7, 1e-5], 7: [4.7, 4.7, 4.7, 4.7, 0.1, 0.0, 0.3],
+          8: [4.7, 4.7, 4.7, 4.7, 0.1, 0.0, 0.3, 0.3]}
+TOL64 = 1e-12
+
+
+def make_ps(n, **opts):
+    from memflow_b200.phasespace.phasespace import PhaseSpace
+    return PhaseSpace(E, [21, 21], list(range(n)), final_masses=torch.tensor(MASSES[n], dtype=torch.float64),
+                      dev="cuda:0", **opts)
+
+
+def rand_u(N, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(N, 3 * n - 2, dtype=torch.float64, generator=g).clamp(1e-10, 1 - 1e-10)
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 6, 7, 8])
+def test_forward_vs_oracle(oracle, n):
+    N = 100_000
+    u = rand_u(N, n, 100 + n)
+    ps = make_ps(n)
+    mom, w, x1, x2, lw = ps.get_momenta_from_ps(u.cuda(), return_logweight=True)
+    assert mom.dtype == torch.float64 and mom.shape == (N, n + 2, 4) and mom.is_cuda
+    om, ow, ox1, ox2 = oracle.rambo_forward(u.numpy(), MASSES[n], E)
+    kappa = parity.conditioning(u.numpy(), om, n)
+    err = parity.momenta_error(mom.cpu().numpy(), om, ox1, ox2, E)
+    s = parity.summarize(err, TOL64, kappa)
+    print("n=%d momenta" % n, s)
+    assert s["p50"] < 1e-14
+    assert s["p99"] < TOL64
+    assert s["max_over_kappa"] < TOL64, s
+    if n <= 4:  # the tt-bar-H(+j) configurations of BASELINE.json: every single event inside 1e-12
+        assert s["max"] < TOL64, s
+    np.testing.assert_allclose(x1.cpu().numpy(), ox1, rtol=0, atol=TOL64)
+    np.testing.assert_allclose(x2.cpu().numpy(), ox2, rtol=0, atol=TOL64)
+    dl = np.abs(np.log(w.cpu().numpy()) - np.log(ow))
+    sl = parity.summarize(dl, TOL64, kappa)
+    print("n=%d log-weight" % n, sl)
+    assert sl["p99"] < TOL64 and sl["max_over_kappa"] < TOL64, sl
+    assert float((lw - w.log()).abs().max()) < 1e-13
+    assert int(ps.generator.last_status.item()) == 0
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 8])
+def test_forward_vs_reference_golden(golden_dir, n):
+    """Against the UNMODIFIED reference's outputs (fp64-clean variant and literal float32-quirk variant)."""
+    g = np.load(os.path.join(golden_dir, "rambo_n%d.npz" % n))
+    u = torch.from_numpy(g["u"]).cuda()
+    for tag, quirks in (("clean", False), ("lit", True)):
+        ps = make_ps(n, ref_fp32_quirks=quirks)
+        mom, w, x1, x2 = ps.get_momenta_from_ps(u)
+        kappa = parity.conditioning(g["u"], g["mom_" + tag], n)
+        err = parity.momenta_error(mom.cpu().numpy(), g["mom_" + tag], g["x1_" + tag], g["x2_" + tag], E)
+        assert np.nanmax(err / kappa) < TOL64, (tag, np.nanmax(err / kappa))
+        assert np.quantile(err, 0.9) < TOL64
+        rw = g["w_" + tag]
+        assert np.array_equal(np.isinf(w.cpu().numpy()), np.isinf(rw))
+        fin = np.isfinite(rw) & (rw > 0)
+        dl = np.abs(np.log(w.cpu().numpy()[fin]) - np.log(rw[fin]))
+        tol = 5e-7 if quirks else TOL64
+        assert np.nanmax(dl / kappa[fin]) < tol, (tag, np.nanmax(dl / kappa[fin]))
+        if quirks:  # incoming rows carry the reference's float32 rounding exactly
+            assert np.array_equal(mom.cpu().numpy()[24:, 0, 0], g["mom_lit"][24:, 0, 0])
+        # literal weights agree with the clean ones only to float32 precision
+    lit, clean = g["w_lit"], g["w_clean"]
+    f = np.isfinite(lit)
+    assert 1e-9 < np.nanmax(np.abs(lit[f] / clean[f] - 1)) < 1e-6
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 6, 7, 8])
+def test_inverse_vs_oracle(oracle, n):
+    N = 100_000
+    u = rand_u(N, n, 200 + n)
+    om, ow, ox1, ox2 = oracle.rambo_forward(u.numpy(), MASSES[n], E)
+    ps = make_ps(n)
+    full = torch.from_numpy(om).cuda()
+    # the [:, 2:] slice is read in place (event pitch 4(n+2)), no copy
+    out, prob, lp = ps.generator.getPSpoint_batch(full[:, 2:], torch.from_numpy(ox1).cuda(),
+                                                  torch.from_numpy(ox2).cuda(), return_logprob=True)
+    ops, oprob, rc = oracle.rambo_inverse(om[:, 2:], ox1, ox2, MASSES[n], E)
+    assert rc == 0 and int(ps.generator.last_status.item()) == 0
+    kappa = parity.conditioning(u.numpy(), om, n)
+    d = np.abs(out.cpu().numpy() - ops).max(axis=1)
+    s = parity.summarize(d, TOL64, kappa)
+    print("n=%d inverse ps" % n, s)
+    assert s["p99"] < TOL64 and s["max_over_kappa"] < TOL64, s
+    dl = np.abs(np.log(prob.cpu().numpy()) - np.log(oprob))
+    assert np.nanquantile(dl, 0.99) < TOL64 and np.nanmax(dl / kappa) < TOL64
+    assert float((lp - prob.log()).abs().max()) < 1e-13
+
+
+@pytest.mark.parametrize("n", [4, 8])
+def test_inverse_permuted_offshell_and_golden(oracle, golden_dir, n):
+    g = np.load(os.path.join(golden_dir, "rambo_n%d.npz" % n))
+    ps = make_ps(n)
+    mom = torch.from_numpy(g["mom_clean"]).cuda()
+    x1, x2 = torch.from_numpy(g["x1_clean"]).cuda(), torch.from_numpy(g["x2_clean"]).cuda()
+    kappa = parity.conditioning(g["u"], g["mom_clean"], n)
+    out, prob = ps.generator.getPSpoint_batch(mom[:, 2:], x1, x2)
+    assert np.nanmax(np.abs(out.cpu().numpy() - g["inv_ps_clean"]).max(axis=1) / kappa) < TOL64
+    perm = [int(i) for i in g["perm"]]
+    out, prob = ps.generator.getPSpoint_batch(mom[:, 2:].contiguous(), x1, x2, order=perm)
+    ops, oprob, _ = oracle.rambo_inverse(g["mom_clean"][:, 2:], g["x1_clean"], g["x2_clean"], MASSES[n], E, order=perm)
+    d = np.abs(out.cpu().numpy() - ops)
+    assert np.array_equal(np.isnan(out.cpu().numpy()), np.isnan(ops))
+    assert np.nanquantile(d, 0.9) < TOL64
+    out, prob = ps.generator.getPSpoint_batch(mom[:, 2:], x1, x2, order=perm, target_mass=torch.from_numpy(g["target_mass"]),
+                                              ensure_onShell=False)
+    ref = g["inv_ps_offshell_clean"]
+    assert np.array_equal(np.isnan(out.cpu().numpy()), np.isnan(ref))
+    assert np.nanquantile(np.abs(out.cpu().numpy() - ref), 0.9) < TOL64
+
+
+def test_round_trip_config2_full_size():
+    """BASELINE config 2: u -> p -> u' for the 8-body final state, 16M events, fp64 (size-independent property;
+    the oracle is not involved). Also prob * weight == 1 and 4-momentum conservation."""
+    n, N = 8, 16_000_000
+    ps = make_ps(n)
+    g = torch.Generator(device="cuda").manual_seed(2024)
+    u = torch.rand(N, 3 * n - 2, dtype=torch.float64, device="cuda", generator=g).clamp_(1e-10, 1 - 1e-10)
+    mom, w, x1, x2 = ps.get_momenta_from_ps(u)
+    back, prob = ps.generator.getPSpoint_batch(mom[:, 2:], x1, x2)
+    assert int(ps.generator.last_status.item()) == 0
+    res = (back - u).abs()
+    del back
+    med = float(res.flatten()[::97].median())
+    frac = float((res.max(dim=1).values > 1e-9).double().mean())
+    print("config 2 round trip: median %.2e, max %.2e, frac(>1e-9) %.2e" % (med, float(res.max()), frac))
+    assert med < 1e-15 and frac < 1e-3
+    pw = (prob * w - 1).abs()
+    assert float(pw.median()) < 1e-14 and float((pw > 1e-9).double().mean()) < 1e-3
+    tot = mom[:, 2:].sum(dim=1)
+    ecm = torch.sqrt(x1 * x2) * E
+    assert float(((tot[:, 0] - ecm).abs() / ecm).max()) < 1e-12
+    assert float((tot[:, 1:].abs().max(dim=1).values / ecm).max()) < 1e-12
+
+
+def test_edges_and_status_flags(oracle):
+    n = 3
+    ps = make_ps(n)
+    u = torch.full((64, 7), 0.5, dtype=torch.float64)
+    u[1, 0] = 0.0; u[2, 0] = 1.0; u[3, 5] = 1.0   # mass variable 0 / 1 (bisection floor 2^-180 / 1), u_x1 = 1 -> NaN
+    mom, w, x1, x2 = ps.get_momenta_from_ps(u.cuda())
+    om, ow, ox1, ox2 = oracle.rambo_forward(u.numpy(), MASSES[n], E)
+    a, b = mom.cpu().numpy(), om
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(b)
+    assert np.abs(a[ok] - b[ok]).max() / E < 1e-12
+    wn = w.cpu().numpy()
+    assert np.array_equal(np.isnan(wn), np.isnan(ow)) and np.isnan(wn[3])
+    assert int(ps.generator.last_status.item()) == 0
+    u[5, 2] = float("nan")
+    ps.get_momenta_from_ps(u.cuda())
+    assert int(ps.generator.last_status.item()) & 1                # MF_ST_NAN_INPUT, no host sync needed
+    from memflow_b200.phasespace.rambo_generator import PhaseSpaceGeneratorError
+    strict = make_ps(n, sync_errors=True)
+    with pytest.raises(PhaseSpaceGeneratorError):                  # reference behaviour on request (:191-199)
+        strict.get_momenta_from_ps(u.cuda())
+    bad = torch.zeros(8, 3, 4, dtype=torch.float64, device="cuda"); bad[:, :, 0] = 300.0; bad[:, 0, 1] = 50.0
+    with pytest.raises(Exception, match="not in the CM"):          # :634-635
+        strict.get_ps_from_momenta(bad, torch.full((8,), 0.1, device="cuda"), torch.full((8,), 0.2, device="cuda"))
+    with pytest.raises(AssertionError):                            # :251 wrong column count
+        ps.get_momenta_from_ps(torch.rand(4, 6, dtype=torch.float64, device="cuda"))
+    # empty batch
+    mom, w, x1, x2 = ps.get_momenta_from_ps(torch.empty(0, 7, dtype=torch.float64, device="cuda"))
+    assert mom.shape == (0, 5, 4) and w.numel() == 0
+    # ragged sizes around the block size
+    for N in (1, 255, 257):
+        uu = rand_u(N, n, N)
+        m1 = ps.get_momenta_from_ps(uu.cuda())[0].cpu().numpy()
+        m2 = oracle.rambo_forward(uu.numpy(), MASSES[n], E)[0]
+        assert np.abs(m1 - m2).max() / E < 1e-12
+
+
+def test_cuts_lab_frame_and_float_inputs(oracle):
+    n, N = 4, 50_000
+    u = rand_u(N, n, 9)
+    ps = make_ps(n)
+    mom, w, x1, x2 = ps.get_momenta_from_ps(u.cuda(), pT_mincut=20.0, delR_mincut=0.4, rap_maxcut=5.0)
+    _, ow, _, _ = oracle.rambo_forward(u.numpy(), MASSES[n], E, pT_mincut=20.0, delR_mincut=0.4, rap_maxcut=5.0)
+    z, oz = (w.cpu().numpy() == 0), (ow == 0)
+    assert 0.05 < oz.mean() < 0.95
+    assert (z != oz).mean() < 1e-4                                  # cut decisions: only knife-edge events may differ
+    # lab frame fused == reference's boost_to_lab_frame applied to the CM output
+    from memflow_b200.phasespace import utils as U
+    mom_cm, _, x1, x2 = ps.get_momenta_from_ps(u.cuda())
+    mom_lab = ps.get_momenta_from_ps(u.cuda(), lab_frame=True)[0]
+    ref_lab = U.boost_to_lab_frame(mom_cm, x1, x2)
+    assert float((mom_lab - ref_lab).abs().max()) / E < 1e-12
+    # float32 points in -> float64 out, like the reference (rambo_generator.py:201-215)
+    m32 = ps.get_momenta_from_ps(u.float().cuda())[0]
+    assert m32.dtype == torch.float64
+    # generate_random_phase_space_points (phasespace.py:64-80)
+    r, m, ww, a, b = ps.generate_random_phase_space_points(1000)
+    assert r.shape == (1000, 10) and m.shape == (1000, 6, 4) and bool((ww > 0).all())
+
+
+def test_fp32_kernels(oracle):
+    """fp32 compute path: 1e-5 relative to E_cm against the fp64 oracle on the same (fp32-rounded) inputs."""
+    n, N = 3, 100_000
+    u32 = rand_u(N, n, 77).float().clamp(1e-6, 1 - 1e-6)
+    ps = make_ps(n, compute_dtype=torch.float32)
+    mom, w, x1, x2 = ps.get_momenta_from_ps(u32.cuda())
+    om, ow, ox1, ox2 = oracle.rambo_forward(u32.double().numpy(), MASSES[n], E)
+    err = parity.momenta_error(mom.cpu().numpy(), om, ox1, ox2, E)
+    print("fp32 forward", parity.summarize(err, 1e-5))
+    assert np.quantile(err, 0.999) < 1e-5
+    dl = np.abs(np.log(w.cpu().numpy()) - np.log(ow))
+    assert np.nanquantile(dl, 0.99) < 1e-4
+    back, prob = ps.generator.getPSpoint_batch(torch.from_numpy(om[:, 2:]).float().cuda(),
+                                               torch.from_numpy(ox1).float().cuda(), torch.from_numpy(ox2).float().cuda())
+    assert np.quantile(np.abs(back.cpu().numpy() - u32.double().numpy()).max(axis=1), 0.99) < 2e-4
+
+
+def test_massvar_solver_vs_bisection(oracle):
+    """bisect_vec_batch replacement: solves v = u^e((e+1) - e u) to <= 2 ulp-level residual for all exponents."""
+    n = 8
+    ps = make_ps(n)
+    g = torch.Generator().manual_seed(3)
+    v = torch.rand(200_000, n - 2, dtype=torch.float64, generator=g)
+    v[:1000] = 10.0 ** (-30 * torch.rand(1000, n - 2, dtype=torch.float64, generator=g))
+    v[1000:2000] = 1 - 10.0 ** (-16 * torch.rand(1000, n - 2, dtype=torch.float64, generator=g))
+    u = ps.generator.bisect_vec_batch(v.cuda()).cpu()
+    e = torch.arange(n - 2, 0, -1, dtype=torch.float64)
+    res = ((u ** e) * ((e + 1) - e * u) - v).abs()
+    assert float((res / v.clamp_min(1e-300)).max()) < 5e-15 or float(res.max()) < 1e-15
+    assert bool(((u >= 0) & (u <= 1)).all())

@@ -1,0 +1,145 @@
+"""GPU parity of K3/K4 (rational-quadratic spline) against the oracle / torch restatement.
+
+fp64: 1e-12-level agreement. fp32: the problem itself is ill-conditioned in fp32 for narrow bins (knots are
+differences of a cumulative sum of O(1) values: one fp32 ulp of x moves z = (x-x_k)/(x_{k+1}-x_k) by
+6e-8/width), so the bound is  1e-5 * (1 + 6e-3/width_bin)  and the kernel must be no worse than the fp32
+oracle itself (both measured against the fp64 oracle on the same fp32 inputs)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def make(B, F, K, dt, bound, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    phi = torch.randn(B, F, 3 * K - 1, generator=g, dtype=torch.float64).to(dt)
+    x = ((torch.rand(B, F, generator=g, dtype=torch.float64) * 2.6 - 1.3) * bound).to(dt)
+    return phi, x
+
+
+def bin_width(oracle, phi64, x64, bound, inverse=False):
+    """width of the selected bin in the searched coordinate (conditioning of the fp32 problem)."""
+    K = (phi64.shape[-1] + 1) // 3
+    a = phi64[..., K:2 * K] if inverse else phi64[..., :K]
+    L = np.log(1e-3)
+    a = a / (1 + np.abs(2 * a / L))
+    p = np.exp(a - a.max(-1, keepdims=True)); p /= p.sum(-1, keepdims=True)
+    return 2 * bound * p
+
+
+@pytest.mark.parametrize("F,K,bound", [(7, 10, 1.0), (10, 40, 1.1), (20, 64, 1.1), (3, 9, 5.0), (1, 1, 2.0), (5, 128, 1.0)])
+def test_fp64_forward_inverse(oracle, F, K, bound):
+    from memflow_b200 import transforms as TR
+    B = 3001
+    phi, x = make(B, F, K, torch.float64, bound)
+    y, ladj, lsum, bins = TR.rqs_forward(phi.cuda(), x.cuda(), bound=bound, return_bins=True)
+    oy, ol, ob = oracle.rqs_forward(phi.numpy(), x.numpy(), bound=bound)
+    assert np.array_equal(bins.cpu().numpy(), ob)                      # integer indexing bit-exact
+    assert np.abs(y.cpu().numpy() - oy).max() < 1e-12
+    assert np.abs(ladj.cpu().numpy() - ol).max() < 5e-11               # log J, J built from knot differences
+    assert np.quantile(np.abs(ladj.cpu().numpy() - ol), 0.99) < 1e-12
+    np.testing.assert_allclose(lsum.cpu().numpy(), ol.sum(1), atol=1e-10)
+    out = np.abs(x.numpy()) > bound * 1.0001                           # identity tails
+    assert out.any() and np.array_equal(y.cpu().numpy()[out], x.numpy()[out]) and np.all(ladj.cpu().numpy()[out] == 0)
+    xi, li, _, bi = TR.rqs_inverse(phi.cuda(), x.cuda(), bound=bound, return_bins=True)
+    ox, oli, obi = oracle.rqs_inverse(phi.numpy(), x.numpy(), bound=bound)
+    assert np.array_equal(bi.cpu().numpy(), obi)
+    assert np.abs(xi.cpu().numpy() - ox).max() < 1e-12
+    assert np.quantile(np.abs(li.cpu().numpy() - oli), 0.99) < 1e-12
+    # inverse o forward = identity, and the inverse's ladj equals the forward's at the recovered point
+    y2, l2, _ = TR.rqs_forward(phi.cuda(), xi, bound=bound)
+    assert float((y2.cpu() - x).abs().max()) < 1e-12
+    assert float((l2 - li).abs().max()) < 1e-9
+
+
+@pytest.mark.parametrize("F,K,bound", [(20, 64, 1.1), (7, 10, 1.0), (10, 40, 1.1)])
+def test_fp32_forward_inverse(oracle, F, K, bound):
+    from memflow_b200 import transforms as TR
+    B = 20000
+    phi, x = make(B, F, K, torch.float32, bound)
+    p64, x64 = phi.double().numpy(), x.double().numpy()
+    for inverse in (False, True):
+        run = TR.rqs_inverse if inverse else TR.rqs_forward
+        orc = oracle.rqs_inverse if inverse else oracle.rqs_forward
+        out, ladj, lsum, bins = run(phi.cuda(), x.cuda(), bound=bound, return_bins=True)
+        o64, l64, b64 = orc(p64, x64, bound=bound)                      # fp64 truth on the same inputs
+        o32, l32, b32 = orc(phi.numpy(), x.numpy(), bound=bound)        # fp32 oracle (what torch-fp32 zuko computes)
+        bins = bins.cpu().numpy()
+        mism = bins != b64
+        assert mism.mean() < 1e-4                                       # only x within an ulp of a knot may move bin
+        ok = ~mism & (b32 == b64)
+        width = np.take_along_axis(bin_width(oracle, p64, x64, bound, inverse), np.clip(b64, 0, K - 1)[..., None], -1)[..., 0]
+        cond = 1.0 + 6e-3 / width
+        e_out = np.abs(out.cpu().numpy() - o64)
+        e_l = np.abs(ladj.cpu().numpy() - l64)
+        print("fp32 F=%d K=%d inv=%s: out p50 %.1e max %.1e | ladj p50 %.1e p99 %.1e max %.1e | fp32-oracle ladj max %.1e"
+              % (F, K, inverse, np.median(e_out), e_out[ok].max(), np.median(e_l), np.quantile(e_l, 0.99), e_l[ok].max(),
+                 np.abs(l32 - l64)[ok].max()))
+        assert (e_out[ok] / cond[ok]).max() < 1e-5
+        assert (e_l[ok] / cond[ok]).max() < 1e-5 * 10
+        assert np.median(e_l) < 1e-5 and np.median(e_out) < 1e-6
+        # never materially worse than the fp32 reference arithmetic itself
+        assert e_l[ok].max() < 3 * np.abs(l32 - l64)[ok].max() + 1e-5
+        np.testing.assert_allclose(lsum.cpu().numpy(), ladj.cpu().numpy().sum(1), atol=2e-4)
+
+
+def test_searchsorted_bit_exact():
+    """Bin search with the knots GIVEN must equal torch.searchsorted exactly."""
+    from memflow_b200 import transforms as TR
+    g = torch.Generator().manual_seed(0)
+    for dt in (torch.float32, torch.float64):
+        knots = torch.sort(torch.rand(5000, 65, generator=g, dtype=torch.float64).to(dt) * 2 - 1, dim=-1).values
+        v = (torch.rand(5000, generator=g, dtype=torch.float64) * 2.4 - 1.2).to(dt)
+        v[:100] = knots[:100, 7]                                        # exact hits on a knot: right=False semantics
+        idx = TR.searchsorted(knots.cuda(), v.cuda()).cpu()
+        ref = torch.searchsorted(knots, v[:, None]).squeeze(-1)
+        assert torch.equal(idx.long(), ref)
+
+
+def test_transform_api_and_golden(golden_dir):
+    """zuko-shaped Transform surface; zero-copy packing of split views; golden fixture of the torch restatement."""
+    from memflow_b200.transforms import MonotonicRQSTransform
+    g = np.load(os.path.join(golden_dir, "rqs_f64_F7K10.npz"))
+    phi = torch.from_numpy(g["phi"]).cuda()
+    x = torch.from_numpy(g["x"]).cuda()
+    K = 10
+    w, h, d = phi.split([K, K, K - 1], dim=-1)                           # what zuko's MAF hands to the univariate
+    t = MonotonicRQSTransform(w, h, d, bound=float(g["bound"]))
+    assert t.phi.data_ptr() == phi.data_ptr()                            # no concatenation copy
+    y, ladj = t.call_and_ladj(x)
+    assert np.abs(y.cpu().numpy() - g["y"]).max() < 1e-12
+    assert np.abs(ladj.cpu().numpy() - g["ladj"]).max() < 1e-11
+    assert torch.equal(t(x), y)
+    assert torch.equal(t.log_abs_det_jacobian(x, y), ladj)
+    xi = t.inv(x)
+    assert np.abs(xi.cpu().numpy() - g["x_inv"]).max() < 1e-12
+    t2 = MonotonicRQSTransform(w.clone(), h.clone(), d.clone(), bound=float(g["bound"]))  # separate tensors -> packed copy
+    assert torch.equal(t2(x), y)
+    t3 = MonotonicRQSTransform(w, h, d, bound=float(g["bound"]), slope=None)              # zuko <= 0.1: no soft clip
+    assert not torch.equal(t3(x), y)
+    g32 = np.load(os.path.join(golden_dir, "rqs_f32_F20K64.npz"))
+    p32, x32 = torch.from_numpy(g32["phi"]).cuda(), torch.from_numpy(g32["x"]).cuda()
+    t = MonotonicRQSTransform(*p32.split([64, 64, 63], dim=-1), bound=float(g32["bound"]))
+    y, ladj = t.call_and_ladj(x32)
+    assert np.median(np.abs(y.cpu().numpy() - g32["y"])) < 1e-6
+
+
+def test_ragged_and_unaligned(oracle):
+    from memflow_b200 import transforms as TR
+    for B in (1, 5, 127, 131):
+        phi, x = make(B, 7, 10, torch.float32, 1.0, seed=B)
+        y, l, s = TR.rqs_forward(phi.cuda(), x.cuda(), bound=1.0)
+        oy, ol, _ = oracle.rqs_forward(phi.numpy(), x.numpy(), bound=1.0)
+        assert np.abs(y.cpu().numpy() - oy).max() < 1e-4
+    # parameter block whose base address is only 4-byte aligned -> cooperative-copy path instead of TMA
+    phi, x = make(301, 7, 10, torch.float32, 1.0)
+    buf = torch.empty(phi.numel() + 1, dtype=torch.float32, device="cuda")
+    view = buf[1:].view(phi.shape); view.copy_(phi)
+    y1 = TR._run("forward", view, x.cuda(), 1.0, 1e-3)[0] if view.is_contiguous() else None
+    y0 = TR.rqs_forward(phi.cuda(), x.cuda(), bound=1.0)[0]
+    assert y1 is not None and torch.equal(y1, y0)
+    e = TR.rqs_forward(torch.empty(0, 7, 29, device="cuda"), torch.empty(0, 7, device="cuda"), bound=1.0)
+    assert e[0].shape == (0, 7)
