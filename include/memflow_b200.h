@@ -107,6 +107,14 @@ int mf_rambo_inverse_f32(const float* momenta, int64_t event_stride, const float
                          const float* target_mass, float e_collider, uint32_t flags, float* ps, float* prob,
                          float* logprob, int32_t* status, mf_stream_t stream);
 
+/* K2 with the semantics of Compute_ParticlesTensor.get_PS, memflow/unfolding_flow/utils.py:1056-1152 (called every
+ * training step, unfolding_flow.py:163): x1,x2 = (E +- pz)/e_collider of the reconstructed boost [N,4], clamped to [0,1];
+ * masses = target_mass[order] (host [n]); no RAMBO weight: jac0 [N] or NULL receives 0 * jac_x1x2 like the reference;
+ * mask [N] (uint8) or NULL = x out of range | |sum p|^2 > 1e-5 | any RAMBO variable outside [0,1]. */
+int mf_get_ps_f64(const double* momenta, int64_t event_stride, const double* boost, int64_t N, int n_final,
+                  const int32_t* order, const double* target_mass, double e_collider, double* ps, double* jac0,
+                  uint8_t* mask, mf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K3 / K4  monotonic rational-quadratic spline, zuko.transforms.MonotonicRQSTransform
  * (third-party; constructed at memflow/unfolding_flow/unfolding_flow.py:88-97 and

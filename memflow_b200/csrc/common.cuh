@@ -51,11 +51,13 @@ template <> struct Limits<double> {
     static MF_HD double huge() { return 1.7976931348623157e308; }
     static MF_HD double sqrt_eps() { return 1.4901161193847656e-08; }  // np.finfo(float).eps ** 0.5
     static MF_HD double tiny_u() { return 6.525304467998525e-55; }     // 2^-180, bisection floor (see rambo.cuh)
+    static MF_HD double max_u() { return 0.9999999999999999; }         // 1 - 2^-53
 };
 template <> struct Limits<float> {
     static MF_HD float huge() { return 3.4028234663852886e38f; }
     static MF_HD float sqrt_eps() { return 1.4901161193847656e-08f; }
     static MF_HD float tiny_u() { return 1e-30f; }
+    static MF_HD float max_u() { return 0.99999994f; }
 };
 
 // integer power by repeated multiplication, compile-time exponent

@@ -10,6 +10,8 @@
 // double-buffered 1-D TMA bulk copy per (tile, transform). Phase-space phase: the first E threads, one
 // event each, fp64, registers only. Nothing but the 3 accumulators is written to HBM unless the
 // optional debug outputs are requested. Algorithmic bytes per event: T F (3K-1) 4.
+#include <cstdlib>
+
 #include "philox.cuh"
 #include "rambo.cuh"
 #include "reduce.cuh"
@@ -19,8 +21,8 @@ namespace mf {
 
 constexpr int kChainThreads = 256;
 
-template <int NF>
-__global__ void __launch_bounds__(kChainThreads)
+template <int NF, int MINB>
+__global__ void __launch_bounds__(kChainThreads, MINB)
 is_chain_kernel(const float* __restrict__ phi, int64_t N, int T, int K, RqsConst<float> C, int E /*events per tile*/,
                 int bulk_ok, uint64_t seed, uint64_t event_offset, const __grid_constant__ RamboParams<double, NF> P,
                 double inv_2s, double* __restrict__ acc, void* workspace, double* __restrict__ u_out,
@@ -32,7 +34,7 @@ is_chain_kernel(const float* __restrict__ phi, int64_t N, int T, int K, RqsConst
     const int rows = E * F;
     const size_t tile_elems = (size_t)rows * PW;
     const size_t tile_bytes_al = (tile_elems * sizeof(float) + 127) / 128 * 128;
-    float* stage_base[2] = {reinterpret_cast<float*>(smem_raw), reinterpret_cast<float*>(smem_raw + tile_bytes_al)};
+    auto stage_ptr = [&](int st) { return reinterpret_cast<float*>(smem_raw + (size_t)st * tile_bytes_al); };
     unsigned char* tail = smem_raw + 2 * tile_bytes_al;
     float* val = reinterpret_cast<float*>(tail);                // [kChainThreads] current x per row
     float* lsum = val + kChainThreads;                          // [kChainThreads] sum_t ladj per row
@@ -50,13 +52,13 @@ is_chain_kernel(const float* __restrict__ phi, int64_t N, int T, int K, RqsConst
         if (tid == 0 && tile < num_tiles && tile_is_bulk(tile)) {
             const uint32_t bytes = (uint32_t)(tile_elems * sizeof(float));
             mbar_expect_tx(&bars[st], bytes);
-            bulk_g2s(stage_base[st], phi + (size_t)t * transform_pitch + (size_t)tile * tile_elems, bytes, &bars[st]);
+            bulk_g2s(stage_ptr(st), phi + (size_t)t * transform_pitch + (size_t)tile * tile_elems, bytes, &bars[st]);
         }
     };
 
     Kahan k1, k2;
     double cnt = 0.0;
-    uint32_t parity[2] = {0u, 0u};
+    uint32_t parity0 = 0u, parity1 = 0u;
     int item = 0;
     int64_t tile = blockIdx.x;
     issue(tile, T - 1, 0);  // sampling applies the transforms in reverse order: f_T^-1 first
@@ -79,10 +81,10 @@ is_chain_kernel(const float* __restrict__ phi, int64_t N, int T, int K, RqsConst
             const int st = item & 1;
             // prefetch the next (tile, transform) item into the other stage
             if (tt + 1 < T) issue(tile, t - 1, st ^ 1); else issue(tile + gridDim.x, T - 1, st ^ 1);
-            float* sm = stage_base[st];
+            float* sm = stage_ptr(st);
             if (tile_is_bulk(tile)) {
-                mbar_wait(&bars[st], parity[st]);
-                parity[st] ^= 1u;
+                mbar_wait(&bars[st], st ? parity1 : parity0);
+                if (st) parity1 ^= 1u; else parity0 ^= 1u;
             } else {
                 const float* src = phi + (size_t)t * transform_pitch + (size_t)tile * tile_elems;
                 const size_t ne = (size_t)nrows * PW;
@@ -92,7 +94,14 @@ is_chain_kernel(const float* __restrict__ phi, int64_t N, int T, int K, RqsConst
             if (row_active) {
                 float out, ladj;
                 int bin;
-                rqs_row_1lane<float, true>(sm + (size_t)tid * PW, K, C, x, out, ladj, bin);
+                float* rowp = sm + (size_t)tid * PW;
+                switch (K) {  // register-resident fast path for the common small bin counts
+                case 8: rqs_row_reg<8, true>(rowp, C, x, out, ladj, bin); break;
+                case 10: rqs_row_reg<10, true>(rowp, C, x, out, ladj, bin); break;
+                case 12: rqs_row_reg<12, true>(rowp, C, x, out, ladj, bin); break;
+                case 16: rqs_row_reg<16, true>(rowp, C, x, out, ladj, bin); break;
+                default: rqs_row_1lane<float, true>(rowp, K, C, x, out, ladj, bin); break;
+                }
                 x = out;
                 ladj_acc += ladj;
             }
@@ -168,16 +177,26 @@ static int chain_launch(const float* phi, int64_t N, int T, int K, float bound, 
     const RamboParams<double, NF> P = make_forward_params<double, NF>(masses, e_collider, nullptr, flags & ~MF_FLAG_CUTS);
     const double inv_2s = 1.0 / (2.0 * e_collider * e_collider);
     const int64_t num_tiles = (N + E - 1) / E;
-    int ctas_per_sm = (int)((size_t)smem_max / smem);
-    if (ctas_per_sm > 8) ctas_per_sm = 8;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    int64_t grid = (int64_t)sms * ctas_per_sm;
-    if (grid > num_tiles) grid = num_tiles;
-    if (grid > kReduceMaxBlocks) grid = kReduceMaxBlocks;
-    auto kern = is_chain_kernel<NF>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<(unsigned)grid, kChainThreads, smem, stream>>>(phi, N, T, K, C, E, bulk_ok, seed, event_offset, P, inv_2s, acc,
-                                                          workspace, u_out, logq, momenta, weight, x1, x2);
+    static int minb_env = -1;
+    if (minb_env < 0) { const char* e = getenv("MF_CHAIN_MINB"); minb_env = e ? atoi(e) : 2; }
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int ctas_per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kChainThreads, smem);
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        int64_t grid = (int64_t)sms * ctas_per_sm;
+        if (grid > num_tiles) grid = num_tiles;
+        if (grid > kReduceMaxBlocks) grid = kReduceMaxBlocks;
+        kern<<<(unsigned)grid, kChainThreads, smem, stream>>>(phi, N, T, K, C, E, bulk_ok, seed, event_offset, P, inv_2s,
+                                                              acc, workspace, u_out, logq, momenta, weight, x1, x2);
+    };
+    switch (minb_env) {
+    case 1: go(is_chain_kernel<NF, 1>); break;
+    case 3: go(is_chain_kernel<NF, 3>); break;
+    case 4: go(is_chain_kernel<NF, 4>); break;
+    default: go(is_chain_kernel<NF, 2>); break;
+    }
     return launch_status();
 }
 

@@ -58,7 +58,8 @@ template <typename T> MF_D void boost(const T (&p)[4], T bx, T by, T bz, T (&o)[
 //            1 - v = x^2 P_E(x)  (polynomial, no cancellation). fp32 asymptotic start + 2 fp32
 //            Newton steps (MUFU log2/exp2), then 2 fp64 Halley steps (cubic): converged to <= 2 ulp of
 //            the exact root for all v in (1e-30, 1), tests/test_massvar_solver.py.
-// Edge semantics follow the bisection: v <= 0 -> 2^-180 (its floor after 180 levels), v >= 1 -> 1.
+// Edge semantics follow the bisection: v <= 0 -> 2^-180 (its floor after 180 levels); v >= 1 -> the largest
+// double below 1 (the bisection stalls just below 1, so the reference's weight stays finite there).
 // ---------------------------------------------------------------------------------------------
 MF_HD constexpr double binom(int n, int k) {
     if (k < 0 || k > n) return 0.0;
@@ -122,7 +123,7 @@ template <int E> MF_D float massvar_start_f32(bool small, float tf) {
 template <int E> MF_D double solve_massvar(double v) {
     if constexpr (E == 1) {
         double u = v / (1.0 + sqrt(1.0 - v));
-        return (v <= 0.0) ? Limits<double>::tiny_u() : ((v >= 1.0) ? 1.0 : u);
+        return (v <= 0.0) ? Limits<double>::tiny_u() : ((v >= 1.0 || u > Limits<double>::max_u()) ? Limits<double>::max_u() : u);
     } else {
         const bool small = v < 0.65;
         const double t = small ? v : 1.0 - v;
@@ -142,13 +143,14 @@ template <int E> MF_D double solve_massvar(double v) {
             x = (xn > 0.0 && xn < 1.0) ? xn : x;
         }
         double u = small ? x : 1.0 - x;
+        u = (u > Limits<double>::max_u()) ? Limits<double>::max_u() : u;
         return (u < Limits<double>::tiny_u()) ? Limits<double>::tiny_u() : u;  // NaN stays NaN
     }
 }
 template <int E> MF_D float solve_massvar(float v) {
     if constexpr (E == 1) {
         float u = v / (1.0f + sqrtf(1.0f - v));
-        return (v <= 0.0f) ? Limits<float>::tiny_u() : ((v >= 1.0f) ? 1.0f : u);
+        return (v <= 0.0f) ? Limits<float>::tiny_u() : ((v >= 1.0f || u > Limits<float>::max_u()) ? Limits<float>::max_u() : u);
     } else {
         const bool small = v < 0.65f;
         const float t = small ? v : 1.0f - v;
@@ -158,6 +160,7 @@ template <int E> MF_D float solve_massvar(float v) {
         float xn = x - f / d1;
         x = (xn > 0.0f && xn < 1.0f) ? xn : x;
         float u = small ? x : 1.0f - x;
+        u = (u > Limits<float>::max_u()) ? Limits<float>::max_u() : u;
         return (u < Limits<float>::tiny_u()) ? Limits<float>::tiny_u() : u;
     }
 }

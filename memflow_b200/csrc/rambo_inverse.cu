@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256)
 rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const T* __restrict__ x1a,
                      const T* __restrict__ x2a, int64_t N, const __grid_constant__ RamboParams<T, NF> P,
                      T* __restrict__ ps, T* __restrict__ prob, T* __restrict__ logprob,
-                     int32_t* __restrict__ status) {
+                     int32_t* __restrict__ status, const T* __restrict__ boost_reco, uint8_t* __restrict__ mask) {
     constexpr int D = 3 * NF - 4, W = D + 2;
     const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ev >= N) return;
@@ -26,14 +26,30 @@ rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const 
 #pragma unroll
         for (int k = 0; k < NF; ++k) ld4(base + 4 * P.order[k], Pm[k][0], Pm[k][1], Pm[k][2], Pm[k][3]);
     }
-    const T x1 = x1a[ev], x2 = x2a[ev];
+    // get_PS mode (memflow/unfolding_flow/utils.py:1056-1152): x1,x2 from the reconstructed boost, problems -> mask
+    const bool getps = boost_reco != nullptr;
+    bool problem = false;
+    T x1, x2;
+    if (getps) {
+        T b0, b1, b2, b3;
+        ld4(boost_reco + 4 * ev, b0, b1, b2, b3);
+        x1 = (b0 + b3) / P.e_collider;
+        x2 = (b0 - b3) / P.e_collider;
+        problem = (x1 > (T)1) | (x1 < (T)0) | (x2 < (T)0) | (x1 > (T)1);  // sic (:1068): x2 > 1 is never tested
+        x1 = x1 < (T)0 ? (T)0 : (x1 > (T)1 ? (T)1 : x1);
+        x2 = x2 < (T)0 ? (T)0 : (x2 > (T)1 ? (T)1 : x2);
+    } else {
+        x1 = x1a[ev];
+        x2 = x2a[ev];
+    }
 
-    if (!(P.flags & MF_FLAG_NO_CM_CHECK) && status != nullptr) {  // :630-635
+    if (getps || (!(P.flags & MF_FLAG_NO_CM_CHECK) && status != nullptr)) {  // :630-635 / get_PS :1079-1081
         T s1 = (T)0, s2 = (T)0, s3 = (T)0;
 #pragma unroll
         for (int k = 0; k < NF; ++k) { s1 += Pm[k][1]; s2 += Pm[k][2]; s3 += Pm[k][3]; }
         T r2 = (s1 * s1 + s2 * s2) + s3 * s3;
-        if (!(r2 < (T)1e-3)) atomicOr(status, MF_ST_NOT_CM);
+        if (getps) problem |= (r2 > (T)1e-5);
+        else if (!(r2 < (T)1e-3)) atomicOr(status, MF_ST_NOT_CM);
     }
 
     // M_j = sqrt((sum_{k>=j} P_k)^2), K_j = M_j - sum_{k>=j} m_k   (:656-660; sums in the reference's order)
@@ -83,6 +99,14 @@ rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const 
         r[D + 1] = ml2 / (P.q - ml1);
         jacinv = (T)1 / ((P.A * x1) * x2);
     }
+    if (getps) {  // no RAMBO weight in get_PS: returns 0 * jac_x1x2 (:1139,1152) and the problem mask
+#pragma unroll
+        for (int c = 0; c < D; ++c) problem |= (r[c] < (T)0) | (r[c] > (T)1);
+        store_row<W>(ps + ev * W, r);
+        if (prob != nullptr) prob[ev] = (T)0 * jacinv;
+        if (mask != nullptr) mask[ev] = problem ? 1 : 0;
+        return;
+    }
     const T E_cm = sqrt_(x1 * x2) * P.e_collider;
     const bool quirks = (P.flags & MF_FLAG_REF_FP32_QUIRKS) != 0;
     const T jac = rambo_weight<T, NF>(P, E_cm, K, M, quirks);
@@ -101,7 +125,8 @@ rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const 
 template <typename T, int NF>
 static int launch_inverse(const T* momenta, int64_t event_stride, const T* x1, const T* x2, int64_t N,
                           const int32_t* order, const T* masses, const T* target_mass, T e_collider,
-                          uint32_t flags, T* ps, T* prob, T* logprob, int32_t* status, cudaStream_t stream) {
+                          uint32_t flags, T* ps, T* prob, T* logprob, int32_t* status, cudaStream_t stream,
+                          const T* boost = nullptr, uint8_t* mask = nullptr, bool permute_target = false) {
     RamboParams<T, NF> P{};
     bool seen[NF] = {};
     for (int i = 0; i < NF; ++i) {
@@ -109,7 +134,7 @@ static int launch_inverse(const T* momenta, int64_t event_stride, const T* x1, c
         if (o < 0 || o >= NF || seen[o]) return MF_E_SHAPE;
         seen[o] = true;
         P.order[i] = o;
-        P.m[i] = target_mass ? target_mass[i] : masses[o];  // :649-652
+        P.m[i] = target_mass ? target_mass[permute_target ? o : i] : masses[o];  // :649-652 (get_PS permutes, :1074)
     }
     for (int j = 0; j < NF; ++j) {  // torch.sum(masses_t[:, j:]) in forward order (:660)
         T s = (T)0;
@@ -118,7 +143,7 @@ static int launch_inverse(const T* momenta, int64_t event_stride, const T* x1, c
     }
     {
         T s = (T)0;
-        for (int i = 0; i < NF; ++i) s += masses[i];  // self.tot_final_state_masses
+        for (int i = 0; i < NF; ++i) s += (permute_target && target_mass) ? target_mass[i] : masses[i];  // tot_final_state_masses / target_mass.sum()
         P.msum = s;
         T ratio = P.msum / e_collider;
         T logtau = (sizeof(T) == 4) ? (T)logf((float)(ratio * ratio)) : (T)std::log((double)(ratio * ratio));
@@ -143,7 +168,7 @@ static int launch_inverse(const T* momenta, int64_t event_stride, const T* x1, c
     const int threads = 256;
     const int64_t blocks = (N + threads - 1) / threads;
     rambo_inverse_kernel<T, NF><<<(unsigned)blocks, threads, 0, stream>>>(momenta, event_stride, x1, x2, N, P, ps,
-                                                                          prob, logprob, status);
+                                                                          prob, logprob, status, boost, mask);
     return launch_status();
 }
 
@@ -168,7 +193,33 @@ static int inverse_dispatch(const T* momenta, int64_t event_stride, const T* x1,
     return MF_E_NFINAL;
 }
 
+template <typename T>
+static int getps_dispatch(const T* momenta, int64_t event_stride, const T* boost, int64_t N, int n, const int32_t* order,
+                          const T* target_mass, T e_collider, T* ps, T* jac0, uint8_t* mask, cudaStream_t stream) {
+    if (N < 0 || target_mass == nullptr) return MF_E_BADARG;
+    if (n < MF_MIN_FINAL || n > MF_MAX_FINAL) return MF_E_NFINAL;
+    if (N > 0 && (!momenta || !boost || !ps)) return MF_E_BADARG;
+    if (event_stride < 4 * n || event_stride % 4 != 0) return MF_E_SHAPE;
+    const int W = 3 * n - 2;
+    const size_t row_align = (W % 4 == 0) ? 4 * sizeof(T) : ((W % 2 == 0) ? 2 * sizeof(T) : sizeof(T));
+    if (!aligned(momenta, 4 * sizeof(T)) || !aligned(boost, 4 * sizeof(T)) || !aligned(ps, row_align)) return MF_E_ALIGN;
+    switch (n) {
+#define MF_CASE(NF) \
+    case NF: return launch_inverse<T, NF>(momenta, event_stride, nullptr, nullptr, N, order, target_mass, target_mass, e_collider, 0u, ps, jac0, nullptr, nullptr, stream, boost, mask, true);
+        MF_CASE(3) MF_CASE(4) MF_CASE(5) MF_CASE(6) MF_CASE(7) MF_CASE(8)
+#undef MF_CASE
+    }
+    return MF_E_NFINAL;
+}
+
 }  // namespace mf
+
+extern "C" int mf_get_ps_f64(const double* momenta, int64_t event_stride, const double* boost, int64_t N, int n_final,
+                             const int32_t* order, const double* target_mass, double e_collider, double* ps,
+                             double* jac0, uint8_t* mask, mf_stream_t stream) {
+    return mf::getps_dispatch<double>(momenta, event_stride, boost, N, n_final, order, target_mass, e_collider, ps, jac0,
+                                      mask, (cudaStream_t)stream);
+}
 
 extern "C" int mf_rambo_inverse_f64(const double* momenta, int64_t event_stride, const double* x1, const double* x2,
                                     int64_t N, int n_final, const int32_t* order, const double* masses,

@@ -25,7 +25,7 @@ rqs_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t B, int 
     const int rows_per_tile = ept * F;
     const size_t tile_elems = (size_t)rows_per_tile * PW;
     const size_t tile_bytes_al = (tile_elems * sizeof(T) + 127) / 128 * 128;
-    T* stage_base[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw + tile_bytes_al)};
+    auto stage_ptr = [&](int st) { return reinterpret_cast<T*>(smem_raw + (size_t)st * tile_bytes_al); };
     unsigned char* tail = smem_raw + tile_bytes_al * stages;
     T* scratch = reinterpret_cast<T*>(tail);                         // [kRqsThreads] per-row ladj
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail + kRqsThreads * sizeof(T));  // [2]
@@ -44,11 +44,11 @@ rqs_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t B, int 
         if (tid == 0 && tile < num_tiles && tile_is_bulk(tile)) {
             const uint32_t bytes = (uint32_t)(tile_elems * sizeof(T));
             mbar_expect_tx(&bars[st], bytes);
-            bulk_g2s(stage_base[st], phi + (size_t)tile * tile_elems, bytes, &bars[st]);
+            bulk_g2s(stage_ptr(st), phi + (size_t)tile * tile_elems, bytes, &bars[st]);
         }
     };
 
-    uint32_t parity[2] = {0u, 0u};
+    uint32_t parity0 = 0u, parity1 = 0u;
     int64_t tile = blockIdx.x;
     issue(tile, 0);
     for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -57,10 +57,10 @@ rqs_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t B, int 
         const int64_t ev0 = tile * ept;
         const int nev = (int)((B - ev0) < ept ? (B - ev0) : ept);
         const int nrows = nev * F;
-        T* sm = stage_base[st];
+        T* sm = stage_ptr(st);
         if (tile_is_bulk(tile)) {
-            mbar_wait(&bars[st], parity[st]);
-            parity[st] ^= 1u;
+            mbar_wait(&bars[st], st ? parity1 : parity0);
+            if (st) parity1 ^= 1u; else parity0 ^= 1u;
         } else {  // ragged last tile or unaligned phi: plain cooperative copy
             const T* src = phi + (size_t)tile * tile_elems;
             const size_t ne = (size_t)nrows * PW;
@@ -77,7 +77,17 @@ rqs_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t B, int 
             T* r = sm + (size_t)row * PW;
             v = __ldg(vin + ev0 * F + row);
             if constexpr (LANES == 1) {
-                rqs_row_1lane<T, INV>(r, K, C, v, out, ladj, bin);
+                if constexpr (sizeof(T) == 4) {
+                    switch (K) {  // register-resident rows for small bin counts (rqs.cuh)
+                    case 8: rqs_row_reg<8, INV>(r, C, v, out, ladj, bin); break;
+                    case 10: rqs_row_reg<10, INV>(r, C, v, out, ladj, bin); break;
+                    case 12: rqs_row_reg<12, INV>(r, C, v, out, ladj, bin); break;
+                    case 16: rqs_row_reg<16, INV>(r, C, v, out, ladj, bin); break;
+                    default: rqs_row_1lane<T, INV>(r, K, C, v, out, ladj, bin); break;
+                    }
+                } else {
+                    rqs_row_1lane<T, INV>(r, K, C, v, out, ladj, bin);
+                }
             } else {
                 // lane 0 -> widths/X knots, lane 1 -> heights/Y knots; the searched array gets v
                 const bool searching = INV ? (sub == 1) : (sub == 0);
@@ -179,6 +189,7 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
     if (grid > num_tiles) grid = num_tiles;
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         kern<<<(unsigned)grid, kRqsThreads, smem, stream>>>(phi, vin, B, F, K, C, ept, stages, bulk_ok, vout, ladj,
                                                             ladj_sum, bin);
     };

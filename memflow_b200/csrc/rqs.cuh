@@ -125,6 +125,92 @@ MF_D void rqs_row_1lane(T* __restrict__ row, int K, const RqsConst<T>& C, T v, T
     rqs_eval<T, INV>(row, row + K, row + 2 * K, K, C, bin, v, out, ladj);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident row for small compile-time K (the fused chain: K = 8..16). One thread, fully unrolled:
+// both softmax arrays are exponentiated once into registers; the bin is found by comparing the UNNORMALISED
+// running sum with v mapped into that space ((v/B+1)/2 * S), so no per-element normalisation, no stores;
+// the other coordinate's two knots are the prefix sums at bin / bin+1. fp32 only.
+// ---------------------------------------------------------------------------------------------
+template <int K, bool INV>
+MF_D void rqs_row_reg(const float* __restrict__ row, const RqsConst<float>& C, float v, float& out, float& ladj,
+                      int& bin) {
+    const float* as = row + (INV ? K : 0);  // searched array: heights for the inverse, widths for the forward
+    const float* ao = row + (INV ? 0 : K);
+    float es[K], eo[K];
+    float Ss = 0.0f, So = 0.0f;
+    if (C.clip) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            es[k] = FastMath<float>::exp(soft_clip(as[k], C.two_over_L));
+            eo[k] = FastMath<float>::exp(soft_clip(ao[k], C.two_over_L));
+            Ss += es[k];
+            So += eo[k];
+        }
+    } else {
+        float ms = as[0], mo = ao[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) { ms = fmaxf(ms, as[k]); mo = fmaxf(mo, ao[k]); }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            es[k] = FastMath<float>::exp(as[k] - ms);
+            eo[k] = FastMath<float>::exp(ao[k] - mo);
+            Ss += es[k];
+            So += eo[k];
+        }
+    }
+    const float B = C.bound;
+    const float target = fmaf(v, 0.5f / B, 0.5f) * Ss;  // v in units of the unnormalised cumulative sum
+    int cnt = (-B < v) ? 1 : 0;
+    float c = 0.0f, c_lo = 0.0f, c_hi = 3.0e38f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        c += es[k];
+        const bool below = c < target;
+        cnt += below ? 1 : 0;
+        c_lo = below ? c : c_lo;
+        c_hi = below ? c_hi : fminf(c_hi, c);
+    }
+    bin = cnt - 1;
+    if (bin < 0 || bin >= K) { out = v; ladj = 0.0f; return; }
+    float o = 0.0f, o_lo = 0.0f, o_hi = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        o += eo[k];
+        o_lo = (k < bin) ? o : o_lo;
+        o_hi = (k <= bin) ? o : o_hi;
+    }
+    const float is2 = 2.0f * FastMath<float>::rcp(Ss), io2 = 2.0f * FastMath<float>::rcp(So);
+    const float s0 = B * fmaf(c_lo, is2, -1.0f), s1 = B * fmaf(c_hi, is2, -1.0f);
+    const float o0 = B * fmaf(o_lo, io2, -1.0f), o1 = B * fmaf(o_hi, io2, -1.0f);
+    const float x0 = INV ? o0 : s0, x1 = INV ? o1 : s1, y0 = INV ? s0 : o0, y1 = INV ? s1 : o1;
+    const float* d = row + 2 * K;
+    float d0 = 1.0f, d1 = 1.0f;
+    if (bin > 0) { float t = d[bin - 1]; if (C.clip) t = soft_clip(t, C.one_over_L); d0 = FastMath<float>::exp(t); }
+    if (bin < K - 1) { float t = d[bin]; if (C.clip) t = soft_clip(t, C.one_over_L); d1 = FastMath<float>::exp(t); }
+    const float dx = x1 - x0, dy = y1 - y0;
+    const float rdx = FastMath<float>::rcp(dx);
+    const float s = dy * rdx;
+    const float dd = d0 + d1 - 2.0f * s;
+    float z;
+    if constexpr (!INV) {
+        z = (v - x0) * rdx;
+        const float zz = z * (1.0f - z);
+        out = y0 + dy * (s * (z * z) + d0 * zz) * FastMath<float>::rcp(s + dd * zz);
+    } else {
+        const float y_ = v - y0;
+        const float a = dy * (s - d0) + y_ * dd;
+        const float b = dy * d0 - y_ * dd;
+        const float cc = -s * y_;
+        z = 2.0f * cc * FastMath<float>::rcp(-b - sqrtf(b * b - 4.0f * a * cc));
+        out = x0 + z * dx;
+    }
+    const float zz = z * (1.0f - z);
+    const float rden = FastMath<float>::rcp(s + dd * zz);
+    const float omz = 1.0f - z;
+    const float jac = (s * s) * (2.0f * s * zz + d0 * (omz * omz) + d1 * (z * z)) * (rden * rden);
+    ladj = logf(jac);
+}
+
 // Bulk async copy (TMA, 1-D) global -> shared with mbarrier completion.
 MF_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 MF_D void mbar_init(uint64_t* bar, uint32_t count) {

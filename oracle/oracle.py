@@ -35,6 +35,7 @@ def lib():
         _lib = ctypes.CDLL(_LIB_PATH)
         _lib.mfo_rambo_forward.restype = ctypes.c_int
         _lib.mfo_rambo_inverse.restype = ctypes.c_int
+        _lib.mfo_get_ps.restype = ctypes.c_int
         for n in ("mfo_rqs_forward_f32", "mfo_rqs_forward_f64", "mfo_rqs_inverse_f32",
                   "mfo_rqs_inverse_f64", "mfo_is_reduce", "mfo_max_threads", "mfo_get_threads"):
             getattr(_lib, n).restype = ctypes.c_int
@@ -100,6 +101,24 @@ def rambo_inverse(momenta, x1, x2, masses, e_collider, order=None, target_mass=N
     if rc not in (0, 2):
         raise RuntimeError("mfo_rambo_inverse rc=%d" % rc)
     return ps, prob, rc
+
+
+def get_ps(momenta, boost, target_mass, e_collider, order=None):
+    """memflow/unfolding_flow/utils.py:1056-1152: returns ps [N,3n-2], 0*jac [N], mask [N] bool."""
+    momenta = np.ascontiguousarray(momenta, dtype=np.float64)
+    boost = np.ascontiguousarray(boost, dtype=np.float64)
+    N, n, _ = momenta.shape
+    order = np.ascontiguousarray(list(range(n)) if order is None else order, dtype=np.intc)
+    tm = np.ascontiguousarray(np.asarray(target_mass, dtype=np.float64).reshape(-1))
+    ps = np.empty((N, 3 * n - 2), dtype=np.float64)
+    jac0 = np.empty(N, dtype=np.float64)
+    mask = np.empty(N, dtype=np.uint8)
+    rc = lib().mfo_get_ps(_dp(momenta), _dp(boost), ctypes.c_int64(N), ctypes.c_int(n), order.ctypes.data_as(c_int_p),
+                          _dp(tm), ctypes.c_double(e_collider), _dp(ps), _dp(jac0),
+                          mask.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)))
+    if rc != 0:
+        raise RuntimeError("mfo_get_ps rc=%d" % rc)
+    return ps, jac0, mask.astype(bool)
 
 
 def _rqs(direction, phi, v, bound, slope):

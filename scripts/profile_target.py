@@ -1,0 +1,39 @@
+"""Small single-GPU program for ncu: a few launches of each kernel at benchmark shapes.
+usage: python scripts/profile_target.py [chain|k1|k2|rqs|all]"""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from memflow_b200 import estimator as ES, transforms as TR
+from memflow_b200.phasespace.phasespace import PhaseSpace
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+dev = torch.device("cuda:0")
+E = 13000.0
+if what in ("chain", "all"):
+    N = 1 << 21
+    phi = torch.randn(2, N, 7, 29, device=dev, dtype=torch.float32)
+    smp = ES.ImportanceSampler([125.25, 172.5, 172.5], E, seed=1, device=dev)
+    acc = ES.new_accumulator(dev)
+    for i in range(4):
+        smp.run_chunk(phi, event_offset=i * N, acc=acc)
+    torch.cuda.synchronize()
+    del phi
+if what in ("k1", "all"):
+    for n, m in ((3, [125.25, 172.5, 172.5]), (8, [4.7, 4.7, 4.7, 4.7, 0.1, 0.0, 0.3, 0.3])):
+        ps = PhaseSpace(E, [21, 21], list(range(n)), final_masses=torch.tensor(m, dtype=torch.float64), dev=dev)
+        u = torch.rand(1 << 22, 3 * n - 2, dtype=torch.float64, device=dev).clamp_(1e-10, 1 - 1e-10)
+        for i in range(3):
+            mom, w, x1, x2 = ps.get_momenta_from_ps(u)
+        if what in ("k2", "all"):
+            for i in range(3):
+                ps.generator.getPSpoint_batch(mom[:, 2:], x1, x2)
+        torch.cuda.synchronize()
+if what in ("rqs", "all"):
+    B, F, K = 1 << 19, 20, 64
+    phi = torch.randn(B, F, 3 * K - 1, device=dev, dtype=torch.float32)
+    x = (torch.rand(B, F, device=dev) * 2.6 - 1.3) * 1.1
+    for i in range(3):
+        TR.rqs_forward(phi, x, bound=1.1)
+        TR.rqs_inverse(phi, x, bound=1.1)
+    torch.cuda.synchronize()
+print("done")

@@ -118,6 +118,29 @@ def main():
         print("n=%d written; max|w_lit/w_clean-1| = %.3g" % (
             n, np.nanmax(np.abs(out["w_lit"] / out["w_clean"] - 1))))
 
+    # ---- get_PS (memflow/unfolding_flow/utils.py:1056-1152), n = 4 only in the reference ----
+    for name in ("vector", "awkward"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    from memflow.unfolding_flow.utils import Compute_ParticlesTensor
+    g4 = np.load(os.path.join(HERE, "rambo_n4.npz"))
+    mom = torch.from_numpy(g4["mom_clean"][:, 2:]).clone()
+    x1, x2 = torch.from_numpy(g4["x1_clean"]), torch.from_numpy(g4["x2_clean"])
+    boost = torch.stack((E_CM / 2 * (x1 + x2), torch.zeros_like(x1), torch.zeros_like(x1), E_CM / 2 * (x1 - x2)), dim=1)
+    mom[30:40, 0, 1] += torch.linspace(1e-4, 5.0, 10, dtype=torch.float64)   # not in the CM
+    boost[40:44, 0] *= 3.0                                                    # x1 > 1
+    boost[44:48, 3] = boost[44:48, 0] * 1.5                                   # x2 < 0
+    mom[50:54, 3] *= 1.3                                                      # off-shell -> r outside [0,1] for some
+    tmass = torch.tensor([[125.25, 172.5, 172.5, 1e-5]], dtype=torch.float64)
+    out = {}
+    for tag, order in (("id", [0, 1, 2, 3]), ("perm", [1, 0, 2, 3])):
+        with contextlib.redirect_stdout(io.StringIO()):
+            ps_, jac_, mask_ = Compute_ParticlesTensor.get_PS(mom, boost, order=order, target_mass=tmass, E_CM=E_CM)
+        out["ps_" + tag], out["jac_" + tag], out["mask_" + tag] = ps_.numpy(), jac_.numpy(), mask_.numpy()
+        out["order_" + tag] = np.array(order, dtype=np.int32)
+    np.savez_compressed(os.path.join(HERE, "get_ps_n4.npz"), mom=mom.numpy(), boost=boost.numpy(), target_mass=tmass.numpy(),
+                        e_cm=np.float64(E_CM), **out)
+    print("get_PS written; masked:", int(out["mask_id"].sum()))
+
     # ---- spline fixture from the torch restatement (parity unpinned) ----
     sys.path.insert(0, ROOT)
     from oracle import rqs_torch

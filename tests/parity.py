@@ -18,8 +18,10 @@ def momenta_error(mom, mom_ref, x1_ref, x2_ref, e_collider):
     return np.abs(mom - mom_ref).reshape(mom.shape[0], -1).max(axis=1) / ecm
 
 
-def conditioning(u, mom_ref, n):
-    """kappa per event from the oracle's momenta (final rows 2..) and the input point u."""
+def conditioning(u, mom_ref, n, masses=None):
+    """kappa per event from the oracle's momenta (final rows 2..) and the input point u.
+    With `masses`, also the threshold cancellation of rho(M_i, M_{i+1}, m_i) (rambo_generator.py:145-149):
+    M_i^2 - (M_{i+1} + m_i)^2 loses M_i^2 / (M_i^2 - (M_{i+1}+m_i)^2) digits."""
     N = u.shape[0]
     fin = mom_ref[:, 2:, :]
     # gamma of every intermediate system Q_k = sum_{j>=k} p_j, in the frame the decay is boosted from
@@ -39,7 +41,15 @@ def conditioning(u, mom_ref, n):
         k_mass = (1.0 / np.maximum(np.minimum(uv, 1 - uv), 1e-300) ** 2).max(axis=1) * 1e-2 + 1.0
     else:
         k_mass = np.ones(N)
-    return np.maximum(g2, 1.0) * k_angle * k_mass
+    k_thr = np.ones(N)
+    if masses is not None:
+        M = np.sqrt(np.maximum(m2, 0.0))                      # M_i, i = 0..n-1 (M_{n-1} = m_{n-1})
+        for i in range(n - 1):
+            nxt = M[:, i + 1] if i + 1 < n - 1 else np.full(N, float(masses[n - 1]))
+            gap = m2[:, i] - (nxt + float(masses[i])) ** 2
+            with np.errstate(divide="ignore", invalid="ignore"):
+                k_thr = np.maximum(k_thr, np.where(gap > 0, m2[:, i] / gap, np.inf))
+    return np.maximum(g2, 1.0) * k_angle * k_mass * k_thr
 
 
 def summarize(err, tol, kappa=None):

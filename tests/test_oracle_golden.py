@@ -169,3 +169,14 @@ def test_philox_known_answer():
     assert [int(v[0]) for v in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     r = P.philox4x32_10([0xffffffff], [0xffffffff], [0xffffffff], [0xffffffff], 0xffffffff, 0xffffffff)
     assert [int(v[0]) for v in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+
+
+def test_get_ps_matches_reference(oracle, golden_dir):
+    """Compute_ParticlesTensor.get_PS (memflow/unfolding_flow/utils.py:1056-1152), incl. the problem mask."""
+    g = np.load(os.path.join(golden_dir, "get_ps_n4.npz"))
+    for tag in ("id", "perm"):
+        ps, jac, mask = oracle.get_ps(g["mom"], g["boost"], g["target_mass"], float(g["e_cm"]), order=g["order_" + tag])
+        assert np.array_equal(mask, g["mask_" + tag]) and 10 < mask.sum() < 40
+        assert np.array_equal(np.isnan(ps), np.isnan(g["ps_" + tag]))
+        assert np.nanmax(np.abs(ps - g["ps_" + tag])) < 1e-13
+        assert np.array_equal(np.isnan(jac), np.isnan(g["jac_" + tag])) and np.nanmax(np.abs(jac)) == 0.0

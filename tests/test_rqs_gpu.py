@@ -1,9 +1,9 @@
 """GPU parity of K3/K4 (rational-quadratic spline) against the oracle / torch restatement.
 
-fp64: 1e-12-level agreement. fp32: the problem itself is ill-conditioned in fp32 for narrow bins (knots are
-differences of a cumulative sum of O(1) values: one fp32 ulp of x moves z = (x-x_k)/(x_{k+1}-x_k) by
-6e-8/width), so the bound is  1e-5 * (1 + 6e-3/width_bin)  and the kernel must be no worse than the fp32
-oracle itself (both measured against the fp64 oracle on the same fp32 inputs)."""
+fp64: 1e-12-level agreement. fp32: the problem itself is ill-conditioned in fp32 for narrow bins / steep
+derivative ratios (knots are differences of a cumulative sum of O(1) values: one fp32 ulp of x moves
+z = (x-x_k)/(x_{k+1}-x_k) by 6e-8/width), so the bound is  1e-5 + 8 * (change of the fp64 result when x moves by
+4e-7 * bound), and the kernel must be no worse than the fp32 oracle itself (both measured against the fp64 oracle on the same fp32 inputs)."""
 import os
 
 import numpy as np
@@ -20,14 +20,18 @@ def make(B, F, K, dt, bound, seed=7):
     return phi, x
 
 
-def bin_width(oracle, phi64, x64, bound, inverse=False):
-    """width of the selected bin in the searched coordinate (conditioning of the fp32 problem)."""
-    K = (phi64.shape[-1] + 1) // 3
-    a = phi64[..., K:2 * K] if inverse else phi64[..., :K]
-    L = np.log(1e-3)
-    a = a / (1 + np.abs(2 * a / L))
-    p = np.exp(a - a.max(-1, keepdims=True)); p /= p.sum(-1, keepdims=True)
-    return 2 * bound * p
+def fp32_conditioning(orc, p64, x64, bound):
+    """Intrinsic sensitivity of the fp32 problem: how much the fp64 result moves when the input moves by a
+    few fp32 ulps of the knot scale (knots are cumulative sums of O(1) fp32 values). Returns (d_out, d_ladj)."""
+    delta = 4e-7 * bound
+    o0, l0, b0 = orc(p64, x64, bound=bound)
+    d_o, d_l = np.zeros_like(o0), np.zeros_like(l0)
+    for sgn in (-1.0, 1.0):
+        o1, l1, b1 = orc(p64, x64 + sgn * delta, bound=bound)
+        same = b1 == b0
+        d_o = np.maximum(d_o, np.where(same, np.abs(o1 - o0), np.inf))
+        d_l = np.maximum(d_l, np.where(same, np.abs(l1 - l0), np.inf))
+    return d_o, d_l
 
 
 @pytest.mark.parametrize("F,K,bound", [(7, 10, 1.0), (10, 40, 1.1), (20, 64, 1.1), (3, 9, 5.0), (1, 1, 2.0), (5, 128, 1.0)])
@@ -71,15 +75,15 @@ def test_fp32_forward_inverse(oracle, F, K, bound):
         mism = bins != b64
         assert mism.mean() < 1e-4                                       # only x within an ulp of a knot may move bin
         ok = ~mism & (b32 == b64)
-        width = np.take_along_axis(bin_width(oracle, p64, x64, bound, inverse), np.clip(b64, 0, K - 1)[..., None], -1)[..., 0]
-        cond = 1.0 + 6e-3 / width
+        c_out, c_l = fp32_conditioning(orc, p64, x64, bound)
         e_out = np.abs(out.cpu().numpy() - o64)
         e_l = np.abs(ladj.cpu().numpy() - l64)
         print("fp32 F=%d K=%d inv=%s: out p50 %.1e max %.1e | ladj p50 %.1e p99 %.1e max %.1e | fp32-oracle ladj max %.1e"
               % (F, K, inverse, np.median(e_out), e_out[ok].max(), np.median(e_l), np.quantile(e_l, 0.99), e_l[ok].max(),
                  np.abs(l32 - l64)[ok].max()))
-        assert (e_out[ok] / cond[ok]).max() < 1e-5
-        assert (e_l[ok] / cond[ok]).max() < 1e-5 * 10
+        assert (e_out[ok] <= 1e-5 + 8 * c_out[ok]).all()
+        assert (e_l[ok] <= 1e-5 + 8 * c_l[ok]).all()
+        assert np.quantile(e_l, 0.9) < 1e-5
         assert np.median(e_l) < 1e-5 and np.median(e_out) < 1e-6
         # never materially worse than the fp32 reference arithmetic itself
         assert e_l[ok].max() < 3 * np.abs(l32 - l64)[ok].max() + 1e-5
