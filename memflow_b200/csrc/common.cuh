@@ -46,6 +46,60 @@ MF_D float fmax_(float a, float b) { return fmaxf(a, b); }
 MF_D double pow_(double a, double b) { return pow(a, b); }
 MF_D float pow_(float a, float b) { return powf(a, b); }
 
+// ---------------------------------------------------------------------------------------------
+// fp64 reciprocal / division / square root without the special-case slow paths of the CUDA math library
+// (each `a / b` or `sqrt(x)` there costs ~25 issue slots: MUFU seed + Newton + range checks + a call stub).
+// The operands on this path are masses, energies and their ratios, far from the denormal / overflow range.
+// MUFU.RCP64H / RSQ64H seed (~2^-20) + 2 Newton steps + one residual correction: faithfully rounded, equal to
+// the IEEE result except for rare last-bit ties. 0, inf, NaN and negative operands keep their IEEE results through a
+// final select (the MUFU seeds are IEEE-exact there); magnitudes outside [1e-280, 1e280] are not supported.
+// ---------------------------------------------------------------------------------------------
+MF_D bool in_fast_range(double x) { const double a = fabs(x); return a > 1e-280 && a < 1e280; }  // false for 0, inf, NaN
+MF_D double rcp_seed(double b) { double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b)); return r; }
+MF_D double rsqrt_seed(double x) { double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
+MF_D double rcp_fast(double b) {
+    const double r0 = rcp_seed(b);  // already IEEE for 0 / inf / NaN
+    double e = fma(-b, r0, 1.0);
+    double r = fma(r0, e, r0);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    return in_fast_range(b) ? r : r0;
+}
+MF_D float rcp_fast(float b) { return 1.0f / b; }
+MF_D double div_fast(double a, double b) {
+    const double r0 = rcp_seed(b);
+    double e = fma(-b, r0, 1.0);
+    double r = fma(r0, e, r0);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    double q = a * r;
+    const double rem = fma(-b, q, a);
+    q = fma(rem, r, q);
+    return (in_fast_range(b) && fabs(a) < 1e280) ? q : a * r0;  // a/0, a/inf, inf/b, NaN keep their IEEE results
+}
+MF_D float div_fast(float a, float b) { return a / b; }
+MF_D double rsqrt_fast(double x) {
+    const double y0 = rsqrt_seed(x);  // IEEE for 0 / inf / negative / NaN
+    const double h = 0.5 * x;
+    double y = y0 * fma(-h * y0, y0, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return (x > 1e-280 && x < 1e280) ? y : y0;
+}
+MF_D float rsqrt_fast(float x) { return rsqrtf(x); }
+MF_D double sqrt_fast(double x) {
+    const double y0 = rsqrt_seed(x);
+    const double h = 0.5 * x;
+    double y = y0 * fma(-h * y0, y0, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    double s = x * y;
+    s = fma(0.5 * y, fma(-s, s, x), s);
+    // outside the fast range: sqrt(+-0) = +-0, sqrt(inf) = inf, sqrt(negative or NaN) = NaN
+    return (x > 1e-280 && x < 1e280) ? s : ((x >= 0.0) ? x : __longlong_as_double(0x7ff8000000000000LL));
+}
+MF_D float sqrt_fast(float x) { return sqrtf(x); }
+
 template <typename T> struct Limits;
 template <> struct Limits<double> {
     static MF_HD double huge() { return 1.7976931348623157e308; }

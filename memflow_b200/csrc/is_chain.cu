@@ -143,6 +143,133 @@ is_chain_kernel(const float* __restrict__ phi, int64_t N, int T, int K, RqsConst
     grid_accumulate<kChainThreads>(k1.value(), k2.value(), cnt, acc, workspace);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Split variant: two launches per chunk.
+//   A  flow_sample_kernel : Philox -> T spline inverses, one thread per (event, feature) row, ~40 registers ->
+//      high occupancy; writes u[N,F] (fp64) and log q[N]   (+ (F+1)*8 B/event of HBM traffic)
+//   B  rambo_is_kernel<NF>: K1 + weight + K5 fused, one event per thread, fp64 registers.
+// The fused kernel above keeps everything on chip but carries the fp64 phase's register budget into the
+// fp32 spline phase; which one is faster is measured and selected by MF_CHAIN_MODE.
+// ---------------------------------------------------------------------------------------------
+template <int MINB>
+__global__ void __launch_bounds__(kChainThreads, MINB)
+flow_sample_kernel(const float* __restrict__ phi, int64_t N, int F, int T, int K, RqsConst<float> C, int E, int stages,
+                   int bulk_ok, uint64_t seed, uint64_t event_offset, double* __restrict__ u_out,
+                   double* __restrict__ logq_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int PW = 3 * K - 1;
+    const int rows = E * F;
+    const size_t tile_elems = (size_t)rows * PW;
+    const size_t tile_bytes_al = (tile_elems * sizeof(float) + 127) / 128 * 128;
+    auto stage_ptr = [&](int st) { return reinterpret_cast<float*>(smem_raw + (size_t)st * tile_bytes_al); };
+    unsigned char* tail = smem_raw + (size_t)stages * tile_bytes_al;
+    float* lsum = reinterpret_cast<float*>(tail);  // [kChainThreads]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lsum + kChainThreads);
+
+    const int tid = threadIdx.x;
+    const int64_t num_tiles = (N + E - 1) / E;
+    const size_t transform_pitch = (size_t)N * F * PW;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    __syncthreads();
+    auto tile_is_bulk = [&](int64_t tile) { return bulk_ok && (tile + 1) * (int64_t)E <= N; };
+    auto issue = [&](int64_t tile, int t, int st) {
+        if (tid == 0 && tile < num_tiles && tile_is_bulk(tile)) {
+            const uint32_t bytes = (uint32_t)(tile_elems * sizeof(float));
+            mbar_expect_tx(&bars[st], bytes);
+            bulk_g2s(stage_ptr(st), phi + (size_t)t * transform_pitch + (size_t)tile * tile_elems, bytes, &bars[st]);
+        }
+    };
+    uint32_t parity0 = 0u, parity1 = 0u;
+    int item = 0;
+    int64_t tile = blockIdx.x;
+    issue(tile, T - 1, 0);
+    for (; tile < num_tiles; tile += gridDim.x) {
+        const int64_t ev0 = tile * E;
+        const int nev = (int)((N - ev0) < E ? (N - ev0) : E);
+        const int nrows = nev * F;
+        const int e = tid / F, f = tid - e * F;
+        const bool row_active = tid < nrows;
+        float x = 0.0f, ladj_acc = 0.0f;
+        if (row_active) {
+            const uint64_t gev = event_offset + (uint64_t)(ev0 + e);
+            Philox4 r4 = philox4x32_10((uint32_t)gev, (uint32_t)(gev >> 32), (uint32_t)(f >> 2), 0u, (uint32_t)seed,
+                                       (uint32_t)(seed >> 32));
+            const uint32_t bits = (f & 3) == 0 ? r4.x : ((f & 3) == 1 ? r4.y : ((f & 3) == 2 ? r4.z : r4.w));
+            x = C.bound * (2.0f * u01_from_bits(bits) - 1.0f);
+        }
+        for (int tt = 0; tt < T; ++tt, ++item) {
+            const int t = T - 1 - tt;
+            const int st = (stages == 2) ? (item & 1) : 0;
+            if (stages == 2) { if (tt + 1 < T) issue(tile, t - 1, st ^ 1); else issue(tile + gridDim.x, T - 1, st ^ 1); }
+            float* sm = stage_ptr(st);
+            if (tile_is_bulk(tile)) {
+                mbar_wait(&bars[st], st ? parity1 : parity0);
+                if (st) parity1 ^= 1u; else parity0 ^= 1u;
+            } else {
+                const float* src = phi + (size_t)t * transform_pitch + (size_t)tile * tile_elems;
+                const size_t ne = (size_t)nrows * PW;
+                for (size_t i = tid; i < ne; i += kChainThreads) sm[i] = __ldg(src + i);
+                __syncthreads();
+            }
+            if (row_active) {
+                float out, ladj;
+                int bin;
+                float* rowp = sm + (size_t)tid * PW;
+                switch (K) {
+                case 8: rqs_row_reg<8, true>(rowp, C, x, out, ladj, bin); break;
+                case 10: rqs_row_reg<10, true>(rowp, C, x, out, ladj, bin); break;
+                case 12: rqs_row_reg<12, true>(rowp, C, x, out, ladj, bin); break;
+                case 16: rqs_row_reg<16, true>(rowp, C, x, out, ladj, bin); break;
+                default: rqs_row_1lane<float, true>(rowp, K, C, x, out, ladj, bin); break;
+                }
+                x = out;
+                ladj_acc += ladj;
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (stages == 1) { if (tt + 1 < T) issue(tile, t - 1, 0); else issue(tile + gridDim.x, T - 1, 0); }
+        }
+        lsum[tid] = ladj_acc;
+        if (row_active) u_out[ev0 * F + tid] = ((double)x + (double)C.bound) / (2.0 * (double)C.bound);
+        __syncthreads();
+        if (tid < nev) {
+            double lq = 0.0;
+            for (int j = 0; j < F; ++j) lq += (double)lsum[tid * F + j];
+            logq_out[ev0 + tid] = lq;
+        }
+        __syncthreads();
+    }
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256)
+rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, int64_t N,
+                const __grid_constant__ RamboParams<double, NF> P, double inv_2s, double* __restrict__ acc,
+                void* workspace, double* __restrict__ momenta, double* __restrict__ weight, double* __restrict__ x1o,
+                double* __restrict__ x2o) {
+    constexpr int F = 3 * NF - 2, NP = NF + 2;
+    Kahan k1, k2;
+    double cnt = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ev < N; ev += stride) {
+        double r[F];
+        load_row<F>(u + ev * F, r);
+        double out[NP][4], jac, x1, x2;
+        rambo_forward_event<double, NF>(r, P, out, jac, x1, x2);
+        const double target = inv_2s / (x1 * x2);
+        const double w = target * jac / exp(__ldg(logq + ev));
+        if (target > 0.0 && jac == jac) { k1.add(w); k2.add(w * w); cnt += 1.0; }
+        if (momenta) {
+#pragma unroll
+            for (int k = 0; k < NP; ++k) st4(momenta + ev * (NP * 4) + 4 * k, out[k][0], out[k][1], out[k][2], out[k][3]);
+        }
+        if (weight) weight[ev] = jac;
+        if (x1o) x1o[ev] = x1;
+        if (x2o) x2o[ev] = x2;
+    }
+    grid_accumulate<256>(k1.value(), k2.value(), cnt, acc, workspace);
+}
+
 template <int NF>
 static int chain_launch(const float* phi, int64_t N, int T, int K, float bound, float slope, uint64_t seed,
                         uint64_t event_offset, const double* masses, double e_collider, uint32_t flags, double* acc,
@@ -177,8 +304,52 @@ static int chain_launch(const float* phi, int64_t N, int T, int K, float bound, 
     const RamboParams<double, NF> P = make_forward_params<double, NF>(masses, e_collider, nullptr, flags & ~MF_FLAG_CUTS);
     const double inv_2s = 1.0 / (2.0 * e_collider * e_collider);
     const int64_t num_tiles = (N + E - 1) / E;
-    static int minb_env = -1;
-    if (minb_env < 0) { const char* e = getenv("MF_CHAIN_MINB"); minb_env = e ? atoi(e) : 2; }
+    static int minb_env = -1, mode_env = -1, stages_env = -1;
+    if (minb_env < 0) { const char* e = getenv("MF_CHAIN_MINB"); minb_env = e ? atoi(e) : 8; }
+    if (mode_env < 0) { const char* e = getenv("MF_CHAIN_MODE"); mode_env = (e && e[0] == 'f') ? 0 : 1; }  // fused | split
+    if (stages_env < 0) { const char* e = getenv("MF_CHAIN_STAGES"); stages_env = e ? atoi(e) : 1; }
+    if (mode_env == 1) {
+        // ---- split: A (flow sample) then B (phase space + weight + reduce) on the same stream ----
+        double *u_buf = u_out, *lq_buf = logq;
+        void* scratch = nullptr;
+        if (!u_buf || !lq_buf) {
+            const size_t bytes = (size_t)N * (F + 1) * sizeof(double);
+            if (cudaMallocAsync(&scratch, bytes, stream) != cudaSuccess) return launch_status();
+            if (!u_buf) u_buf = reinterpret_cast<double*>(scratch);
+            if (!lq_buf) lq_buf = reinterpret_cast<double*>(scratch) + (size_t)N * F;
+        }
+        const int stages = stages_env == 1 ? 1 : 2;
+        const size_t smem_a = (((size_t)E * F * PW * sizeof(float) + 127) / 128 * 128) * stages + kChainThreads * sizeof(float) +
+                              2 * sizeof(uint64_t) + 128;
+        auto go_a = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            int ctas = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, kChainThreads, smem_a);
+            if (ctas < 1) ctas = 1;
+            int64_t grid_a = (int64_t)sms * ctas;
+            if (grid_a > num_tiles) grid_a = num_tiles;
+            kern<<<(unsigned)grid_a, kChainThreads, smem_a, stream>>>(phi, N, F, T, K, C, E, stages, bulk_ok, seed, event_offset,
+                                                                      u_buf, lq_buf);
+        };
+        switch (minb_env) {
+        case 8: go_a(flow_sample_kernel<8>); break;
+        case 6: go_a(flow_sample_kernel<6>); break;
+        case 5: go_a(flow_sample_kernel<5>); break;
+        default: go_a(flow_sample_kernel<4>); break;
+        }
+        int ctas_b = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_b, rambo_is_kernel<NF>, 256, 0);
+        if (ctas_b < 1) ctas_b = 1;
+        int64_t grid_b = (int64_t)sms * ctas_b;
+        const int64_t want_b = (N + 255) / 256;
+        if (grid_b > want_b) grid_b = want_b;
+        if (grid_b > kReduceMaxBlocks) grid_b = kReduceMaxBlocks;
+        rambo_is_kernel<NF><<<(unsigned)grid_b, 256, 0, stream>>>(u_buf, lq_buf, N, P, inv_2s, acc, workspace, momenta, weight,
+                                                                  x1, x2);
+        if (scratch) cudaFreeAsync(scratch, stream);
+        return launch_status();
+    }
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -193,9 +364,9 @@ static int chain_launch(const float* phi, int64_t N, int T, int K, float bound, 
     };
     switch (minb_env) {
     case 1: go(is_chain_kernel<NF, 1>); break;
+    case 2: go(is_chain_kernel<NF, 2>); break;
     case 3: go(is_chain_kernel<NF, 3>); break;
-    case 4: go(is_chain_kernel<NF, 4>); break;
-    default: go(is_chain_kernel<NF, 2>); break;
+    default: go(is_chain_kernel<NF, 4>); break;
     }
     return launch_status();
 }

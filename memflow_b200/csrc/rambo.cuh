@@ -16,7 +16,7 @@ template <typename T, int NF> struct RamboParams {
     T msum_rev[NF];  // forward: flip(cumsum(flip(m))) (:484-486).  inverse: sum(m[j:]) forward order (:660)
     T msum;       // torch.sum(masses_t)
     T q, A;       // x1x2 map constants, utils.py:266-269
-    T t1, t1sq, neg_inv_A;
+    T t1, t1sq, neg_inv_A, inv_A, neg_A;
     T e_collider;
     T flat_c, flat_ff;  // get_flatWeights: c = (2pi)^(4-3n) (pi/2)^(n-1), ff = (n-1)!(n-2)!
     float flat_c32, flat_ff32;
@@ -33,14 +33,21 @@ template <typename T> MF_D T rho_f(T M, T N, T m) {
     return sqrt_(t) / ((T)8 * Msqr);
 }
 
+// sqrt((M^2-(N+m)^2)(M^2-(N-m)^2)): numerator of 8 M^2 rho(M,N,m); the products are non-contractible
+template <typename T> MF_D T rho_num(T M, T N, T m) {
+    T Msqr = mul_rn(M, M);
+    T a = N + m, b = N - m;
+    return sqrt_fast(mul_rn(sub_rn(Msqr, mul_rn(a, a)), sub_rn(Msqr, mul_rn(b, b))));
+}
+
 template <typename T> MF_D T rho2_3(T x, T y, T z) { return (x * x + y * y) + z * z; }
 
 // utils.py:88-118 boost_t: general Lorentz boost by velocity bv
 template <typename T> MF_D void boost(const T (&p)[4], T bx, T by, T bz, T (&o)[4]) {
     T b2 = add_rn(add_rn(mul_rn(bx, bx), mul_rn(by, by)), mul_rn(bz, bz));
-    T gamma = (T)1 / sqrt_(sub_rn((T)1, b2));
+    T gamma = rsqrt_fast(sub_rn((T)1, b2));
     T bp = (p[1] * bx + p[2] * by) + p[3] * bz;
-    T gamma2 = (b2 > (T)0) ? (gamma - (T)1) / b2 : (T)0;
+    T gamma2 = (b2 > (T)0) ? div_fast(gamma - (T)1, b2) : (T)0;
     T factor = gamma2 * bp + gamma * p[0];
     o[1] = p[1] + factor * bx;
     o[2] = p[2] + factor * by;
@@ -122,7 +129,7 @@ template <int E> MF_D float massvar_start_f32(bool small, float tf) {
 
 template <int E> MF_D double solve_massvar(double v) {
     if constexpr (E == 1) {
-        double u = v / (1.0 + sqrt(1.0 - v));
+        double u = div_fast(v, 1.0 + sqrt_fast(1.0 - v));
         return (v <= 0.0) ? Limits<double>::tiny_u() : ((v >= 1.0 || u > Limits<double>::max_u()) ? Limits<double>::max_u() : u);
     } else {
         const bool small = v < 0.65;
@@ -139,7 +146,7 @@ template <int E> MF_D double solve_massvar(double v) {
         for (int it = 0; it < 2; ++it) {
             double f, d1, d2;
             MassVarFn<E, double>::eval(small, x, t, f, d1, d2);
-            double xn = x - (2.0 * f * d1) / (2.0 * d1 * d1 - f * d2);
+            double xn = x - div_fast(2.0 * f * d1, 2.0 * d1 * d1 - f * d2);
             x = (xn > 0.0 && xn < 1.0) ? xn : x;
         }
         double u = small ? x : 1.0 - x;
@@ -165,16 +172,24 @@ template <int E> MF_D float solve_massvar(float v) {
     }
 }
 
-// get_flatWeights (:111-140) * massive correction (:489-507), from K_i, M_i. quirks reproduces the
-// reference's float32 in-place chain.
+// get_flatWeights (:111-140) * massive correction (:489-507), from K_i, M_i and the shared pieces
+// sM_i = sqrt((M_i^2-(M_{i+1}+m_i)^2)(M_i^2-(M_{i+1}-m_i)^2)), invM_i = 1/M_i:
+//   8 rho(M_{n-2}, m_{n-1}, m_{n-2})                         = sM_{n-2} invM_{n-2}^2
+//   prod_i rho(M_i,M_{i+1},m_i)/rho(K_i,K_{i+1},0) M_{i+1}/K_{i+1} = prod sM_i invM_i^2 K_i^2 M_{i+1} / prod (K_i^2-K_{i+1}^2) K_{i+1}
+// (rho(K,K',0) = |K^2-K'^2|/(8K^2) exactly: sqrt(fl(t*t)) == |t|). One division instead of 4(n-2)+2.
+// quirks reproduces the reference's float32 in-place chain.
 template <typename T, int NF>
-MF_D T rambo_weight(const RamboParams<T, NF>& P, T E_cm, const T (&K)[NF], const T (&M)[NF], bool quirks) {
-    T f8 = (T)8 * rho_f(M[NF - 2], P.m[NF - 1], P.m[NF - 2]);
-    T pr = (T)1;
+MF_D T rambo_weight(const RamboParams<T, NF>& P, T E_cm, const T (&K)[NF], const T (&M)[NF], const T (&sM)[NF],
+                    const T (&invM)[NF], bool quirks) {
+    const T f8 = sM[NF - 2] * (invM[NF - 2] * invM[NF - 2]);
+    T num = (T)1, den = (T)1;
 #pragma unroll
-    for (int i = 0; i <= NF - 3; ++i)
-        pr *= (rho_f(M[i], M[i + 1], P.m[i]) / rho_f(K[i], K[i + 1], (T)0)) * (M[i + 1] / K[i + 1]);
-    T pw = ipow<2 * NF - 4>(K[0] / M[0]);
+    for (int i = 0; i <= NF - 3; ++i) {
+        num *= (sM[i] * (invM[i] * invM[i])) * ((K[i] * K[i]) * M[i + 1]);
+        den *= fabs_(sub_rn(mul_rn(K[i], K[i]), mul_rn(K[i + 1], K[i + 1]))) * K[i + 1];
+    }
+    const T pr = (NF >= 3) ? div_fast(num, den) : (T)1;
+    const T pw = ipow<2 * NF - 4>(K[0] * invM[0]);
     if (!quirks) {
         T w = P.flat_c * (ipow<NF - 2>(E_cm * E_cm) / P.flat_ff);
         w *= f8;
@@ -217,13 +232,13 @@ MF_D void rambo_forward_event(const T (&r)[3 * NF - 2], const RamboParams<T, NF>
     if (P.flags & MF_FLAG_X1X2_DIRECT) {  // uniform_x1x2=False, rambo_generator.py:229-234
         x1 = r[D]; x2 = r[D + 1]; wx = (T)1;
     } else {
-        T ml1 = (P.t1 + sqrt_(P.t1sq + ((T)-2 * r[D]) / P.A)) / P.neg_inv_A;
+        T ml1 = (P.t1 + sqrt_fast(P.t1sq + ((T)-2 * r[D]) * P.inv_A)) * P.neg_A;
         T ml2 = (P.q - ml1) * r[D + 1];
         x1 = exp_(-ml1);
         x2 = exp_(-ml2);
-        wx = (T)1 / ((T)1 / ((P.A * x1) * x2));
+        wx = (P.A * x1) * x2;
     }
-    const T E_cm = sqrt_(x1 * x2) * P.e_collider;  // :226
+    const T E_cm = sqrt_fast(x1 * x2) * P.e_collider;  // :226
 
     // ---- intermediate masses: :448-509. K_i = K_0 * prod_{j<i} t_j, M_i = K_i + sum_{j>=i} m_j ----
     T K[NF], M[NF];
@@ -240,32 +255,45 @@ MF_D void rambo_forward_event(const T (&r)[3 * NF - 2], const RamboParams<T, NF>
         M[NF - 1] = P.m[NF - 1];
         K[NF - 1] = (T)0;  // unused
     }
+    T sM[NF], invM[NF];
+#pragma unroll
+    for (int k = 0; k <= NF - 2; ++k) {
+        sM[k] = rho_num(M[k], M[k + 1], P.m[k]);
+        invM[k] = rcp_fast(M[k]);
+    }
+    sM[NF - 1] = (T)0; invM[NF - 1] = (T)0;  // unused
     const bool quirks = (P.flags & MF_FLAG_REF_FP32_QUIRKS) != 0;
-    wgt = wx * rambo_weight<T, NF>(P, E_cm, K, M, quirks);
+    wgt = wx * rambo_weight<T, NF>(P, E_cm, K, M, sM, invM, quirks);
 
     // ---- sequential two-body decays: :294-345 ----
     T Q[4] = {M[0], (T)0, (T)0, (T)0};
 #pragma unroll
     for (int k = 0; k <= NF - 2; ++k) {
-        const T qk = (T)4 * M[k] * rho_f(M[k], M[k + 1], P.m[k]);
+        const T qk = sM[k] * ((T)0.5 * invM[k]);  // 4 M_k rho(M_k, M_{k+1}, m_k)
         const T ct = (T)2 * r[NE + 2 * k] - (T)1;
-        const T st = sqrt_(sub_rn((T)1, mul_rn(ct, ct)));
+        const T st = sqrt_fast(sub_rn((T)1, mul_rn(ct, ct)));
         const T phi = (T)6.283185307179586 * r[NE + 2 * k + 1];
         const T cp = cos_(phi);
-        const T sq = sqrt_(sub_rn((T)1, mul_rn(cp, cp)));
+        const T sq = sqrt_fast(sub_rn((T)1, mul_rn(cp, cp)));
         const T sp = (phi > (T)3.141592653589793) ? -sq : sq;
         T p2[4], pb[4];
         p2[1] = (qk * st) * cp;
         p2[2] = (qk * st) * sp;
         p2[3] = qk * ct;
         const T m2 = P.m[k] * P.m[k];
-        p2[0] = sqrt_(rho2_3(p2[1], p2[2], p2[3]) + m2);
-        boost(p2, Q[1] / Q[0], Q[2] / Q[0], Q[3] / Q[0], pb);
-        pb[0] = sqrt_(rho2_3(pb[1], pb[2], pb[3]) + m2);
+        p2[0] = sqrt_fast(rho2_3(p2[1], p2[2], p2[3]) + m2);
+        if (k == 0) {  // Q = (M_0, 0, 0, 0): the boost is the identity (beta = 0 exactly)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pb[c] = p2[c];
+        } else {
+            const T iq = rcp_fast(Q[0]);
+            boost(p2, Q[1] * iq, Q[2] * iq, Q[3] * iq, pb);
+            pb[0] = sqrt_fast(rho2_3(pb[1], pb[2], pb[3]) + m2);
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) out[2 + k][c] = pb[c];
         Q[1] -= pb[1]; Q[2] -= pb[2]; Q[3] -= pb[3];
-        Q[0] = sqrt_(rho2_3(Q[1], Q[2], Q[3]) + M[k + 1] * M[k + 1]);
+        Q[0] = sqrt_fast(rho2_3(Q[1], Q[2], Q[3]) + M[k + 1] * M[k + 1]);
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) out[NP - 1][c] = Q[c];
@@ -281,9 +309,9 @@ MF_D void rambo_forward_event(const T (&r)[3 * NF - 2], const RamboParams<T, NF>
         if (x1 != (T)1 || x2 != (T)1) {
             T ref0 = out[0][0] * x1 + out[1][0] * x2;
             T ref3 = out[0][3] * x1 + out[1][3] * x2;
-            T bz = ref3 / ref0;
+            T bz = div_fast(ref3, ref0);
 #pragma unroll
-            for (int k = 0; k < NP; ++k) boost(out[k], (T)0 / ref0, (T)0 / ref0, bz, lab[k]);
+            for (int k = 0; k < NP; ++k) boost(out[k], (T)0, (T)0, bz, lab[k]);
         } else {
 #pragma unroll
             for (int k = 0; k < NP; ++k)
@@ -352,6 +380,8 @@ static RamboParams<T, NF> make_forward_params(const T* masses, T e_collider, con
         P.t1 = (-P.q) / P.A;
         P.t1sq = P.t1 * P.t1;
         P.neg_inv_A = (T)-1 * ((T)1 / P.A);
+        P.inv_A = (T)1 / P.A;
+        P.neg_A = -P.A;
     }
     P.e_collider = e_collider;
     {

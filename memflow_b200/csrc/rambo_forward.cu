@@ -14,7 +14,7 @@
 namespace mf {
 
 template <typename T, int NF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NF <= 4 ? 3 : 2))
 rambo_forward_kernel(const T* __restrict__ u, int64_t N, const __grid_constant__ RamboParams<T, NF> P,
                      T* __restrict__ momenta, T* __restrict__ weight, T* __restrict__ logweight,
                      T* __restrict__ x1o, T* __restrict__ x2o, int32_t* __restrict__ status) {

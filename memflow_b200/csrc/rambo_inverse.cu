@@ -11,7 +11,7 @@
 namespace mf {
 
 template <typename T, int NF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NF <= 4 ? 3 : 2))
 rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const T* __restrict__ x1a,
                      const T* __restrict__ x2a, int64_t N, const __grid_constant__ RamboParams<T, NF> P,
                      T* __restrict__ ps, T* __restrict__ prob, T* __restrict__ logprob,
@@ -62,7 +62,7 @@ rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const 
 #pragma unroll
             for (int c = 0; c < 4; ++c) s[c] += Pm[k][c];
         T sq = sub_rn(sub_rn(sub_rn(mul_rn(s[0], s[0]), mul_rn(s[1], s[1])), mul_rn(s[2], s[2])), mul_rn(s[3], s[3]));
-        M[j] = sqrt_(sq);
+        M[j] = sqrt_fast(sq);
         K[j] = M[j] - P.msum_rev[j];
     }
 
@@ -73,19 +73,20 @@ rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const 
         ((void)[&] {
             constexpr int i = NF - I;  // NF, NF-1, ..., 2
             constexpr int j = i - 1;
-            const T uu = K[j] / K[j - 1];
+            const T uu = div_fast(K[j], K[j - 1]);
             if constexpr (i < NF)  // i == NF writes r[NF-2] = 1, overwritten by the i == 2 angle (:672,:681)
                 r[j - 1] = (T)(NF + 1 - i) * ipow<NF - i>(uu) - (T)(NF - i) * ipow<NF + 1 - i>(uu);
 #pragma unroll
             for (int c = 0; c < 4; ++c) Q[c] = Q[c] + Pm[j - 1][c];
             T pb[4];
-            boost(Pm[j - 1], (T)-1 * (Q[1] / Q[0]), (T)-1 * (Q[2] / Q[0]), (T)-1 * (Q[3] / Q[0]), pb);
-            r[NF - 5 + 2 * i - 1] = ((pb[3] / sqrt_(rho2_3(pb[1], pb[2], pb[3]))) + (T)1) / (T)2;
-            T phi = atan_(pb[2] / pb[1]);
+            const T niq = -rcp_fast(Q[0]);
+            boost(Pm[j - 1], Q[1] * niq, Q[2] * niq, Q[3] * niq, pb);
+            r[NF - 5 + 2 * i - 1] = ((pb[3] * rsqrt_fast(rho2_3(pb[1], pb[2], pb[3]))) + (T)1) * (T)0.5;
+            T phi = atan_(div_fast(pb[2], pb[1]));
             T dphi = (pb[2] < (T)0 && pb[1] > (T)0) ? (T)6.283185307179586 : (T)0;
             dphi += (pb[1] < (T)0) ? (T)3.141592653589793 : (T)0;
             phi += dphi;
-            r[NF - 4 + 2 * i - 1] = phi / (T)6.283185307179586;
+            r[NF - 4 + 2 * i - 1] = phi * (T)0.15915494309189535;  // 1 / (2 pi)
         }(), ...);
     }(std::make_integer_sequence<int, NF - 1>{});
 
@@ -95,9 +96,9 @@ rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const 
         r[D] = x1; r[D + 1] = x2; jacinv = (T)1;
     } else {
         const T ml1 = -log_(x1), ml2 = -log_(x2);
-        r[D] = ((T)(-0.5) * (ml1 * ml1) + P.q * ml1) / P.A;
-        r[D + 1] = ml2 / (P.q - ml1);
-        jacinv = (T)1 / ((P.A * x1) * x2);
+        r[D] = ((T)(-0.5) * (ml1 * ml1) + P.q * ml1) * P.inv_A;
+        r[D + 1] = div_fast(ml2, P.q - ml1);
+        jacinv = rcp_fast((P.A * x1) * x2);
     }
     if (getps) {  // no RAMBO weight in get_PS: returns 0 * jac_x1x2 (:1139,1152) and the problem mask
 #pragma unroll
@@ -107,12 +108,19 @@ rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const 
         if (mask != nullptr) mask[ev] = problem ? 1 : 0;
         return;
     }
-    const T E_cm = sqrt_(x1 * x2) * P.e_collider;
+    const T E_cm = sqrt_fast(x1 * x2) * P.e_collider;
     const bool quirks = (P.flags & MF_FLAG_REF_FP32_QUIRKS) != 0;
-    const T jac = rambo_weight<T, NF>(P, E_cm, K, M, quirks);
+    T sM[NF], invM[NF];
+#pragma unroll
+    for (int k = 0; k <= NF - 2; ++k) {
+        sM[k] = rho_num(M[k], (k == NF - 2) ? P.m[NF - 1] : M[k + 1], P.m[k]);  // :709-713 uses m_{n-1}, not M_{n-1}
+        invM[k] = rcp_fast(M[k]);
+    }
+    sM[NF - 1] = (T)0; invM[NF - 1] = (T)0;
+    const T jac = rambo_weight<T, NF>(P, E_cm, K, M, sM, invM, quirks);
     T pr;
     if (!quirks) {
-        pr = ((T)1 / jac) * jacinv;
+        pr = rcp_fast(jac) * jacinv;
     } else {
         float pf = __fdiv_rn(1.0f, (float)jac);
         pr = (T)(float)((double)pf * (double)jacinv);
@@ -152,6 +160,8 @@ static int launch_inverse(const T* momenta, int64_t event_stride, const T* x1, c
         P.t1 = (-P.q) / P.A;
         P.t1sq = P.t1 * P.t1;
         P.neg_inv_A = (T)-1 * ((T)1 / P.A);
+        P.inv_A = (T)1 / P.A;
+        P.neg_A = -P.A;
     }
     P.e_collider = e_collider;
     {

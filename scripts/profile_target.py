@@ -18,7 +18,7 @@ if what in ("chain", "all"):
         smp.run_chunk(phi, event_offset=i * N, acc=acc)
     torch.cuda.synchronize()
     del phi
-if what in ("k1", "all"):
+if what in ("k1", "k2", "all"):
     for n, m in ((3, [125.25, 172.5, 172.5]), (8, [4.7, 4.7, 4.7, 4.7, 0.1, 0.0, 0.3, 0.3])):
         ps = PhaseSpace(E, [21, 21], list(range(n)), final_masses=torch.tensor(m, dtype=torch.float64), dev=dev)
         u = torch.rand(1 << 22, 3 * n - 2, dtype=torch.float64, device=dev).clamp_(1e-10, 1 - 1e-10)

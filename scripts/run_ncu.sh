@@ -18,9 +18,11 @@ prof() {  # name kernel-regex target launch-skip
 for w in $WHAT; do
   case $w in
     chain)  prof chain  "is_chain_kernel" chain 2 ;;
+    flowA)  prof flowA  "flow_sample_kernel" chain 2 ;;
+    flowB)  prof flowB  "rambo_is_kernel" chain 2 ;;
     k1n3)   prof k1n3   "rambo_forward_kernel" k1 1 ;;
     k1n8)   prof k1n8   "rambo_forward_kernel" k1 4 ;;
-    k2n8)   prof k2n8   "rambo_inverse_kernel" all 4 ;;
+    k2n8)   prof k2n8   "rambo_inverse_kernel" k2 4 ;;
     rqsfwd) prof rqsfwd "rqs_kernel" rqs 2 ;;
     rqsinv) prof rqsinv "rqs_kernel" rqs 3 ;;
     launches) ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_$TAG.csv python scripts/profile_target.py all > /dev/null 2>&1 ;;
