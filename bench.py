@@ -9,7 +9,8 @@ N > 1): one STEP = one chunk of 2^22 ttH points through the fused chain
     Philox base sample -> 2 RQ-spline inverses (F=7, K=10, per-event parameters streamed from HBM)
     -> PhaseSpace map u -> momenta (n=3: H, t, tbar at sqrt(s) = 13 TeV, fp64) + Jacobian
     -> weight w = jac / (2 x1 x2 s) / q(u) -> (sum w, sum w^2, n_valid),
-one kernel launch per step (memflow_b200/csrc/is_chain.cu), one all-reduce of the 3 accumulators at the end.
+two kernel launches per step (memflow_b200/csrc/is_chain.cu: A = flow sample, B = phase space + weight + reduce),
+one all-reduce of the 3 accumulators at the end.
 Metric: phase-space points/sec (map + Jacobian + weights), whole job.
 
 Prints ONE JSON line (rank 0). Keys follow the driver's contract; see DESIGN.md "Measurement".
@@ -245,17 +246,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # scratch of the two launches of one step (A: flow sample -> u, log q;  B: phase space + weight + reduce)
+    u_buf = torch.empty((CHUNK, F_DIM), dtype=torch.float64, device=dev)
+    lq_buf = torch.empty(CHUNK, dtype=torch.float64, device=dev)
+
+    def step(i):
+        smp.sample_flow(phi, event_offset=base + i * CHUNK, u=u_buf, logq=lq_buf)
+        smp.weigh(u_buf, lq_buf, acc=acc)
+
     for i in range(W):
-        smp.run_chunk(phi, event_offset=base + i * CHUNK, acc=acc)
+        step(i)
     barrier()
     acc.zero_()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     barrier()
     t_wall = time.perf_counter()
     evs[0].record()
     for i in range(K):
-        smp.run_chunk(phi, event_offset=base + (W + i) * CHUNK, acc=acc)
+        smp.sample_flow(phi, event_offset=base + (W + i) * CHUNK, u=u_buf, logq=lq_buf)
+        mids[i].record()              # between the two launches: times the dominant kernel alone
+        smp.weigh(u_buf, lq_buf, acc=acc)
         evs[i + 1].record()
     allreduce_accumulators(acc)       # the path's only collective: 3 doubles, once
     end = torch.cuda.Event(enable_timing=True)
@@ -264,7 +276,8 @@ def main():
     t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop() if sampler else None
     t_dev = evs[0].elapsed_time(end) * 1e-3
-    kern_ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(K))
+    kern_ms = sorted(evs[i].elapsed_time(mids[i]) for i in range(K))          # launch A (flow_sample_kernel)
+    kern_b_ms = sorted(mids[i].elapsed_time(evs[i + 1]) for i in range(K))    # launch B (rambo_is_kernel)
     t = torch.tensor([t_dev], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -323,7 +336,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("is_chain_kernel_bytes_per_launch")
+            traffic = json.load(open(tp)).get("flow_sample_kernel_bytes_per_launch_4M")
         except Exception:
             traffic = None
     line = {
@@ -333,12 +346,15 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": 24,
                 "steps": e2e_steps, "chunk_events": e2e_chunk,
                 "note": "spline parameters start in pinned host memory; H2D double-buffered against the kernel"},
-        "gpu_launches": K * world,
+        "gpu_launches": 2 * K * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic, "kernel": "is_chain_kernel<3>", "peak_source": peak_src,
+                     "traffic": traffic, "kernel": "flow_sample_kernel (launch A of each step)", "peak_source": peak_src,
                      "algorithmic_bytes_per_event": BYTES_PER_EVENT, "events_per_launch": CHUNK,
                      "kernel_ms_avg": avg_kernel_s * 1e3, "kernel_ms_median": med_kernel_s * 1e3,
-                     "note": "kernel is FP32/FP64-issue bound, not HBM bound: see DESIGN.md and profiles/"},
+                     "second_kernel": {"name": "rambo_is_kernel<3> (launch B)", "ms_avg": sum(kern_b_ms) / len(kern_b_ms),
+                                       "algorithmic_bytes_per_event": 64, "note": "FP64-pipe bound, see profiles/"},
+                     "share_of_step": avg_kernel_s / (t_max / K),
+                     "note": "achieved counts only the spline parameters (SURVEY 8d); the kernel also writes 64 B/event (u, log q)"},
         "clocks": clocks,
         "estimate": {"I": I, "sigma": sigma, "n_valid": nvalid, "n_total": total_events},
         "wall_s_timed_region": t_wall,

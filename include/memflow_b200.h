@@ -154,7 +154,7 @@ int mf_is_reduce_f64(const double* target, const double* jac, const double* logq
                      void* workspace, mf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Fused importance-sampling chain (TestFlows_ImportanceSampling.ipynb [45,50-54] in one launch):
+ * Importance-sampling chain (TestFlows_ImportanceSampling.ipynb [45,50-54] in one call, two launches A+B below):
  *   Philox4x32-10 base sample z ~ U[-bound,bound]^F (counter = global event index, key = seed)
  *   -> T spline inverses (K4, parameters phi[t] given)  -> u = (x + bound) / (2 bound)
  *   -> K1 (n_final bodies, F = 3n-2)  -> w = jac / (2 x1 x2 s) / q(u)  -> K5 accumulation.
@@ -166,6 +166,17 @@ int mf_is_chain_f64(const float* phi, int64_t N, int n_final, int T, int K, floa
                     uint64_t seed, uint64_t event_offset, const double* masses, double e_collider,
                     uint32_t flags, double* acc, void* workspace, double* u_out, double* logq,
                     double* momenta, double* weight, double* x1, double* x2, mf_stream_t stream);
+
+/* The two stages of the chain as separate entry points (mf_is_chain_f64 runs them back to back):
+ *  A  mf_flow_sample_f32: Philox base sample + T spline inverses -> u [N,F] (fp64, in [0,1]) and log q [N]
+ *                         (flow().sample + flow().log_prob of TestFlows_ImportanceSampling.ipynb [45,50] in one pass)
+ *  B  mf_rambo_is_f64   : K1 + w = jac / (2 x1 x2 s) / exp(log q) + K5 accumulation, on given u / log q
+ *                         (cells [50-54]); optional momenta / weight / x1 / x2 outputs. */
+int mf_flow_sample_f32(const float* phi, int64_t N, int F, int T, int K, float bound, float slope, uint64_t seed,
+                       uint64_t event_offset, double* u, double* logq, mf_stream_t stream);
+int mf_rambo_is_f64(const double* u, const double* logq, int64_t N, int n_final, const double* masses,
+                    double e_collider, uint32_t flags, double* acc, void* workspace, double* momenta, double* weight,
+                    double* x1, double* x2, mf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -270,46 +270,105 @@ rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, i
     grid_accumulate<256>(k1.value(), k2.value(), cnt, acc, workspace);
 }
 
-template <int NF>
-static int chain_launch(const float* phi, int64_t N, int T, int K, float bound, float slope, uint64_t seed,
-                        uint64_t event_offset, const double* masses, double e_collider, uint32_t flags, double* acc,
-                        void* workspace, double* u_out, double* logq, double* momenta, double* weight, double* x1,
-                        double* x2, cudaStream_t stream) {
-    constexpr int F = 3 * NF - 2;
-    const int PW = 3 * K - 1;
-    int dev = 0, sms = 148, smem_max = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    int E = kChainThreads / F;
-    if (E >= 32) E = E / 32 * 32;  // whole warps in the phase-space phase
-    const size_t extra = 2 * kChainThreads * sizeof(float) + 2 * sizeof(uint64_t) + 256;
-    auto need = [&](int e) { return (((size_t)e * F * PW * sizeof(float) + 127) / 128 * 128) * 2 + extra; };
-    while (E > 1 && need(E) > (size_t)smem_max / 2) --E;  // aim for >= 2 CTAs per SM
-    while (E > 1 && need(E) > (size_t)smem_max) --E;
-    if (need(E) > (size_t)smem_max) return MF_E_SHAPE;
-    int bulk_ok = aligned(phi, 16) && (((size_t)N * F * PW * sizeof(float)) % 16 == 0 || T == 1) ? 1 : 0;
-    if (bulk_ok) {
-        int e = E;
-        while (e > 0 && ((size_t)e * F * PW * sizeof(float)) % 16 != 0) --e;
-        if (e > 0) E = e; else bulk_ok = 0;
-    }
-    const size_t smem = need(E);
+static RqsConst<float> make_rqs_const(float bound, float slope) {
     RqsConst<float> C;
     C.bound = bound;
     C.clip = slope > 0.0f ? 1 : 0;
     const double L = C.clip ? std::log((double)slope) : 1.0;
     C.two_over_L = C.clip ? (float)(2.0 / L) : 0.0f;
     C.one_over_L = C.clip ? (float)(1.0 / L) : 0.0f;
+    return C;
+}
+
+struct ChainGeom { int E, bulk_ok, sms, smem_max; };
+static ChainGeom chain_geometry(const float* phi, int64_t N, int F, int T, int K, int stages) {
+    ChainGeom g{};
+    const int PW = 3 * K - 1;
+    int dev = 0;
+    g.sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&g.smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    int E = kChainThreads / F;
+    if (E >= 32) E = E / 32 * 32;
+    const size_t extra = 2 * kChainThreads * sizeof(float) + 2 * sizeof(uint64_t) + 256;
+    auto need = [&](int e) { return (((size_t)e * F * PW * sizeof(float) + 127) / 128 * 128) * stages + extra; };
+    while (E > 1 && need(E) > (size_t)g.smem_max / 2) --E;
+    while (E > 1 && need(E) > (size_t)g.smem_max) --E;
+    if (need(E) > (size_t)g.smem_max) { g.E = 0; return g; }
+    g.bulk_ok = aligned(phi, 16) && (((size_t)N * F * PW * sizeof(float)) % 16 == 0 || T == 1) ? 1 : 0;
+    if (g.bulk_ok) {
+        int e = E;
+        while (e > 0 && ((size_t)e * F * PW * sizeof(float)) % 16 != 0) --e;
+        if (e > 0) E = e; else g.bulk_ok = 0;
+    }
+    g.E = E;
+    return g;
+}
+
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
+// A: Philox base sample + T spline inverses -> u [N,F] fp64, log q [N]
+static int flow_sample_launch(const float* phi, int64_t N, int F, int T, int K, float bound, float slope, uint64_t seed,
+                              uint64_t event_offset, double* u, double* logq, cudaStream_t stream) {
+    static const int minb = env_int("MF_CHAIN_MINB", 8), stages_env = env_int("MF_CHAIN_STAGES", 1);
+    const int stages = stages_env == 2 ? 2 : 1;
+    const ChainGeom g = chain_geometry(phi, N, F, T, K, stages);
+    if (g.E == 0) return MF_E_SHAPE;
+    const int PW = 3 * K - 1;
+    const RqsConst<float> C = make_rqs_const(bound, slope);
+    const int64_t num_tiles = (N + g.E - 1) / g.E;
+    const size_t smem = (((size_t)g.E * F * PW * sizeof(float) + 127) / 128 * 128) * stages + kChainThreads * sizeof(float) +
+                        2 * sizeof(uint64_t) + 128;
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int ctas = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, kChainThreads, smem);
+        if (ctas < 1) ctas = 1;
+        int64_t grid = (int64_t)g.sms * ctas;
+        if (grid > num_tiles) grid = num_tiles;
+        kern<<<(unsigned)grid, kChainThreads, smem, stream>>>(phi, N, F, T, K, C, g.E, stages, g.bulk_ok, seed, event_offset, u,
+                                                              logq);
+    };
+    switch (minb) {
+    case 4: go(flow_sample_kernel<4>); break;
+    case 5: go(flow_sample_kernel<5>); break;
+    case 6: go(flow_sample_kernel<6>); break;
+    default: go(flow_sample_kernel<8>); break;
+    }
+    return launch_status();
+}
+
+// B: K1 + weight + K5 on given u, log q
+template <int NF>
+static int rambo_is_launch(const double* u, const double* logq, int64_t N, const double* masses, double e_collider,
+                           uint32_t flags, double* acc, void* workspace, double* momenta, double* weight, double* x1,
+                           double* x2, cudaStream_t stream) {
     const RamboParams<double, NF> P = make_forward_params<double, NF>(masses, e_collider, nullptr, flags & ~MF_FLAG_CUTS);
     const double inv_2s = 1.0 / (2.0 * e_collider * e_collider);
-    const int64_t num_tiles = (N + E - 1) / E;
-    static int minb_env = -1, mode_env = -1, stages_env = -1;
-    if (minb_env < 0) { const char* e = getenv("MF_CHAIN_MINB"); minb_env = e ? atoi(e) : 8; }
-    if (mode_env < 0) { const char* e = getenv("MF_CHAIN_MODE"); mode_env = (e && e[0] == 'f') ? 0 : 1; }  // fused | split
-    if (stages_env < 0) { const char* e = getenv("MF_CHAIN_STAGES"); stages_env = e ? atoi(e) : 1; }
-    if (mode_env == 1) {
-        // ---- split: A (flow sample) then B (phase space + weight + reduce) on the same stream ----
+    int dev = 0, sms = 148, ctas = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, rambo_is_kernel<NF>, 256, 0);
+    if (ctas < 1) ctas = 1;
+    int64_t grid = (int64_t)sms * ctas;
+    const int64_t want = (N + 255) / 256;
+    if (grid > want) grid = want;
+    if (grid > kReduceMaxBlocks) grid = kReduceMaxBlocks;
+    rambo_is_kernel<NF><<<(unsigned)grid, 256, 0, stream>>>(u, logq, N, P, inv_2s, acc, workspace, momenta, weight, x1, x2);
+    return launch_status();
+}
+
+template <int NF>
+static int chain_launch(const float* phi, int64_t N, int T, int K, float bound, float slope, uint64_t seed,
+                        uint64_t event_offset, const double* masses, double e_collider, uint32_t flags, double* acc,
+                        void* workspace, double* u_out, double* logq, double* momenta, double* weight, double* x1,
+                        double* x2, cudaStream_t stream) {
+    constexpr int F = 3 * NF - 2;
+    static const int fused = []() { const char* e = getenv("MF_CHAIN_MODE"); return (e && e[0] == 'f') ? 1 : 0; }();
+    if (!fused) {
+        // default: two launches on the same stream, A (flow sample) then B (phase space + weight + reduce)
         double *u_buf = u_out, *lq_buf = logq;
         void* scratch = nullptr;
         if (!u_buf || !lq_buf) {
@@ -318,51 +377,36 @@ static int chain_launch(const float* phi, int64_t N, int T, int K, float bound, 
             if (!u_buf) u_buf = reinterpret_cast<double*>(scratch);
             if (!lq_buf) lq_buf = reinterpret_cast<double*>(scratch) + (size_t)N * F;
         }
-        const int stages = stages_env == 1 ? 1 : 2;
-        const size_t smem_a = (((size_t)E * F * PW * sizeof(float) + 127) / 128 * 128) * stages + kChainThreads * sizeof(float) +
-                              2 * sizeof(uint64_t) + 128;
-        auto go_a = [&](auto kern) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
-            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            int ctas = 1;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, kChainThreads, smem_a);
-            if (ctas < 1) ctas = 1;
-            int64_t grid_a = (int64_t)sms * ctas;
-            if (grid_a > num_tiles) grid_a = num_tiles;
-            kern<<<(unsigned)grid_a, kChainThreads, smem_a, stream>>>(phi, N, F, T, K, C, E, stages, bulk_ok, seed, event_offset,
-                                                                      u_buf, lq_buf);
-        };
-        switch (minb_env) {
-        case 8: go_a(flow_sample_kernel<8>); break;
-        case 6: go_a(flow_sample_kernel<6>); break;
-        case 5: go_a(flow_sample_kernel<5>); break;
-        default: go_a(flow_sample_kernel<4>); break;
-        }
-        int ctas_b = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_b, rambo_is_kernel<NF>, 256, 0);
-        if (ctas_b < 1) ctas_b = 1;
-        int64_t grid_b = (int64_t)sms * ctas_b;
-        const int64_t want_b = (N + 255) / 256;
-        if (grid_b > want_b) grid_b = want_b;
-        if (grid_b > kReduceMaxBlocks) grid_b = kReduceMaxBlocks;
-        rambo_is_kernel<NF><<<(unsigned)grid_b, 256, 0, stream>>>(u_buf, lq_buf, N, P, inv_2s, acc, workspace, momenta, weight,
-                                                                  x1, x2);
+        int rc = flow_sample_launch(phi, N, F, T, K, bound, slope, seed, event_offset, u_buf, lq_buf, stream);
+        if (rc == MF_OK)
+            rc = rambo_is_launch<NF>(u_buf, lq_buf, N, masses, e_collider, flags, acc, workspace, momenta, weight, x1, x2, stream);
         if (scratch) cudaFreeAsync(scratch, stream);
-        return launch_status();
+        return rc;
     }
+    // MF_CHAIN_MODE=fused: single launch, nothing but the accumulators leaves the SM (slower: DESIGN.md section 4)
+    static const int minb = env_int("MF_CHAIN_FUSED_MINB", 4);
+    const ChainGeom g = chain_geometry(phi, N, F, T, K, 2);
+    if (g.E == 0) return MF_E_SHAPE;
+    const int PW = 3 * K - 1;
+    const size_t smem = (((size_t)g.E * F * PW * sizeof(float) + 127) / 128 * 128) * 2 + 2 * kChainThreads * sizeof(float) +
+                        2 * sizeof(uint64_t) + 256;
+    const RqsConst<float> C = make_rqs_const(bound, slope);
+    const RamboParams<double, NF> P = make_forward_params<double, NF>(masses, e_collider, nullptr, flags & ~MF_FLAG_CUTS);
+    const double inv_2s = 1.0 / (2.0 * e_collider * e_collider);
+    const int64_t num_tiles = (N + g.E - 1) / g.E;
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int ctas_per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kChainThreads, smem);
         if (ctas_per_sm < 1) ctas_per_sm = 1;
-        int64_t grid = (int64_t)sms * ctas_per_sm;
+        int64_t grid = (int64_t)g.sms * ctas_per_sm;
         if (grid > num_tiles) grid = num_tiles;
         if (grid > kReduceMaxBlocks) grid = kReduceMaxBlocks;
-        kern<<<(unsigned)grid, kChainThreads, smem, stream>>>(phi, N, T, K, C, E, bulk_ok, seed, event_offset, P, inv_2s,
+        kern<<<(unsigned)grid, kChainThreads, smem, stream>>>(phi, N, T, K, C, g.E, g.bulk_ok, seed, event_offset, P, inv_2s,
                                                               acc, workspace, u_out, logq, momenta, weight, x1, x2);
     };
-    switch (minb_env) {
+    switch (minb) {
     case 1: go(is_chain_kernel<NF, 1>); break;
     case 2: go(is_chain_kernel<NF, 2>); break;
     case 3: go(is_chain_kernel<NF, 3>); break;
@@ -385,6 +429,32 @@ extern "C" int mf_is_chain_f64(const float* phi, int64_t N, int n_final, int T, 
     switch (n_final) {
 #define MF_CASE(NF) \
     case NF: return mf::chain_launch<NF>(phi, N, T, K, bound, slope, seed, event_offset, masses, e_collider, flags, acc, workspace, u_out, logq, momenta, weight, x1, x2, (cudaStream_t)stream);
+        MF_CASE(3) MF_CASE(4) MF_CASE(5) MF_CASE(6) MF_CASE(7) MF_CASE(8)
+#undef MF_CASE
+    }
+    return MF_E_NFINAL;
+}
+
+extern "C" int mf_flow_sample_f32(const float* phi, int64_t N, int F, int T, int K, float bound, float slope, uint64_t seed,
+                                  uint64_t event_offset, double* u, double* logq, mf_stream_t stream) {
+    if (N < 0 || T < 1 || F < 1 || F > mf::kChainThreads || (N > 0 && (!phi || !u || !logq))) return MF_E_BADARG;
+    if (K < 1 || K > 128) return MF_E_SHAPE;
+    if (N == 0) return MF_OK;
+    return mf::flow_sample_launch(phi, N, F, T, K, bound, slope, seed, event_offset, u, logq, (cudaStream_t)stream);
+}
+
+extern "C" int mf_rambo_is_f64(const double* u, const double* logq, int64_t N, int n_final, const double* masses,
+                               double e_collider, uint32_t flags, double* acc, void* workspace, double* momenta,
+                               double* weight, double* x1, double* x2, mf_stream_t stream) {
+    if (N < 0 || !masses || !acc || !workspace || (N > 0 && (!u || !logq))) return MF_E_BADARG;
+    if (n_final < MF_MIN_FINAL || n_final > MF_MAX_FINAL) return MF_E_NFINAL;
+    const int W = 3 * n_final - 2;
+    const size_t row_align = (W % 4 == 0) ? 32 : ((W % 2 == 0) ? 16 : 8);
+    if (!mf::aligned(u, row_align) || (momenta && !mf::aligned(momenta, 32))) return MF_E_ALIGN;
+    if (N == 0) return MF_OK;
+    switch (n_final) {
+#define MF_CASE(NF) \
+    case NF: return mf::rambo_is_launch<NF>(u, logq, N, masses, e_collider, flags, acc, workspace, momenta, weight, x1, x2, (cudaStream_t)stream);
         MF_CASE(3) MF_CASE(4) MF_CASE(5) MF_CASE(6) MF_CASE(7) MF_CASE(8)
 #undef MF_CASE
     }

@@ -125,6 +125,98 @@ rqs_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t B, int 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident variant for long rows (compile-time K = 32..64, fp32): 128 threads per CTA, thread t < 64 owns
+// the SEARCHED softmax array of row t, thread 64 + t the other array of the same row. Each array is read from
+// shared memory once into registers (rows are 3K-1 words apart -> consecutive rows hit distinct banks), the bin is
+// found on the unnormalised running sum, and only {bin, knot pair} crosses between the two sides. Single-stage
+// TMA tile per CTA, several CTAs per SM overlap each other's copies.
+// ---------------------------------------------------------------------------------------------
+template <int K, bool INV>
+__global__ void __launch_bounds__(128, 4)
+rqs_reg2_kernel(const float* __restrict__ phi, const float* __restrict__ vin, int64_t B, int F, RqsConst<float> C, int ept,
+                int bulk_ok, float* __restrict__ vout, float* __restrict__ ladj_out, float* __restrict__ ladj_sum,
+                int32_t* __restrict__ bin_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int PW = 3 * K - 1;
+    const int rows_per_tile = ept * F;
+    const size_t tile_elems = (size_t)rows_per_tile * PW;
+    const size_t tile_bytes_al = (tile_elems * sizeof(float) + 127) / 128 * 128;
+    float* sm = reinterpret_cast<float*>(smem_raw);
+    float4* xch = reinterpret_cast<float4*>(smem_raw + tile_bytes_al);  // [64] {bin, k0, k1, -}
+    float* lad = reinterpret_cast<float*>(xch + 64);                     // [64]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(lad + 64);
+    const int tid = threadIdx.x, side = tid >> 6, row = tid & 63;
+    const int64_t num_tiles = (B + ept - 1) / ept;
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    uint32_t parity = 0u;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t ev0 = tile * ept;
+        const int nev = (int)((B - ev0) < ept ? (B - ev0) : ept);
+        const int nrows = nev * F;
+        const bool bulk = bulk_ok && nev == ept;
+        const float* src = phi + (size_t)tile * tile_elems;
+        if (bulk) {
+            if (tid == 0) {
+                const uint32_t bytes = (uint32_t)(tile_elems * sizeof(float));
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(sm, src, bytes, bar);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            const size_t ne = (size_t)nrows * PW;
+            for (size_t i = tid; i < ne; i += 128) sm[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        const bool active = row < nrows;
+        const int64_t gi = ev0 * F + row;
+        float e[K];
+        float S = 1.0f, v = 0.0f;
+        const float* r = sm + (size_t)row * PW;
+        if (active) {
+            v = __ldg(vin + gi);
+            const int which = (side == 0) ? (INV ? 1 : 0) : (INV ? 0 : 1);  // 0 = widths, 1 = heights
+            S = rqs_exp_row<K>(r + which * K, C, e);
+            if (side == 0) {
+                float k0, k1;
+                const int bin = rqs_search_row<K>(e, S, C.bound, v, k0, k1);
+                xch[row] = make_float4(__int_as_float(bin), k0, k1, 0.0f);
+            }
+        }
+        __syncthreads();
+        if (side == 1) {
+            float out = v, ladj = 0.0f;
+            int bin = -1;
+            if (active) {
+                const float4 x = xch[row];
+                bin = __float_as_int(x.x);
+                if (bin >= 0 && bin < K) {
+                    float o0, o1;
+                    rqs_prefix_row<K>(e, S, C.bound, bin, o0, o1);
+                    const float x0 = INV ? o0 : x.y, x1 = INV ? o1 : x.z, y0 = INV ? x.y : o0, y1 = INV ? x.z : o1;
+                    rqs_eval_fast<INV>(r + 2 * K, K, C, bin, x0, x1, y0, y1, v, out, ladj);
+                }
+                vout[gi] = out;
+                if (ladj_out) ladj_out[gi] = ladj;
+                if (bin_out) bin_out[gi] = bin;
+            }
+            lad[row] = ladj;
+        }
+        if (ladj_sum != nullptr) {
+            __syncthreads();
+            if (tid < nev) {
+                float s = 0.0f;
+                for (int f = 0; f < F; ++f) s += lad[tid * F + f];
+                ladj_sum[ev0 + tid] = s;
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+    }
+}
+
 template <typename T> struct SearchConst {};
 
 template <typename T>
@@ -151,6 +243,50 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
     if (B == 0) return MF_OK;
     const int PW = 3 * K - 1;
     const size_t row_bytes = (size_t)PW * sizeof(T);
+    if constexpr (sizeof(T) == 4) {
+        if ((K == 32 || K == 40 || K == 48 || K == 64) && F <= 64) {
+            int dev = 0, sms = 148, smem_max = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            const size_t extra = 64 * sizeof(float4) + 64 * sizeof(float) + sizeof(uint64_t) + 128;
+            auto need = [&](int e) { return ((size_t)e * F * row_bytes + 127) / 128 * 128 + extra; };
+            int ept = 64 / F;
+            while (ept > 1 && need(ept) > (size_t)smem_max / 4) --ept;  // aim for 4 CTAs per SM
+            int bulk_ok = aligned(phi, 16) ? 1 : 0;
+            if (bulk_ok) {
+                int e = ept;
+                while (e > 0 && ((size_t)e * F * row_bytes) % 16 != 0) --e;
+                if (e > 0) ept = e; else bulk_ok = 0;
+            }
+            const size_t smem = need(ept);
+            RqsConst<float> C;
+            C.bound = bound;
+            C.clip = slope > 0.0f ? 1 : 0;
+            const double L = C.clip ? std::log((double)slope) : 1.0;
+            C.two_over_L = C.clip ? (float)(2.0 / L) : 0.0f;
+            C.one_over_L = C.clip ? (float)(1.0 / L) : 0.0f;
+            const int64_t num_tiles = (B + ept - 1) / ept;
+            auto go = [&](auto kern) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                int ctas = 1;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 128, smem);
+                if (ctas < 1) ctas = 1;
+                int64_t grid = (int64_t)sms * ctas;
+                if (grid > num_tiles) grid = num_tiles;
+                kern<<<(unsigned)grid, 128, smem, stream>>>((const float*)phi, (const float*)vin, B, F, C, ept, bulk_ok,
+                                                            (float*)vout, (float*)ladj, (float*)ladj_sum, bin);
+            };
+            switch (K) {
+            case 32: go(rqs_reg2_kernel<32, INV>); break;
+            case 40: go(rqs_reg2_kernel<40, INV>); break;
+            case 48: go(rqs_reg2_kernel<48, INV>); break;
+            default: go(rqs_reg2_kernel<64, INV>); break;
+            }
+            return launch_status();
+        }
+    }
     // 2 lanes per row when rows are long (more warps for the same shared-memory footprint)
     const int lanes = (K >= 24) ? 2 : 1;
     const int rows_max = kRqsThreads / lanes;

@@ -125,65 +125,10 @@ MF_D void rqs_row_1lane(T* __restrict__ row, int K, const RqsConst<T>& C, T v, T
     rqs_eval<T, INV>(row, row + K, row + 2 * K, K, C, bin, v, out, ladj);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Register-resident row for small compile-time K (the fused chain: K = 8..16). One thread, fully unrolled:
-// both softmax arrays are exponentiated once into registers; the bin is found by comparing the UNNORMALISED
-// running sum with v mapped into that space ((v/B+1)/2 * S), so no per-element normalisation, no stores;
-// the other coordinate's two knots are the prefix sums at bin / bin+1. fp32 only.
-// ---------------------------------------------------------------------------------------------
-template <int K, bool INV>
-MF_D void rqs_row_reg(const float* __restrict__ row, const RqsConst<float>& C, float v, float& out, float& ladj,
-                      int& bin) {
-    const float* as = row + (INV ? K : 0);  // searched array: heights for the inverse, widths for the forward
-    const float* ao = row + (INV ? 0 : K);
-    float es[K], eo[K];
-    float Ss = 0.0f, So = 0.0f;
-    if (C.clip) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            es[k] = FastMath<float>::exp(soft_clip(as[k], C.two_over_L));
-            eo[k] = FastMath<float>::exp(soft_clip(ao[k], C.two_over_L));
-            Ss += es[k];
-            So += eo[k];
-        }
-    } else {
-        float ms = as[0], mo = ao[0];
-#pragma unroll
-        for (int k = 1; k < K; ++k) { ms = fmaxf(ms, as[k]); mo = fmaxf(mo, ao[k]); }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            es[k] = FastMath<float>::exp(as[k] - ms);
-            eo[k] = FastMath<float>::exp(ao[k] - mo);
-            Ss += es[k];
-            So += eo[k];
-        }
-    }
-    const float B = C.bound;
-    const float target = fmaf(v, 0.5f / B, 0.5f) * Ss;  // v in units of the unnormalised cumulative sum
-    int cnt = (-B < v) ? 1 : 0;
-    float c = 0.0f, c_lo = 0.0f, c_hi = 3.0e38f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        c += es[k];
-        const bool below = c < target;
-        cnt += below ? 1 : 0;
-        c_lo = below ? c : c_lo;
-        c_hi = below ? c_hi : fminf(c_hi, c);
-    }
-    bin = cnt - 1;
-    if (bin < 0 || bin >= K) { out = v; ladj = 0.0f; return; }
-    float o = 0.0f, o_lo = 0.0f, o_hi = 0.0f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        o += eo[k];
-        o_lo = (k < bin) ? o : o_lo;
-        o_hi = (k <= bin) ? o : o_hi;
-    }
-    const float is2 = 2.0f * FastMath<float>::rcp(Ss), io2 = 2.0f * FastMath<float>::rcp(So);
-    const float s0 = B * fmaf(c_lo, is2, -1.0f), s1 = B * fmaf(c_hi, is2, -1.0f);
-    const float o0 = B * fmaf(o_lo, io2, -1.0f), o1 = B * fmaf(o_hi, io2, -1.0f);
-    const float x0 = INV ? o0 : s0, x1 = INV ? o1 : s1, y0 = INV ? s0 : o0, y1 = INV ? s1 : o1;
-    const float* d = row + 2 * K;
+// Rational quadratic of one bin from its 4 knot coordinates (fp32, reciprocal-multiply instead of divisions).
+template <bool INV>
+MF_D void rqs_eval_fast(const float* __restrict__ d, int K, const RqsConst<float>& C, int bin, float x0, float x1, float y0,
+                        float y1, float v, float& out, float& ladj) {
     float d0 = 1.0f, d1 = 1.0f;
     if (bin > 0) { float t = d[bin - 1]; if (C.clip) t = soft_clip(t, C.one_over_L); d0 = FastMath<float>::exp(t); }
     if (bin < K - 1) { float t = d[bin]; if (C.clip) t = soft_clip(t, C.one_over_L); d1 = FastMath<float>::exp(t); }
@@ -209,6 +154,76 @@ MF_D void rqs_row_reg(const float* __restrict__ row, const RqsConst<float>& C, f
     const float omz = 1.0f - z;
     const float jac = (s * s) * (2.0f * s * zz + d0 * (omz * omz) + d1 * (z * z)) * (rden * rden);
     ladj = logf(jac);
+}
+
+// One softmax array of a row into registers: e[k] = exp(clip(a_k)), returns the sequential sum.
+template <int K>
+MF_D float rqs_exp_row(const float* __restrict__ arr, const RqsConst<float>& C, float (&e)[K]) {
+    float S = 0.0f;
+    if (C.clip) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { e[k] = FastMath<float>::exp(soft_clip(arr[k], C.two_over_L)); S += e[k]; }
+    } else {
+        float m = arr[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) m = fmaxf(m, arr[k]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) { e[k] = FastMath<float>::exp(arr[k] - m); S += e[k]; }
+    }
+    return S;
+}
+// Bin search on the unnormalised running sum; returns bin = searchsorted - 1 and the two knots of that bin.
+template <int K>
+MF_D int rqs_search_row(const float (&e)[K], float S, float bound, float v, float& k0, float& k1) {
+    const float target = fmaf(v, 0.5f / bound, 0.5f) * S;
+    int cnt = (-bound < v) ? 1 : 0;
+    float c = 0.0f, c_lo = 0.0f, c_hi = 3.0e38f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        c += e[k];
+        const bool below = c < target;
+        cnt += below ? 1 : 0;
+        c_lo = below ? c : c_lo;
+        c_hi = below ? c_hi : fminf(c_hi, c);
+    }
+    const float is2 = 2.0f * FastMath<float>::rcp(S);
+    k0 = bound * fmaf(c_lo, is2, -1.0f);
+    k1 = bound * fmaf(c_hi, is2, -1.0f);
+    return cnt - 1;
+}
+// Knots of bin `bin` of the other coordinate: prefix sums at bin and bin + 1.
+template <int K>
+MF_D void rqs_prefix_row(const float (&e)[K], float S, float bound, int bin, float& k0, float& k1) {
+    float o = 0.0f, o_lo = 0.0f, o_hi = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        o += e[k];
+        o_lo = (k < bin) ? o : o_lo;
+        o_hi = (k <= bin) ? o : o_hi;
+    }
+    const float io2 = 2.0f * FastMath<float>::rcp(S);
+    k0 = bound * fmaf(o_lo, io2, -1.0f);
+    k1 = bound * fmaf(o_hi, io2, -1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Register-resident row for small compile-time K (the fused chain: K = 8..16). One thread, fully unrolled:
+// both softmax arrays are exponentiated once into registers; the bin is found by comparing the UNNORMALISED
+// running sum with v mapped into that space ((v/B+1)/2 * S), so no per-element normalisation, no stores;
+// the other coordinate's two knots are the prefix sums at bin / bin+1. fp32 only.
+// ---------------------------------------------------------------------------------------------
+template <int K, bool INV>
+MF_D void rqs_row_reg(const float* __restrict__ row, const RqsConst<float>& C, float v, float& out, float& ladj,
+                      int& bin) {
+    float es[K], eo[K];
+    const float Ss = rqs_exp_row<K>(row + (INV ? K : 0), C, es);  // searched array: heights (inverse) / widths (forward)
+    const float So = rqs_exp_row<K>(row + (INV ? 0 : K), C, eo);
+    float s0, s1, o0, o1;
+    bin = rqs_search_row<K>(es, Ss, C.bound, v, s0, s1);
+    if (bin < 0 || bin >= K) { out = v; ladj = 0.0f; return; }
+    rqs_prefix_row<K>(eo, So, C.bound, bin, o0, o1);
+    const float x0 = INV ? o0 : s0, x1 = INV ? o1 : s1, y0 = INV ? s0 : o0, y1 = INV ? s1 : o1;
+    rqs_eval_fast<INV>(row + 2 * K, K, C, bin, x0, x1, y0, y1, v, out, ladj);
 }
 
 // Bulk async copy (TMA, 1-D) global -> shared with mbarrier completion.

@@ -45,8 +45,8 @@ def mc_estimate(acc, n_total, variant="N+1"):
 
 
 class ImportanceSampler:
-    """Fused chain: Philox base sample -> T spline inverses -> PhaseSpace map -> weight -> accumulators,
-    one kernel launch per chunk (TestFlows_ImportanceSampling.ipynb [45,50-54]; ME = pdf = 1).
+    """Sampling chain: Philox base sample -> T spline inverses (launch A) -> PhaseSpace map -> weight ->
+    accumulators (launch B), one C-ABI call per chunk (TestFlows_ImportanceSampling.ipynb [45,50-54]; ME = pdf = 1).
 
     phi: float32 [T, N, F, 3K-1] spline parameters (the hyper-network output, given), F = 3 n_final - 2.
     """
@@ -59,6 +59,46 @@ class ImportanceSampler:
         self.slope = slope
         self.seed = int(seed)
         self.device = torch.device(device if device is not None else "cuda:0")
+
+    def _check_phi(self, phi):
+        require_cuda(phi, "phi")
+        if phi.dtype != torch.float32 or phi.dim() != 4:
+            raise AssertionError("phi must be float32 [T, N, F, 3K-1]")
+        T, N, F, PW = phi.shape
+        if F != 3 * self.n_final - 2 or (PW + 1) % 3 != 0:
+            raise AssertionError("phi shape does not match n_final (F must be 3n-2, last dim 3K-1)")
+        return T, N, F, (PW + 1) // 3
+
+    def sample_flow(self, phi, event_offset=0, u=None, logq=None):
+        """Stage A alone (mf_flow_sample_f32): u [N, F] float64 in [0,1] and log q(u) [N] of the flow's samples."""
+        T, N, F, K = self._check_phi(phi)
+        phi = phi.contiguous()
+        dev = phi.device
+        if u is None:
+            u = torch.empty((N, F), dtype=torch.float64, device=dev)
+        if logq is None:
+            logq = torch.empty(N, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib().mf_flow_sample_f32(
+                ptr(phi), ctypes.c_int64(N), ctypes.c_int(F), ctypes.c_int(T), ctypes.c_int(K), ctypes.c_float(self.bound),
+                ctypes.c_float(self.slope if self.slope is not None else 0.0), ctypes.c_uint64(self.seed),
+                ctypes.c_uint64(int(event_offset)), ptr(u), ptr(logq), stream_ptr(dev))
+        check(rc, "mf_flow_sample_f32")
+        return u, logq
+
+    def weigh(self, u, logq, acc=None):
+        """Stage B alone (mf_rambo_is_f64): PhaseSpace map of u + weight + accumulation into acc."""
+        require_cuda(u, "u")
+        dev = u.device
+        if acc is None:
+            acc = new_accumulator(dev)
+        ws = reduce_workspace(dev)
+        with torch.cuda.device(dev):
+            rc = lib().mf_rambo_is_f64(ptr(u), ptr(logq), ctypes.c_int64(u.shape[0]), ctypes.c_int(self.n_final),
+                                       host_array(self.masses, ctypes.c_double), ctypes.c_double(self.collider_energy),
+                                       ctypes.c_uint32(0), ptr(acc), ptr(ws), None, None, None, None, stream_ptr(dev))
+        check(rc, "mf_rambo_is_f64")
+        return acc
 
     def run_chunk(self, phi, event_offset=0, acc=None, debug_outputs=False):
         require_cuda(phi, "phi")

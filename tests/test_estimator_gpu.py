@@ -98,3 +98,17 @@ def test_sharded_integrator_single_rank():
     it = ShardedIntegrator(smp, n_total=10_000, chunk=4096)
     acc = it.run(lambda b, e: buf[:, : e - b])
     assert acc[2].item() == 10_000
+
+
+def test_two_stage_calls_equal_chain_call():
+    """mf_flow_sample_f32 + mf_rambo_is_f64 called separately == mf_is_chain_f64 (bit-identical accumulators)."""
+    from memflow_b200 import estimator as ES
+    n, T, K, N = 4, 2, 10, 10_000
+    phi = torch.randn(T, N, 10, 3 * K - 1, device="cuda", dtype=torch.float32)
+    smp = ES.ImportanceSampler(MASSES[n], E, seed=77, device="cuda:0")
+    acc, out = smp.run_chunk(phi, event_offset=5, debug_outputs=True)
+    u, lq = smp.sample_flow(phi, event_offset=5)
+    assert torch.equal(u, out["u"]) and torch.equal(lq, out["logq"])
+    assert bool(((u >= 0) & (u <= 1)).all())
+    acc2 = smp.weigh(u, lq)
+    assert torch.equal(acc, acc2)
