@@ -14,6 +14,8 @@ prof() {  # name kernel-regex target launch-skip
   ncu -i $OUT/prof_${TAG}_$1.ncu-rep --page details > $OUT/details_${TAG}_$1.txt 2>/dev/null
   ncu -i $OUT/prof_${TAG}_$1.ncu-rep --page source --csv > $OUT/source_${TAG}_$1.csv 2>/dev/null
   ls -la $OUT/prof_${TAG}_$1.ncu-rep
+  # gpurun_out is capped at 64 MiB: keep the binary report only when small, the CSV/text exports always
+  if [ $(stat -c %s $OUT/prof_${TAG}_$1.ncu-rep) -gt 9000000 ]; then rm -f $OUT/prof_${TAG}_$1.ncu-rep; fi
 }
 for w in $WHAT; do
   case $w in
@@ -23,8 +25,8 @@ for w in $WHAT; do
     k1n3)   prof k1n3   "rambo_forward_kernel" k1 1 ;;
     k1n8)   prof k1n8   "rambo_forward_kernel" k1 4 ;;
     k2n8)   prof k2n8   "rambo_inverse_kernel" k2 4 ;;
-    rqsfwd) prof rqsfwd "rqs_kernel" rqs 2 ;;
-    rqsinv) prof rqsinv "rqs_kernel" rqs 3 ;;
+    rqsfwd) prof rqsfwd "rqs_reg2_kernel" rqs 2 ;;
+    rqsinv) prof rqsinv "rqs_reg2_kernel" rqs 3 ;;
     launches) ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_$TAG.csv python scripts/profile_target.py all > /dev/null 2>&1 ;;
   esac
 done
