@@ -27,6 +27,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout. Libraries (NCCL prints its version banner there) must not add
+# lines, so fd 1 is pointed at stderr for the whole run and the JSON goes to the saved original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 METRIC = "phase-space points/sec (map+Jacobian+weights)"
 UNIT = "points/s"
 E_CM = 13000.0
@@ -148,7 +159,7 @@ def run_reference(args, rank):
             "dtype": "f64", "data": "synthetic", "config": CONFIG,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def extras(torch, dev, hbm_peak):
@@ -366,7 +377,7 @@ def main():
         del phi, bufs
         torch.cuda.empty_cache()
         line["extra"] = extras(torch, dev, hbm_peak)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
