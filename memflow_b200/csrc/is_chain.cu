@@ -182,6 +182,7 @@ flow_sample_kernel(const float* __restrict__ phi, int64_t N, int F, int T, int K
     uint32_t parity0 = 0u, parity1 = 0u;
     int item = 0;
     int64_t tile = blockIdx.x;
+    const double inv_2b = 1.0 / (2.0 * (double)C.bound);  // exact for the usual bound = 1
     issue(tile, T - 1, 0);
     for (; tile < num_tiles; tile += gridDim.x) {
         const int64_t ev0 = tile * E;
@@ -230,7 +231,7 @@ flow_sample_kernel(const float* __restrict__ phi, int64_t N, int F, int T, int K
             if (stages == 1) { if (tt + 1 < T) issue(tile, t - 1, 0); else issue(tile + gridDim.x, T - 1, 0); }
         }
         lsum[tid] = ladj_acc;
-        if (row_active) u_out[ev0 * F + tid] = ((double)x + (double)C.bound) / (2.0 * (double)C.bound);
+        if (row_active) u_out[ev0 * F + tid] = ((double)x + (double)C.bound) * inv_2b;
         __syncthreads();
         if (tid < nev) {
             double lq = 0.0;

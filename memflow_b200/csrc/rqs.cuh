@@ -44,7 +44,7 @@ template <typename T> struct RqsConst {
 };
 
 MF_D double soft_clip(double a, double c) { return a / (1.0 + fabs(a * c)); }
-MF_D float soft_clip(float a, float c) { return a * FastMath<float>::rcp(1.0f + fabsf(a * c)); }
+MF_D float soft_clip(float a, float c) { return a * FastMath<float>::rcp(fmaf(fabsf(a), fabsf(c), 1.0f)); }  // 1 FFMA (|.| modifiers)
 
 // One thread transforms one of the two softmax arrays of a row into knots, in place.
 // Returns the number of knots (including X_0 = -B) strictly below v  == torch.searchsorted(knots, v).
