@@ -222,86 +222,129 @@ template <typename T> MF_D T delphi(const T (&a)[4], const T (&b)[4]) {  // util
     return r;
 }
 
-// One event of generateKinematics_batch (rambo_generator.py:168-398): r = the event's 3NF-2 uniforms.
-template <typename T, int NF>
-MF_D void rambo_forward_event(const T (&r)[3 * NF - 2], const RamboParams<T, NF>& P, T (&out)[NF + 2][4], T& wgt,
-                              T& x1, T& x2) {
-    constexpr int D = 3 * NF - 4, NE = NF - 2, NP = NF + 2;
-    // ---- x1, x2 from the last two uniforms: utils.py:260-284 (same operation order) ----
+// ---------------------------------------------------------------------------------------------
+// Streaming core of generateKinematics_batch (rambo_generator.py:168-398). The event is produced decay by decay:
+// each iteration solves one mass variable, updates the weight accumulators, builds one two-body decay, boosts it and
+// hands the finished 4-momentum to `emit(row, p)` immediately, so the live state is O(1) in the multiplicity
+// (Q, two masses, four accumulators) instead of the K/M/sM/invM arrays plus all 4(n+2) output components.
+//   load(i)    -> the event's i-th uniform (i is a compile-time constant after unrolling)
+//   emit(j, p) -> row j of the output (0,1 incoming; 2.. final), p = (E,px,py,pz)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int NF, int K_IDX, typename Load, typename Emit>
+MF_D void rambo_decay_step(const RamboParams<T, NF>& P, Load& load, Emit& emit, const T K0, T& prod, T& Kk, T& Mk,
+                           T (&Q)[4], T& num, T& den, T& f8, T& pw) {
+    constexpr int NE = NF - 2;
+    constexpr int k = K_IDX;
+    // next intermediate mass (:448-509): K_{k+1} = K_0 prod_{j<=k} t_j, M_{k+1} = K_{k+1} + sum_{j>k} m_j
+    T Kn, Mn;
+    if constexpr (k < NF - 2) {
+        prod *= solve_massvar<NF - 2 - k>(load(k));  // exponent of column k is NF-2-k (:405-407)
+        Kn = K0 * prod;
+        Mn = Kn + P.msum_rev[k + 1];
+    } else {
+        Kn = (T)0;
+        Mn = P.m[NF - 1];
+    }
+    const T sM = rho_num(Mk, Mn, P.m[k]);
+    const T invM = rcp_fast(Mk);
+    if constexpr (k == 0) pw = ipow<2 * NF - 4>(K0 * invM);
+    if constexpr (k <= NF - 3) {  // weight accumulators, see rambo_weight() for the algebra
+        num *= (sM * (invM * invM)) * ((Kk * Kk) * Mn);
+        den *= fabs_(sub_rn(mul_rn(Kk, Kk), mul_rn(Kn, Kn))) * Kn;
+    } else {
+        f8 = sM * (invM * invM);
+    }
+    // two-body decay M_k -> m_k + M_{k+1} in the rest frame of Q, then boost (:310-343)
+    const T qk = sM * ((T)0.5 * invM);  // 4 M_k rho(M_k, M_{k+1}, m_k)
+    const T ct = (T)2 * load(NE + 2 * k) - (T)1;
+    const T st = sqrt_fast(sub_rn((T)1, mul_rn(ct, ct)));
+    const T phi = (T)6.283185307179586 * load(NE + 2 * k + 1);
+    const T cp = cos_(phi);
+    const T sq = sqrt_fast(sub_rn((T)1, mul_rn(cp, cp)));
+    const T sp = (phi > (T)3.141592653589793) ? -sq : sq;
+    T p2[4], pb[4];
+    p2[1] = (qk * st) * cp;
+    p2[2] = (qk * st) * sp;
+    p2[3] = qk * ct;
+    const T m2 = P.m[k] * P.m[k];
+    p2[0] = sqrt_fast(rho2_3(p2[1], p2[2], p2[3]) + m2);
+    if constexpr (k == 0) {  // Q = (M_0, 0, 0, 0): the boost is the identity (beta = 0 exactly)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pb[c] = p2[c];
+    } else {
+        const T iq = rcp_fast(Q[0]);
+        boost(p2, Q[1] * iq, Q[2] * iq, Q[3] * iq, pb);
+        pb[0] = sqrt_fast(rho2_3(pb[1], pb[2], pb[3]) + m2);
+    }
+    emit(2 + k, pb);
+    Q[1] -= pb[1]; Q[2] -= pb[2]; Q[3] -= pb[3];
+    Q[0] = sqrt_fast(rho2_3(Q[1], Q[2], Q[3]) + Mn * Mn);
+    Kk = Kn;
+    Mk = Mn;
+}
+
+template <typename T, int NF, typename Load, typename Emit>
+MF_D void rambo_forward_stream(const RamboParams<T, NF>& P, Load&& load, Emit&& emit, T& wgt, T& x1, T& x2) {
+    constexpr int D = 3 * NF - 4, NP = NF + 2;
+    // ---- x1, x2 from the last two uniforms: utils.py:260-284 ----
     T wx;
     if (P.flags & MF_FLAG_X1X2_DIRECT) {  // uniform_x1x2=False, rambo_generator.py:229-234
-        x1 = r[D]; x2 = r[D + 1]; wx = (T)1;
+        x1 = load(D); x2 = load(D + 1); wx = (T)1;
     } else {
-        T ml1 = (P.t1 + sqrt_fast(P.t1sq + ((T)-2 * r[D]) * P.inv_A)) * P.neg_A;
-        T ml2 = (P.q - ml1) * r[D + 1];
+        T ml1 = (P.t1 + sqrt_fast(P.t1sq + ((T)-2 * load(D)) * P.inv_A)) * P.neg_A;
+        T ml2 = (P.q - ml1) * load(D + 1);
         x1 = exp_(-ml1);
         x2 = exp_(-ml2);
         wx = (P.A * x1) * x2;
     }
     const T E_cm = sqrt_fast(x1 * x2) * P.e_collider;  // :226
-
-    // ---- intermediate masses: :448-509. K_i = K_0 * prod_{j<i} t_j, M_i = K_i + sum_{j>=i} m_j ----
-    T K[NF], M[NF];
-    {
-        const T K0 = E_cm - P.msum;
-        T prod = (T)1;
-        K[0] = K0;
-        // exponent of column i is NF-2-i (:405-407); unrolled so each solve has a compile-time exponent
-        [&]<int... I>(std::integer_sequence<int, I...>) {
-            ((prod *= solve_massvar<NF - 2 - I>(r[I]), K[I + 1] = K0 * prod), ...);
-        }(std::make_integer_sequence<int, NE>{});
-#pragma unroll
-        for (int i = 0; i <= NF - 2; ++i) M[i] = K[i] + P.msum_rev[i];
-        M[NF - 1] = P.m[NF - 1];
-        K[NF - 1] = (T)0;  // unused
-    }
-    T sM[NF], invM[NF];
-#pragma unroll
-    for (int k = 0; k <= NF - 2; ++k) {
-        sM[k] = rho_num(M[k], M[k + 1], P.m[k]);
-        invM[k] = rcp_fast(M[k]);
-    }
-    sM[NF - 1] = (T)0; invM[NF - 1] = (T)0;  // unused
     const bool quirks = (P.flags & MF_FLAG_REF_FP32_QUIRKS) != 0;
-    wgt = wx * rambo_weight<T, NF>(P, E_cm, K, M, sM, invM, quirks);
-
-    // ---- sequential two-body decays: :294-345 ----
-    T Q[4] = {M[0], (T)0, (T)0, (T)0};
-#pragma unroll
-    for (int k = 0; k <= NF - 2; ++k) {
-        const T qk = sM[k] * ((T)0.5 * invM[k]);  // 4 M_k rho(M_k, M_{k+1}, m_k)
-        const T ct = (T)2 * r[NE + 2 * k] - (T)1;
-        const T st = sqrt_fast(sub_rn((T)1, mul_rn(ct, ct)));
-        const T phi = (T)6.283185307179586 * r[NE + 2 * k + 1];
-        const T cp = cos_(phi);
-        const T sq = sqrt_fast(sub_rn((T)1, mul_rn(cp, cp)));
-        const T sp = (phi > (T)3.141592653589793) ? -sq : sq;
-        T p2[4], pb[4];
-        p2[1] = (qk * st) * cp;
-        p2[2] = (qk * st) * sp;
-        p2[3] = qk * ct;
-        const T m2 = P.m[k] * P.m[k];
-        p2[0] = sqrt_fast(rho2_3(p2[1], p2[2], p2[3]) + m2);
-        if (k == 0) {  // Q = (M_0, 0, 0, 0): the boost is the identity (beta = 0 exactly)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) pb[c] = p2[c];
-        } else {
-            const T iq = rcp_fast(Q[0]);
-            boost(p2, Q[1] * iq, Q[2] * iq, Q[3] * iq, pb);
-            pb[0] = sqrt_fast(rho2_3(pb[1], pb[2], pb[3]) + m2);
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) out[2 + k][c] = pb[c];
-        Q[1] -= pb[1]; Q[2] -= pb[2]; Q[3] -= pb[3];
-        Q[0] = sqrt_fast(rho2_3(Q[1], Q[2], Q[3]) + M[k + 1] * M[k + 1]);
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) out[NP - 1][c] = Q[c];
     {   // incoming partons :511-551
         T h = quirks ? (T)((float)E_cm / 2.0f) : E_cm / (T)2;
-        out[0][0] = h; out[0][1] = (T)0; out[0][2] = (T)0; out[0][3] = h;
-        out[1][0] = h; out[1][1] = (T)0; out[1][2] = (T)0; out[1][3] = -h;
+        T in1[4] = {h, (T)0, (T)0, h}, in2[4] = {h, (T)0, (T)0, -h};
+        emit(0, in1);
+        emit(1, in2);
     }
+    const T K0 = E_cm - P.msum;
+    T prod = (T)1, Kk = K0, Mk = K0 + P.msum_rev[0];
+    T Q[4] = {Mk, (T)0, (T)0, (T)0};
+    T num = (T)1, den = (T)1, f8 = (T)1, pw = (T)1;
+    [&]<int... I>(std::integer_sequence<int, I...>) {
+        (rambo_decay_step<T, NF, I>(P, load, emit, K0, prod, Kk, Mk, Q, num, den, f8, pw), ...);
+    }(std::make_integer_sequence<int, NF - 1>{});
+    emit(NP - 1, Q);
+    // weight: get_flatWeights (:111-140) * massive correction (:489-507), same product order as the reference
+    const T pr = div_fast(num, den);
+    T w;
+    if (!quirks) {
+        w = P.flat_c * (ipow<NF - 2>(E_cm * E_cm) / P.flat_ff);
+        w *= f8;
+        w *= pr;
+        w *= pw;
+    } else {  // the reference's float32 in-place chain (:132, :489-507)
+        float e = (float)E_cm;
+        float e2 = __fmul_rn(e, e);
+        float wf = __fmul_rn(P.flat_c32, __fdiv_rn(ipow<NF - 2>(e2), P.flat_ff32));
+        wf = (float)((double)wf * (double)f8);
+        wf = (float)((double)wf * (double)pr);
+        wf = (float)((double)wf * (double)pw);
+        w = (T)wf;
+    }
+    wgt = wx * w;
+}
+
+// Array interface (chain kernels, lab-frame / cut epilogue): r = the event's 3NF-2 uniforms, out = all rows.
+template <typename T, int NF>
+MF_D void rambo_forward_event(const T (&r)[3 * NF - 2], const RamboParams<T, NF>& P, T (&out)[NF + 2][4], T& wgt,
+                              T& x1, T& x2) {
+    constexpr int NP = NF + 2;
+    rambo_forward_stream<T, NF>(
+        P, [&](int i) { return r[i]; },
+        [&](int j, const T (&p)[4]) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) out[j][c] = p[c];
+        },
+        wgt, x1, x2);
 
     // ---- lab frame (utils.py:180-202) for the cuts (:350-393) and/or as the requested output ----
     if (P.flags & (MF_FLAG_CUTS | MF_FLAG_LAB_FRAME)) {

@@ -13,32 +13,35 @@
 
 namespace mf {
 
-template <typename T, int NF>
-__global__ void __launch_bounds__(256, (NF <= 4 ? 3 : 2))
+// EPILOGUE == false: plain CM-frame output, every 4-momentum is stored the moment it is final (streaming core).
+// EPILOGUE == true : lab-frame output and / or cuts need the whole event first (array interface).
+template <typename T, int NF, bool EPILOGUE>
+__global__ void __launch_bounds__(256, (EPILOGUE ? (NF <= 4 ? 3 : 2) : 3))
 rambo_forward_kernel(const T* __restrict__ u, int64_t N, const __grid_constant__ RamboParams<T, NF> P,
                      T* __restrict__ momenta, T* __restrict__ weight, T* __restrict__ logweight,
                      T* __restrict__ x1o, T* __restrict__ x2o, int32_t* __restrict__ status) {
     constexpr int W = 3 * NF - 2, NP = NF + 2;
     const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ev >= N) return;
-
-    T r[W];
-    load_row<W>(u + ev * W, r);
-
-    if (status != nullptr) {
-        bool bad = false;
+    const T* __restrict__ urow = u + ev * W;
+    T* mo = momenta + ev * (NP * 4);
+    T wgt, x1, x2;
+    bool bad = false;
+    if constexpr (!EPILOGUE) {
+        rambo_forward_stream<T, NF>(
+            P, [&](int i) { T v = ld1(urow + i); bad |= (v != v); return v; },
+            [&](int j, const T (&p)[4]) { st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, wgt, x1, x2);
+    } else {
+        T r[W];
+        load_row<W>(urow, r);
 #pragma unroll
         for (int i = 0; i < W; ++i) bad |= (r[i] != r[i]);
-        if (bad) atomicOr(status, MF_ST_NAN_INPUT);
-    }
-
-    T out[NP][4], wgt, x1, x2;
-    rambo_forward_event<T, NF>(r, P, out, wgt, x1, x2);
-
-    // ---- stores ----
-    T* mo = momenta + ev * (NP * 4);
+        T out[NP][4];
+        rambo_forward_event<T, NF>(r, P, out, wgt, x1, x2);
 #pragma unroll
-    for (int k = 0; k < NP; ++k) st4(mo + 4 * k, out[k][0], out[k][1], out[k][2], out[k][3]);
+        for (int k = 0; k < NP; ++k) st4(mo + 4 * k, out[k][0], out[k][1], out[k][2], out[k][3]);
+    }
+    if (status != nullptr && bad) atomicOr(status, MF_ST_NAN_INPUT);
     weight[ev] = wgt;
     x1o[ev] = x1;
     x2o[ev] = x2;
@@ -52,8 +55,12 @@ static int launch_forward(const T* u, int64_t N, const T* masses, T e_collider, 
     if (N == 0) return MF_OK;
     const int threads = 256;
     const int64_t blocks = (N + threads - 1) / threads;
-    rambo_forward_kernel<T, NF><<<(unsigned)blocks, threads, 0, stream>>>(u, N, P, momenta, weight, logweight,
-                                                                          x1, x2, status);
+    if (P.flags & (MF_FLAG_CUTS | MF_FLAG_LAB_FRAME))
+        rambo_forward_kernel<T, NF, true><<<(unsigned)blocks, threads, 0, stream>>>(u, N, P, momenta, weight, logweight,
+                                                                                    x1, x2, status);
+    else
+        rambo_forward_kernel<T, NF, false><<<(unsigned)blocks, threads, 0, stream>>>(u, N, P, momenta, weight, logweight,
+                                                                                     x1, x2, status);
     return launch_status();
 }
 
