@@ -110,10 +110,13 @@ int mf_rambo_inverse_f32(const float* momenta, int64_t event_stride, const float
 /* K2 with the semantics of Compute_ParticlesTensor.get_PS, memflow/unfolding_flow/utils.py:1056-1152 (called every
  * training step, unfolding_flow.py:163): x1,x2 = (E +- pz)/e_collider of the reconstructed boost [N,4], clamped to [0,1];
  * masses = target_mass[order] (host [n]); no RAMBO weight: jac0 [N] or NULL receives 0 * jac_x1x2 like the reference;
- * mask [N] (uint8) or NULL = x out of range | |sum p|^2 > 1e-5 | any RAMBO variable outside [0,1]. */
+ * mask [N] (uint8) or NULL = x out of range | |sum p|^2 > 1e-5 | any RAMBO variable outside [0,1].
+ * Fused epilogue of the caller (unfolding_flow.py:170-171, Dataset_Parton_Level.py:428-431): if logit_scaled != NULL,
+ * logit_scaled[N, 3n-2] = (torch.logit(ps, eps=logit_eps) - logit_mean) / logit_scale (host [3n-2] each; NULL = 0 / 1). */
 int mf_get_ps_f64(const double* momenta, int64_t event_stride, const double* boost, int64_t N, int n_final,
                   const int32_t* order, const double* target_mass, double e_collider, double* ps, double* jac0,
-                  uint8_t* mask, mf_stream_t stream);
+                  uint8_t* mask, double logit_eps, const double* logit_mean, const double* logit_scale,
+                  double* logit_scaled, mf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3 / K4  monotonic rational-quadratic spline, zuko.transforms.MonotonicRQSTransform

@@ -23,6 +23,9 @@ template <typename T, int NF> struct RamboParams {
     T cut_pt, cut_dr, cut_eta;
     int order[NF];
     uint32_t flags;
+    // get_PS epilogue (memflow/unfolding_flow/unfolding_flow.py:170-171): logit(ps, eps) then (x - mean) / scale
+    T logit_eps;
+    T lmean[3 * NF - 2], lscale[3 * NF - 2];
 };
 
 // rambo_generator.py:145-149 rho(M,N,m) = sqrt((M^2-(N+m)^2)(M^2-(N-m)^2)) / (8 M^2)

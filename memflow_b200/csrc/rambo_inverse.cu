@@ -15,7 +15,8 @@ __global__ void __launch_bounds__(256, (NF <= 4 ? 3 : 2))
 rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const T* __restrict__ x1a,
                      const T* __restrict__ x2a, int64_t N, const __grid_constant__ RamboParams<T, NF> P,
                      T* __restrict__ ps, T* __restrict__ prob, T* __restrict__ logprob,
-                     int32_t* __restrict__ status, const T* __restrict__ boost_reco, uint8_t* __restrict__ mask) {
+                     int32_t* __restrict__ status, const T* __restrict__ boost_reco, uint8_t* __restrict__ mask,
+                     T* __restrict__ logit_out) {
     constexpr int D = 3 * NF - 4, W = D + 2;
     const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ev >= N) return;
@@ -106,6 +107,15 @@ rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const 
         store_row<W>(ps + ev * W, r);
         if (prob != nullptr) prob[ev] = (T)0 * jacinv;
         if (mask != nullptr) mask[ev] = problem ? 1 : 0;
+        if (logit_out != nullptr) {  // torch.logit(ps, eps) and affine scaling, fused (unfolding_flow.py:170-171)
+            const T lo = P.logit_eps, hi = (T)1 - P.logit_eps;
+#pragma unroll
+            for (int c = 0; c < W; ++c) {
+                T z = r[c] < lo ? lo : (r[c] > hi ? hi : r[c]);
+                r[c] = (log_(z / ((T)1 - z)) - P.lmean[c]) / P.lscale[c];
+            }
+            store_row<W>(logit_out + ev * W, r);
+        }
         return;
     }
     const T E_cm = sqrt_fast(x1 * x2) * P.e_collider;
@@ -134,8 +144,11 @@ template <typename T, int NF>
 static int launch_inverse(const T* momenta, int64_t event_stride, const T* x1, const T* x2, int64_t N,
                           const int32_t* order, const T* masses, const T* target_mass, T e_collider,
                           uint32_t flags, T* ps, T* prob, T* logprob, int32_t* status, cudaStream_t stream,
-                          const T* boost = nullptr, uint8_t* mask = nullptr, bool permute_target = false) {
+                          const T* boost = nullptr, uint8_t* mask = nullptr, bool permute_target = false,
+                          T logit_eps = (T)0, const T* lmean = nullptr, const T* lscale = nullptr, T* logit_out = nullptr) {
     RamboParams<T, NF> P{};
+    P.logit_eps = logit_eps;
+    for (int c = 0; c < 3 * NF - 2; ++c) { P.lmean[c] = lmean ? lmean[c] : (T)0; P.lscale[c] = lscale ? lscale[c] : (T)1; }
     bool seen[NF] = {};
     for (int i = 0; i < NF; ++i) {
         int o = order ? order[i] : i;
@@ -178,7 +191,7 @@ static int launch_inverse(const T* momenta, int64_t event_stride, const T* x1, c
     const int threads = 256;
     const int64_t blocks = (N + threads - 1) / threads;
     rambo_inverse_kernel<T, NF><<<(unsigned)blocks, threads, 0, stream>>>(momenta, event_stride, x1, x2, N, P, ps,
-                                                                          prob, logprob, status, boost, mask);
+                                                                          prob, logprob, status, boost, mask, logit_out);
     return launch_status();
 }
 
@@ -205,7 +218,8 @@ static int inverse_dispatch(const T* momenta, int64_t event_stride, const T* x1,
 
 template <typename T>
 static int getps_dispatch(const T* momenta, int64_t event_stride, const T* boost, int64_t N, int n, const int32_t* order,
-                          const T* target_mass, T e_collider, T* ps, T* jac0, uint8_t* mask, cudaStream_t stream) {
+                          const T* target_mass, T e_collider, T* ps, T* jac0, uint8_t* mask, T logit_eps, const T* lmean,
+                          const T* lscale, T* logit_out, cudaStream_t stream) {
     if (N < 0 || target_mass == nullptr) return MF_E_BADARG;
     if (n < MF_MIN_FINAL || n > MF_MAX_FINAL) return MF_E_NFINAL;
     if (N > 0 && (!momenta || !boost || !ps)) return MF_E_BADARG;
@@ -215,7 +229,7 @@ static int getps_dispatch(const T* momenta, int64_t event_stride, const T* boost
     if (!aligned(momenta, 4 * sizeof(T)) || !aligned(boost, 4 * sizeof(T)) || !aligned(ps, row_align)) return MF_E_ALIGN;
     switch (n) {
 #define MF_CASE(NF) \
-    case NF: return launch_inverse<T, NF>(momenta, event_stride, nullptr, nullptr, N, order, target_mass, target_mass, e_collider, 0u, ps, jac0, nullptr, nullptr, stream, boost, mask, true);
+    case NF: return launch_inverse<T, NF>(momenta, event_stride, nullptr, nullptr, N, order, target_mass, target_mass, e_collider, 0u, ps, jac0, nullptr, nullptr, stream, boost, mask, true, logit_eps, lmean, lscale, logit_out);
         MF_CASE(3) MF_CASE(4) MF_CASE(5) MF_CASE(6) MF_CASE(7) MF_CASE(8)
 #undef MF_CASE
     }
@@ -226,9 +240,11 @@ static int getps_dispatch(const T* momenta, int64_t event_stride, const T* boost
 
 extern "C" int mf_get_ps_f64(const double* momenta, int64_t event_stride, const double* boost, int64_t N, int n_final,
                              const int32_t* order, const double* target_mass, double e_collider, double* ps,
-                             double* jac0, uint8_t* mask, mf_stream_t stream) {
+                             double* jac0, uint8_t* mask, double logit_eps, const double* logit_mean,
+                             const double* logit_scale, double* logit_scaled, mf_stream_t stream) {
+    if (logit_scaled && !mf::aligned(logit_scaled, 8)) return MF_E_ALIGN;
     return mf::getps_dispatch<double>(momenta, event_stride, boost, N, n_final, order, target_mass, e_collider, ps, jac0,
-                                      mask, (cudaStream_t)stream);
+                                      mask, logit_eps, logit_mean, logit_scale, logit_scaled, (cudaStream_t)stream);
 }
 
 extern "C" int mf_rambo_inverse_f64(const double* momenta, int64_t event_stride, const double* x1, const double* x2,

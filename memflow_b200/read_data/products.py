@@ -1,0 +1,51 @@
+"""The phase-space tensors MEMFlow caches on disk for every training.
+
+Reference: `Dataset_Parton_Level.get_PS_intermediateParticles(_onShell)`,
+memflow/read_data/Dataset_Parton_Level.py:410-463. Only the tensor computation is mirrored here -- parquet /
+awkward reading and `torch.save` file handling stay with the caller (I/O is out of scope).
+The inverse map runs on the K2 kernel (2M-event files in milliseconds); the returned dict uses the reference's
+on-disk names as keys.
+"""
+import torch
+
+from ..phasespace.phasespace import PhaseSpace
+
+M_HIGGS = 125.25
+M_TOP = 172.5
+M_GLUON = 1e-5
+
+
+def phasespace_products(momenta_HttISR, boost, on_shell=True, E_CM=13000, masses=None, pdgs=(25, 6, -6, 21)):
+    """momenta_HttISR [N, 4, 4] (H, t, tbar, ISR; CM frame, E,px,py,pz), boost [N, 1, 4] or [N, 4] -> dict.
+
+    on_shell=True  (:410-446): minimal-energy fix of the boost (:418-420), x1/x2 clamped to [0,1], plus
+                   logit(ps, eps=5e-5), its nan-mean / 5*nan-std scaling and the scaled logits.
+    on_shell=False (:448-463): plain x1/x2, ps and det-jacobian only.
+    """
+    dev = momenta_HttISR.device
+    if masses is None:
+        masses = torch.tensor([M_HIGGS, M_TOP, M_TOP, M_GLUON], dtype=torch.float64)
+    masses = torch.as_tensor(masses, dtype=torch.float64)
+    ps_gen = PhaseSpace(E_CM, [21, 21], list(pdgs), final_masses=masses, dev=dev)
+    b = boost.reshape(boost.shape[0], -1, 4)[:, 0, :].to(torch.float64).clone()
+    suffix = "_onShell" if on_shell else ""
+    if on_shell:
+        msum = float(masses.sum())
+        e, pz = b[:, 0], b[:, 3]
+        b[:, 0] = torch.where(torch.sqrt(e ** 2 - pz ** 2) < msum, torch.sqrt(pz ** 2 + msum ** 2 + 1e-3), e)
+        x1 = torch.clamp((b[:, 0] + b[:, 3]) / E_CM, min=0.0, max=1.0)
+        x2 = torch.clamp((b[:, 0] - b[:, 3]) / E_CM, min=0.0, max=1.0)
+    else:
+        x1 = (b[:, 0] + b[:, 3]) / E_CM
+        x2 = (b[:, 0] - b[:, 3]) / E_CM
+    ps, detjinv = ps_gen.get_ps_from_momenta(momenta_HttISR, x1, x2)
+    out = {"phasespace_intermediateParticles" + suffix: ps,
+           "phasespace_rambo_detjacobian" + suffix: detjinv}
+    if on_shell:
+        logit_ps = torch.logit(ps, eps=5e-5)
+        mean = logit_ps.nanmean(0)
+        scale = torch.sqrt(torch.nanmean(logit_ps ** 2, 0) - mean ** 2) * 5
+        out["phasespace_intermediateParticles_onShell_logit"] = logit_ps
+        out["phasespace_intermediateParticles_onShell_logit_scaled"] = (logit_ps - mean) / scale
+        out["mean_std_phasespace_intermediateParticles_onShell_logit"] = (mean, scale)
+    return out

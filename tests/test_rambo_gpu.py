@@ -270,3 +270,41 @@ def test_get_ps_vs_reference_golden(oracle, golden_dir):
     assert (mask.cpu().numpy() != omask).mean() < 1e-4
     assert np.nanquantile(np.abs(ps.cpu().numpy() - ops), 0.999) < TOL64
     assert float(jac.abs().max()) == 0.0
+    # fused logit + affine scaling epilogue == the reference's next two torch lines (unfolding_flow.py:170-171)
+    g_ = torch.Generator().manual_seed(5)
+    mean = torch.randn(10, dtype=torch.float64, generator=g_)
+    scale = torch.rand(10, dtype=torch.float64, generator=g_) + 0.5
+    ps2, _, _, lps = Compute_ParticlesTensor.get_PS(torch.from_numpy(om[:, 2:]).cuda(), torch.from_numpy(b).cuda(), E_CM=E,
+                                                    logit_eps=5e-5, logit_mean=mean, logit_scale=scale)
+    assert torch.equal(ps2, ps)
+    ref = (torch.logit(ps.cpu(), eps=5e-5) - mean) / scale
+    okm = ~torch.isnan(ref)
+    assert torch.equal(torch.isnan(lps.cpu()), torch.isnan(ref))
+    assert float((lps.cpu() - ref)[okm].abs().max()) < 1e-11
+
+
+def test_dataset_products(oracle):
+    """the tensors Dataset_Parton_Level.py:410-463 caches, from K2 (values vs the oracle's inverse)."""
+    from memflow_b200.read_data import phasespace_products
+    n, N = 4, 20_000
+    u = rand_u(N, n, 41)
+    om, ow, ox1, ox2 = oracle.rambo_forward(u.numpy(), MASSES[n], E)
+    boost = np.stack((E / 2 * (ox1 + ox2), 0 * ox1, 0 * ox1, E / 2 * (ox1 - ox2)), axis=1)[:, None, :]
+    out = phasespace_products(torch.from_numpy(om[:, 2:]).cuda(), torch.from_numpy(boost).cuda(), on_shell=True,
+                              masses=MASSES[n])
+    keys = {"phasespace_intermediateParticles_onShell", "phasespace_rambo_detjacobian_onShell",
+            "phasespace_intermediateParticles_onShell_logit", "phasespace_intermediateParticles_onShell_logit_scaled",
+            "mean_std_phasespace_intermediateParticles_onShell_logit"}
+    assert set(out) == keys
+    x1 = np.clip((boost[:, 0, 0] + boost[:, 0, 3]) / E, 0, 1)
+    x2 = np.clip((boost[:, 0, 0] - boost[:, 0, 3]) / E, 0, 1)
+    ops, oprob, _ = oracle.rambo_inverse(om[:, 2:], x1, x2, MASSES[n], E)
+    ps = out["phasespace_intermediateParticles_onShell"].cpu().numpy()
+    assert np.nanquantile(np.abs(ps - ops), 0.999) < TOL64
+    dl = np.abs(np.log(out["phasespace_rambo_detjacobian_onShell"].cpu().numpy()) - np.log(oprob))
+    assert np.nanquantile(dl, 0.99) < TOL64
+    sc = out["phasespace_intermediateParticles_onShell_logit_scaled"]
+    assert float(sc.nanmean(0).abs().max()) < 1e-9 and float(sc[~sc.isnan()].abs().max()) < 5
+    plain = phasespace_products(torch.from_numpy(om[:, 2:]).cuda(), torch.from_numpy(boost).cuda(), on_shell=False,
+                                masses=MASSES[n])
+    assert set(plain) == {"phasespace_intermediateParticles", "phasespace_rambo_detjacobian"}
