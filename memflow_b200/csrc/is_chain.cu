@@ -151,8 +151,8 @@ is_chain_kernel(const float* __restrict__ phi, int64_t N, int T, int K, RqsConst
 // The fused kernel above keeps everything on chip but carries the fp64 phase's register budget into the
 // fp32 spline phase; which one is faster is measured and selected by MF_CHAIN_MODE.
 // ---------------------------------------------------------------------------------------------
-template <int MINB>
-__global__ void __launch_bounds__(kChainThreads, MINB)
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 flow_sample_kernel(const float* __restrict__ phi, int64_t N, int F, int T, int K, RqsConst<float> C, int E, int stages,
                    int bulk_ok, uint64_t seed, uint64_t event_offset, double* __restrict__ u_out,
                    double* __restrict__ logq_out) {
@@ -163,8 +163,8 @@ flow_sample_kernel(const float* __restrict__ phi, int64_t N, int F, int T, int K
     const size_t tile_bytes_al = (tile_elems * sizeof(float) + 127) / 128 * 128;
     auto stage_ptr = [&](int st) { return reinterpret_cast<float*>(smem_raw + (size_t)st * tile_bytes_al); };
     unsigned char* tail = smem_raw + (size_t)stages * tile_bytes_al;
-    float* lsum = reinterpret_cast<float*>(tail);  // [kChainThreads]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lsum + kChainThreads);
+    float* lsum = reinterpret_cast<float*>(tail);  // [THREADS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lsum + THREADS);
 
     const int tid = threadIdx.x;
     const int64_t num_tiles = (N + E - 1) / E;
@@ -209,7 +209,7 @@ flow_sample_kernel(const float* __restrict__ phi, int64_t N, int F, int T, int K
             } else {
                 const float* src = phi + (size_t)t * transform_pitch + (size_t)tile * tile_elems;
                 const size_t ne = (size_t)nrows * PW;
-                for (size_t i = tid; i < ne; i += kChainThreads) sm[i] = __ldg(src + i);
+                for (size_t i = tid; i < ne; i += THREADS) sm[i] = __ldg(src + i);
                 __syncthreads();
             }
             if (row_active) {
@@ -282,7 +282,7 @@ static RqsConst<float> make_rqs_const(float bound, float slope) {
 }
 
 struct ChainGeom { int E, bulk_ok, sms, smem_max; };
-static ChainGeom chain_geometry(const float* phi, int64_t N, int F, int T, int K, int stages) {
+static ChainGeom chain_geometry(const float* phi, int64_t N, int F, int T, int K, int stages, int threads = kChainThreads) {
     ChainGeom g{};
     const int PW = 3 * K - 1;
     int dev = 0;
@@ -290,9 +290,9 @@ static ChainGeom chain_geometry(const float* phi, int64_t N, int F, int T, int K
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&g.smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    int E = kChainThreads / F;
+    int E = threads / F;
     if (E >= 32) E = E / 32 * 32;
-    const size_t extra = 2 * kChainThreads * sizeof(float) + 2 * sizeof(uint64_t) + 256;
+    const size_t extra = 2 * threads * sizeof(float) + 2 * sizeof(uint64_t) + 256;
     auto need = [&](int e) { return (((size_t)e * F * PW * sizeof(float) + 127) / 128 * 128) * stages + extra; };
     while (E > 1 && need(E) > (size_t)g.smem_max / 2) --E;
     while (E > 1 && need(E) > (size_t)g.smem_max) --E;
@@ -312,32 +312,31 @@ static int env_int(const char* name, int dflt) { const char* e = getenv(name); r
 // A: Philox base sample + T spline inverses -> u [N,F] fp64, log q [N]
 static int flow_sample_launch(const float* phi, int64_t N, int F, int T, int K, float bound, float slope, uint64_t seed,
                               uint64_t event_offset, double* u, double* logq, cudaStream_t stream) {
-    static const int minb = env_int("MF_CHAIN_MINB", 8), stages_env = env_int("MF_CHAIN_STAGES", 1);
+    static const int threads = env_int("MF_CHAIN_THREADS", 256), stages_env = env_int("MF_CHAIN_STAGES", 1);
     const int stages = stages_env == 2 ? 2 : 1;
-    const ChainGeom g = chain_geometry(phi, N, F, T, K, stages);
+    if (F > 64) return MF_E_SHAPE;
+    const int thr = (threads == 256 || F > 32) ? 256 : (threads == 64 && F <= 16 ? 64 : 128);
+    const ChainGeom g = chain_geometry(phi, N, F, T, K, stages, thr);
     if (g.E == 0) return MF_E_SHAPE;
     const int PW = 3 * K - 1;
     const RqsConst<float> C = make_rqs_const(bound, slope);
     const int64_t num_tiles = (N + g.E - 1) / g.E;
-    const size_t smem = (((size_t)g.E * F * PW * sizeof(float) + 127) / 128 * 128) * stages + kChainThreads * sizeof(float) +
+    const size_t smem = (((size_t)g.E * F * PW * sizeof(float) + 127) / 128 * 128) * stages + thr * sizeof(float) +
                         2 * sizeof(uint64_t) + 128;
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int ctas = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, kChainThreads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, thr, smem);
         if (ctas < 1) ctas = 1;
         int64_t grid = (int64_t)g.sms * ctas;
         if (grid > num_tiles) grid = num_tiles;
-        kern<<<(unsigned)grid, kChainThreads, smem, stream>>>(phi, N, F, T, K, C, g.E, stages, g.bulk_ok, seed, event_offset, u,
-                                                              logq);
+        kern<<<(unsigned)grid, thr, smem, stream>>>(phi, N, F, T, K, C, g.E, stages, g.bulk_ok, seed, event_offset, u, logq);
     };
-    switch (minb) {
-    case 4: go(flow_sample_kernel<4>); break;
-    case 5: go(flow_sample_kernel<5>); break;
-    case 6: go(flow_sample_kernel<6>); break;
-    default: go(flow_sample_kernel<8>); break;
-    }
+    // 32 registers per thread -> 2048 resident threads per SM for every CTA size
+    if (thr == 256) go(flow_sample_kernel<256, 8>);
+    else if (thr == 64) go(flow_sample_kernel<64, 32>);
+    else go(flow_sample_kernel<128, 16>);
     return launch_status();
 }
 

@@ -207,21 +207,42 @@ MF_D void rqs_prefix_row(const float (&e)[K], float S, float bound, int bin, flo
 }
 
 // ---------------------------------------------------------------------------------------------
-// Register-resident row for small compile-time K (the fused chain: K = 8..16). One thread, fully unrolled:
-// both softmax arrays are exponentiated once into registers; the bin is found by comparing the UNNORMALISED
-// running sum with v mapped into that space ((v/B+1)/2 * S), so no per-element normalisation, no stores;
-// the other coordinate's two knots are the prefix sums at bin / bin+1. fp32 only.
+// Register-resident row for small compile-time K (the sampling chain: K = 8..16). One thread, fully unrolled:
+// each softmax array is exponentiated once into registers; the bin is found by comparing the UNNORMALISED
+// running sum with v mapped into that space ((v/B+1)/2 * S), so there is no per-element normalisation; the
+// running sums go back to the row in place and the 4 knots of the selected bin are 4 indexed loads. fp32 only.
 // ---------------------------------------------------------------------------------------------
 template <int K, bool INV>
-MF_D void rqs_row_reg(const float* __restrict__ row, const RqsConst<float>& C, float v, float& out, float& ladj,
-                      int& bin) {
-    float es[K], eo[K];
-    const float Ss = rqs_exp_row<K>(row + (INV ? K : 0), C, es);  // searched array: heights (inverse) / widths (forward)
-    const float So = rqs_exp_row<K>(row + (INV ? 0 : K), C, eo);
-    float s0, s1, o0, o1;
-    bin = rqs_search_row<K>(es, Ss, C.bound, v, s0, s1);
+MF_D void rqs_row_reg(float* __restrict__ row, const RqsConst<float>& C, float v, float& out, float& ladj, int& bin) {
+    // searched array (heights for the inverse, widths for the forward): exponentiate into registers, running sums in
+    // registers, written back in place so that the two knots of the (data-dependent) bin are two indexed loads
+    float* rs = row + (INV ? K : 0);
+    float* ro = row + (INV ? 0 : K);
+    float e[K];
+    const float Ss = rqs_exp_row<K>(rs, C, e);
+    const float target = fmaf(v, 0.5f / C.bound, 0.5f) * Ss;  // v in units of the unnormalised cumulative sum
+    int cnt = (-C.bound < v) ? 1 : 0;
+    float c = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        c += e[k];
+        rs[k] = c;
+        cnt += (c < target) ? 1 : 0;
+    }
+    bin = cnt - 1;
     if (bin < 0 || bin >= K) { out = v; ladj = 0.0f; return; }
-    rqs_prefix_row<K>(eo, So, C.bound, bin, o0, o1);
+    const float So = rqs_exp_row<K>(ro, C, e);
+    c = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        c += e[k];
+        ro[k] = c;
+    }
+    const float is2 = 2.0f * FastMath<float>::rcp(Ss), io2 = 2.0f * FastMath<float>::rcp(So);
+    const float c_lo = bin > 0 ? rs[bin - 1] : 0.0f, c_hi = rs[bin];
+    const float o_lo = bin > 0 ? ro[bin - 1] : 0.0f, o_hi = ro[bin];
+    const float s0 = C.bound * fmaf(c_lo, is2, -1.0f), s1 = C.bound * fmaf(c_hi, is2, -1.0f);
+    const float o0 = C.bound * fmaf(o_lo, io2, -1.0f), o1 = C.bound * fmaf(o_hi, io2, -1.0f);
     const float x0 = INV ? o0 : s0, x1 = INV ? o1 : s1, y0 = INV ? s0 : o0, y1 = INV ? s1 : o1;
     rqs_eval_fast<INV>(row + 2 * K, K, C, bin, x0, x1, y0, y1, v, out, ladj);
 }

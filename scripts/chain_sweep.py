@@ -16,8 +16,8 @@ if len(sys.argv) > 1:
     for i in range(20): smp.run_chunk(phi, event_offset=i * N, acc=acc)
     b.record(); torch.cuda.synchronize()
     t = a.elapsed_time(b) / 20
-    print("MODE=%s STAGES=%s MINB=%s: %.3f ms  %.3e ev/s  %.0f GB/s" % (os.environ.get("MF_CHAIN_MODE"), os.environ.get("MF_CHAIN_STAGES"), os.environ.get("MF_CHAIN_MINB"), t, N / t * 1e3, 1624 * N / t / 1e6))
+    print("MODE=%s STAGES=%s THREADS=%s: %.3f ms  %.3e ev/s  %.0f GB/s" % (os.environ.get("MF_CHAIN_MODE"), os.environ.get("MF_CHAIN_STAGES"), os.environ.get("MF_CHAIN_MINB"), t, N / t * 1e3, 1624 * N / t / 1e6))
 else:
-    for mode, st, m in (("split", "1", "4"), ("split", "1", "5"), ("split", "1", "6"), ("split", "1", "8"), ("split", "2", "6")):
-        env = dict(os.environ, MF_CHAIN_MINB=m, MF_CHAIN_MODE=mode, MF_CHAIN_STAGES=st)
+    for mode, st, m in (("split", "1", "256"), ("split", "1", "256"), ("split", "1", "128")):
+        env = dict(os.environ, MF_CHAIN_MINB=m, MF_CHAIN_THREADS=m, MF_CHAIN_MODE=mode, MF_CHAIN_STAGES=st)
         subprocess.run([sys.executable, __file__, "x"], env=env)

@@ -308,3 +308,37 @@ def test_dataset_products(oracle):
     plain = phasespace_products(torch.from_numpy(om[:, 2:]).cuda(), torch.from_numpy(boost).cuda(), on_shell=False,
                                 masses=MASSES[n])
     assert set(plain) == {"phasespace_intermediateParticles", "phasespace_rambo_detjacobian"}
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_masses_and_energies(oracle, seed):
+    """Sweep over multiplicity, mass spectra (incl. exactly massless bodies) and collider energies."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(3, 9))
+    kinds = rng.integers(0, 3, n)
+    masses = [float({0: 0.0, 1: 10.0 ** rng.uniform(-3, 0.5), 2: rng.uniform(1.0, 200.0)}[int(k)]) for k in kinds]
+    if sum(masses) == 0.0:
+        masses[0] = 1.0   # the x1x2 map needs sum(m) > 0 (log of (sum m / sqrt(s))^2)
+    e_coll = float(10.0 ** rng.uniform(3.0, 5.0))
+    from memflow_b200.phasespace.phasespace import PhaseSpace
+    ps = PhaseSpace(e_coll, [21, 21], list(range(n)), final_masses=torch.tensor(masses, dtype=torch.float64), dev="cuda:0")
+    N = 20_000
+    u = rand_u(N, n, 500 + seed)
+    mom, w, x1, x2 = ps.get_momenta_from_ps(u.cuda())
+    om, ow, ox1, ox2 = oracle.rambo_forward(u.numpy(), masses, e_coll)
+    kappa = parity.conditioning(u.numpy(), om, n, masses)
+    err = parity.momenta_error(mom.cpu().numpy(), om, ox1, ox2, e_coll)
+    fin = np.isfinite(kappa) & np.isfinite(err)
+    assert fin.mean() > 0.99
+    assert np.nanmax(err[fin] / kappa[fin]) < TOL64, (n, masses, e_coll, np.nanmax(err[fin] / kappa[fin]))
+    assert np.nanquantile(err[fin], 0.9) < TOL64
+    okw = fin & np.isfinite(ow) & (ow > 0)
+    dl = np.abs(np.log(w.cpu().numpy()[okw]) - np.log(ow[okw]))
+    assert np.nanmax(dl / kappa[okw]) < TOL64 and np.nanquantile(dl, 0.9) < TOL64
+    back, prob = ps.generator.getPSpoint_batch(torch.from_numpy(om[:, 2:]).cuda(), torch.from_numpy(ox1).cuda(),
+                                               torch.from_numpy(ox2).cuda())
+    ops, oprob, _ = oracle.rambo_inverse(om[:, 2:], ox1, ox2, masses, e_coll)
+    d = np.abs(back.cpu().numpy() - ops).max(axis=1)
+    finb = fin & np.isfinite(d)
+    assert np.array_equal(np.isnan(back.cpu().numpy()), np.isnan(ops))
+    assert np.nanmax(d[finb] / kappa[finb]) < TOL64 and np.nanquantile(d[finb], 0.9) < TOL64
