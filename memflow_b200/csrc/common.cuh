@@ -54,7 +54,11 @@ MF_D float pow_(float a, float b) { return powf(a, b); }
 // the IEEE result except for rare last-bit ties. 0, inf, NaN and negative operands keep their IEEE results through a
 // final select (the MUFU seeds are IEEE-exact there); magnitudes outside [1e-280, 1e280] are not supported.
 // ---------------------------------------------------------------------------------------------
-MF_D bool in_fast_range(double x) { const double a = fabs(x); return a > 1e-280 && a < 1e280; }  // false for 0, inf, NaN
+// Range tests on the exponent field with integer instructions (a DSETP would occupy the half-rate FP64 pipe):
+// biased exponent in [93, 1953] <=> |x| in [2^-930, 2^931) ~ [1e-280, 1e280]; false for 0, denormals, inf, NaN.
+MF_D bool in_fast_range(double x) { return ((((unsigned)__double2hiint(x) >> 20) & 0x7ffu) - 93u) < 1861u; }
+MF_D bool in_fast_range_pos(double x) { return (((unsigned)__double2hiint(x) >> 20) - 93u) < 1861u; }  // and x > 0
+MF_D bool below_fast_max(double x) { return (((unsigned)__double2hiint(x) >> 20) & 0x7ffu) < 1954u; }   // |x| < 2^931, not NaN/inf
 MF_D double rcp_seed(double b) { double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b)); return r; }
 MF_D double rsqrt_seed(double x) { double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
 MF_D double rcp_fast(double b) {
@@ -75,7 +79,7 @@ MF_D double div_fast(double a, double b) {
     double q = a * r;
     const double rem = fma(-b, q, a);
     q = fma(rem, r, q);
-    return (in_fast_range(b) && fabs(a) < 1e280) ? q : a * r0;  // a/0, a/inf, inf/b, NaN keep their IEEE results
+    return (in_fast_range(b) && below_fast_max(a)) ? q : a * r0;  // a/0, a/inf, inf/b, NaN keep their IEEE results
 }
 MF_D float div_fast(float a, float b) { return a / b; }
 MF_D double rsqrt_fast(double x) {
@@ -84,7 +88,7 @@ MF_D double rsqrt_fast(double x) {
     double y = y0 * fma(-h * y0, y0, 1.5);
     y = y * fma(-h * y, y, 1.5);
     y = y * fma(-h * y, y, 1.5);
-    return (x > 1e-280 && x < 1e280) ? y : y0;
+    return in_fast_range_pos(x) ? y : y0;
 }
 MF_D float rsqrt_fast(float x) { return rsqrtf(x); }
 MF_D double sqrt_fast(double x) {
@@ -96,7 +100,7 @@ MF_D double sqrt_fast(double x) {
     double s = x * y;
     s = fma(0.5 * y, fma(-s, s, x), s);
     // outside the fast range: sqrt(+-0) = +-0, sqrt(inf) = inf, sqrt(negative or NaN) = NaN
-    return (x > 1e-280 && x < 1e280) ? s : ((x >= 0.0) ? x : __longlong_as_double(0x7ff8000000000000LL));
+    return in_fast_range_pos(x) ? s : ((x >= 0.0) ? x : __longlong_as_double(0x7ff8000000000000LL));
 }
 MF_D float sqrt_fast(float x) { return sqrtf(x); }
 
