@@ -243,7 +243,7 @@ flow_sample_kernel(const float* __restrict__ phi, int64_t N, int F, int T, int K
 }
 
 template <int NF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, int64_t N,
                 const __grid_constant__ RamboParams<double, NF> P, double inv_2s, double* __restrict__ acc,
                 void* workspace, double* __restrict__ momenta, double* __restrict__ weight, double* __restrict__ x1o,
@@ -253,32 +253,21 @@ rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, i
     double cnt = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ev < N; ev += stride) {
-        double r[F];
-        load_row<F>(u + ev * F, r);
-        double out[NP][4], jac, x1, x2;
-        rambo_forward_event<double, NF>(r, P, out, jac, x1, x2);
-        const double target = inv_2s / (x1 * x2);
-        const double w = target * jac / exp(__ldg(logq + ev));
+        const double* __restrict__ urow = u + ev * F;
+        double* mo = momenta ? momenta + ev * (NP * 4) : nullptr;
+        double jac, x1, x2;
+        // streaming core (rambo.cuh): O(1) live state; momenta leave the registers only if they were asked for
+        rambo_forward_stream<double, NF>(
+            P, [&](int i) { return ld1(urow + i); },
+            [&](int j, const double (&p)[4]) { if (mo) st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, jac, x1, x2);
+        const double target = inv_2s * rcp_fast(x1 * x2);  // 1 / (2 x1 x2 s): ME = pdf = 1
+        const double w = target * jac * exp(-__ldg(logq + ev));
         if (target > 0.0 && jac == jac) { k1.add(w); k2.add(w * w); cnt += 1.0; }
-        if (momenta) {
-#pragma unroll
-            for (int k = 0; k < NP; ++k) st4(momenta + ev * (NP * 4) + 4 * k, out[k][0], out[k][1], out[k][2], out[k][3]);
-        }
         if (weight) weight[ev] = jac;
         if (x1o) x1o[ev] = x1;
         if (x2o) x2o[ev] = x2;
     }
     grid_accumulate<256>(k1.value(), k2.value(), cnt, acc, workspace);
-}
-
-static RqsConst<float> make_rqs_const(float bound, float slope) {
-    RqsConst<float> C;
-    C.bound = bound;
-    C.clip = slope > 0.0f ? 1 : 0;
-    const double L = C.clip ? std::log((double)slope) : 1.0;
-    C.two_over_L = C.clip ? (float)(2.0 / L) : 0.0f;
-    C.one_over_L = C.clip ? (float)(1.0 / L) : 0.0f;
-    return C;
 }
 
 struct ChainGeom { int E, bulk_ok, sms, smem_max; };
@@ -319,7 +308,7 @@ static int flow_sample_launch(const float* phi, int64_t N, int F, int T, int K, 
     const ChainGeom g = chain_geometry(phi, N, F, T, K, stages, thr);
     if (g.E == 0) return MF_E_SHAPE;
     const int PW = 3 * K - 1;
-    const RqsConst<float> C = make_rqs_const(bound, slope);
+    const RqsConst<float> C = make_rqs_const<float>(bound, slope);
     const int64_t num_tiles = (N + g.E - 1) / g.E;
     const size_t smem = (((size_t)g.E * F * PW * sizeof(float) + 127) / 128 * 128) * stages + thr * sizeof(float) +
                         2 * sizeof(uint64_t) + 128;
@@ -334,7 +323,10 @@ static int flow_sample_launch(const float* phi, int64_t N, int F, int T, int K, 
         kern<<<(unsigned)grid, thr, smem, stream>>>(phi, N, F, T, K, C, g.E, stages, g.bulk_ok, seed, event_offset, u, logq);
     };
     // 32 registers per thread -> 2048 resident threads per SM for every CTA size
-    if (thr == 256) go(flow_sample_kernel<256, 8>);
+    static const int minb = env_int("MF_CHAIN_MINB", 8);
+    if (thr == 256 && minb == 6) go(flow_sample_kernel<256, 6>);
+    else if (thr == 256 && minb == 5) go(flow_sample_kernel<256, 5>);
+    else if (thr == 256) go(flow_sample_kernel<256, 8>);
     else if (thr == 64) go(flow_sample_kernel<64, 32>);
     else go(flow_sample_kernel<128, 16>);
     return launch_status();
@@ -390,7 +382,7 @@ static int chain_launch(const float* phi, int64_t N, int T, int K, float bound, 
     const int PW = 3 * K - 1;
     const size_t smem = (((size_t)g.E * F * PW * sizeof(float) + 127) / 128 * 128) * 2 + 2 * kChainThreads * sizeof(float) +
                         2 * sizeof(uint64_t) + 256;
-    const RqsConst<float> C = make_rqs_const(bound, slope);
+    const RqsConst<float> C = make_rqs_const<float>(bound, slope);
     const RamboParams<double, NF> P = make_forward_params<double, NF>(masses, e_collider, nullptr, flags & ~MF_FLAG_CUTS);
     const double inv_2s = 1.0 / (2.0 * e_collider * e_collider);
     const int64_t num_tiles = (N + g.E - 1) / g.E;

@@ -260,12 +260,7 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
                 if (e > 0) ept = e; else bulk_ok = 0;
             }
             const size_t smem = need(ept);
-            RqsConst<float> C;
-            C.bound = bound;
-            C.clip = slope > 0.0f ? 1 : 0;
-            const double L = C.clip ? std::log((double)slope) : 1.0;
-            C.two_over_L = C.clip ? (float)(2.0 / L) : 0.0f;
-            C.one_over_L = C.clip ? (float)(1.0 / L) : 0.0f;
+            const RqsConst<float> C = make_rqs_const<float>((float)bound, (float)slope);
             const int64_t num_tiles = (B + ept - 1) / ept;
             auto go = [&](auto kern) {
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -311,12 +306,7 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
         if (e > 0) ept = e; else bulk_ok = 0;
     }
     const size_t smem = need(ept, stages);
-    RqsConst<T> C;
-    C.bound = bound;
-    C.clip = slope > (T)0 ? 1 : 0;
-    const double L = C.clip ? std::log((double)slope) : 1.0;
-    C.two_over_L = C.clip ? (T)(2.0 / L) : (T)0;
-    C.one_over_L = C.clip ? (T)(1.0 / L) : (T)0;
+    const RqsConst<T> C = make_rqs_const<T>(bound, slope);
     const int64_t num_tiles = (B + ept - 1) / ept;
     int ctas_per_sm = (int)((size_t)smem_max / smem);
     if (ctas_per_sm < 1) ctas_per_sm = 1;

@@ -10,6 +10,8 @@
 //   epilogue (one lane)  gather the 4 knots + 2 derivatives of the selected bin, evaluate.
 // Only the two derivatives of the selected bin are exponentiated (the reference exponentiates all K-1).
 #pragma once
+#include <cmath>
+
 #include "common.cuh"
 
 namespace mf {
@@ -40,8 +42,24 @@ template <typename T> struct RqsConst {
     T bound;
     T two_over_L;  // 2 / log(slope)   (soft clip of widths/heights), 0 when clip disabled
     T one_over_L;  // 1 / log(slope)   (soft clip of derivatives)
+    // exp(a / (1 + |a| c)) = exp2(a / (ln2 + |a| c ln2)): the log2(e) factor folded into the reciprocal's argument
+    T ln2, k1w, k1d;  // ln 2, |2/L| ln 2, |1/L| ln 2
     int clip;      // slope > 0
 };
+
+template <typename T> inline RqsConst<T> make_rqs_const(T bound, T slope) {
+    RqsConst<T> C;
+    C.bound = bound;
+    C.clip = slope > (T)0 ? 1 : 0;
+    const double L = C.clip ? std::log((double)slope) : 1.0;
+    const double ln2 = 0.6931471805599453;
+    C.two_over_L = C.clip ? (T)(2.0 / L) : (T)0;
+    C.one_over_L = C.clip ? (T)(1.0 / L) : (T)0;
+    C.ln2 = (T)ln2;
+    C.k1w = C.clip ? (T)(std::fabs(2.0 / L) * ln2) : (T)0;
+    C.k1d = C.clip ? (T)(std::fabs(1.0 / L) * ln2) : (T)0;
+    return C;
+}
 
 MF_D double soft_clip(double a, double c) { return a / (1.0 + fabs(a * c)); }
 MF_D float soft_clip(float a, float c) { return a * FastMath<float>::rcp(fmaf(fabsf(a), fabsf(c), 1.0f)); }  // 1 FFMA (|.| modifiers)
@@ -125,13 +143,27 @@ MF_D void rqs_row_1lane(T* __restrict__ row, int K, const RqsConst<T>& C, T v, T
     rqs_eval<T, INV>(row, row + K, row + 2 * K, K, C, bin, v, out, ladj);
 }
 
+// exp(soft_clip(a)) in 4 instructions: FFMA (|a| modifier), MUFU.RCP, FMUL, MUFU.EX2
+MF_D float exp_clip_w(float a, const RqsConst<float>& C) {
+    float r, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(fabsf(a), C.k1w, C.ln2)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * r));
+    return e;
+}
+MF_D float exp_clip_d(float a, const RqsConst<float>& C) {
+    float r, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(fabsf(a), C.k1d, C.ln2)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * r));
+    return e;
+}
+
 // Rational quadratic of one bin from its 4 knot coordinates (fp32, reciprocal-multiply instead of divisions).
 template <bool INV>
 MF_D void rqs_eval_fast(const float* __restrict__ d, int K, const RqsConst<float>& C, int bin, float x0, float x1, float y0,
                         float y1, float v, float& out, float& ladj) {
     float d0 = 1.0f, d1 = 1.0f;
-    if (bin > 0) { float t = d[bin - 1]; if (C.clip) t = soft_clip(t, C.one_over_L); d0 = FastMath<float>::exp(t); }
-    if (bin < K - 1) { float t = d[bin]; if (C.clip) t = soft_clip(t, C.one_over_L); d1 = FastMath<float>::exp(t); }
+    if (bin > 0) d0 = C.clip ? exp_clip_d(d[bin - 1], C) : FastMath<float>::exp(d[bin - 1]);
+    if (bin < K - 1) d1 = C.clip ? exp_clip_d(d[bin], C) : FastMath<float>::exp(d[bin]);
     const float dx = x1 - x0, dy = y1 - y0;
     const float rdx = FastMath<float>::rcp(dx);
     const float s = dy * rdx;
@@ -162,7 +194,7 @@ MF_D float rqs_exp_row(const float* __restrict__ arr, const RqsConst<float>& C, 
     float S = 0.0f;
     if (C.clip) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) { e[k] = FastMath<float>::exp(soft_clip(arr[k], C.two_over_L)); S += e[k]; }
+        for (int k = 0; k < K; ++k) { e[k] = exp_clip_w(arr[k], C); S += e[k]; }
     } else {
         float m = arr[0];
 #pragma unroll
@@ -214,30 +246,53 @@ MF_D void rqs_prefix_row(const float (&e)[K], float S, float bound, int bin, flo
 // ---------------------------------------------------------------------------------------------
 template <int K, bool INV>
 MF_D void rqs_row_reg(float* __restrict__ row, const RqsConst<float>& C, float v, float& out, float& ladj, int& bin) {
-    // searched array (heights for the inverse, widths for the forward): exponentiate into registers, running sums in
-    // registers, written back in place so that the two knots of the (data-dependent) bin are two indexed loads
+    // x = searched array (heights for the inverse, widths for the forward), y = the other one, handled as float2
+    // pairs so that the multiply and the two running sums issue as packed FMUL2 / FADD2 (sm_100 f32x2). One pass:
+    // exponentiate, accumulate, write the running sums back in place; then a binary search for the bin and 4 indexed
+    // loads for its knots.
     float* rs = row + (INV ? K : 0);
     float* ro = row + (INV ? 0 : K);
-    float e[K];
-    const float Ss = rqs_exp_row<K>(rs, C, e);
-    const float target = fmaf(v, 0.5f / C.bound, 0.5f) * Ss;  // v in units of the unnormalised cumulative sum
-    int cnt = (-C.bound < v) ? 1 : 0;
-    float c = 0.0f;
+    float2 c = make_float2(0.0f, 0.0f);  // running sums (searched, other); live state is O(1) in K
+    if (C.clip) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        c += e[k];
-        rs[k] = c;
-        cnt += (c < target) ? 1 : 0;
+        for (int k = 0; k < K; ++k) {
+            const float2 a = make_float2(rs[k], ro[k]);
+            float2 r, e;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(fmaf(fabsf(a.x), C.k1w, C.ln2)));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(fmaf(fabsf(a.y), C.k1w, C.ln2)));
+            const float2 y = __fmul2_rn(a, r);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(y.x));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(y.y));
+            c = __fadd2_rn(c, e);
+            rs[k] = c.x;
+            ro[k] = c.y;
+        }
+    } else {
+        float ms = rs[0], mo = ro[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) { ms = fmaxf(ms, rs[k]); mo = fmaxf(mo, ro[k]); }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            c = __fadd2_rn(c, make_float2(FastMath<float>::exp(rs[k] - ms), FastMath<float>::exp(ro[k] - mo)));
+            rs[k] = c.x;
+            ro[k] = c.y;
+        }
     }
+    const float Ss = c.x, So = c.y;
+    const float target = fmaf(v, 0.5f / C.bound, 0.5f) * Ss;  // v in units of the unnormalised cumulative sum
+    // number of running sums below the target: binary search on the (ascending) sums just written
+    int lo = 0, hi = K;
+#pragma unroll
+    for (int step = 0; (1 << step) <= K; ++step) {
+        const int mid = (lo + hi) >> 1;
+        const bool go_right = (lo < hi) && (rs[mid < K ? mid : K - 1] < target);
+        const bool go_left = (lo < hi) && !go_right;
+        lo = go_right ? mid + 1 : lo;
+        hi = go_left ? mid : hi;
+    }
+    const int cnt = ((-C.bound < v) ? 1 : 0) + lo;
     bin = cnt - 1;
     if (bin < 0 || bin >= K) { out = v; ladj = 0.0f; return; }
-    const float So = rqs_exp_row<K>(ro, C, e);
-    c = 0.0f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        c += e[k];
-        ro[k] = c;
-    }
     const float is2 = 2.0f * FastMath<float>::rcp(Ss), io2 = 2.0f * FastMath<float>::rcp(So);
     const float c_lo = bin > 0 ? rs[bin - 1] : 0.0f, c_hi = rs[bin];
     const float o_lo = bin > 0 ? ro[bin - 1] : 0.0f, o_hi = ro[bin];
