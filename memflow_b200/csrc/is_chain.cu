@@ -242,6 +242,112 @@ flow_sample_kernel(const float* __restrict__ phi, int64_t N, int F, int T, int K
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Flow-sample kernel for long rows (compile-time K = 32..64, e.g. the production flow F=10, K=40, T=6 of BASELINE
+// config 5): same two-sided register scheme as rqs_reg2_kernel (rqs.cu) -- thread t < 64 owns the searched (height)
+// array of row t, thread 64 + t the width array, both exponentiated once into registers -- chained over the T
+// transforms of a tile: the new x goes back to the searching side through shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128, 4)
+flow_sample_reg2_kernel(const float* __restrict__ phi, int64_t N, int F, int T, RqsConst<float> C, int E, int bulk_ok,
+                        uint64_t seed, uint64_t event_offset, double* __restrict__ u_out, double* __restrict__ logq_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int PW = 3 * K - 1;
+    const int rows = E * F;  // <= 64
+    const size_t tile_elems = (size_t)rows * PW;
+    const size_t tile_bytes_al = (tile_elems * sizeof(float) + 127) / 128 * 128;
+    float* sm = reinterpret_cast<float*>(smem_raw);
+    float4* xch = reinterpret_cast<float4*>(smem_raw + tile_bytes_al);  // [64] {bin, k0, k1, -}
+    float* xnext = reinterpret_cast<float*>(xch + 64);                   // [64] x after the current transform
+    float* lsum = xnext + 64;                                            // [64]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(lsum + 64);
+    const int tid = threadIdx.x, side = tid >> 6, row = tid & 63;
+    const int64_t num_tiles = (N + E - 1) / E;
+    const size_t transform_pitch = (size_t)N * F * PW;
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    auto tile_is_bulk = [&](int64_t tile) { return bulk_ok && (tile + 1) * (int64_t)E <= N; };
+    auto issue = [&](int64_t tile, int t) {
+        if (tid == 0 && tile < num_tiles && tile_is_bulk(tile)) {
+            const uint32_t bytes = (uint32_t)(tile_elems * sizeof(float));
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(sm, phi + (size_t)t * transform_pitch + (size_t)tile * tile_elems, bytes, bar);
+        }
+    };
+    uint32_t parity = 0u;
+    const double inv_2b = 1.0 / (2.0 * (double)C.bound);
+    int64_t tile = blockIdx.x;
+    issue(tile, T - 1);
+    for (; tile < num_tiles; tile += gridDim.x) {
+        const int64_t ev0 = tile * E;
+        const int nev = (int)((N - ev0) < E ? (N - ev0) : E);
+        const int nrows = nev * F;
+        const bool active = row < nrows;
+        const int e = row / F, f = row - e * F;
+        float x = 0.0f, ladj_acc = 0.0f;
+        if (active) {  // both sides draw the same base sample (counter = global event index)
+            const uint64_t gev = event_offset + (uint64_t)(ev0 + e);
+            Philox4 r4 = philox4x32_10((uint32_t)gev, (uint32_t)(gev >> 32), (uint32_t)(f >> 2), 0u, (uint32_t)seed,
+                                       (uint32_t)(seed >> 32));
+            const uint32_t bits = (f & 3) == 0 ? r4.x : ((f & 3) == 1 ? r4.y : ((f & 3) == 2 ? r4.z : r4.w));
+            x = C.bound * (2.0f * u01_from_bits(bits) - 1.0f);
+        }
+        for (int tt = 0; tt < T; ++tt) {
+            const int t = T - 1 - tt;
+            if (tile_is_bulk(tile)) {
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+            } else {
+                const float* src = phi + (size_t)t * transform_pitch + (size_t)tile * tile_elems;
+                const size_t ne = (size_t)nrows * PW;
+                for (size_t i = tid; i < ne; i += 128) sm[i] = __ldg(src + i);
+                __syncthreads();
+            }
+            float ev_[K];
+            float S = 1.0f;
+            const float* r = sm + (size_t)row * PW;
+            if (active) {
+                S = rqs_exp_row<K>(r + (side == 0 ? K : 0), C, ev_);  // inverse: heights are searched (side 0)
+                if (side == 0) {
+                    float k0, k1;
+                    const int bin = rqs_search_row<K>(ev_, S, C.bound, x, k0, k1);
+                    xch[row] = make_float4(__int_as_float(bin), k0, k1, 0.0f);
+                }
+            }
+            __syncthreads();
+            if (side == 1 && active) {
+                const float4 q = xch[row];
+                const int bin = __float_as_int(q.x);
+                float out = x, ladj = 0.0f;
+                if (bin >= 0 && bin < K) {
+                    float o0, o1;
+                    rqs_prefix_row<K>(ev_, S, C.bound, bin, o0, o1);
+                    rqs_eval_fast<true>(r + 2 * K, K, C, bin, o0, o1, q.y, q.z, x, out, ladj);
+                }
+                x = out;
+                ladj_acc += ladj;
+                xnext[row] = x;
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (tt + 1 < T) issue(tile, t - 1); else issue(tile + gridDim.x, T - 1);
+            if (side == 0 && active) x = xnext[row];
+        }
+        if (side == 1) {
+            lsum[row] = ladj_acc;
+            if (active) u_out[ev0 * F + row] = ((double)x + (double)C.bound) * inv_2b;
+        }
+        __syncthreads();
+        if (tid < nev) {
+            double lq = 0.0;
+            for (int j = 0; j < F; ++j) lq += (double)lsum[tid * F + j];
+            logq_out[ev0 + tid] = lq;
+        }
+        // lsum / xnext / xch are rewritten only after the next transform's first barrier
+    }
+}
+
 template <int NF>
 __global__ void __launch_bounds__(256, 3)
 rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, int64_t N,
@@ -304,6 +410,43 @@ static int flow_sample_launch(const float* phi, int64_t N, int F, int T, int K, 
     static const int threads = env_int("MF_CHAIN_THREADS", 256), stages_env = env_int("MF_CHAIN_STAGES", 1);
     const int stages = stages_env == 2 ? 2 : 1;
     if (F > 64) return MF_E_SHAPE;
+    if (K == 32 || K == 40 || K == 48 || K == 64) {  // long rows: two-sided register kernel
+        const int PWl = 3 * K - 1;
+        int dev = 0, sms = 148, smem_max = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const size_t extra = 64 * sizeof(float4) + 128 * sizeof(float) + sizeof(uint64_t) + 128;
+        auto need = [&](int e) { return ((size_t)e * F * PWl * sizeof(float) + 127) / 128 * 128 + extra; };
+        int E = 64 / F;
+        while (E > 1 && need(E) > (size_t)smem_max / 4) --E;
+        int bulk_ok = aligned(phi, 16) && (((size_t)N * F * PWl * sizeof(float)) % 16 == 0 || T == 1) ? 1 : 0;
+        if (bulk_ok) {
+            int e = E;
+            while (e > 0 && ((size_t)e * F * PWl * sizeof(float)) % 16 != 0) --e;
+            if (e > 0) E = e; else bulk_ok = 0;
+        }
+        const size_t smem_l = need(E);
+        const RqsConst<float> Cl = make_rqs_const<float>(bound, slope);
+        const int64_t tiles = (N + E - 1) / E;
+        auto gol = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            int ctas = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 128, smem_l);
+            if (ctas < 1) ctas = 1;
+            int64_t grid = (int64_t)sms * ctas;
+            if (grid > tiles) grid = tiles;
+            kern<<<(unsigned)grid, 128, smem_l, stream>>>(phi, N, F, T, Cl, E, bulk_ok, seed, event_offset, u, logq);
+        };
+        switch (K) {
+        case 32: gol(flow_sample_reg2_kernel<32>); break;
+        case 40: gol(flow_sample_reg2_kernel<40>); break;
+        case 48: gol(flow_sample_reg2_kernel<48>); break;
+        default: gol(flow_sample_reg2_kernel<64>); break;
+        }
+        return launch_status();
+    }
     const int thr = (threads == 256 || F > 32) ? 256 : (threads == 64 && F <= 16 ? 64 : 128);
     const ChainGeom g = chain_geometry(phi, N, F, T, K, stages, thr);
     if (g.E == 0) return MF_E_SHAPE;

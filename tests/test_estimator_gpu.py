@@ -32,7 +32,7 @@ def test_is_reduce_vs_oracle(oracle):
     assert acc.tolist() == [10.0, 10.0, 10.0]
 
 
-@pytest.mark.parametrize("n,T,K", [(3, 2, 10), (4, 3, 8), (3, 1, 16)])
+@pytest.mark.parametrize("n,T,K", [(3, 2, 10), (4, 3, 8), (3, 1, 16), (4, 2, 40), (3, 2, 64), (3, 2, 9)])
 def test_chain_vs_oracle_composition(oracle, n, T, K):
     """Fused chain == Philox -> K4 x T -> affine -> K1 -> weight -> K5 done step by step with the oracle."""
     from memflow_b200 import estimator as ES
@@ -54,7 +54,8 @@ def test_chain_vs_oracle_composition(oracle, n, T, K):
     # spline part is fp32: medians at fp32 precision, tails limited by narrow bins (tests/test_rqs_gpu.py)
     assert np.median(np.abs(ug - uo)) < 2e-7 and np.quantile(np.abs(ug - uo), 0.999) < 1e-4
     dq = np.abs(out["logq"].cpu().numpy() - lsum)
-    assert np.median(dq) < 2e-5 and np.quantile(dq, 0.99) < 2e-3
+    ksc = max(1.0, K / 10.0)   # narrower bins -> larger fp32 rounding of every log-det (both sides are fp32 here)
+    assert np.median(dq) < 2e-5 * ksc and np.quantile(dq, 0.99) < 2e-3 * ksc
     # phase-space part is fp64: feed the oracle the kernel's own u
     om, ow, ox1, ox2 = oracle.rambo_forward(ug, MASSES[n], E)
     kappa = parity.conditioning(ug, om, n, MASSES[n])
