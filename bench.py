@@ -206,6 +206,22 @@ def extras(torch, dev, hbm_peak):
         ti = timeit(lambda: TR.rqs_inverse(phi, x, bound=1.1))
         out["K3_rqs_forward_F20_K64_f32_1M"] = {"points_per_s": B / tf, "GBps": by * B / tf / 1e9, "frac_hbm": by * B / tf / 1e9 / hbm_peak}
         out["K4_rqs_inverse_F20_K64_f32_1M"] = {"points_per_s": B / ti, "GBps": by * B / ti / 1e9, "frac_hbm": by * B / ti / 1e9 / hbm_peak}
+        del phi, x
+        torch.cuda.empty_cache()
+        # BASELINE config 5 shape on this GPU: tt-bar-H + 1 jet (n=4), production flow F=10, K=40, T=6
+        from memflow_b200 import estimator as ES
+        T5, N5, F5, K5 = 6, 1 << 19, 10, 40
+        phi5 = torch.randn(T5, N5, F5, 3 * K5 - 1, device=dev, dtype=torch.float32)
+        smp5 = ES.ImportanceSampler([125.25, 172.5, 172.5, 1e-5], E_CM, seed=3, device=dev)
+        u5 = torch.empty(N5, F5, dtype=torch.float64, device=dev)
+        lq5 = torch.empty(N5, dtype=torch.float64, device=dev)
+        acc5 = ES.new_accumulator(dev)
+        ta = timeit(lambda: smp5.sample_flow(phi5, u=u5, logq=lq5))
+        tb = timeit(lambda: smp5.weigh(u5, lq5, acc=acc5))
+        by5 = T5 * F5 * (3 * K5 - 1) * 4
+        out["chain_config5_shape_n4_F10_K40_T6_512k"] = {
+            "points_per_s": N5 / (ta + tb), "flow_sample_GBps": by5 * N5 / ta / 1e9, "frac_hbm": by5 * N5 / ta / 1e9 / hbm_peak,
+            "algorithmic_bytes_per_event": by5, "ms_flow_sample": ta * 1e3, "ms_phase_space_and_reduce": tb * 1e3}
         out["note"] = "wrapper-level timings (include the output allocations of the Python API)"
     except Exception as e:  # extras must never break the headline line
         out["error"] = repr(e)

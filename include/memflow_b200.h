@@ -170,6 +170,18 @@ int mf_is_chain_f64(const float* phi, int64_t N, int n_final, int T, int K, floa
                     uint32_t flags, double* acc, void* workspace, double* u_out, double* logq,
                     double* momenta, double* weight, double* x1, double* x2, mf_stream_t stream);
 
+/* Two-body decay epilogues of the sampled propagators, cartesian or (E, pt, eta, phi) output:
+ *   mf_higgs_decay_f64: Compute_ParticlesTensor.higgs_decayProducts, memflow/unfolding_flow/utils.py:745-770
+ *                       parent [N] rows of 4 (row stride parent_stride elements), angles [N,2] = (eta, phi) of b1 in
+ *                       the Higgs rest frame -> out [N,3,4] = (H, b1, b2)
+ *   mf_top_decay_f64  : Compute_ParticlesTensor.top_decayProducts, memflow/unfolding_flow/utils.py:772-815
+ *                       b_angles / w_angles [N,2] (b in the top frame, q1 in the W frame) -> out [N,4,4] = (t, b, q1, q2) */
+int mf_higgs_decay_f64(const double* parent, int64_t parent_stride, const double* angles, int64_t N, double mass,
+                       int as_ptetaphi, double* out, mf_stream_t stream);
+int mf_top_decay_f64(const double* parent, int64_t parent_stride, const double* b_angles, const double* w_angles,
+                     int64_t N, double top_mass, double w_mass, double b_mass, int as_ptetaphi, double* out,
+                     mf_stream_t stream);
+
 /* The two stages of the chain as separate entry points (mf_is_chain_f64 runs them back to back):
  *  A  mf_flow_sample_f32: Philox base sample + T spline inverses -> u [N,F] (fp64, in [0,1]) and log q [N]
  *                         (flow().sample + flow().log_prob of TestFlows_ImportanceSampling.ipynb [45,50] in one pass)

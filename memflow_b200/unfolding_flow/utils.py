@@ -1,8 +1,11 @@
-"""`Compute_ParticlesTensor.get_PS` of memflow/unfolding_flow/utils.py:1056-1152 on the K2 kernel.
+"""The phase-space entries of `Compute_ParticlesTensor` (memflow/unfolding_flow/utils.py) on CUDA kernels:
 
-Only this method of the reference's 1100-line glue class is on the hot path (it is called every training
-step, memflow/unfolding_flow/unfolding_flow.py:163); the rest of the class (pt/eta/phi conversions, decay
-products, regression scalings) is model glue and out of scope.
+  get_PS               :1056-1152  K2 in get_PS mode (called every training step, unfolding_flow.py:163)
+  higgs_decayProducts  :745-770    H -> b b two-body decay + boost           
+  top_decayProducts    :772-815    t -> b W -> b q q' decays + boosts        
+
+The rest of the reference's 1100-line glue class (regression scalings, dataset-specific conversions) is model
+glue and out of scope.
 """
 import ctypes
 
@@ -64,3 +67,46 @@ class Compute_ParticlesTensor:
         if logit_eps is not None:
             return ps, jac0, mask.bool(), lps
         return ps, jac0, mask.bool()
+
+    @staticmethod
+    def _rows(p):
+        """[N,4] momenta as (tensor, row stride) readable in place by the kernels (32 B-aligned rows)."""
+        p = p.detach().to(torch.float64)
+        if not (p.dim() == 2 and p.shape[1] == 4 and p.stride(1) == 1 and p.stride(0) % 4 == 0 and p.stride(0) >= 4
+                and p.data_ptr() % 32 == 0):
+            p = p.contiguous()
+        return p, p.stride(0)
+
+    @staticmethod
+    def higgs_decayProducts(higgs_momenta, higgs_angles, higgs_mass=125.25, ptetaphi=True, device=None):
+        """(H, b1, b2) [N,3,4]: b1 has (eta, phi) = higgs_angles in the Higgs rest frame, E = m_H/2, b2 is back to back;
+        both boosted by the Higgs velocity. ptetaphi=True returns (E, pt, eta, phi) rows like the reference."""
+        require_cuda(higgs_momenta, "higgs_momenta")
+        dev = higgs_momenta.device
+        mom, stride = Compute_ParticlesTensor._rows(higgs_momenta)
+        ang = higgs_angles.detach().to(torch.float64).contiguous()
+        N = mom.shape[0]
+        out = torch.empty((N, 3, 4), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().mf_higgs_decay_f64(ptr(mom), ctypes.c_int64(stride), ptr(ang), ctypes.c_int64(N),
+                                           ctypes.c_double(float(higgs_mass)), ctypes.c_int(int(bool(ptetaphi))), ptr(out),
+                                           stream_ptr(dev)), "mf_higgs_decay_f64")
+        return out
+
+    @staticmethod
+    def top_decayProducts(top_momenta, top_b_angles, top_W_angles, top_mass=172.5, W_mass=80.4, b_mass=0.0, ptetaphi=True,
+                          device=None):
+        """(t, b, q1, q2) [N,4,4]: t -> b W in the top rest frame, W -> q1 q2 in the W rest frame, boosted in turn."""
+        require_cuda(top_momenta, "top_momenta")
+        dev = top_momenta.device
+        mom, stride = Compute_ParticlesTensor._rows(top_momenta)
+        ab = top_b_angles.detach().to(torch.float64).contiguous()
+        aw = top_W_angles.detach().to(torch.float64).contiguous()
+        N = mom.shape[0]
+        out = torch.empty((N, 4, 4), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().mf_top_decay_f64(ptr(mom), ctypes.c_int64(stride), ptr(ab), ptr(aw), ctypes.c_int64(N),
+                                         ctypes.c_double(float(top_mass)), ctypes.c_double(float(W_mass)),
+                                         ctypes.c_double(float(b_mass)), ctypes.c_int(int(bool(ptetaphi))), ptr(out),
+                                         stream_ptr(dev)), "mf_top_decay_f64")
+        return out

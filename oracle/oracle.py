@@ -121,6 +121,29 @@ def get_ps(momenta, boost, target_mass, e_collider, order=None):
     return ps, jac0, mask.astype(bool)
 
 
+def higgs_decay(parent, angles, mass=125.25, ptetaphi=True):
+    """memflow/unfolding_flow/utils.py:745-770: parent [N,4], angles [N,2] -> [N,3,4] = (H, b1, b2)."""
+    parent = np.ascontiguousarray(parent, dtype=np.float64)
+    angles = np.ascontiguousarray(angles, dtype=np.float64)
+    N = parent.shape[0]
+    out = np.empty((N, 3, 4), dtype=np.float64)
+    lib().mfo_higgs_decay(_dp(parent), _dp(angles), ctypes.c_int64(N), ctypes.c_double(mass), ctypes.c_int(int(ptetaphi)),
+                          _dp(out))
+    return out
+
+
+def top_decay(parent, b_angles, w_angles, top_mass=172.5, w_mass=80.4, b_mass=0.0, ptetaphi=True):
+    """memflow/unfolding_flow/utils.py:772-815: -> [N,4,4] = (t, b, q1, q2)."""
+    parent = np.ascontiguousarray(parent, dtype=np.float64)
+    b_angles = np.ascontiguousarray(b_angles, dtype=np.float64)
+    w_angles = np.ascontiguousarray(w_angles, dtype=np.float64)
+    N = parent.shape[0]
+    out = np.empty((N, 4, 4), dtype=np.float64)
+    lib().mfo_top_decay(_dp(parent), _dp(b_angles), _dp(w_angles), ctypes.c_int64(N), ctypes.c_double(top_mass),
+                        ctypes.c_double(w_mass), ctypes.c_double(b_mass), ctypes.c_int(int(ptetaphi)), _dp(out))
+    return out
+
+
 def _rqs(direction, phi, v, bound, slope):
     phi = np.ascontiguousarray(phi)
     dt = phi.dtype

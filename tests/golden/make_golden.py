@@ -15,6 +15,7 @@ restatement of upstream zuko) -> "parity unpinned" for the spline.
 import contextlib
 import io
 import json
+import math
 import os
 import sys
 import types
@@ -140,6 +141,25 @@ def main():
     np.savez_compressed(os.path.join(HERE, "get_ps_n4.npz"), mom=mom.numpy(), boost=boost.numpy(), target_mass=tmass.numpy(),
                         e_cm=np.float64(E_CM), **out)
     print("get_PS written; masked:", int(out["mask_id"].sum()))
+
+    # ---- decay products (memflow/unfolding_flow/utils.py:745-815) on lab-frame propagators ----
+    g3 = np.load(os.path.join(HERE, "rambo_n3.npz"))
+    mom3 = torch.from_numpy(g3["mom_clean"])
+    lab = utils.boost_to_lab_frame(mom3, torch.from_numpy(g3["x1_clean"]), torch.from_numpy(g3["x2_clean"]))
+    gen = torch.Generator().manual_seed(99)
+    def angles():
+        return torch.stack((torch.randn(N, generator=gen, dtype=torch.float64) * 1.5,
+                            (torch.rand(N, generator=gen, dtype=torch.float64) * 2 - 1) * math.pi), dim=1)
+    ha, tb, tw = angles(), angles(), angles()
+    dk = {"higgs": lab[:, 2].numpy(), "top": lab[:, 3].numpy(), "higgs_angles": ha.numpy(), "top_b_angles": tb.numpy(),
+          "top_W_angles": tw.numpy()}
+    for flag in (True, False):
+        tag = "ptetaphi" if flag else "cart"
+        dk["higgs_out_" + tag] = Compute_ParticlesTensor.higgs_decayProducts(lab[:, 2], ha, ptetaphi=flag).numpy()
+        dk["top_out_" + tag] = Compute_ParticlesTensor.top_decayProducts(lab[:, 3], tb, tw, ptetaphi=flag).numpy()
+    dk["top_out_massive_b"] = Compute_ParticlesTensor.top_decayProducts(lab[:, 3], tb, tw, b_mass=4.7, ptetaphi=False).numpy()
+    np.savez_compressed(os.path.join(HERE, "decays_n3.npz"), **dk)
+    print("decay products written")
 
     # ---- spline fixture from the torch restatement (parity unpinned) ----
     sys.path.insert(0, ROOT)

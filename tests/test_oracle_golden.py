@@ -180,3 +180,20 @@ def test_get_ps_matches_reference(oracle, golden_dir):
         assert np.array_equal(np.isnan(ps), np.isnan(g["ps_" + tag]))
         assert np.nanmax(np.abs(ps - g["ps_" + tag])) < 1e-13
         assert np.array_equal(np.isnan(jac), np.isnan(g["jac_" + tag])) and np.nanmax(np.abs(jac)) == 0.0
+
+
+def test_decay_products_match_reference(oracle, golden_dir):
+    """higgs_decayProducts / top_decayProducts (memflow/unfolding_flow/utils.py:745-815), both output conventions."""
+    g = np.load(os.path.join(golden_dir, "decays_n3.npz"))
+    for tag, flag in (("ptetaphi", True), ("cart", False)):
+        h = oracle.higgs_decay(g["higgs"], g["higgs_angles"], ptetaphi=flag)
+        t = oracle.top_decay(g["top"], g["top_b_angles"], g["top_W_angles"], ptetaphi=flag)
+        assert np.nanmax(np.abs(h - g["higgs_out_" + tag]) / (1 + np.abs(g["higgs_out_" + tag]))) < 1e-13
+        assert np.nanmax(np.abs(t - g["top_out_" + tag]) / (1 + np.abs(g["top_out_" + tag]))) < 1e-12
+    t = oracle.top_decay(g["top"], g["top_b_angles"], g["top_W_angles"], b_mass=4.7, ptetaphi=False)
+    assert np.nanmax(np.abs(t - g["top_out_massive_b"]) / (1 + np.abs(g["top_out_massive_b"]))) < 1e-12
+    # physics sanity: daughters sum to the parent, b quarks massless, W on shell
+    c = g["top_out_cart"]
+    assert np.abs(c[:, 1:].sum(1) - c[:, 0]).max() / 13000.0 < 1e-12
+    w = c[:, 2] + c[:, 3]
+    assert np.abs(np.sqrt(w[:, 0] ** 2 - (w[:, 1:] ** 2).sum(1)) - 80.4).max() < 1e-8

@@ -342,3 +342,29 @@ def test_random_masses_and_energies(oracle, seed):
     finb = fin & np.isfinite(d)
     assert np.array_equal(np.isnan(back.cpu().numpy()), np.isnan(ops))
     assert np.nanmax(d[finb] / kappa[finb]) < TOL64 and np.nanquantile(d[finb], 0.9) < TOL64
+
+
+def test_decay_products_vs_reference_golden(oracle, golden_dir):
+    """H -> bb and t -> bW -> bqq' epilogues on the GPU vs the reference's outputs."""
+    from memflow_b200.unfolding_flow.utils import Compute_ParticlesTensor as CPT
+    g = np.load(os.path.join(golden_dir, "decays_n3.npz"))
+    H, t = torch.from_numpy(g["higgs"]).cuda(), torch.from_numpy(g["top"]).cuda()
+    ha, tb, tw = (torch.from_numpy(g[k]).cuda() for k in ("higgs_angles", "top_b_angles", "top_W_angles"))
+    for tag, flag in (("ptetaphi", True), ("cart", False)):
+        h = CPT.higgs_decayProducts(H, ha, ptetaphi=flag).cpu().numpy()
+        tt = CPT.top_decayProducts(t, tb, tw, ptetaphi=flag).cpu().numpy()
+        assert h.shape == (H.shape[0], 3, 4) and tt.shape == (H.shape[0], 4, 4)
+        assert np.nanmax(np.abs(h - g["higgs_out_" + tag]) / (1 + np.abs(g["higgs_out_" + tag]))) < TOL64
+        assert np.nanmax(np.abs(tt - g["top_out_" + tag]) / (1 + np.abs(g["top_out_" + tag]))) < TOL64
+    tt = CPT.top_decayProducts(t, tb, tw, b_mass=4.7, ptetaphi=False).cpu().numpy()
+    assert np.nanmax(np.abs(tt - g["top_out_massive_b"]) / (1 + np.abs(g["top_out_massive_b"]))) < TOL64
+    # rows of a K1 output read in place (row stride 4(n+2)), chained after the fused lab boost
+    n, N = 3, 30_000
+    ps = make_ps(n)
+    mom = ps.get_momenta_from_ps(rand_u(N, n, 61).cuda(), lab_frame=True)[0]
+    gsm = torch.Generator().manual_seed(3)
+    ang = torch.stack((torch.randn(N, generator=gsm, dtype=torch.float64), (torch.rand(N, generator=gsm, dtype=torch.float64) * 2 - 1) * 3.14), 1)
+    out = CPT.higgs_decayProducts(mom[:, 2], ang.cuda(), ptetaphi=False)
+    ref = oracle.higgs_decay(mom[:, 2].cpu().numpy(), ang.numpy(), ptetaphi=False)
+    assert np.abs(out.cpu().numpy() - ref).max() / E < TOL64
+    assert float((out[:, 1] + out[:, 2] - out[:, 0]).abs().max()) / E < TOL64
