@@ -80,6 +80,16 @@ int mf_rambo_forward_f32(const float* u, int64_t N, int n_final, const float* ma
                          const float* cuts, uint32_t flags, float* momenta, float* weight, float* logweight,
                          float* x1, float* x2, int32_t* status, mf_stream_t stream);
 
+/* Vector-Jacobian product of K1 with the gradient semantics of the reference's autograd graph
+ * (generateKinematics_batch(..., requires_grad=True)): grad_u [N, 3n-2] from the cotangents of the four
+ * outputs (each may be NULL = zero). Mass-variable columns get 0; angle columns the true derivative through the decay
+ * chain; the x1/x2 columns reach x1, x2, the weight and the incoming rows only. u / momenta / weight / x1 / x2 are the
+ * forward's input and outputs. Not available with MF_FLAG_LAB_FRAME / MF_FLAG_CUTS. */
+int mf_rambo_forward_bwd_f64(const double* u, const double* momenta, const double* weight, const double* x1,
+                             const double* x2, const double* g_momenta, const double* g_weight, const double* g_x1,
+                             const double* g_x2, int64_t N, int n_final, const double* masses, double e_collider,
+                             uint32_t flags, double* grad_u, mf_stream_t stream);
+
 /* Mass-variable root solve alone: u[i, j] solves v = u^e ((e+1) - e u), e = n_final-2-j.
  * replaces FlatInvertiblePhasespace.bisect_vec_batch, rambo_generator.py:400-446. v, u: [N, n_final-2]. */
 int mf_massvar_solve_f64(const double* v, int64_t N, int n_final, double* u, mf_stream_t stream);

@@ -9,6 +9,8 @@ Deviations from the reference, all deliberate (DESIGN.md "Reference quirks"):
   * data-dependent raises (NaN scan :191-199, CM check :630-635) cost host syncs in the reference. Here
     they set bits in `generator.last_status` (device int32); `sync_errors=True` restores the raises.
   * CUDA tensors only: there is no CPU fallback.
+  * autograd: an input that requires grad goes through `_RamboForwardFn` (backward kernel with the reference graph's
+    gradient semantics); the inverse map has no backward yet.
 """
 import ctypes
 import math
@@ -33,6 +35,40 @@ MF_ST_NOT_CM = 2
 
 class PhaseSpaceGeneratorError(Exception):
     pass
+
+
+class _RamboForwardFn(torch.autograd.Function):
+    """K1 with a backward (mf_rambo_forward_bwd_f64) that reproduces the gradient of the reference's autograd graph
+    (SURVEY 8f-4): zero for the mass-variable columns, the true Jacobian for the angle columns, and x1/x2 columns that
+    reach x1, x2, the weight and the incoming rows only."""
+
+    @staticmethod
+    def forward(ctx, points, gen):
+        u = points.detach().to(torch.float64).contiguous()
+        momenta, weight, x1, x2, _ = gen._launch_forward(u, torch.float64, -1, -1, -1, False, False)
+        ctx.save_for_backward(u, momenta, weight, x1, x2)
+        ctx.gen = gen
+        ctx.in_dtype = points.dtype
+        return momenta, weight, x1, x2
+
+    @staticmethod
+    def backward(ctx, g_mom, g_w, g_x1, g_x2):
+        u, momenta, weight, x1, x2 = ctx.saved_tensors
+        gen = ctx.gen
+
+        def c(t):
+            return None if t is None else t.detach().to(torch.float64).contiguous()
+
+        g_mom, g_w, g_x1, g_x2 = c(g_mom), c(g_w), c(g_x1), c(g_x2)
+        grad_u = torch.empty_like(u)
+        flags = 0 if gen.uniform_x1x2 else MF_FLAG_X1X2_DIRECT
+        with torch.cuda.device(u.device):
+            rc = lib().mf_rambo_forward_bwd_f64(
+                ptr(u), ptr(momenta), ptr(weight), ptr(x1), ptr(x2), ptr(g_mom), ptr(g_w), ptr(g_x1), ptr(g_x2),
+                ctypes.c_int64(u.shape[0]), ctypes.c_int(gen.n_final), host_array(gen._masses_host, ctypes.c_double),
+                ctypes.c_double(float(gen.collider_energy)), ctypes.c_uint32(flags), ptr(grad_u), stream_ptr(u.device))
+        check(rc, "mf_rambo_forward_bwd_f64")
+        return grad_u.to(ctx.in_dtype), None
 
 
 class VirtualPhaseSpaceGenerator(object):
@@ -132,14 +168,35 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
             # reference: E_cm is never assigned on this branch (:264-266) -> NameError
             raise PhaseSpaceGeneratorError("pdf_active=False is not supported (it is broken in the reference too)")
         require_cuda(random_variables_full, "random_variables_full")
-        if requires_grad or random_variables_full.requires_grad:
-            if torch.is_grad_enabled() and random_variables_full.requires_grad:
-                raise MemflowB200Error("autograd through the CUDA phase-space map is not implemented yet "
-                                       "(SURVEY 8f-4); call under torch.no_grad() or detach the input")
         assert random_variables_full.shape[1] - 2 == self.nDimPhaseSpace
-        dev = random_variables_full.device
+        cuts_on = (pT_mincut > 0) or (delR_mincut > 0) or (rap_maxcut > 0)
         dt = self.compute_dtype
+        if torch.is_grad_enabled() and random_variables_full.requires_grad:
+            # differentiable path (the reference's requires_grad=True, scripts/run_model_labframe_sampling.py:432)
+            if cuts_on or lab_frame or dt != torch.float64 or self.ref_fp32_quirks:
+                raise MemflowB200Error("autograd through the phase-space map supports the plain fp64 CM-frame output only "
+                                       "(no cuts, no lab_frame, no fp32 compute / quirks)")
+            momenta, weight, x1, x2 = _RamboForwardFn.apply(random_variables_full, self)
+            if self.sync_errors and int(self.last_status.item()) & MF_ST_NAN_INPUT:
+                raise PhaseSpaceGeneratorError("Some of the random variables passed to the phase-space generator are NaN")
+            if return_logweight:
+                return momenta, weight, x1, x2, weight.log()
+            return momenta, weight, x1, x2
         u = random_variables_full.detach().to(dt).contiguous()
+        momenta, weight, x1, x2, logw = self._launch_forward(u, dt, pT_mincut, delR_mincut, rap_maxcut, lab_frame,
+                                                             return_logweight)
+        if self.sync_errors and int(self.last_status.item()) & MF_ST_NAN_INPUT:
+            raise PhaseSpaceGeneratorError("Some of the random variables passed to the phase-space generator are NaN")
+        if dt != torch.float64:  # reference contract: outputs are float64
+            momenta, weight, x1, x2 = momenta.double(), weight.double(), x1.double(), x2.double()
+            logw = logw.double() if logw is not None else None
+        if return_logweight:
+            return momenta, weight, x1, x2, logw
+        return momenta, weight, x1, x2
+
+    def _launch_forward(self, u, dt, pT_mincut, delR_mincut, rap_maxcut, lab_frame, return_logweight):
+        """One K1 launch on a contiguous [N, 3n-2] tensor of dtype dt; returns (momenta, weight, x1, x2, logw)."""
+        dev = u.device
         N, n = u.shape[0], self.n_final
         momenta = torch.empty((N, n + 2, 4), dtype=dt, device=dev)
         weight = torch.empty(N, dtype=dt, device=dev)
@@ -172,14 +229,7 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
                     stream_ptr(dev))
         check(rc, "mf_rambo_forward")
         self.last_status = status
-        if self.sync_errors and int(status.item()) & MF_ST_NAN_INPUT:
-            raise PhaseSpaceGeneratorError("Some of the random variables passed to the phase-space generator are NaN")
-        if dt != torch.float64:  # reference contract: outputs are float64
-            momenta, weight, x1, x2 = momenta.double(), weight.double(), x1.double(), x2.double()
-            logw = logw.double() if logw is not None else None
-        if return_logweight:
-            return momenta, weight, x1, x2, logw
-        return momenta, weight, x1, x2
+        return momenta, weight, x1, x2, logw
 
     # ------------------------------------------------------------------ K2
     def getPSpoint_batch(self, momenta_batch, x1, x2, order=None, target_mass=None, ensure_CM=True,

@@ -142,6 +142,25 @@ def main():
                         e_cm=np.float64(E_CM), **out)
     print("get_PS written; masked:", int(out["mask_id"].sum()))
 
+    # ---- gradients of the forward map from the reference's own autograd graph (requires_grad=True) ----
+    for n in (3, 4, 5):
+        m = torch.tensor(CASES[n], dtype=torch.float64)
+        ps = phasespace.PhaseSpace(E_CM, [21, 21], list(range(n)), final_masses=m, dev=torch.device("cpu"))
+        u = make_u(n, 1000 + n)[24:24 + 96].clone().requires_grad_(True)      # bulk rows only
+        gen = torch.Generator().manual_seed(77 + n)
+        with fp64_clean():
+            mom, w, x1, x2 = ps.get_momenta_from_ps(u, requires_grad=True)
+        gm = torch.randn(mom.shape, generator=gen, dtype=torch.float64)
+        gw = torch.randn(w.shape, generator=gen, dtype=torch.float64) / w.detach()
+        gx1 = torch.randn(w.shape, generator=gen, dtype=torch.float64)
+        gx2 = torch.randn(w.shape, generator=gen, dtype=torch.float64)
+        loss = (mom * gm).sum() + (w * gw).sum() + (x1 * gx1).sum() + (x2 * gx2).sum()
+        loss.backward()
+        np.savez_compressed(os.path.join(HERE, "rambo_grad_n%d.npz" % n), u=u.detach().numpy(), masses=m.numpy(),
+                            e_cm=np.float64(E_CM), g_mom=gm.numpy(), g_w=gw.numpy(), g_x1=gx1.numpy(), g_x2=gx2.numpy(),
+                            grad_u=u.grad.numpy())
+        print("grad n=%d written; |grad| per column:" % n, np.array2string(u.grad.abs().mean(0).numpy(), precision=2))
+
     # ---- decay products (memflow/unfolding_flow/utils.py:745-815) on lab-frame propagators ----
     g3 = np.load(os.path.join(HERE, "rambo_n3.npz"))
     mom3 = torch.from_numpy(g3["mom_clean"])

@@ -368,3 +368,43 @@ def test_decay_products_vs_reference_golden(oracle, golden_dir):
     ref = oracle.higgs_decay(mom[:, 2].cpu().numpy(), ang.numpy(), ptetaphi=False)
     assert np.abs(out.cpu().numpy() - ref).max() / E < TOL64
     assert float((out[:, 1] + out[:, 2] - out[:, 0]).abs().max()) / E < TOL64
+
+
+@pytest.mark.parametrize("n", [3, 4, 5])
+def test_autograd_matches_reference_graph(golden_dir, oracle, n):
+    """d(loss)/d(points) through get_momenta_from_ps == the reference's autograd (golden), incl. its
+    semantics: zero for the mass-variable columns, x columns reaching x1/x2/weight/incoming rows only."""
+    g = np.load(os.path.join(golden_dir, "rambo_grad_n%d.npz" % n))
+    masses = [float(x) for x in g["masses"]]
+    from memflow_b200.phasespace.phasespace import PhaseSpace
+    ps = PhaseSpace(E, [21, 21], list(range(n)), final_masses=torch.tensor(masses, dtype=torch.float64), dev="cuda:0")
+    u = torch.from_numpy(g["u"]).cuda().requires_grad_(True)
+    mom, w, x1, x2 = ps.get_momenta_from_ps(u, requires_grad=True)
+    assert mom.requires_grad and w.requires_grad
+    gm, gw, gx1, gx2 = (torch.from_numpy(g[k]).cuda() for k in ("g_mom", "g_w", "g_x1", "g_x2"))
+    loss = (mom * gm).sum() + (w * gw).sum() + (x1 * gx1).sum() + (x2 * gx2).sum()
+    loss.backward()
+    got, ref = u.grad.cpu().numpy(), g["grad_u"]
+    assert np.all(got[:, : n - 2] == 0.0) and np.all(ref[:, : n - 2] == 0.0)
+    scale = np.abs(ref).max(axis=1, keepdims=True) + 1e-300
+    rel = np.abs(got - ref) / scale
+    print("autograd n=%d: max rel err %.2e, median %.2e" % (n, rel.max(), np.median(rel)))
+    assert np.median(rel) < 1e-12 and np.quantile(rel, 0.99) < 1e-9 and rel.max() < 1e-6
+    # partial cotangents (momenta only / weight only) are accepted
+    u2 = torch.from_numpy(g["u"]).cuda().requires_grad_(True)
+    ps.get_momenta_from_ps(u2)[1].log().sum().backward()
+    assert float(u2.grad[:, : 3 * n - 4].abs().max()) == 0.0 and float(u2.grad[:, 3 * n - 4:].abs().min()) > 0.0
+    # independent check of the angle columns: central differences of the ORACLE forward
+    uu = g["u"][:8].copy()
+    h = 1e-7
+    for col in (n - 2, n - 1, 3 * n - 5):
+        up, um = uu.copy(), uu.copy()
+        up[:, col] += h; um[:, col] -= h
+        mp = oracle.rambo_forward(up, masses, E)[0]; mm = oracle.rambo_forward(um, masses, E)[0]
+        fd = (((mp - mm) / (2 * h))[:, 2:] * g["g_mom"][:8, 2:]).sum(axis=(1, 2))
+        # cotangents of w, x1, x2 do not touch angle columns, so this is the whole gradient of those columns
+        assert np.abs(fd - got[:8, col]).max() / (np.abs(fd).max() + 1e-300) < 1e-5
+    # no_grad / detached inputs stay on the plain path
+    with torch.no_grad():
+        m2 = ps.get_momenta_from_ps(u)[0]
+    assert not m2.requires_grad and torch.equal(m2, mom.detach())
