@@ -113,3 +113,28 @@ def test_two_stage_calls_equal_chain_call():
     assert bool(((u >= 0) & (u <= 1)).all())
     acc2 = smp.weigh(u, lq)
     assert torch.equal(acc, acc2)
+
+
+def test_fused_single_kernel_mode_agrees():
+    """MF_CHAIN_MODE=fused (one launch, nothing but the accumulators leaves the SM; kept as the measured alternative of
+    DESIGN.md section 4) gives the same estimator inputs as the default two-launch chain."""
+    import json, os, subprocess, sys
+    code = (
+        "import sys, json, torch; sys.path.insert(0, %r);"
+        "from memflow_b200 import estimator as ES;"
+        "g = torch.Generator().manual_seed(5);"
+        "phi = torch.randn(2, 6000, 7, 29, generator=g, dtype=torch.float32).cuda();"
+        "smp = ES.ImportanceSampler([125.25, 172.5, 172.5], 13000.0, seed=3, device='cuda:0');"
+        "acc, out = smp.run_chunk(phi, event_offset=9, debug_outputs=True);"
+        "print(json.dumps({'acc': acc.tolist(), 'u': out['u'].sum().item(), 'w': out['weight'].log().sum().item()}))"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("split", "fused"):
+        env = dict(os.environ, MF_CHAIN_MODE=mode)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[mode] = json.loads(out.stdout.strip().splitlines()[-1])
+    a, b = res["split"], res["fused"]
+    assert a["acc"][2] == b["acc"][2] == 6000
+    np.testing.assert_allclose(a["acc"][:2], b["acc"][:2], rtol=1e-11)
+    assert abs(a["u"] - b["u"]) < 1e-9 and abs(a["w"] - b["w"]) < 1e-7
