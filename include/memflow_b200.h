@@ -90,6 +90,16 @@ int mf_rambo_forward_bwd_f64(const double* u, const double* momenta, const doubl
                              const double* g_x2, int64_t N, int n_final, const double* masses, double e_collider,
                              uint32_t flags, double* grad_u, mf_stream_t stream);
 
+/* Vector-Jacobian product of K2 / get_PS: gradient of ps [N, 3n-2] w.r.t. the final-state momenta (g_momenta [N, n, 4],
+ * packed, original particle order) and x1, x2 (g_x1, g_x2 [N], both or neither NULL), as torch autograd computes it on the
+ * reference graph (rambo_generator.py:615-736; memflow/unfolding_flow/utils.py:1056-1152 -- pass the x1, x2 get_PS derived
+ * from the boost). order / masses / target_mass as in the forward; permute_target != 0 = get_PS convention
+ * (target_mass[order]). `prob` has no gradient. */
+int mf_rambo_inverse_bwd_f64(const double* momenta, int64_t event_stride, const double* x1, const double* x2,
+                             const double* g_ps, int64_t N, int n_final, const int32_t* order, const double* masses,
+                             const double* target_mass, int permute_target, double e_collider, uint32_t flags,
+                             double* g_momenta, double* g_x1, double* g_x2, mf_stream_t stream);
+
 /* Mass-variable root solve alone: u[i, j] solves v = u^e ((e+1) - e u), e = n_final-2-j.
  * replaces FlatInvertiblePhasespace.bisect_vec_batch, rambo_generator.py:400-446. v, u: [N, n_final-2]. */
 int mf_massvar_solve_f64(const double* v, int64_t N, int n_final, double* u, mf_stream_t stream);

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmemflow_b200.so")
 #: every symbol include/memflow_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = (
     "mf_abi_version", "mf_error_string", "mf_device_info",
-    "mf_rambo_forward_f64", "mf_rambo_forward_f32", "mf_massvar_solve_f64", "mf_rambo_forward_bwd_f64", "mf_rambo_inverse_f64", "mf_rambo_inverse_f32", "mf_get_ps_f64",
+    "mf_rambo_forward_f64", "mf_rambo_forward_f32", "mf_massvar_solve_f64", "mf_rambo_forward_bwd_f64", "mf_rambo_inverse_bwd_f64", "mf_rambo_inverse_f64", "mf_rambo_inverse_f32", "mf_get_ps_f64",
     "mf_rqs_forward_f32", "mf_rqs_forward_f64", "mf_rqs_inverse_f32", "mf_rqs_inverse_f64",
     "mf_searchsorted_f32", "mf_searchsorted_f64",
     "mf_is_reduce_workspace_bytes", "mf_is_reduce_f64", "mf_is_chain_f64", "mf_flow_sample_f32", "mf_rambo_is_f64", "mf_higgs_decay_f64", "mf_top_decay_f64",

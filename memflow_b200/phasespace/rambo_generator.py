@@ -10,7 +10,7 @@ Deviations from the reference, all deliberate (DESIGN.md "Reference quirks"):
     they set bits in `generator.last_status` (device int32); `sync_errors=True` restores the raises.
   * CUDA tensors only: there is no CPU fallback.
   * autograd: an input that requires grad goes through `_RamboForwardFn` (backward kernel with the reference graph's
-    gradient semantics); the inverse map has no backward yet.
+    gradient semantics); the inverse map (`getPSpoint_batch`, `get_PS`) is differentiable in `ps` (not in `prob`).
 """
 import ctypes
 import math
@@ -69,6 +69,48 @@ class _RamboForwardFn(torch.autograd.Function):
                 ctypes.c_double(float(gen.collider_energy)), ctypes.c_uint32(flags), ptr(grad_u), stream_ptr(u.device))
         check(rc, "mf_rambo_forward_bwd_f64")
         return grad_u.to(ctx.in_dtype), None
+
+
+def _inverse_vjp(mom, x1, x2, g_ps, n, order, masses_host, target_host, permute_target, e_collider, flags, want_x):
+    """mf_rambo_inverse_bwd_f64 on contiguous fp64 tensors; returns (g_momenta [N,n,4], g_x1, g_x2)."""
+    dev = mom.device
+    N = mom.shape[0]
+    g_mom = torch.empty((N, n, 4), dtype=torch.float64, device=dev)
+    g_x1 = torch.empty(N, dtype=torch.float64, device=dev) if want_x else None
+    g_x2 = torch.empty(N, dtype=torch.float64, device=dev) if want_x else None
+    tm = host_array(target_host, ctypes.c_double) if target_host is not None else None
+    with torch.cuda.device(dev):
+        rc = lib().mf_rambo_inverse_bwd_f64(
+            ptr(mom), ctypes.c_int64(mom.stride(0)), ptr(x1), ptr(x2), ptr(g_ps), ctypes.c_int64(N), ctypes.c_int(n),
+            host_array(order, ctypes.c_int32), host_array(masses_host, ctypes.c_double), tm,
+            ctypes.c_int(int(permute_target)), ctypes.c_double(float(e_collider)), ctypes.c_uint32(flags), ptr(g_mom),
+            ptr(g_x1), ptr(g_x2), stream_ptr(dev))
+    check(rc, "mf_rambo_inverse_bwd_f64")
+    return g_mom, g_x1, g_x2
+
+
+class _RamboInverseFn(torch.autograd.Function):
+    """K2 with a backward for `ps` (mf_rambo_inverse_bwd_f64); `prob` is returned as non-differentiable."""
+
+    @staticmethod
+    def forward(ctx, momenta, x1, x2, gen, order, target_host, ensure_CM):
+        mom = momenta.detach().to(torch.float64).contiguous()
+        x1c, x2c = x1.detach().to(torch.float64).contiguous(), x2.detach().to(torch.float64).contiguous()
+        ps, prob, _ = gen._launch_inverse(mom, x1c, x2c, order, target_host, ensure_CM, False)
+        ctx.save_for_backward(mom, x1c, x2c)
+        ctx.gen, ctx.order, ctx.target_host = gen, order, target_host
+        ctx.dtypes = (momenta.dtype, x1.dtype, x2.dtype)
+        ctx.mark_non_differentiable(prob)
+        return ps, prob
+
+    @staticmethod
+    def backward(ctx, g_ps, _g_prob):
+        mom, x1, x2 = ctx.saved_tensors
+        gen = ctx.gen
+        flags = 0 if gen.uniform_x1x2 else MF_FLAG_X1X2_DIRECT
+        g_mom, g_x1, g_x2 = _inverse_vjp(mom, x1, x2, g_ps.detach().to(torch.float64).contiguous(), gen.n_final, ctx.order,
+                                         gen._masses_host, ctx.target_host, False, gen.collider_energy, flags, True)
+        return (g_mom.to(ctx.dtypes[0]), g_x1.to(ctx.dtypes[1]), g_x2.to(ctx.dtypes[2]), None, None, None, None)
 
 
 class VirtualPhaseSpaceGenerator(object):
@@ -238,29 +280,57 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         `order=None` means the identity permutation for any n (the reference's default [0,1,2,3] only
         fits n=4). `target_mass` ([n] or [1,n]) is used when ensure_onShell=False (:649-652)."""
         require_cuda(momenta_batch, "momenta_batch")
-        dev = momenta_batch.device
         n = self.n_final
         if momenta_batch.dim() != 3 or momenta_batch.shape[1] != n or momenta_batch.shape[2] != 4:
             raise AssertionError("momenta_batch must be [N, %d, 4]" % n)
+        order = list(range(n)) if order is None else [int(o) for o in order]
+        if len(order) != n:
+            raise AssertionError("order must have n_final=%d entries" % n)
+        target_host = None
+        if not ensure_onShell:
+            if target_mass is None:
+                raise AssertionError("ensure_onShell=False needs target_mass")
+            target_host = torch.as_tensor(target_mass).detach().cpu().double().reshape(-1).tolist()
+            if len(target_host) != n:
+                raise AssertionError("target_mass must hold n_final=%d masses ([n] or [1,n])" % n)
         dt = self.compute_dtype
-        mom = momenta_batch.detach()
-        if mom.dtype != dt:
-            mom = mom.to(dt)
-        # read a [:, 2:] slice of a forward output in place when its strides allow it
+        needs_grad = torch.is_grad_enabled() and (momenta_batch.requires_grad or
+                                                  (torch.is_tensor(x1) and x1.requires_grad) or
+                                                  (torch.is_tensor(x2) and x2.requires_grad))
+        if needs_grad:
+            if dt != torch.float64 or self.ref_fp32_quirks:
+                raise MemflowB200Error("autograd through the inverse map supports fp64 compute without quirks only")
+            ps, prob = _RamboInverseFn.apply(momenta_batch, x1, x2, self, order, target_host, ensure_CM)
+            logp = prob.log() if return_logprob else None
+        else:
+            mom = momenta_batch.detach()
+            if mom.dtype != dt:
+                mom = mom.to(dt)
+            ps, prob, logp = self._launch_inverse(mom, x1.detach().to(dt).contiguous(), x2.detach().to(dt).contiguous(), order,
+                                                  target_host, ensure_CM, return_logprob)
+        if ensure_CM and self.sync_errors and int(self.last_status.item()) & MF_ST_NOT_CM:
+            raise Exception("Momenta batch not in the CM, failing to convert back to PS point")
+        if dt != torch.float64:
+            ps, prob = ps.double(), prob.double()
+            logp = logp.double() if logp is not None else None
+        if return_logprob:
+            return ps, prob, logp
+        return ps, prob
+
+    def _launch_inverse(self, mom, x1c, x2c, order, target_host, ensure_CM, return_logprob):
+        """One K2 launch; mom may be a strided [N, n, 4] view (e.g. forward_output[:, 2:]) that is read in place."""
+        dev = mom.device
+        n = self.n_final
+        dt = mom.dtype
         esz = mom.element_size()
         if not (mom.stride(2) == 1 and mom.stride(1) == 4 and mom.stride(0) % 4 == 0 and mom.stride(0) >= 4 * n
                 and mom.data_ptr() % (4 * esz) == 0):
             mom = mom.contiguous()
         N = mom.shape[0]
-        x1c = x1.detach().to(dt).contiguous()
-        x2c = x2.detach().to(dt).contiguous()
         ps = torch.empty((N, 3 * n - 2), dtype=dt, device=dev)
         prob = torch.empty(N, dtype=dt, device=dev)
         logp = torch.empty(N, dtype=dt, device=dev) if return_logprob else None
         status = torch.zeros(1, dtype=torch.int32, device=dev)
-        order = list(range(n)) if order is None else [int(o) for o in order]
-        if len(order) != n:
-            raise AssertionError("order must have n_final=%d entries" % n)
         flags = 0
         if self.ref_fp32_quirks:
             flags |= MF_FLAG_REF_FP32_QUIRKS
@@ -273,28 +343,14 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         else:
             fn, ct = lib().mf_rambo_inverse_f32, ctypes.c_float
         masses = host_array(self._masses_host, ct)
-        tm = None
-        if not ensure_onShell:
-            if target_mass is None:
-                raise AssertionError("ensure_onShell=False needs target_mass")
-            tmv = torch.as_tensor(target_mass).detach().cpu().double().reshape(-1).tolist()
-            if len(tmv) != n:
-                raise AssertionError("target_mass must hold n_final=%d masses ([n] or [1,n])" % n)
-            tm = host_array(tmv, ct)
+        tm = host_array(target_host, ct) if target_host is not None else None
         with torch.cuda.device(dev):
             rc = fn(ptr(mom), ctypes.c_int64(mom.stride(0)), ptr(x1c), ptr(x2c), ctypes.c_int64(N), ctypes.c_int(n),
                     host_array(order, ctypes.c_int32), masses, tm, ct(float(self.collider_energy)),
                     ctypes.c_uint32(flags), ptr(ps), ptr(prob), ptr(logp), ptr(status), stream_ptr(dev))
         check(rc, "mf_rambo_inverse")
         self.last_status = status
-        if ensure_CM and self.sync_errors and int(status.item()) & MF_ST_NOT_CM:
-            raise Exception("Momenta batch not in the CM, failing to convert back to PS point")
-        if dt != torch.float64:
-            ps, prob = ps.double(), prob.double()
-            logp = logp.double() if logp is not None else None
-        if return_logprob:
-            return ps, prob, logp
-        return ps, prob
+        return ps, prob, logp
 
     def setInitialStateMomenta_batch(self, output_momenta, E_cm):
         """Rows 0,1 <- (E/2, 0, 0, +-E/2) for massless beams (:511-551); in place, like the reference."""

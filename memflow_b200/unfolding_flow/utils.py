@@ -18,6 +18,36 @@ M_TOP = 172.5
 M_GLUON = 1e-5  # memflow/unfolding_flow/utils.py:10
 
 
+class _GetPSFn(torch.autograd.Function):
+    """get_PS with a backward for `ps` w.r.t. the regressed momenta and boost (mf_rambo_inverse_bwd_f64)."""
+
+    @staticmethod
+    def forward(ctx, data, boost_reco, order, tm, E_CM):
+        ps, jac0, mask = Compute_ParticlesTensor._launch_get_ps(data.detach(), boost_reco.detach(), order, tm, E_CM, None,
+                                                               None, None)[:3]
+        ctx.save_for_backward(data.detach().to(torch.float64).contiguous(), boost_reco.detach().to(torch.float64).contiguous())
+        ctx.order, ctx.tm, ctx.E_CM, ctx.dtypes = order, tm, float(E_CM), (data.dtype, boost_reco.dtype)
+        ctx.mark_non_differentiable(jac0, mask)
+        return ps, jac0, mask
+
+    @staticmethod
+    def backward(ctx, g_ps, _gj, _gm):
+        from ..phasespace.rambo_generator import _inverse_vjp
+        mom, boost = ctx.saved_tensors
+        E = ctx.E_CM
+        x1r, x2r = (boost[:, 0] + boost[:, 3]) / E, (boost[:, 0] - boost[:, 3]) / E
+        x1, x2 = x1r.clamp(0.0, 1.0), x2r.clamp(0.0, 1.0)
+        n = mom.shape[1]
+        g_mom, g_x1, g_x2 = _inverse_vjp(mom, x1.contiguous(), x2.contiguous(), g_ps.detach().to(torch.float64).contiguous(), n,
+                                         ctx.order, ctx.tm, ctx.tm, True, E, 0, True)
+        g_x1 = g_x1 * ((x1r >= 0) & (x1r <= 1))   # torch.clamp passes the gradient inside [min, max] only
+        g_x2 = g_x2 * ((x2r >= 0) & (x2r <= 1))
+        g_boost = torch.zeros_like(boost)
+        g_boost[:, 0] = (g_x1 + g_x2) / E
+        g_boost[:, 3] = (g_x1 - g_x2) / E
+        return g_mom.to(ctx.dtypes[0]), g_boost.to(ctx.dtypes[1]), None, None, None
+
+
 class Compute_ParticlesTensor:
     @staticmethod
     def get_PS(data_HttISR, boost_reco, order=[0, 1, 2, 3], target_mass=None, E_CM=13000, logit_eps=None,
@@ -31,18 +61,37 @@ class Compute_ParticlesTensor:
         With `logit_eps` the caller's next two lines (unfolding_flow.py:170-171) are fused into the same kernel and a
         fourth value is returned: (torch.logit(ps, eps=logit_eps) - logit_mean) / logit_scale."""
         require_cuda(data_HttISR, "data_HttISR")
-        dev = data_HttISR.device
         n = data_HttISR.shape[1]
         if target_mass is None:
             target_mass = torch.tensor([[M_HIGGS, M_TOP, M_TOP, M_GLUON]], dtype=torch.float64)
         tm = torch.as_tensor(target_mass).detach().cpu().double().reshape(-1).tolist()
+        order = [int(o) for o in order]
         if len(tm) != n or len(order) != n:
             raise AssertionError("target_mass / order must have %d entries" % n)
-        mom = data_HttISR.detach().to(torch.float64)
+        if torch.is_grad_enabled() and (data_HttISR.requires_grad or boost_reco.requires_grad):
+            ps, jac0, mask = _GetPSFn.apply(data_HttISR, boost_reco, order, tm, E_CM)
+            if logit_eps is None:
+                return ps, jac0, mask
+            # differentiable path: the epilogue stays in torch so that autograd sees it (unfolding_flow.py:170-171)
+            lps = torch.logit(ps, eps=logit_eps)
+            if logit_mean is not None:
+                lps = lps - torch.as_tensor(logit_mean, dtype=ps.dtype, device=ps.device)
+            if logit_scale is not None:
+                lps = lps / torch.as_tensor(logit_scale, dtype=ps.dtype, device=ps.device)
+            return ps, jac0, mask, lps
+        out = Compute_ParticlesTensor._launch_get_ps(data_HttISR.detach(), boost_reco.detach(), order, tm, E_CM, logit_eps,
+                                                     logit_mean, logit_scale)
+        return out if logit_eps is not None else out[:3]
+
+    @staticmethod
+    def _launch_get_ps(data_HttISR, boost_reco, order, tm, E_CM, logit_eps, logit_mean, logit_scale):
+        dev = data_HttISR.device
+        n = data_HttISR.shape[1]
+        mom = data_HttISR.to(torch.float64)
         if not (mom.stride(2) == 1 and mom.stride(1) == 4 and mom.stride(0) % 4 == 0 and mom.stride(0) >= 4 * n
                 and mom.data_ptr() % 32 == 0):
             mom = mom.contiguous()
-        boost = boost_reco.detach().to(torch.float64).contiguous()
+        boost = boost_reco.to(torch.float64).contiguous()
         N = mom.shape[0]
         ps = torch.empty((N, 3 * n - 2), dtype=torch.float64, device=dev)
         jac0 = torch.empty(N, dtype=torch.float64, device=dev)
@@ -64,9 +113,7 @@ class Compute_ParticlesTensor:
                                      ctypes.c_double(float(logit_eps) if logit_eps is not None else 0.0), lm, ls, ptr(lps),
                                      stream_ptr(dev))
         check(rc, "mf_get_ps_f64")
-        if logit_eps is not None:
-            return ps, jac0, mask.bool(), lps
-        return ps, jac0, mask.bool()
+        return ps, jac0, mask.bool(), lps
 
     @staticmethod
     def _rows(p):

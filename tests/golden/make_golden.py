@@ -161,6 +161,37 @@ def main():
                             grad_u=u.grad.numpy())
         print("grad n=%d written; |grad| per column:" % n, np.array2string(u.grad.abs().mean(0).numpy(), precision=2))
 
+    # ---- gradients of the inverse map / get_PS from the reference's autograd graph ----
+    for n in (3, 4, 5):
+        m = torch.tensor(CASES[n], dtype=torch.float64)
+        ps = phasespace.PhaseSpace(E_CM, [21, 21], list(range(n)), final_masses=m, dev=torch.device("cpu"))
+        gsrc = np.load(os.path.join(HERE, "rambo_n%d.npz" % n))
+        mom = torch.from_numpy(gsrc["mom_clean"][24:24 + 96, 2:]).clone().requires_grad_(True)
+        x1 = torch.from_numpy(gsrc["x1_clean"][24:24 + 96]).clone().requires_grad_(True)
+        x2 = torch.from_numpy(gsrc["x2_clean"][24:24 + 96]).clone().requires_grad_(True)
+        gen = torch.Generator().manual_seed(177 + n)
+        perm = list(range(n)) if n != 4 else [1, 0, 2, 3]
+        with fp64_clean(), contextlib.redirect_stdout(io.StringIO()):
+            psb, prob = ps.generator.getPSpoint_batch(mom, x1, x2, order=perm)
+        gps = torch.randn(psb.shape, generator=gen, dtype=torch.float64)
+        (psb * gps).sum().backward()
+        np.savez_compressed(os.path.join(HERE, "rambo_inv_grad_n%d.npz" % n), mom=mom.detach().numpy(), x1=x1.detach().numpy(),
+                            x2=x2.detach().numpy(), masses=m.numpy(), e_cm=np.float64(E_CM), order=np.array(perm, dtype=np.int32),
+                            g_ps=gps.numpy(), g_mom=mom.grad.numpy(), g_x1=x1.grad.numpy(), g_x2=x2.grad.numpy())
+        print("inverse grad n=%d written" % n)
+    g4 = np.load(os.path.join(HERE, "get_ps_n4.npz"))
+    mom = torch.from_numpy(g4["mom"][60:160]).clone().requires_grad_(True)
+    boost = torch.from_numpy(g4["boost"][60:160]).clone().requires_grad_(True)
+    tmass = torch.from_numpy(g4["target_mass"])
+    gen = torch.Generator().manual_seed(31)
+    ps_, jac_, mask_ = Compute_ParticlesTensor.get_PS(mom, boost, order=[1, 0, 2, 3], target_mass=tmass, E_CM=E_CM)
+    gps = torch.randn(ps_.shape, generator=gen, dtype=torch.float64)
+    (ps_ * gps).sum().backward()
+    np.savez_compressed(os.path.join(HERE, "get_ps_grad_n4.npz"), mom=mom.detach().numpy(), boost=boost.detach().numpy(),
+                        target_mass=tmass.numpy(), e_cm=np.float64(E_CM), order=np.array([1, 0, 2, 3], dtype=np.int32),
+                        g_ps=gps.numpy(), g_mom=mom.grad.numpy(), g_boost=boost.grad.numpy())
+    print("get_PS grad written")
+
     # ---- decay products (memflow/unfolding_flow/utils.py:745-815) on lab-frame propagators ----
     g3 = np.load(os.path.join(HERE, "rambo_n3.npz"))
     mom3 = torch.from_numpy(g3["mom_clean"])
