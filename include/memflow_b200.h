@@ -159,6 +159,20 @@ int mf_rqs_inverse_f32(const float* phi, const float* y, int64_t B, int F, int K
                        float* x, float* ladj, float* ladj_sum, int32_t* bin, mf_stream_t stream);
 int mf_rqs_inverse_f64(const double* phi, const double* y, int64_t B, int F, int K, double bound, double slope,
                        double* x, double* ladj, double* ladj_sum, int32_t* bin, mf_stream_t stream);
+/* Vector-Jacobian products of K3 / K4: from the cotangents g_out [B,F] of the output and g_ladj [B,F] of the
+ * per-element log-det (either may be NULL = zero; for a cotangent of ladj_sum broadcast it over F), the gradients
+ * g_phi [B,F,3K-1] w.r.t. the unconstrained parameters and g_in [B,F] w.r.t. the input, through soft clip, softmax, cumsum,
+ * gather and the rational quadratic. forward_bwd differentiates mf_rqs_forward (in = x), inverse_bwd mf_rqs_inverse
+ * (in = y; ladj = forward log-det at the recovered x). */
+int mf_rqs_forward_bwd_f32(const float* phi, const float* x, const float* g_y, const float* g_ladj, int64_t B, int F, int K,
+                           float bound, float slope, float* g_phi, float* g_x, mf_stream_t stream);
+int mf_rqs_forward_bwd_f64(const double* phi, const double* x, const double* g_y, const double* g_ladj, int64_t B, int F, int K,
+                           double bound, double slope, double* g_phi, double* g_x, mf_stream_t stream);
+int mf_rqs_inverse_bwd_f32(const float* phi, const float* y, const float* g_x, const float* g_ladj, int64_t B, int F, int K,
+                           float bound, float slope, float* g_phi, float* g_y, mf_stream_t stream);
+int mf_rqs_inverse_bwd_f64(const double* phi, const double* y, const double* g_x, const double* g_ladj, int64_t B, int F, int K,
+                           double bound, double slope, double* g_phi, double* g_y, mf_stream_t stream);
+
 /* bin search alone, knots given: idx = torch.searchsorted(knots[b,f,:], v[b,f], right=False) (bit-exact) */
 int mf_searchsorted_f32(const float* knots, const float* v, int64_t BF, int len, int32_t* idx, mf_stream_t stream);
 int mf_searchsorted_f64(const double* knots, const double* v, int64_t BF, int len, int32_t* idx, mf_stream_t stream);

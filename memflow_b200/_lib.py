@@ -16,6 +16,7 @@ SYMBOLS = (
     "mf_rambo_forward_f64", "mf_rambo_forward_f32", "mf_massvar_solve_f64", "mf_rambo_forward_bwd_f64", "mf_rambo_inverse_bwd_f64", "mf_rambo_inverse_f64", "mf_rambo_inverse_f32", "mf_get_ps_f64",
     "mf_rqs_forward_f32", "mf_rqs_forward_f64", "mf_rqs_inverse_f32", "mf_rqs_inverse_f64",
     "mf_searchsorted_f32", "mf_searchsorted_f64",
+    "mf_rqs_forward_bwd_f32", "mf_rqs_forward_bwd_f64", "mf_rqs_inverse_bwd_f32", "mf_rqs_inverse_bwd_f64",
     "mf_is_reduce_workspace_bytes", "mf_is_reduce_f64", "mf_is_chain_f64", "mf_flow_sample_f32", "mf_rambo_is_f64", "mf_higgs_decay_f64", "mf_top_decay_f64",
 )
 

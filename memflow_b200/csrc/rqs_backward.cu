@@ -1,0 +1,166 @@
+// rqs_backward.cu -- vector-Jacobian product of K3/K4: gradients of the spline output and of its
+// log-det with respect to the input and to the unconstrained parameters phi = [w | h | d] of every (event, feature) row,
+// as autograd computes them through zuko's soft clip -> softmax -> cumsum -> gather -> rational quadratic.
+// One row per thread. The 14 local partials (output and log-det w.r.t. x0, x1, y0, y1, d0, d1, v) come from one
+// evaluation of the rational quadratic in forward-mode dual numbers; the softmax / cumsum part is closed form:
+//   knot X_j = B(2 c_j - 1), c_j = sum_{i<j} p_i  =>  dL/da_i = clip'(a_i) p_i 2B [gX_hi ([i<=bin] - c_hi) + gX_lo ([i<bin] - c_lo)]
+// so no per-row arrays are needed: two passes over the row (sums, then gradients).
+// Written for correctness first (parameters read with plain loads, one thread per row); not a roofline kernel yet.
+#include "rqs.cuh"
+
+namespace mf {
+
+template <typename T> struct Dual {
+    T v;
+    T d[7];
+};
+template <typename T> MF_D Dual<T> dconst(T c) { Dual<T> r; r.v = c; for (int i = 0; i < 7; ++i) r.d[i] = (T)0; return r; }
+template <typename T> MF_D Dual<T> dvar(T c, int k) { Dual<T> r = dconst(c); r.d[k] = (T)1; return r; }
+template <typename T> MF_D Dual<T> operator+(const Dual<T>& a, const Dual<T>& b) { Dual<T> r; r.v = a.v + b.v; for (int i = 0; i < 7; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+template <typename T> MF_D Dual<T> operator-(const Dual<T>& a, const Dual<T>& b) { Dual<T> r; r.v = a.v - b.v; for (int i = 0; i < 7; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+template <typename T> MF_D Dual<T> operator-(const Dual<T>& a) { Dual<T> r; r.v = -a.v; for (int i = 0; i < 7; ++i) r.d[i] = -a.d[i]; return r; }
+template <typename T> MF_D Dual<T> operator*(const Dual<T>& a, const Dual<T>& b) { Dual<T> r; r.v = a.v * b.v; for (int i = 0; i < 7; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+template <typename T> MF_D Dual<T> operator*(T a, const Dual<T>& b) { Dual<T> r; r.v = a * b.v; for (int i = 0; i < 7; ++i) r.d[i] = a * b.d[i]; return r; }
+template <typename T> MF_D Dual<T> operator/(const Dual<T>& a, const Dual<T>& b) {
+    Dual<T> r; const T ib = (T)1 / b.v; r.v = a.v * ib;
+    for (int i = 0; i < 7; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
+    return r;
+}
+template <typename T> MF_D Dual<T> dsqrt(const Dual<T>& a) { Dual<T> r; r.v = sqrt_(a.v); const T h = (T)0.5 / r.v; for (int i = 0; i < 7; ++i) r.d[i] = a.d[i] * h; return r; }
+template <typename T> MF_D Dual<T> dlog(const Dual<T>& a) { Dual<T> r; r.v = log_(a.v); const T ia = (T)1 / a.v; for (int i = 0; i < 7; ++i) r.d[i] = a.d[i] * ia; return r; }
+
+// exact (library) soft clip and its derivative: c / (1 + |a c'|), d/da = 1 / (1 + |a c'|)^2
+template <typename T> MF_D T clip_val(T a, T c, int clip) { return clip ? a / ((T)1 + fabs_(a * c)) : a; }
+template <typename T> MF_D T clip_der(T a, T c, int clip) { if (!clip) return (T)1; const T t = (T)1 + fabs_(a * c); return (T)1 / (t * t); }
+
+template <typename T, bool INV>
+__global__ void __launch_bounds__(128)
+rqs_backward_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const T* __restrict__ g_out,
+                    const T* __restrict__ g_ladj, int64_t rows, int K, RqsConst<T> C, T* __restrict__ g_phi,
+                    T* __restrict__ g_v) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const int PW = 3 * K - 1;
+    const T* r = phi + row * PW;
+    T* gr = g_phi + row * PW;
+    const T v = vin[row];
+    const T go = g_out ? g_out[row] : (T)0, gl = g_ladj ? g_ladj[row] : (T)0;
+    const T B = C.bound;
+    // ---- pass 1: softmax sums (max-subtracted like torch.softmax), bin, prefix sums at the bin ----
+    T mw = clip_val(r[0], C.two_over_L, C.clip), mh = clip_val(r[K], C.two_over_L, C.clip);
+    for (int k = 1; k < K; ++k) {
+        mw = fmax_(mw, clip_val(r[k], C.two_over_L, C.clip));
+        mh = fmax_(mh, clip_val(r[K + k], C.two_over_L, C.clip));
+    }
+    T Sw = (T)0, Sh = (T)0;
+    for (int k = 0; k < K; ++k) {
+        Sw += exp_(clip_val(r[k], C.two_over_L, C.clip) - mw);
+        Sh += exp_(clip_val(r[K + k], C.two_over_L, C.clip) - mh);
+    }
+    // searchsorted on the searched coordinate (X for the forward, Y for the inverse), knots as the forward builds them
+    int cnt = ((T)-B < v) ? 1 : 0;
+    {
+        T c = (T)0;
+        for (int k = 0; k < K; ++k) {
+            c += exp_(clip_val(r[(INV ? K : 0) + k], C.two_over_L, C.clip) - (INV ? mh : mw)) / (INV ? Sh : Sw);
+            cnt += (B * ((T)2 * c - (T)1) < v) ? 1 : 0;
+        }
+    }
+    const int bin = cnt - 1;
+    if (bin < 0 || bin >= K) {  // identity tails: out = v, ladj = 0
+        for (int i = 0; i < PW; ++i) gr[i] = (T)0;
+        g_v[row] = go;
+        return;
+    }
+    T cw_lo = (T)0, cw_hi = (T)0, ch_lo = (T)0, ch_hi = (T)0;
+    {
+        T cw = (T)0, ch = (T)0;
+        for (int k = 0; k <= bin; ++k) {
+            if (k == bin) { cw_lo = cw; ch_lo = ch; }
+            cw += exp_(clip_val(r[k], C.two_over_L, C.clip) - mw) / Sw;
+            ch += exp_(clip_val(r[K + k], C.two_over_L, C.clip) - mh) / Sh;
+        }
+        cw_hi = cw; ch_hi = ch;
+    }
+    const T x0v = B * ((T)2 * cw_lo - (T)1), x1v = B * ((T)2 * cw_hi - (T)1);
+    const T y0v = B * ((T)2 * ch_lo - (T)1), y1v = B * ((T)2 * ch_hi - (T)1);
+    const T d0v = bin > 0 ? exp_(clip_val(r[2 * K + bin - 1], C.one_over_L, C.clip)) : (T)1;
+    const T d1v = bin < K - 1 ? exp_(clip_val(r[2 * K + bin], C.one_over_L, C.clip)) : (T)1;
+    // ---- local partials by forward-mode duals: variables 0..6 = x0, x1, y0, y1, d0, d1, v ----
+    const Dual<T> x0 = dvar(x0v, 0), x1 = dvar(x1v, 1), y0 = dvar(y0v, 2), y1 = dvar(y1v, 3), d0 = dvar(d0v, 4),
+                  d1 = dvar(d1v, 5), vv = dvar(v, 6);
+    const Dual<T> dx = x1 - x0, dy = y1 - y0;
+    const Dual<T> s = dy / dx;
+    const Dual<T> dd = d0 + d1 - (T)2 * s;
+    const Dual<T> one = dconst((T)1);
+    Dual<T> z, out;
+    if constexpr (!INV) {
+        z = (vv - x0) / dx;
+        const Dual<T> zz = z * (one - z);
+        out = y0 + dy * (s * (z * z) + d0 * zz) / (s + dd * zz);
+    } else {
+        const Dual<T> y_ = vv - y0;
+        const Dual<T> a = dy * (s - d0) + y_ * dd;
+        const Dual<T> b = dy * d0 - y_ * dd;
+        const Dual<T> c = -(s * y_);
+        z = ((T)2 * c) / (-b - dsqrt(b * b - (T)4 * (a * c)));
+        out = x0 + z * dx;
+    }
+    const Dual<T> zz = z * (one - z);
+    const Dual<T> den = s + dd * zz;
+    const Dual<T> omz = one - z;
+    const Dual<T> jac = (s * s) * ((T)2 * (s * zz) + d0 * (omz * omz) + d1 * (z * z)) / (den * den);
+    const Dual<T> ladj = dlog(jac);
+    T adj[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) adj[i] = go * out.d[i] + gl * ladj.d[i];
+    g_v[row] = adj[6];
+    // ---- pass 2: parameter gradients ----
+    const T twoB = (T)2 * B;
+    for (int i = 0; i < K; ++i) {
+        const T aw = r[i], ah = r[K + i];
+        const T pw = exp_(clip_val(aw, C.two_over_L, C.clip) - mw) / Sw;
+        const T ph = exp_(clip_val(ah, C.two_over_L, C.clip) - mh) / Sh;
+        const T iw_hi = (i <= bin) ? (T)1 : (T)0, iw_lo = (i < bin) ? (T)1 : (T)0;
+        gr[i] = clip_der(aw, C.two_over_L, C.clip) * pw * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
+        gr[K + i] = clip_der(ah, C.two_over_L, C.clip) * ph * twoB * (adj[3] * (iw_hi - ch_hi) + adj[2] * (iw_lo - ch_lo));
+    }
+    for (int i = 0; i < K - 1; ++i) {
+        T gd = (T)0;
+        if (i == bin - 1) gd = adj[4] * d0v * clip_der(r[2 * K + i], C.one_over_L, C.clip);
+        if (i == bin) gd = adj[5] * d1v * clip_der(r[2 * K + i], C.one_over_L, C.clip);
+        gr[2 * K + i] = gd;
+    }
+}
+
+template <typename T, bool INV>
+static int rqs_bwd_launch(const T* phi, const T* vin, const T* g_out, const T* g_ladj, int64_t B, int F, int K, T bound,
+                          T slope, T* g_phi, T* g_v, cudaStream_t stream) {
+    if (B < 0 || F < 1 || K < 1 || K > 128) return MF_E_SHAPE;
+    if (B > 0 && (!phi || !vin || !g_phi || !g_v)) return MF_E_BADARG;
+    const int64_t rows = B * (int64_t)F;
+    if (rows == 0) return MF_OK;
+    const RqsConst<T> C = make_rqs_const<T>(bound, slope);
+    rqs_backward_kernel<T, INV><<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(phi, vin, g_out, g_ladj, rows, K, C,
+                                                                                    g_phi, g_v);
+    return launch_status();
+}
+
+}  // namespace mf
+
+extern "C" int mf_rqs_forward_bwd_f32(const float* phi, const float* x, const float* g_y, const float* g_ladj, int64_t B,
+                                      int F, int K, float bound, float slope, float* g_phi, float* g_x, mf_stream_t s) {
+    return mf::rqs_bwd_launch<float, false>(phi, x, g_y, g_ladj, B, F, K, bound, slope, g_phi, g_x, (cudaStream_t)s);
+}
+extern "C" int mf_rqs_forward_bwd_f64(const double* phi, const double* x, const double* g_y, const double* g_ladj, int64_t B,
+                                      int F, int K, double bound, double slope, double* g_phi, double* g_x, mf_stream_t s) {
+    return mf::rqs_bwd_launch<double, false>(phi, x, g_y, g_ladj, B, F, K, bound, slope, g_phi, g_x, (cudaStream_t)s);
+}
+extern "C" int mf_rqs_inverse_bwd_f32(const float* phi, const float* y, const float* g_x, const float* g_ladj, int64_t B,
+                                      int F, int K, float bound, float slope, float* g_phi, float* g_y, mf_stream_t s) {
+    return mf::rqs_bwd_launch<float, true>(phi, y, g_x, g_ladj, B, F, K, bound, slope, g_phi, g_y, (cudaStream_t)s);
+}
+extern "C" int mf_rqs_inverse_bwd_f64(const double* phi, const double* y, const double* g_x, const double* g_ladj, int64_t B,
+                                      int F, int K, double bound, double slope, double* g_phi, double* g_y, mf_stream_t s) {
+    return mf::rqs_bwd_launch<double, true>(phi, y, g_x, g_ladj, B, F, K, bound, slope, g_phi, g_y, (cudaStream_t)s);
+}

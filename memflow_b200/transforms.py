@@ -7,7 +7,8 @@ memflow/unfolding_flow/custom_spline_flow_ps.py:16-33): `t(x)`, `t.inv(y)`, `t.c
 `t.log_abs_det_jacobian(x, y)`. The functional forms `rqs_forward / rqs_inverse` take the hyper-network
 output row `phi[B, F, 3K-1]` directly and also return the per-event sum of log-dets.
 
-Inference only (no autograd yet). CUDA tensors only.
+Differentiable: when phi / the input require grad the calls go through `_RqsFn` (backward kernels
+mf_rqs_{forward,inverse}_bwd). CUDA tensors only.
 """
 import ctypes
 
@@ -25,9 +26,55 @@ def _fn(direction, dtype):
     raise MemflowB200Error("spline kernels support float32 / float64, got %s" % dtype)
 
 
+class _RqsFn(torch.autograd.Function):
+    """K3 / K4 with their backward kernels (mf_rqs_{forward,inverse}_bwd): differentiable in phi and in the input."""
+
+    @staticmethod
+    def forward(ctx, phi, v, direction, bound, slope):
+        phi_c = phi.detach().contiguous()
+        v_c = v.detach().to(phi_c.dtype).contiguous()
+        out, ladj, _, _ = _launch(direction, phi_c, v_c, bound, slope, True, False, False)
+        ctx.save_for_backward(phi_c, v_c)
+        ctx.cfg = (direction, bound, slope, v.dtype)
+        return out, ladj
+
+    @staticmethod
+    def backward(ctx, g_out, g_ladj):
+        phi, v = ctx.saved_tensors
+        direction, bound, slope, vdt = ctx.cfg
+        B, F, PW = phi.shape
+        K = (PW + 1) // 3
+        g_phi = torch.empty_like(phi)
+        g_v = torch.empty_like(v)
+        go = None if g_out is None else g_out.detach().to(phi.dtype).contiguous()
+        gl = None if g_ladj is None else g_ladj.detach().to(phi.dtype).contiguous()
+        suffix = "f32" if phi.dtype == torch.float32 else "f64"
+        ct = ctypes.c_float if phi.dtype == torch.float32 else ctypes.c_double
+        fn = getattr(lib(), "mf_rqs_%s_bwd_%s" % (direction, suffix))
+        with torch.cuda.device(phi.device):
+            rc = fn(ptr(phi), ptr(v), ptr(go), ptr(gl), ctypes.c_int64(B), ctypes.c_int(F), ctypes.c_int(K), ct(float(bound)),
+                    ct(float(slope) if slope is not None else 0.0), ptr(g_phi), ptr(g_v), stream_ptr(phi.device))
+        check(rc, "mf_rqs_%s_bwd" % direction)
+        return g_phi, g_v.to(vdt), None, None, None
+
+
 def _run(direction, phi, v, bound, slope, want_ladj=True, want_sum=False, want_bin=False):
     require_cuda(phi, "phi")
     require_cuda(v, "x")
+    if torch.is_grad_enabled() and (phi.requires_grad or v.requires_grad):
+        if phi.dim() != 3 or v.shape != phi.shape[:2]:
+            raise AssertionError("phi must be [B, F, 3K-1] and x [B, F]")
+        out, ladj = _RqsFn.apply(phi, v, direction, bound, slope)
+        lsum = ladj.sum(dim=1) if want_sum else None
+        bins = None
+        if want_bin:
+            bins = _launch(direction, phi.detach().contiguous(), v.detach().to(phi.dtype).contiguous(), bound, slope, False,
+                           False, True)[3]
+        return out, (ladj if want_ladj else None), lsum, bins
+    return _launch(direction, phi.detach(), v.detach(), bound, slope, want_ladj, want_sum, want_bin)
+
+
+def _launch(direction, phi, v, bound, slope, want_ladj=True, want_sum=False, want_bin=False):
     if phi.dim() != 3:
         raise AssertionError("phi must be [B, F, 3K-1]")
     B, F, PW = phi.shape
@@ -87,7 +134,8 @@ def _pack(widths, heights, derivatives):
     lead = torch.broadcast_shapes(widths.shape[:-1], heights.shape[:-1], derivatives.shape[:-1])
     PW = 3 * K - 1
     es = widths.element_size()
-    same = (widths.dtype == heights.dtype == derivatives.dtype and widths.shape[:-1] == lead
+    needs_grad = torch.is_grad_enabled() and (widths.requires_grad or heights.requires_grad or derivatives.requires_grad)
+    same = (not needs_grad and widths.dtype == heights.dtype == derivatives.dtype and widths.shape[:-1] == lead
             and heights.shape[:-1] == lead and derivatives.shape[:-1] == lead
             and widths.stride() == heights.stride() == derivatives.stride()
             and widths.stride(-1) == 1

@@ -151,3 +151,51 @@ def test_ragged_and_unaligned(oracle):
     assert y1 is not None and torch.equal(y1, y0)
     e = TR.rqs_forward(torch.empty(0, 7, 29, device="cuda"), torch.empty(0, 7, device="cuda"), bound=1.0)
     assert e[0].shape == (0, 7)
+
+
+@pytest.mark.parametrize("F,K,bound,slope", [(7, 10, 1.0, 1e-3), (4, 33, 1.1, 1e-3), (3, 8, 5.0, None)])
+def test_spline_autograd_vs_torch_restatement(F, K, bound, slope):
+    """SURVEY 8f-4 for K3/K4: gradients w.r.t. the parameters and the input == torch autograd through the op-for-op
+    restatement of zuko (oracle/rqs_torch.py), both directions, cotangents on the output AND on the log-det."""
+    from memflow_b200 import transforms as TR
+    from oracle import rqs_torch
+    B = 257
+    g = torch.Generator().manual_seed(21)
+    phi0 = torch.randn(B, F, 3 * K - 1, generator=g, dtype=torch.float64)
+    x0 = (torch.rand(B, F, generator=g, dtype=torch.float64) * 2.4 - 1.2) * bound
+    gy = torch.randn(B, F, generator=g, dtype=torch.float64)
+    gl = torch.randn(B, F, generator=g, dtype=torch.float64)
+    for inverse in (False, True):
+        # reference gradients (CPU, torch autograd)
+        phi_r, x_r = phi0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        t = rqs_torch.MonotonicRQSTransform(phi_r[..., :K], phi_r[..., K:2 * K], phi_r[..., 2 * K:], bound=bound, slope=slope)
+        if not inverse:
+            y_r, l_r = t.call_and_ladj(x_r)
+        else:
+            y_r = t._inverse(x_r)
+            l_r = t.call_and_ladj(y_r)[1]          # forward log-det at the recovered point
+        ((y_r * gy).sum() + (l_r * gl).sum()).backward()
+        # kernels
+        phi_k, x_k = phi0.clone().cuda().requires_grad_(True), x0.clone().cuda().requires_grad_(True)
+        run = TR.rqs_inverse if inverse else TR.rqs_forward
+        y_k, l_k, ls_k = run(phi_k, x_k, bound=bound, slope=slope)
+        assert y_k.requires_grad and l_k.requires_grad
+        ((y_k * gy.cuda()).sum() + (l_k * gl.cuda()).sum()).backward()
+        for got, ref, name in ((phi_k.grad, phi_r.grad, "phi"), (x_k.grad, x_r.grad, "x")):
+            got, ref = got.cpu().numpy().reshape(B, -1), ref.numpy().reshape(B, -1)
+            rel = np.abs(got - ref) / (np.abs(ref).max(axis=1, keepdims=True) + 1e-300)
+            print("spline autograd K=%d inv=%s %s: max rel %.2e median %.2e" % (K, inverse, name, rel.max(), np.median(rel)))
+            assert np.median(rel) < 1e-12 and np.quantile(rel, 0.999) < 1e-8 and rel.max() < 1e-6
+    # the Transform surface is differentiable too, separate parameter tensors get their own gradients
+    w = phi0[..., :K].clone().cuda().requires_grad_(True)
+    h = phi0[..., K:2 * K].clone().cuda().requires_grad_(True)
+    d = phi0[..., 2 * K:].clone().cuda().requires_grad_(True)
+    tk = TR.MonotonicRQSTransform(w, h, d, bound=bound, slope=slope)
+    yk, lk = tk.call_and_ladj(x0.cuda())
+    (yk.sum() + lk.sum()).backward()
+    assert w.grad is not None and h.grad is not None and d.grad is not None and float(w.grad.abs().sum()) > 0
+    # fp32 path runs and is close to the fp64 gradient
+    p32, x32 = phi0.float().cuda().requires_grad_(True), x0.float().cuda()
+    y32, l32, _ = TR.rqs_forward(p32, x32, bound=bound, slope=slope)
+    (y32 * gy.float().cuda()).sum().backward()
+    assert torch.isfinite(p32.grad).all()
