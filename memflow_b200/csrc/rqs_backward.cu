@@ -4,8 +4,9 @@
 // One row per thread. The 14 local partials (output and log-det w.r.t. x0, x1, y0, y1, d0, d1, v) come from one
 // evaluation of the rational quadratic in forward-mode dual numbers; the softmax / cumsum part is closed form:
 //   knot X_j = B(2 c_j - 1), c_j = sum_{i<j} p_i  =>  dL/da_i = clip'(a_i) p_i 2B [gX_hi ([i<=bin] - c_hi) + gX_lo ([i<bin] - c_lo)]
-// so no per-row arrays are needed: two passes over the row (sums, then gradients).
-// Written for correctness first (parameters read with plain loads, one thread per row); not a roofline kernel yet.
+// so no per-row arrays are needed: passes over the row staged in shared memory (sums, bin, gradients written in place).
+// Tiles come in by TMA bulk load and the gradient tile leaves by TMA bulk store; the per-row math uses library
+// exp/log (accuracy first), so this kernel is compute-bound rather than at the HBM roofline.
 #include "rqs.cuh"
 
 namespace mf {
@@ -33,18 +34,10 @@ template <typename T> MF_D Dual<T> dlog(const Dual<T>& a) { Dual<T> r; r.v = log
 template <typename T> MF_D T clip_val(T a, T c, int clip) { return clip ? a / ((T)1 + fabs_(a * c)) : a; }
 template <typename T> MF_D T clip_der(T a, T c, int clip) { if (!clip) return (T)1; const T t = (T)1 + fabs_(a * c); return (T)1 / (t * t); }
 
+// Row gradient, in place: on entry r[0..3K-2] = parameters of the row, on exit = their gradients. Returns g_v.
 template <typename T, bool INV>
-__global__ void __launch_bounds__(128)
-rqs_backward_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const T* __restrict__ g_out,
-                    const T* __restrict__ g_ladj, int64_t rows, int K, RqsConst<T> C, T* __restrict__ g_phi,
-                    T* __restrict__ g_v) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows) return;
+MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T go, T gl) {
     const int PW = 3 * K - 1;
-    const T* r = phi + row * PW;
-    T* gr = g_phi + row * PW;
-    const T v = vin[row];
-    const T go = g_out ? g_out[row] : (T)0, gl = g_ladj ? g_ladj[row] : (T)0;
     const T B = C.bound;
     // ---- pass 1: softmax sums (max-subtracted like torch.softmax), bin, prefix sums at the bin ----
     T mw = clip_val(r[0], C.two_over_L, C.clip), mh = clip_val(r[K], C.two_over_L, C.clip);
@@ -68,9 +61,8 @@ rqs_backward_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const 
     }
     const int bin = cnt - 1;
     if (bin < 0 || bin >= K) {  // identity tails: out = v, ladj = 0
-        for (int i = 0; i < PW; ++i) gr[i] = (T)0;
-        g_v[row] = go;
-        return;
+        for (int i = 0; i < PW; ++i) r[i] = (T)0;
+        return go;
     }
     T cw_lo = (T)0, cw_hi = (T)0, ch_lo = (T)0, ch_hi = (T)0;
     {
@@ -114,23 +106,78 @@ rqs_backward_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const 
     T adj[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) adj[i] = go * out.d[i] + gl * ladj.d[i];
-    g_v[row] = adj[6];
-    // ---- pass 2: parameter gradients ----
+    // ---- pass 2: parameter gradients, overwriting the parameters ----
     const T twoB = (T)2 * B;
+    const T gd0 = bin > 0 ? adj[4] * d0v * clip_der(r[2 * K + bin - 1], C.one_over_L, C.clip) : (T)0;
+    const T gd1 = bin < K - 1 ? adj[5] * d1v * clip_der(r[2 * K + bin], C.one_over_L, C.clip) : (T)0;
     for (int i = 0; i < K; ++i) {
         const T aw = r[i], ah = r[K + i];
         const T pw = exp_(clip_val(aw, C.two_over_L, C.clip) - mw) / Sw;
         const T ph = exp_(clip_val(ah, C.two_over_L, C.clip) - mh) / Sh;
         const T iw_hi = (i <= bin) ? (T)1 : (T)0, iw_lo = (i < bin) ? (T)1 : (T)0;
-        gr[i] = clip_der(aw, C.two_over_L, C.clip) * pw * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
-        gr[K + i] = clip_der(ah, C.two_over_L, C.clip) * ph * twoB * (adj[3] * (iw_hi - ch_hi) + adj[2] * (iw_lo - ch_lo));
+        r[i] = clip_der(aw, C.two_over_L, C.clip) * pw * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
+        r[K + i] = clip_der(ah, C.two_over_L, C.clip) * ph * twoB * (adj[3] * (iw_hi - ch_hi) + adj[2] * (iw_lo - ch_lo));
     }
-    for (int i = 0; i < K - 1; ++i) {
-        T gd = (T)0;
-        if (i == bin - 1) gd = adj[4] * d0v * clip_der(r[2 * K + i], C.one_over_L, C.clip);
-        if (i == bin) gd = adj[5] * d1v * clip_der(r[2 * K + i], C.one_over_L, C.clip);
-        gr[2 * K + i] = gd;
+    for (int i = 0; i < K - 1; ++i) r[2 * K + i] = (i == bin - 1) ? gd0 : ((i == bin) ? gd1 : (T)0);
+    return adj[6];
+}
+
+// Persistent CTAs; a tile of `rpt` rows comes in by one TMA bulk load, every thread turns its row into its gradient in
+// place, and the tile leaves by one TMA bulk store (cp.async.bulk.global.shared::cta): parameters and gradients each
+// cross HBM exactly once, fully coalesced.
+template <typename T, bool INV>
+__global__ void __launch_bounds__(128)
+rqs_backward_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const T* __restrict__ g_out,
+                    const T* __restrict__ g_ladj, int64_t rows, int K, RqsConst<T> C, int rpt, int bulk_ok,
+                    T* __restrict__ g_phi, T* __restrict__ g_v) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int PW = 3 * K - 1;
+    const size_t tile_elems = (size_t)rpt * PW;
+    T* sm = reinterpret_cast<T*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (tile_elems * sizeof(T) + 127) / 128 * 128);
+    const int tid = threadIdx.x;
+    const int64_t num_tiles = (rows + rpt - 1) / rpt;
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    uint32_t parity = 0u;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * rpt;
+        const int nrows = (int)((rows - row0) < rpt ? (rows - row0) : rpt);
+        const bool bulk = bulk_ok && nrows == rpt;
+        const T* src = phi + (size_t)row0 * PW;
+        T* dst = g_phi + (size_t)row0 * PW;
+        if (bulk) {
+            if (tid == 0) {
+                bulk_store_wait_read();  // the previous tile's store has finished reading the buffer
+                const uint32_t bytes = (uint32_t)(tile_elems * sizeof(T));
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(sm, src, bytes, bar);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            if (tid == 0) bulk_store_wait_read();
+            __syncthreads();
+            const size_t ne = (size_t)nrows * PW;
+            for (size_t i = tid; i < ne; i += 128) sm[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        for (int rr = tid; rr < nrows; rr += 128) {
+            const int64_t row = row0 + rr;
+            const T go = g_out ? g_out[row] : (T)0, gl = g_ladj ? g_ladj[row] : (T)0;
+            g_v[row] = rqs_row_backward<T, INV>(sm + (size_t)rr * PW, K, C, vin[row], go, gl);
+        }
+        fence_proxy_async();  // generic writes of the gradients -> visible to the bulk store
+        __syncthreads();
+        if (bulk) {
+            if (tid == 0) bulk_s2g(dst, sm, (uint32_t)(tile_elems * sizeof(T)));
+        } else {
+            const size_t ne = (size_t)nrows * PW;
+            for (size_t i = tid; i < ne; i += 128) dst[i] = sm[i];
+            __syncthreads();
+        }
     }
+    if (tid == 0) bulk_store_wait_read();
 }
 
 template <typename T, bool INV>
@@ -141,8 +188,28 @@ static int rqs_bwd_launch(const T* phi, const T* vin, const T* g_out, const T* g
     const int64_t rows = B * (int64_t)F;
     if (rows == 0) return MF_OK;
     const RqsConst<T> C = make_rqs_const<T>(bound, slope);
-    rqs_backward_kernel<T, INV><<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(phi, vin, g_out, g_ladj, rows, K, C,
-                                                                                    g_phi, g_v);
+    const int PW = 3 * K - 1;
+    int dev = 0, sms = 148, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    auto need = [&](int r) { return ((size_t)r * PW * sizeof(T) + 127) / 128 * 128 + 128; };
+    int rpt = 128;
+    while (rpt > 4 && need(rpt) > (size_t)smem_max / 2) rpt -= 4;   // >= 2 CTAs per SM when possible
+    while (rpt > 4 && need(rpt) > (size_t)smem_max) rpt -= 4;
+    if (need(rpt) > (size_t)smem_max) return MF_E_SHAPE;
+    const int bulk_ok = (aligned(phi, 16) && aligned(g_phi, 16) && ((size_t)rpt * PW * sizeof(T)) % 16 == 0) ? 1 : 0;
+    const size_t smem = need(rpt);
+    const int64_t tiles = (rows + rpt - 1) / rpt;
+    auto kern = rqs_backward_kernel<T, INV>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int ctas = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 128, smem);
+    if (ctas < 1) ctas = 1;
+    int64_t grid = (int64_t)sms * ctas;
+    if (grid > tiles) grid = tiles;
+    kern<<<(unsigned)grid, 128, smem, stream>>>(phi, vin, g_out, g_ladj, rows, K, C, rpt, bulk_ok, g_phi, g_v);
     return launch_status();
 }
 
