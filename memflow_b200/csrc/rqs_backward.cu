@@ -34,29 +34,47 @@ template <typename T> MF_D Dual<T> dlog(const Dual<T>& a) { Dual<T> r; r.v = log
 template <typename T> MF_D T clip_val(T a, T c, int clip) { return clip ? a / ((T)1 + fabs_(a * c)) : a; }
 template <typename T> MF_D T clip_der(T a, T c, int clip) { if (!clip) return (T)1; const T t = (T)1 + fabs_(a * c); return (T)1 / (t * t); }
 
+// exp(clip(a) - m): fp32 with the soft clip uses the 4-instruction exp-clip of the forward (bounded argument, m = 0)
+template <typename T> MF_D T bw_exp(T a, T m, const RqsConst<T>& C) { return exp_(clip_val(a, C.two_over_L, C.clip) - m); }
+template <> MF_D float bw_exp<float>(float a, float m, const RqsConst<float>& C) {
+    return C.clip ? exp_clip_w(a, C) : FastMath<float>::exp(a - m);
+}
+
 // Row gradient, in place: on entry r[0..3K-2] = parameters of the row, on exit = their gradients. Returns g_v.
 template <typename T, bool INV>
 MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T go, T gl) {
     const int PW = 3 * K - 1;
     const T B = C.bound;
-    // ---- pass 1: softmax sums (max-subtracted like torch.softmax), bin, prefix sums at the bin ----
-    T mw = clip_val(r[0], C.two_over_L, C.clip), mh = clip_val(r[K], C.two_over_L, C.clip);
-    for (int k = 1; k < K; ++k) {
-        mw = fmax_(mw, clip_val(r[k], C.two_over_L, C.clip));
-        mh = fmax_(mh, clip_val(r[K + k], C.two_over_L, C.clip));
+    // ---- pass 1: softmax sums. torch.softmax subtracts the row maximum; with the soft clip the arguments are bounded
+    //      by |log slope| / 2, so in fp32 the subtraction is skipped (same value up to rounding) ----
+    T mw = (T)0, mh = (T)0;
+    if (!(C.clip && sizeof(T) == 4)) {
+        mw = clip_val(r[0], C.two_over_L, C.clip); mh = clip_val(r[K], C.two_over_L, C.clip);
+        for (int k = 1; k < K; ++k) {
+            mw = fmax_(mw, clip_val(r[k], C.two_over_L, C.clip));
+            mh = fmax_(mh, clip_val(r[K + k], C.two_over_L, C.clip));
+        }
     }
     T Sw = (T)0, Sh = (T)0;
     for (int k = 0; k < K; ++k) {
-        Sw += exp_(clip_val(r[k], C.two_over_L, C.clip) - mw);
-        Sh += exp_(clip_val(r[K + k], C.two_over_L, C.clip) - mh);
+        Sw += bw_exp(r[k], mw, C);
+        Sh += bw_exp(r[K + k], mh, C);
     }
-    // searchsorted on the searched coordinate (X for the forward, Y for the inverse), knots as the forward builds them
+    const T iSw = (T)1 / Sw, iSh = (T)1 / Sh;
+    // ---- pass 2: searchsorted on the searched coordinate (X forward / Y inverse) with the knots as the forward builds
+    //      them, keeping the cumulative sums on both sides of the bin; then the other coordinate's prefix sums ----
+    T cs_lo = (T)0, cs_hi = (T)0;
     int cnt = ((T)-B < v) ? 1 : 0;
     {
+        const T ms = INV ? mh : mw, is = INV ? iSh : iSw;
         T c = (T)0;
+        bool found = false;
         for (int k = 0; k < K; ++k) {
-            c += exp_(clip_val(r[(INV ? K : 0) + k], C.two_over_L, C.clip) - (INV ? mh : mw)) / (INV ? Sh : Sw);
-            cnt += (B * ((T)2 * c - (T)1) < v) ? 1 : 0;
+            const T cprev = c;
+            c += bw_exp(r[(INV ? K : 0) + k], ms, C) * is;
+            const bool below = B * ((T)2 * c - (T)1) < v;
+            cnt += below ? 1 : 0;
+            if (!below && !found) { cs_lo = cprev; cs_hi = c; found = true; }
         }
     }
     const int bin = cnt - 1;
@@ -64,16 +82,17 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
         for (int i = 0; i < PW; ++i) r[i] = (T)0;
         return go;
     }
-    T cw_lo = (T)0, cw_hi = (T)0, ch_lo = (T)0, ch_hi = (T)0;
+    T co_lo = (T)0, co_hi = (T)0;
     {
-        T cw = (T)0, ch = (T)0;
+        const T mo = INV ? mw : mh, io = INV ? iSw : iSh;
+        T c = (T)0;
         for (int k = 0; k <= bin; ++k) {
-            if (k == bin) { cw_lo = cw; ch_lo = ch; }
-            cw += exp_(clip_val(r[k], C.two_over_L, C.clip) - mw) / Sw;
-            ch += exp_(clip_val(r[K + k], C.two_over_L, C.clip) - mh) / Sh;
+            if (k == bin) co_lo = c;
+            c += bw_exp(r[(INV ? 0 : K) + k], mo, C) * io;
         }
-        cw_hi = cw; ch_hi = ch;
+        co_hi = c;
     }
+    const T cw_lo = INV ? co_lo : cs_lo, cw_hi = INV ? co_hi : cs_hi, ch_lo = INV ? cs_lo : co_lo, ch_hi = INV ? cs_hi : co_hi;
     const T x0v = B * ((T)2 * cw_lo - (T)1), x1v = B * ((T)2 * cw_hi - (T)1);
     const T y0v = B * ((T)2 * ch_lo - (T)1), y1v = B * ((T)2 * ch_hi - (T)1);
     const T d0v = bin > 0 ? exp_(clip_val(r[2 * K + bin - 1], C.one_over_L, C.clip)) : (T)1;
@@ -112,8 +131,8 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
     const T gd1 = bin < K - 1 ? adj[5] * d1v * clip_der(r[2 * K + bin], C.one_over_L, C.clip) : (T)0;
     for (int i = 0; i < K; ++i) {
         const T aw = r[i], ah = r[K + i];
-        const T pw = exp_(clip_val(aw, C.two_over_L, C.clip) - mw) / Sw;
-        const T ph = exp_(clip_val(ah, C.two_over_L, C.clip) - mh) / Sh;
+        const T pw = bw_exp(aw, mw, C) * iSw;
+        const T ph = bw_exp(ah, mh, C) * iSh;
         const T iw_hi = (i <= bin) ? (T)1 : (T)0, iw_lo = (i < bin) ? (T)1 : (T)0;
         r[i] = clip_der(aw, C.two_over_L, C.clip) * pw * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
         r[K + i] = clip_der(ah, C.two_over_L, C.clip) * ph * twoB * (adj[3] * (iw_hi - ch_hi) + adj[2] * (iw_lo - ch_lo));
