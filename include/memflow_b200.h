@@ -216,6 +216,38 @@ int mf_top_decay_f64(const double* parent, int64_t parent_stride, const double* 
                      int64_t N, double top_mass, double w_mass, double b_mass, int as_ptetaphi, double* out,
                      mf_stream_t stream);
 
+/* The whole parton-level event from the lab-frame propagators, the decay angles and the boost:
+ *   Compute_ParticlesTensor.get_decayPartons_fromlab_propagators_angles, memflow/unfolding_flow/utils.py:826-935
+ *   (call site memflow/unfolding_flow/unfolding_flow_withDecay_v2.py:399-417), fused into one launch:
+ *   unscale -> pt = exp|log pt| - 1 -> cartesian -> H->bb, t->bqq', t->blv -> ISR gluon = boost - partons
+ *   -> (E, pt, eta, phi) -> log(pt + 1) and affine scaling.
+ *   propagators [N,3,3] = scaled (log(pt+1), eta, phi) of H, thad, tlep (NOT modified; the reference unscales its
+ *   argument in place); *_angles [N,2] = (eta, phi) in the parent rest frame; boost [N,2] = scaled (log(E+1), pz);
+ *   out [N,12,4] rows: H b1 b2 | thad b q1 q2 | tlep b l nu | ISR.
+ *   The reference pairs propagator 1 with (tlep_mass, tlep angles) and propagator 2 with (thad_mass, thad angles)
+ *   (:866-873); kept. final_scaling && !ptetaphi reads an undefined name in the reference (:913): MF_E_BADARG. */
+typedef struct mf_decay_partons_cfg {
+    double mean_prop[3], std_prop[3];   /* log_mean/std_parton_Hthadtlep: (log(pt+1), eta, phi) */
+    double mean_lab[3], std_lab[3];     /* log_mean/std_parton_lab:       (log(pt+1), eta, phi) */
+    double mean_boost[2], std_boost[2]; /* log_mean/std_boost:            (log(E+1), pz) */
+    double higgs_mass, thad_mass, tlep_mass, w_had_mass, w_lep_mass, b_mass, eps;
+    int32_t ptetaphi, unscale_phi, final_scaling, reserved;
+} mf_decay_partons_cfg;
+int mf_decay_partons_f64(const double* propagators, const double* higgs_angles, const double* thad_b_angles,
+                         const double* thad_w_angles, const double* tlep_b_angles, const double* tlep_w_angles,
+                         const double* boost, int64_t N, const mf_decay_partons_cfg* cfg, double* out,
+                         mf_stream_t stream);
+
+/* Vector-Jacobian product of mf_decay_partons_f64: g_out [N,12,4] -> gradients w.r.t. every input (same shapes).
+ * Replaces the autograd graph of get_decayPartons_fromlab_propagators_angles in the sampling loss
+ * (memflow/unfolding_flow/unfolding_flow_withDecay_v2.py:376-417). g_boost[:,0] = 0: only pz of the boost enters. */
+int mf_decay_partons_bwd_f64(const double* propagators, const double* higgs_angles, const double* thad_b_angles,
+                             const double* thad_w_angles, const double* tlep_b_angles, const double* tlep_w_angles,
+                             const double* boost, int64_t N, const mf_decay_partons_cfg* cfg, const double* g_out,
+                             double* g_propagators, double* g_higgs_angles, double* g_thad_b_angles,
+                             double* g_thad_w_angles, double* g_tlep_b_angles, double* g_tlep_w_angles, double* g_boost,
+                             mf_stream_t stream);
+
 /* The two stages of the chain as separate entry points (mf_is_chain_f64 runs them back to back):
  *  A  mf_flow_sample_f32: Philox base sample + T spline inverses -> u [N,F] (fp64, in [0,1]) and log q [N]
  *                         (flow().sample + flow().log_prob of TestFlows_ImportanceSampling.ipynb [45,50] in one pass)

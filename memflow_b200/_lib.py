@@ -18,11 +18,24 @@ SYMBOLS = (
     "mf_searchsorted_f32", "mf_searchsorted_f64",
     "mf_rqs_forward_bwd_f32", "mf_rqs_forward_bwd_f64", "mf_rqs_inverse_bwd_f32", "mf_rqs_inverse_bwd_f64",
     "mf_is_reduce_workspace_bytes", "mf_is_reduce_f64", "mf_is_chain_f64", "mf_flow_sample_f32", "mf_rambo_is_f64", "mf_higgs_decay_f64", "mf_top_decay_f64",
+    "mf_decay_partons_f64", "mf_decay_partons_bwd_f64",
 )
 
 
 class MemflowB200Error(RuntimeError):
     pass
+
+
+class DecayPartonsCfg(ctypes.Structure):
+    """mf_decay_partons_cfg of include/memflow_b200.h."""
+    _fields_ = [("mean_prop", ctypes.c_double * 3), ("std_prop", ctypes.c_double * 3),
+                ("mean_lab", ctypes.c_double * 3), ("std_lab", ctypes.c_double * 3),
+                ("mean_boost", ctypes.c_double * 2), ("std_boost", ctypes.c_double * 2),
+                ("higgs_mass", ctypes.c_double), ("thad_mass", ctypes.c_double), ("tlep_mass", ctypes.c_double),
+                ("w_had_mass", ctypes.c_double), ("w_lep_mass", ctypes.c_double), ("b_mass", ctypes.c_double),
+                ("eps", ctypes.c_double),
+                ("ptetaphi", ctypes.c_int32), ("unscale_phi", ctypes.c_int32), ("final_scaling", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
 
 
 _lib = None

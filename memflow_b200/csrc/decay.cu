@@ -5,38 +5,10 @@
 // boosted by the parent's velocity (utils.boost_t) -- the W daughters by the boosted W. One event per thread; the
 // parent 4-momentum is one 256-bit load (row stride given, so a row of a K1 output is read in place), every
 // output row one 256-bit store. Optionally converted to (E, pt, eta, phi) like the reference's ptetaphi=True.
-#include "rambo.cuh"
+#include "decay.cuh"
 
 namespace mf {
 
-// (pt, eta, phi) + mass -> (E, px, py, pz): get_cartesian_comp, utils.py:109-119
-MF_D void cartesian(double pt, double eta, double phi, double mass, double (&p)[4]) {
-    p[1] = pt * cos(phi);
-    p[2] = pt * sin(phi);
-    p[3] = pt * sinh(eta);
-    p[0] = sqrt(((p[1] * p[1] + p[2] * p[2]) + p[3] * p[3]) + mass * mass);
-}
-// (E, px, py, pz) -> (E, pt, eta, phi): get_ptetaphi_comp, utils.py:169-173
-MF_D void ptetaphi(const double (&p)[4], double (&o)[4]) {
-    const double pt = sqrt(p[1] * p[1] + p[2] * p[2]);
-    o[0] = p[0];
-    o[1] = pt;
-    o[2] = -log(tan(atan2(pt, p[3]) / 2.0));
-    o[3] = atan2(p[2], p[1]);
-}
-MF_D void boost_by_parent(const double (&p)[4], const double (&parent)[4], double (&o)[4]) {
-    // utils.boost_t(p, utils.boostVector_t(parent)): library divisions, this kernel is store-bound
-    const double bx = parent[1] / parent[0], by = parent[2] / parent[0], bz = parent[3] / parent[0];
-    const double b2 = (bx * bx + by * by) + bz * bz;
-    const double gamma = 1.0 / sqrt(1.0 - b2);
-    const double bp = (p[1] * bx + p[2] * by) + p[3] * bz;
-    const double gamma2 = (b2 > 0.0) ? (gamma - 1.0) / b2 : 0.0;
-    const double factor = gamma2 * bp + gamma * p[0];
-    o[1] = p[1] + factor * bx;
-    o[2] = p[2] + factor * by;
-    o[3] = p[3] + factor * bz;
-    o[0] = gamma * (p[0] + bp);
-}
 MF_D void emit_row(double* dst, const double (&p)[4], int as_ptetaphi) {
     if (as_ptetaphi) {
         double o[4];
@@ -52,16 +24,10 @@ higgs_decay_kernel(const double* __restrict__ parent, int64_t parent_stride, con
                    double mass, int as_ptetaphi, double* __restrict__ out) {
     const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ev >= N) return;
-    double H[4], eta, phi;
+    double H[4], eta, phi, l1[4], l2[4];
     ld4(parent + ev * parent_stride, H[0], H[1], H[2], H[3]);
     ld2(angles + 2 * ev, eta, phi);
-    const double E = mass / 2.0;
-    const double pt = E / cosh(eta);
-    double b1[4], b2[4], l1[4], l2[4];
-    cartesian(pt, eta, phi, 0.0, b1);
-    cartesian(pt, -eta, 3.141592653589793 + phi, 0.0, b2);  // b2 = "-b1" in the rest frame (:754)
-    boost_by_parent(b1, H, l1);
-    boost_by_parent(b2, H, l2);
+    higgs_decay_rows(H, eta, phi, mass, l1, l2);
     double* o = out + ev * 12;
     emit_row(o, H, as_ptetaphi);
     emit_row(o + 4, l1, as_ptetaphi);
@@ -70,37 +36,85 @@ higgs_decay_kernel(const double* __restrict__ parent, int64_t parent_stride, con
 
 __global__ void __launch_bounds__(256)
 top_decay_kernel(const double* __restrict__ parent, int64_t parent_stride, const double* __restrict__ b_angles,
-                 const double* __restrict__ w_angles, int64_t N, double E_b, double E_W, double w_mass, double b_mass,
+                 const double* __restrict__ w_angles, int64_t N, double E_b, double w_mass, double b_mass,
                  int as_ptetaphi, double* __restrict__ out) {
     const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ev >= N) return;
-    const double two_pi = 2.0 * 3.141592653589793, pi = 3.141592653589793;
-    double t[4], eb, pb, ew, pw;
+    double t[4], eb, pb, ew, pw, bl[4], q1l[4], q2l[4];
     ld4(parent + ev * parent_stride, t[0], t[1], t[2], t[3]);
     ld2(b_angles + 2 * ev, eb, pb);
     ld2(w_angles + 2 * ev, ew, pw);
-    const double pt_b = sqrt(E_b * E_b - b_mass * b_mass) / cosh(eb);  // pt of W = pt of b (:781-785)
-    double phiW = pi + pb;
-    if (pb > 0.0) phiW = phiW - two_pi;
-    const double Eq = w_mass / 2.0;
-    const double pt_q = Eq / cosh(ew);
-    double phi2 = pi + pw;
-    if (pw > 0.0) phi2 = phi2 - two_pi;
-    double b[4], W[4], q1[4], q2[4], bl[4], Wl[4], q1l[4], q2l[4];
-    cartesian(pt_b, eb, pb, b_mass, b);
-    cartesian(pt_q, ew, pw, 0.0, q1);
-    cartesian(pt_q, -ew, phi2, 0.0, q2);
-    cartesian(pt_b, -eb, phiW, w_mass, W);
-    (void)E_W;  // the reference computes E_W but rebuilds the W energy from its momentum and mass (:800)
-    boost_by_parent(b, t, bl);
-    boost_by_parent(W, t, Wl);
-    boost_by_parent(q1, Wl, q1l);
-    boost_by_parent(q2, Wl, q2l);
+    top_decay_rows(t, eb, pb, ew, pw, E_b, w_mass, b_mass, bl, q1l, q2l);
     double* o = out + ev * 16;
     emit_row(o, t, as_ptetaphi);
     emit_row(o + 4, bl, as_ptetaphi);
     emit_row(o + 8, q1l, as_ptetaphi);
     emit_row(o + 12, q2l, as_ptetaphi);
+}
+
+// ---- the whole parton-level event from the three lab-frame propagators, the five decay angle pairs and the boost:
+//      Compute_ParticlesTensor.get_decayPartons_fromlab_propagators_angles, memflow/unfolding_flow/utils.py:826-935
+//      (call site: unfolding_flow_withDecay_v2.py:399-417). One event per thread: unscale -> pt = exp|.|-1 -> cartesian
+//      -> H->bb, t->bqq', t->blv -> ISR gluon from the momentum balance -> (E,pt,eta,phi) -> log(pt+1) + scaling.
+//      Output rows: H b1 b2 | thad b q1 q2 | tlep b l nu | ISR. The reference's naming quirk is kept: propagator 1
+//      takes (tlep_mass, tlep angles), propagator 2 takes (thad_mass, thad angles) (:866-873). ----
+__global__ void __launch_bounds__(128)
+decay_partons_kernel(const double* __restrict__ prop, const double* __restrict__ higgs_angles,
+                     const double* __restrict__ thad_b_angles, const double* __restrict__ thad_w_angles,
+                     const double* __restrict__ tlep_b_angles, const double* __restrict__ tlep_w_angles,
+                     const double* __restrict__ boost, int64_t N, const __grid_constant__ mf_decay_partons_cfg C,
+                     double* __restrict__ out) {
+    const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ev >= N) return;
+    const double mass[3] = {C.higgs_mass, C.tlep_mass, C.thad_mass};
+    double P[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double k[3] = {prop[ev * 9 + 3 * i], prop[ev * 9 + 3 * i + 1], prop[ev * 9 + 3 * i + 2]};
+        propagator_cartesian(k, mass[i], C, P[i]);
+    }
+    const double boost_pz = boost[2 * ev + 1] * C.std_boost[1] + C.mean_boost[1];
+    double* o = out + ev * 48;
+    auto emit = [&](int row, const double (&p)[4], bool is_prop, bool is_gluon_pad) {
+        double r[4];
+        finish_row(p, is_prop, is_gluon_pad, C, r);
+        st4(o + 4 * row, r[0], r[1], r[2], r[3]);
+    };
+    {
+        double eta, phi, l1[4], l2[4];
+        ld2(higgs_angles + 2 * ev, eta, phi);
+        higgs_decay_rows(P[0], eta, phi, C.higgs_mass, l1, l2);
+        emit(0, P[0], true, false);
+        emit(1, l1, false, false);
+        emit(2, l2, false, false);
+    }
+    {
+        double eb, pb, ew, pw, bl[4], q1l[4], q2l[4];
+        ld2(thad_b_angles + 2 * ev, eb, pb);
+        ld2(thad_w_angles + 2 * ev, ew, pw);
+        top_decay_rows(P[2], eb, pb, ew, pw, top_Eb(C.thad_mass, C.w_had_mass, C.b_mass), C.w_had_mass, C.b_mass, bl, q1l, q2l);
+        emit(3, P[2], true, false);
+        emit(4, bl, false, false);
+        emit(5, q1l, false, false);
+        emit(6, q2l, false, false);
+    }
+    {
+        double eb, pb, ew, pw, bl[4], q1l[4], q2l[4];
+        ld2(tlep_b_angles + 2 * ev, eb, pb);
+        ld2(tlep_w_angles + 2 * ev, ew, pw);
+        top_decay_rows(P[1], eb, pb, ew, pw, top_Eb(C.tlep_mass, C.w_lep_mass, C.b_mass), C.w_lep_mass, C.b_mass, bl, q1l, q2l);
+        emit(7, P[1], true, false);
+        emit(8, bl, false, false);
+        emit(9, q1l, false, false);
+        emit(10, q2l, false, false);
+    }
+    // ISR gluon = boost - partons (:881-905); the all-soft case is replaced by the reference's padding row
+    double g[4];
+    g[1] = -((P[0][1] + P[2][1]) + P[1][1]);
+    g[2] = -((P[0][2] + P[2][2]) + P[1][2]);
+    g[3] = boost_pz - ((P[0][3] + P[2][3]) + P[1][3]);
+    g[0] = sqrt((g[1] * g[1] + g[2] * g[2]) + g[3] * g[3]) + C.eps;
+    emit(11, g, false, gluon_pad(g, C));
 }
 
 }  // namespace mf
@@ -124,9 +138,27 @@ extern "C" int mf_top_decay_f64(const double* parent, int64_t parent_stride, con
     if (!mf::aligned(parent, 32) || !mf::aligned(b_angles, 16) || !mf::aligned(w_angles, 16) || !mf::aligned(out, 32))
         return MF_E_ALIGN;
     if (N == 0) return MF_OK;
-    const double E_b = (top_mass * top_mass - w_mass * w_mass + b_mass * b_mass) / 2. / top_mass;
-    const double E_W = (top_mass * top_mass + w_mass * w_mass - b_mass * b_mass) / 2. / top_mass;
+    const double E_b = mf::top_Eb(top_mass, w_mass, b_mass);
     mf::top_decay_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        parent, parent_stride, b_angles, w_angles, N, E_b, E_W, w_mass, b_mass, as_ptetaphi, out);
+        parent, parent_stride, b_angles, w_angles, N, E_b, w_mass, b_mass, as_ptetaphi, out);
+    return mf::launch_status();
+}
+
+extern "C" int mf_decay_partons_f64(const double* propagators, const double* higgs_angles, const double* thad_b_angles,
+                                    const double* thad_w_angles, const double* tlep_b_angles, const double* tlep_w_angles,
+                                    const double* boost, int64_t N, const mf_decay_partons_cfg* cfg, double* out,
+                                    mf_stream_t stream) {
+    if (N < 0 || !cfg) return MF_E_BADARG;
+    if (N > 0 && (!propagators || !higgs_angles || !thad_b_angles || !thad_w_angles || !tlep_b_angles || !tlep_w_angles ||
+                  !boost || !out))
+        return MF_E_BADARG;
+    // the reference's cartesian final scaling reads an undefined name (utils.py:913): there is nothing to reproduce
+    if (cfg->final_scaling && !cfg->ptetaphi) return MF_E_BADARG;
+    if (!mf::aligned(higgs_angles, 16) || !mf::aligned(thad_b_angles, 16) || !mf::aligned(thad_w_angles, 16) ||
+        !mf::aligned(tlep_b_angles, 16) || !mf::aligned(tlep_w_angles, 16) || !mf::aligned(boost, 16) || !mf::aligned(out, 32))
+        return MF_E_ALIGN;
+    if (N == 0) return MF_OK;
+    mf::decay_partons_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        propagators, higgs_angles, thad_b_angles, thad_w_angles, tlep_b_angles, tlep_w_angles, boost, N, *cfg, out);
     return mf::launch_status();
 }

@@ -11,7 +11,7 @@ import ctypes
 
 import torch
 
-from .._lib import check, host_array, lib, ptr, require_cuda, stream_ptr
+from .._lib import DecayPartonsCfg, check, host_array, lib, ptr, require_cuda, stream_ptr
 
 M_HIGGS = 125.25
 M_TOP = 172.5
@@ -157,3 +157,81 @@ class Compute_ParticlesTensor:
                                          ctypes.c_double(float(b_mass)), ctypes.c_int(int(bool(ptetaphi))), ptr(out),
                                          stream_ptr(dev)), "mf_top_decay_f64")
         return out
+
+    @staticmethod
+    def get_decayPartons_fromlab_propagators_angles(propagators_kinematics, higgs_angles, thad_b_angles, thad_W_angles,
+                                                    tlep_b_angles, tlep_W_angles, boost, log_mean_parton_lab,
+                                                    log_std_parton_lab, log_mean_boost, log_std_boost,
+                                                    log_mean_parton_Hthadtlep, log_std_parton_Hthadtlep, device=None,
+                                                    higgs_mass=125.25, thad_mass=172.5, tlep_mass=172.5, W_had_mass=80.4,
+                                                    W_lep_mass=80.4, b_mass=0.0, ptetaphi=True, eps=1e-4, pt_cut=None,
+                                                    unscale_phi=False, debug=False, final_scaling=True):
+        """Full parton-level event [N,12,4] (H b1 b2 | thad b q1 q2 | tlep b l nu | ISR) from the scaled lab-frame
+        propagators [N,3,3], the five decay-angle pairs [N,2] and the scaled boost [N,1,2], in one launch
+        (`mf_decay_partons_f64`; reference memflow/unfolding_flow/utils.py:826-935, same argument list).
+        Differences: `propagators_kinematics` is not unscaled in place; the result is differentiable w.r.t. every
+        tensor input (backward kernel); `final_scaling=True, ptetaphi=False` raises NameError like the reference
+        (its cartesian scaling reads an undefined name, :913)."""
+        if final_scaling and not ptetaphi:
+            raise NameError("name 'log_mean_parton' is not defined (memflow/unfolding_flow/utils.py:913: the cartesian "
+                            "final scaling of the reference never worked; use ptetaphi=True or final_scaling=False)")
+        require_cuda(propagators_kinematics, "propagators_kinematics")
+        cfg = DecayPartonsCfg()
+        def put(field, t, n):
+            v = [float(x) for x in torch.as_tensor(t).detach().reshape(-1).tolist()]
+            if len(v) < n:
+                raise ValueError("get_decayPartons_fromlab_propagators_angles: scaling vector shorter than %d" % n)
+            for i in range(n):
+                field[i] = v[i]
+        put(cfg.mean_prop, log_mean_parton_Hthadtlep, 3 if unscale_phi else 2)
+        put(cfg.std_prop, log_std_parton_Hthadtlep, 3 if unscale_phi else 2)
+        put(cfg.mean_lab, log_mean_parton_lab, 3 if unscale_phi else 2)
+        put(cfg.std_lab, log_std_parton_lab, 3 if unscale_phi else 2)
+        put(cfg.mean_boost, log_mean_boost, 2)
+        put(cfg.std_boost, log_std_boost, 2)
+        cfg.higgs_mass, cfg.thad_mass, cfg.tlep_mass = float(higgs_mass), float(thad_mass), float(tlep_mass)
+        cfg.w_had_mass, cfg.w_lep_mass, cfg.b_mass, cfg.eps = float(W_had_mass), float(W_lep_mass), float(b_mass), float(eps)
+        cfg.ptetaphi, cfg.unscale_phi, cfg.final_scaling = int(bool(ptetaphi)), int(bool(unscale_phi)), int(bool(final_scaling))
+        N = propagators_kinematics.shape[0]
+        if tuple(propagators_kinematics.shape) != (N, 3, 3):
+            raise ValueError("propagators_kinematics must be [N,3,3] (H, thad, tlep) x (log(pt+1), eta, phi)")
+        ins = [propagators_kinematics, higgs_angles, thad_b_angles, thad_W_angles, tlep_b_angles, tlep_W_angles, boost]
+        for a in ins[1:6]:
+            if tuple(a.shape) != (N, 2):
+                raise ValueError("decay angles must be [N,2] = (eta, phi)")
+        if boost.numel() != 2 * N:
+            raise ValueError("boost must be [N,1,2] = scaled (log(E+1), pz)")
+        out = _DecayPartonsFn.apply(cfg, *ins)
+        return out.to(propagators_kinematics.dtype)
+
+
+class _DecayPartonsFn(torch.autograd.Function):
+    """mf_decay_partons_f64 and its backward kernel mf_decay_partons_bwd_f64."""
+
+    @staticmethod
+    def forward(ctx, cfg, *ins):
+        dev = ins[0].device
+        d = [t.detach().to(torch.float64).contiguous() for t in ins]
+        N = d[0].shape[0]
+        out = torch.empty((N, 12, 4), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().mf_decay_partons_f64(*[ptr(t) for t in d], ctypes.c_int64(N), ctypes.byref(cfg), ptr(out),
+                                             stream_ptr(dev)), "mf_decay_partons_f64")
+        ctx.cfg = cfg
+        ctx.save_for_backward(*d)
+        ctx.in_meta = [(t.shape, t.dtype) for t in ins]
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        d = ctx.saved_tensors
+        dev = d[0].device
+        N = d[0].shape[0]
+        g = g_out.detach().to(torch.float64).contiguous()
+        grads = [torch.empty_like(t) for t in d]
+        with torch.cuda.device(dev):
+            check(lib().mf_decay_partons_bwd_f64(*[ptr(t) for t in d], ctypes.c_int64(N), ctypes.byref(ctx.cfg), ptr(g),
+                                                 *[ptr(t) for t in grads], stream_ptr(dev)), "mf_decay_partons_bwd_f64")
+        outs = [gr.reshape(shape).to(dt) if need else None
+                for gr, (shape, dt), need in zip(grads, ctx.in_meta, ctx.needs_input_grad[1:])]
+        return (None, *outs)

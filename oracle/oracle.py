@@ -144,6 +144,28 @@ def top_decay(parent, b_angles, w_angles, top_mass=172.5, w_mass=80.4, b_mass=0.
     return out
 
 
+def decay_partons_cfg(mean_prop, std_prop, mean_lab, std_lab, mean_boost, std_boost, higgs_mass=125.25, thad_mass=172.5,
+                      tlep_mass=172.5, W_had_mass=80.4, W_lep_mass=80.4, b_mass=0.0, eps=1e-4, ptetaphi=True,
+                      unscale_phi=False, final_scaling=True):
+    return np.array(list(mean_prop) + list(std_prop) + list(mean_lab) + list(std_lab) + list(mean_boost) + list(std_boost)
+                    + [higgs_mass, thad_mass, tlep_mass, W_had_mass, W_lep_mass, b_mass, eps, float(ptetaphi),
+                       float(unscale_phi), float(final_scaling)], dtype=np.float64)
+
+
+def decay_partons(prop, higgs_angles, thad_b_angles, thad_w_angles, tlep_b_angles, tlep_w_angles, boost, cfg):
+    """memflow/unfolding_flow/utils.py:826-935: prop [N,3,3], angles [N,2], boost [N,2] (or [N,1,2]) -> [N,12,4]."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in
+            (prop, higgs_angles, thad_b_angles, thad_w_angles, tlep_b_angles, tlep_w_angles, boost)]
+    N = arrs[0].shape[0]
+    out = np.empty((N, 12, 4), dtype=np.float64)
+    cfg = np.ascontiguousarray(cfg, dtype=np.float64)
+    assert cfg.size == 26
+    rc = lib().mfo_decay_partons(*[_dp(a) for a in arrs], ctypes.c_int64(N), _dp(cfg), _dp(out))
+    if rc != 0:
+        raise RuntimeError("mfo_decay_partons rc=%d" % rc)
+    return out
+
+
 def _rqs(direction, phi, v, bound, slope):
     phi = np.ascontiguousarray(phi)
     dt = phi.dtype

@@ -232,5 +232,84 @@ def main():
     print(known)
 
 
+def make_decay_partons():
+    """decay_partons_*.npz: Compute_ParticlesTensor.get_decayPartons_fromlab_propagators_angles (utils.py:826-935) on
+    lab-frame H / thad / tlep taken from the n=4 (real ISR gluon) and n=3 (no ISR: the reference's padding row) events.
+    Also stores the reference's autograd gradient of sum(out * g_out) w.r.t. every input of the first variant."""
+    _, _, utils = import_reference()
+    for name in ("vector", "awkward"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    from memflow.unfolding_flow.utils import Compute_ParticlesTensor as CPT
+    rows = []
+    for n in (4, 3):
+        g = np.load(os.path.join(HERE, "rambo_n%d.npz" % n))
+        lab = utils.boost_to_lab_frame(torch.from_numpy(g["mom_clean"]), torch.from_numpy(g["x1_clean"]),
+                                       torch.from_numpy(g["x2_clean"]))
+        keep = torch.isfinite(lab).all(dim=(1, 2))
+        lab = lab[keep][:160 if n == 4 else 32]
+        e_cm = float(g["e_cm"])
+        x1, x2 = torch.from_numpy(g["x1_clean"])[keep][:lab.shape[0]], torch.from_numpy(g["x2_clean"])[keep][:lab.shape[0]]
+        rows.append((lab[:, 2:5], torch.stack((e_cm * (x1 + x2) / 2, e_cm * (x1 - x2) / 2), dim=1)))
+    Htt = torch.cat([r[0] for r in rows])          # [N,3,4] cartesian lab, order H, t, t
+    boost_Epz = torch.cat([r[1] for r in rows])    # [N,2]
+    N = Htt.shape[0]
+    gen = torch.Generator().manual_seed(1234)
+    mean_prop, std_prop = torch.tensor([4.9, 0.02, 0.01]), torch.tensor([0.8, 1.4, 1.8])
+    mean_lab, std_lab = torch.tensor([3.9, -0.01, 0.02]), torch.tensor([0.9, 1.6, 1.81])
+    mean_boost, std_boost = torch.tensor([6.8, 11.0]), torch.tensor([0.45, 610.0])
+    pep = CPT.get_ptetaphi_comp_batch(Htt)
+    def angles():
+        return torch.stack((torch.randn(N, generator=gen, dtype=torch.float64) * 1.3,
+                            (torch.rand(N, generator=gen, dtype=torch.float64) * 2 - 1) * math.pi), dim=1)
+    ang = [angles() for _ in range(5)]
+    out = {"mean_prop": mean_prop.numpy(), "std_prop": std_prop.numpy(), "mean_lab": mean_lab.numpy(),
+           "std_lab": std_lab.numpy(), "mean_boost": mean_boost.numpy(), "std_boost": std_boost.numpy(),
+           "angles": torch.stack(ang).numpy()}
+    boost_scaled = boost_Epz.clone()
+    boost_scaled[:, 0] = torch.log(boost_Epz[:, 0] + 1)
+    boost_scaled = ((boost_scaled - mean_boost) / std_boost)[:, None, :]
+    out["boost"] = boost_scaled.numpy()
+    variants = {  # name: (unscale_phi, ptetaphi, final_scaling, masses kw)
+        "default": (False, True, True, {}),
+        "unscalephi": (True, True, True, {}),
+        "noscale": (False, True, False, {}),
+        "cart": (False, False, False, {}),
+        "masses": (True, True, True, dict(thad_mass=171.0, tlep_mass=174.0, W_had_mass=79.0, W_lep_mass=81.5, b_mass=4.7,
+                                          higgs_mass=124.0, eps=1e-3)),
+    }
+    for name, (unscale_phi, ptetaphi, final_scaling, kw) in variants.items():
+        prop = pep[..., 1:].clone()
+        prop[..., 0] = torch.log(prop[..., 0] + 1)
+        if unscale_phi:
+            prop = (prop - mean_prop) / std_prop
+        else:
+            prop[..., :2] = (prop[..., :2] - mean_prop[:2]) / std_prop[:2]
+        out["prop_" + name] = prop.numpy().copy()
+        leaves = [prop.clone().requires_grad_(name == "default")] + [a.clone().requires_grad_(name == "default") for a in ang] \
+            + [boost_scaled.clone().requires_grad_(name == "default")]
+        # the reference writes into its first argument: hand it a non-leaf copy
+        res = CPT.get_decayPartons_fromlab_propagators_angles(
+            leaves[0] * 1.0, higgs_angles=leaves[1], thad_b_angles=leaves[2], thad_W_angles=leaves[3],
+            tlep_b_angles=leaves[4], tlep_W_angles=leaves[5], boost=leaves[6], log_mean_parton_lab=mean_lab,
+            log_std_parton_lab=std_lab, log_mean_boost=mean_boost, log_std_boost=std_boost,
+            log_mean_parton_Hthadtlep=mean_prop, log_std_parton_Hthadtlep=std_prop, device=torch.device("cpu"),
+            ptetaphi=ptetaphi, unscale_phi=unscale_phi, final_scaling=final_scaling, **kw)
+        out["out_" + name] = res.detach().numpy()
+        if name == "default":
+            g_out = torch.randn(res.shape, generator=gen, dtype=torch.float64)
+            (res * g_out).sum().backward()
+            out["g_out"] = g_out.numpy()
+            out["g_prop"] = leaves[0].grad.numpy()
+            out["g_angles"] = torch.stack([l.grad for l in leaves[1:6]]).numpy()
+            out["g_boost"] = leaves[6].grad.numpy()
+    out["kw_masses"] = np.array([124.0, 171.0, 174.0, 79.0, 81.5, 4.7, 1e-3])
+    np.savez_compressed(os.path.join(HERE, "decay_partons.npz"), **out)
+    print("decay_partons written:", N, "events;", int((np.abs(out["out_default"][:, 11, 0] - 0.001) < 1e-12).sum()), "padded ISR rows")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "decay_partons":
+        make_decay_partons()
+    else:
+        main()
+        make_decay_partons()

@@ -58,3 +58,26 @@ def summarize(err, tol, kappa=None):
     if kappa is not None:
         out["max_over_kappa"] = float(np.nanmax(err / kappa))
     return out
+
+
+# ---- get_decayPartons_fromlab_propagators_angles (tests/golden/decay_partons.npz) ----
+DECAY_PARTONS_VARIANTS = {  # name: (unscale_phi, ptetaphi, final_scaling, reference keyword arguments)
+    "default": (False, True, True, {}),
+    "unscalephi": (True, True, True, {}),
+    "noscale": (False, True, False, {}),
+    "cart": (False, False, False, {}),
+    "masses": (True, True, True, dict(higgs_mass=124.0, thad_mass=171.0, tlep_mass=174.0, W_had_mass=79.0,
+                                      W_lep_mass=81.5, b_mass=4.7, eps=1e-3)),
+}
+
+
+def decay_partons_scaled_err(out, ref, ref_cart, ptetaphi):
+    """|out - ref| in units of what fp64 can resolve for that row: cartesian components carry the rounding of the
+    event's largest momentum S (the ISR row is a difference of TeV-scale numbers); (pt, eta, phi) of a row inherit
+    it amplified by S / pt."""
+    S = np.nanmax(np.abs(ref_cart), axis=(1, 2))[:, None, None]
+    if not ptetaphi:
+        return np.abs(out - ref) / S
+    pt = np.sqrt(ref_cart[..., 1] ** 2 + ref_cart[..., 2] ** 2)[..., None]
+    kappa = np.maximum(S / np.maximum(pt, 1e-300), 1.0)
+    return np.abs(out - ref) / (1.0 + np.abs(ref)) / kappa

@@ -197,3 +197,22 @@ def test_decay_products_match_reference(oracle, golden_dir):
     assert np.abs(c[:, 1:].sum(1) - c[:, 0]).max() / 13000.0 < 1e-12
     w = c[:, 2] + c[:, 3]
     assert np.abs(np.sqrt(w[:, 0] ** 2 - (w[:, 1:] ** 2).sum(1)) - 80.4).max() < 1e-8
+
+
+def test_decay_partons_match_reference(oracle, golden_dir):
+    """get_decayPartons_fromlab_propagators_angles (memflow/unfolding_flow/utils.py:826-935): every option the
+    reference accepts, incl. distinct thad/tlep masses (pins the reference's propagator-1 = tlep pairing) and the
+    ISR padding row."""
+    from tests.parity import DECAY_PARTONS_VARIANTS, decay_partons_scaled_err
+    g = np.load(os.path.join(golden_dir, "decay_partons.npz"))
+    a = g["angles"]
+    for name, (unscale_phi, pep, fs, kw) in DECAY_PARTONS_VARIANTS.items():
+        cfg = oracle.decay_partons_cfg(g["mean_prop"], g["std_prop"], g["mean_lab"], g["std_lab"], g["mean_boost"],
+                                       g["std_boost"], ptetaphi=pep, unscale_phi=unscale_phi, final_scaling=fs, **kw)
+        out = oracle.decay_partons(g["prop_" + name], a[0], a[1], a[2], a[3], a[4], g["boost"], cfg)
+        ref = g["out_" + name]
+        assert out.shape == ref.shape == (a.shape[1], 12, 4)
+        assert np.array_equal(np.isfinite(out), np.isfinite(ref))
+        assert np.nanmax(decay_partons_scaled_err(out, ref, g["out_cart"], pep)) < 1e-12, name
+    padded = np.abs(g["out_noscale"][:, 11, 0] - 0.001) < 1e-15
+    assert padded.sum() >= 32 and (~padded).sum() >= 100  # both branches of :897-905 are in the fixture

@@ -370,6 +370,81 @@ def test_decay_products_vs_reference_golden(oracle, golden_dir):
     assert float((out[:, 1] + out[:, 2] - out[:, 0]).abs().max()) / E < TOL64
 
 
+def _decay_partons_call(g, name, device="cuda", dtype=torch.float64, requires_grad=False):
+    from memflow_b200.unfolding_flow.utils import Compute_ParticlesTensor as CPT
+    unscale_phi, pep, fs, kw = parity.DECAY_PARTONS_VARIANTS[name]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype).requires_grad_(requires_grad)
+    ins = [t(g["prop_" + name])] + [t(g["angles"][i]) for i in range(5)] + [t(g["boost"])]
+    c = lambda k: torch.from_numpy(g[k])
+    out = CPT.get_decayPartons_fromlab_propagators_angles(
+        ins[0], higgs_angles=ins[1], thad_b_angles=ins[2], thad_W_angles=ins[3], tlep_b_angles=ins[4], tlep_W_angles=ins[5],
+        boost=ins[6], log_mean_parton_lab=c("mean_lab"), log_std_parton_lab=c("std_lab"), log_mean_boost=c("mean_boost"),
+        log_std_boost=c("std_boost"), log_mean_parton_Hthadtlep=c("mean_prop"), log_std_parton_Hthadtlep=c("std_prop"),
+        device=torch.device(device), ptetaphi=pep, unscale_phi=unscale_phi, final_scaling=fs, **kw)
+    return ins, out
+
+
+def test_decay_partons_vs_reference_golden(oracle, golden_dir):
+    """the fused parton-level event (get_decayPartons_fromlab_propagators_angles, utils.py:826-935) on the
+    GPU vs the unmodified reference, every option; then vs the oracle on 50k random events."""
+    g = np.load(os.path.join(golden_dir, "decay_partons.npz"))
+    for name, (unscale_phi, pep, fs, kw) in parity.DECAY_PARTONS_VARIANTS.items():
+        ins, out = _decay_partons_call(g, name)
+        ref = g["out_" + name]
+        assert out.dtype == torch.float64 and tuple(out.shape) == ref.shape
+        assert np.array_equal(ins[0].cpu().numpy(), g["prop_" + name])  # the argument is not unscaled in place
+        o = out.cpu().numpy()
+        assert np.array_equal(np.isfinite(o), np.isfinite(ref))
+        assert np.nanmax(parity.decay_partons_scaled_err(o, ref, g["out_cart"], pep)) < TOL64, name
+    # float32 in -> float32 out (the model dtype of the reference's training), computed in fp64 inside
+    _, out32 = _decay_partons_call(g, "default", dtype=torch.float32)
+    assert out32.dtype == torch.float32
+    ok = np.abs(g["out_default"][:, 11, 0] - 0.001) > 1e-9  # fp32 inputs move events across the padding threshold
+    assert np.nanquantile(np.abs(out32.cpu().numpy()[ok] - g["out_default"][ok]) / (1 + np.abs(g["out_default"][ok])), 0.9) < 1e-4
+    from memflow_b200.unfolding_flow.utils import Compute_ParticlesTensor as CPT
+    with pytest.raises(NameError):  # the reference's cartesian final scaling reads an undefined name (:913)
+        CPT.get_decayPartons_fromlab_propagators_angles(*[x for x in _decay_partons_call(g, "cart")[0]],
+                                                        g["mean_lab"], g["std_lab"], g["mean_boost"], g["std_boost"],
+                                                        g["mean_prop"], g["std_prop"], ptetaphi=False, final_scaling=True)
+    # random events at size: same kernel vs the oracle
+    N = 50_000
+    rng = np.random.default_rng(5)
+    prop = np.stack((rng.normal(0, 1, (N, 3)), rng.normal(0, 1, (N, 3)), rng.uniform(-3.1, 3.1, (N, 3))), axis=2)
+    ang = np.stack((rng.normal(0, 1.3, (5, N)), rng.uniform(-3.14, 3.14, (5, N))), axis=2)
+    boost = rng.normal(0, 1, (N, 1, 2))
+    gg = {k: g[k] for k in ("mean_prop", "std_prop", "mean_lab", "std_lab", "mean_boost", "std_boost")}
+    gg.update(prop_default=prop, prop_cart=prop, angles=ang, boost=boost)
+    cart = oracle.decay_partons(prop, *ang, boost, oracle.decay_partons_cfg(
+        g["mean_prop"], g["std_prop"], g["mean_lab"], g["std_lab"], g["mean_boost"], g["std_boost"], ptetaphi=False,
+        final_scaling=False))
+    for name in ("default", "cart"):
+        unscale_phi, pep, fs, kw = parity.DECAY_PARTONS_VARIANTS[name]
+        ref = oracle.decay_partons(prop, *ang, boost, oracle.decay_partons_cfg(
+            g["mean_prop"], g["std_prop"], g["mean_lab"], g["std_lab"], g["mean_boost"], g["std_boost"], ptetaphi=pep,
+            unscale_phi=unscale_phi, final_scaling=fs))
+        o = _decay_partons_call(gg, name)[1].cpu().numpy()
+        assert np.array_equal(np.isfinite(o), np.isfinite(ref))
+        err = parity.decay_partons_scaled_err(o, ref, cart, pep)
+        assert np.nanquantile(err, 0.999) < TOL64 and np.nanmax(err) < 1e-9, name
+
+
+def test_decay_partons_autograd_matches_reference_graph(golden_dir):
+    """gradient of sum(out * g_out) w.r.t. propagators, angles and boost == the reference's autograd."""
+    g = np.load(os.path.join(golden_dir, "decay_partons.npz"))
+    ins, out = _decay_partons_call(g, "default", requires_grad=True)
+    (out * torch.from_numpy(g["g_out"]).cuda()).sum().backward()
+    got = [ins[0].grad.cpu().numpy(), np.stack([x.grad.cpu().numpy() for x in ins[1:6]]), ins[6].grad.cpu().numpy()]
+    ref = [g["g_prop"], g["g_angles"], g["g_boost"]]
+    for a, r, what in zip(got, ref, ("prop", "angles", "boost")):
+        assert a.shape == r.shape, what
+        fin = np.isfinite(r)
+        assert np.isfinite(a[fin]).all(), what
+        scale = np.nanmax(np.abs(r[fin])) if fin.any() else 1.0
+        rel = np.abs(a - r)[fin] / (np.abs(r[fin]) + 1e-6 * scale)
+        assert np.quantile(rel, 0.5) < 1e-12 and np.quantile(rel, 0.99) < 1e-8 and rel.max() < 1e-5, (what, rel.max())
+    assert np.all(got[2][:, 0, 0] == 0.0)  # only pz of the boost enters the event (:857-862)
+
+
 @pytest.mark.parametrize("n", [3, 4, 5])
 def test_autograd_matches_reference_graph(golden_dir, oracle, n):
     """d(loss)/d(points) through get_momenta_from_ps == the reference's autograd (golden), incl. its
