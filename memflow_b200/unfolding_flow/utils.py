@@ -3,6 +3,7 @@
   get_PS               :1056-1152  K2 in get_PS mode (called every training step, unfolding_flow.py:163)
   higgs_decayProducts  :745-770    H -> b b two-body decay + boost           
   top_decayProducts    :772-815    t -> b W -> b q q' decays + boosts        
+  get_decayPartons_fromlab_propagators_angles :826-935  the whole 12-row parton event in one launch, differentiable
 
 The rest of the reference's 1100-line glue class (regression scalings, dataset-specific conversions) is model
 glue and out of scope.
