@@ -59,6 +59,53 @@ def test_fp64_forward_inverse(oracle, F, K, bound):
     assert float((l2 - li).abs().max()) < 1e-9
 
 
+@pytest.mark.parametrize("F,K,bound,slope", [(7, 10, 1.0, 1e-3), (4, 33, 1.1, 1e-3), (3, 8, 5.0, None)])
+def test_defining_properties_without_the_oracle(F, K, bound, slope):
+    """The spline is pinned here by what DEFINES a monotonic rational-quadratic spline (Durkan et al. 2019, as zuko
+    parameterises it), not by the restatement under oracle/: it interpolates the knots (cumulative softmax of the
+    widths / heights, scaled to [-B, B]), its derivative at an interior knot is exp(d_k) and 1 at the two ends, it is
+    strictly increasing, its log-det is the log of its finite-difference slope, it is the identity outside [-B, B],
+    and the inverse undoes it. The knots are rebuilt with numpy float64 independently of any package code."""
+    from memflow_b200 import transforms as TR
+    import math
+    B = 257
+    phi, _ = make(B, F, K, torch.float64, bound, seed=11)
+    p = phi.numpy()
+    clip = (lambda a, f: a / (1 + np.abs(f * a / math.log(slope)))) if slope is not None else (lambda a, f: a)
+    def knots(a):
+        e = np.exp(clip(a, 2.0) - clip(a, 2.0).max(-1, keepdims=True))
+        c = np.cumsum(e / e.sum(-1, keepdims=True), -1)
+        return bound * (2 * np.concatenate((np.zeros_like(c[..., :1]), c), -1) - 1)
+    kx, ky = knots(p[..., :K]), knots(p[..., K:2 * K])                 # [B,F,K+1]
+    dk = np.concatenate((np.ones((B, F, 1)), np.exp(clip(p[..., 2 * K:], 1.0)), np.ones((B, F, 1))), -1)
+    fwd = lambda x: TR.rqs_forward(phi.cuda(), torch.from_numpy(np.ascontiguousarray(x)).cuda(), bound=bound, slope=slope)
+    for k in range(1, K):                                              # interior knots: value and slope
+        y, ladj, _ = fwd(kx[..., k])
+        assert np.abs(y.cpu().numpy() - ky[..., k]).max() < 1e-12
+        assert np.abs(ladj.cpu().numpy() - np.log(dk[..., k])).max() < 1e-9
+    for k, eps in ((0, 1e-10), (K, -1e-10)):                             # end knots: joins the identity with slope 1
+        y, ladj, _ = fwd(kx[..., k] + eps)
+        assert np.abs(y.cpu().numpy() - (ky[..., k] + eps)).max() < 1e-12 and np.abs(ladj.cpu().numpy()).max() < 1e-6
+    rng = np.random.default_rng(3)
+    x = np.sort(rng.uniform(-1.2 * bound, 1.2 * bound, (B, F, 64)), -1)
+    ys, ls = [], []
+    h = 1e-6 * bound
+    for j in range(64):
+        y, ladj, _ = fwd(x[..., j])
+        yp, ym = fwd(x[..., j] + h)[0], fwd(x[..., j] - h)[0]
+        fd = ((yp - ym) / (2 * h)).cpu().numpy()
+        ys.append(y.cpu().numpy())
+        # away from a knot the central difference is the derivative; within h of one it mixes two bins
+        near = (np.abs(kx - x[..., j][..., None]) < 2 * h).any(-1)
+        dev = np.abs(np.log(fd) - ladj.cpu().numpy())[~near]          # O(h^2 / width^2) truncation in narrow bins
+        assert np.quantile(dev, 0.99) < 1e-6 and dev.max() < 1e-4
+        xi = TR.rqs_inverse(phi.cuda(), y, bound=bound, slope=slope)[0].cpu().numpy()
+        assert np.abs(xi - x[..., j]).max() < 1e-12
+        outside = np.abs(x[..., j]) > bound
+        assert np.array_equal(y.cpu().numpy()[outside], x[..., j][outside])
+    assert (np.diff(np.stack(ys, -1), axis=-1) > 0).all()              # strictly increasing
+
+
 @pytest.mark.parametrize("F,K,bound", [(20, 64, 1.1), (7, 10, 1.0), (10, 40, 1.1)])
 def test_fp32_forward_inverse(oracle, F, K, bound):
     from memflow_b200 import transforms as TR
