@@ -1,34 +1,74 @@
 // rqs_backward.cu -- vector-Jacobian product of K3/K4: gradients of the spline output and of its
 // log-det with respect to the input and to the unconstrained parameters phi = [w | h | d] of every (event, feature) row,
 // as autograd computes them through zuko's soft clip -> softmax -> cumsum -> gather -> rational quadratic.
-// One row per thread. The 14 local partials (output and log-det w.r.t. x0, x1, y0, y1, d0, d1, v) come from one
-// evaluation of the rational quadratic in forward-mode dual numbers; the softmax / cumsum part is closed form:
+// The 14 local partials (output and log-det w.r.t. x0, x1, y0, y1, d0, d1, v) come from one evaluation of the
+// rational quadratic in forward-mode dual numbers; the softmax / cumsum part is closed form:
 //   knot X_j = B(2 c_j - 1), c_j = sum_{i<j} p_i  =>  dL/da_i = clip'(a_i) p_i 2B [gX_hi ([i<=bin] - c_hi) + gX_lo ([i<bin] - c_lo)]
-// so no per-row arrays are needed: passes over the row staged in shared memory (sums, bin, gradients written in place).
-// Tiles come in by TMA bulk load and the gradient tile leaves by TMA bulk store; the per-row math uses library
-// exp/log (accuracy first), so this kernel is compute-bound rather than at the HBM roofline.
+// so no per-row arrays are needed: passes over the row staged in shared memory, each parameter replaced by its
+// exponential in the first pass (clip' is recovered from it, clip_der_from_e) and by its gradient in the last.
+// Tiles come in by TMA bulk load and the gradient tile leaves by TMA bulk store: parameters and gradients cross HBM
+// exactly once. Short rows: one thread per row (rqs_backward_kernel); long rows: 2 / 4 / 8 threads per row
+// (rqs_backward_coop_kernel). Measured on B200 (scripts/rqs_bwd_time.py, read + written bytes): fp32 F=20 K=64
+// 4.5 TB/s, fp32 F=7 K=10 3.1 TB/s, fp64 F=10 K=40 2.1 TB/s.
+#include <cstdlib>
+
 #include "rqs.cuh"
 
 namespace mf {
 
-template <typename T> struct Dual {
+template <typename T, int NT> struct RDual {
     T v;
-    T d[7];
+    T d[NT];
 };
-template <typename T> MF_D Dual<T> dconst(T c) { Dual<T> r; r.v = c; for (int i = 0; i < 7; ++i) r.d[i] = (T)0; return r; }
-template <typename T> MF_D Dual<T> dvar(T c, int k) { Dual<T> r = dconst(c); r.d[k] = (T)1; return r; }
-template <typename T> MF_D Dual<T> operator+(const Dual<T>& a, const Dual<T>& b) { Dual<T> r; r.v = a.v + b.v; for (int i = 0; i < 7; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
-template <typename T> MF_D Dual<T> operator-(const Dual<T>& a, const Dual<T>& b) { Dual<T> r; r.v = a.v - b.v; for (int i = 0; i < 7; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
-template <typename T> MF_D Dual<T> operator-(const Dual<T>& a) { Dual<T> r; r.v = -a.v; for (int i = 0; i < 7; ++i) r.d[i] = -a.d[i]; return r; }
-template <typename T> MF_D Dual<T> operator*(const Dual<T>& a, const Dual<T>& b) { Dual<T> r; r.v = a.v * b.v; for (int i = 0; i < 7; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
-template <typename T> MF_D Dual<T> operator*(T a, const Dual<T>& b) { Dual<T> r; r.v = a * b.v; for (int i = 0; i < 7; ++i) r.d[i] = a * b.d[i]; return r; }
-template <typename T> MF_D Dual<T> operator/(const Dual<T>& a, const Dual<T>& b) {
-    Dual<T> r; const T ib = (T)1 / b.v; r.v = a.v * ib;
-    for (int i = 0; i < 7; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
+#define MF_DUAL template <typename T, int NT> MF_D RDual<T, NT>
+#define MF_DLOOP _Pragma("unroll") for (int i = 0; i < NT; ++i)
+MF_DUAL dconst(T c, const RDual<T, NT>&) { RDual<T, NT> r; r.v = c; MF_DLOOP r.d[i] = (T)0; return r; }
+MF_DUAL operator+(const RDual<T, NT>& a, const RDual<T, NT>& b) { RDual<T, NT> r; r.v = a.v + b.v; MF_DLOOP r.d[i] = a.d[i] + b.d[i]; return r; }
+MF_DUAL operator-(const RDual<T, NT>& a, const RDual<T, NT>& b) { RDual<T, NT> r; r.v = a.v - b.v; MF_DLOOP r.d[i] = a.d[i] - b.d[i]; return r; }
+MF_DUAL operator-(const RDual<T, NT>& a) { RDual<T, NT> r; r.v = -a.v; MF_DLOOP r.d[i] = -a.d[i]; return r; }
+MF_DUAL operator*(const RDual<T, NT>& a, const RDual<T, NT>& b) { RDual<T, NT> r; r.v = a.v * b.v; MF_DLOOP r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+MF_DUAL operator*(T a, const RDual<T, NT>& b) { RDual<T, NT> r; r.v = a * b.v; MF_DLOOP r.d[i] = a * b.d[i]; return r; }
+MF_DUAL operator/(const RDual<T, NT>& a, const RDual<T, NT>& b) {
+    RDual<T, NT> r; const T ib = (T)1 / b.v; r.v = a.v * ib;
+    MF_DLOOP r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
     return r;
 }
-template <typename T> MF_D Dual<T> dsqrt(const Dual<T>& a) { Dual<T> r; r.v = sqrt_(a.v); const T h = (T)0.5 / r.v; for (int i = 0; i < 7; ++i) r.d[i] = a.d[i] * h; return r; }
-template <typename T> MF_D Dual<T> dlog(const Dual<T>& a) { Dual<T> r; r.v = log_(a.v); const T ia = (T)1 / a.v; for (int i = 0; i < 7; ++i) r.d[i] = a.d[i] * ia; return r; }
+MF_DUAL dsqrt(const RDual<T, NT>& a) { RDual<T, NT> r; r.v = sqrt_(a.v); const T h = (T)0.5 / r.v; MF_DLOOP r.d[i] = a.d[i] * h; return r; }
+MF_DUAL dlog(const RDual<T, NT>& a) { RDual<T, NT> r; r.v = log_(a.v); const T ia = (T)1 / a.v; MF_DLOOP r.d[i] = a.d[i] * ia; return r; }
+
+// Adjoints of go * out + gl * ladj w.r.t. variables [base, base + NT) of (x0, x1, y0, y1, d0, d1, v): one evaluation
+// of the rational quadratic (forward: out = y, inverse: out = x; ladj = forward log|dy/dx| at x either way) on dual
+// numbers that carry only those NT tangents, so the seven can be split over the threads that share a row.
+template <typename T, bool INV, int NT>
+MF_D void rq_adjoints(int base, T x0v, T x1v, T y0v, T y1v, T d0v, T d1v, T v, T go, T gl, T (&adj)[NT]) {
+    using D = RDual<T, NT>;
+    auto var = [&](T c, int idx) { D r; r.v = c; MF_DLOOP r.d[i] = (idx - base == i) ? (T)1 : (T)0; return r; };
+    const D x0 = var(x0v, 0), x1 = var(x1v, 1), y0 = var(y0v, 2), y1 = var(y1v, 3), d0 = var(d0v, 4), d1 = var(d1v, 5),
+            vv = var(v, 6);
+    const D dx = x1 - x0, dy = y1 - y0;
+    const D s = dy / dx;
+    const D dd = d0 + d1 - (T)2 * s;
+    const D one = dconst((T)1, s);
+    D z, out;
+    if constexpr (!INV) {
+        z = (vv - x0) / dx;
+        const D zz = z * (one - z);
+        out = y0 + dy * (s * (z * z) + d0 * zz) / (s + dd * zz);
+    } else {
+        const D y_ = vv - y0;
+        const D a = dy * (s - d0) + y_ * dd;
+        const D b = dy * d0 - y_ * dd;
+        const D c = -(s * y_);
+        z = ((T)2 * c) / (-b - dsqrt(b * b - (T)4 * (a * c)));
+        out = x0 + z * dx;
+    }
+    const D zz = z * (one - z);
+    const D den = s + dd * zz;
+    const D omz = one - z;
+    const D jac = (s * s) * ((T)2 * (s * zz) + d0 * (omz * omz) + d1 * (z * z)) / (den * den);
+    const D ladj = dlog(jac);
+    MF_DLOOP adj[i] = go * out.d[i] + gl * ladj.d[i];
+}
 
 // exact (library) soft clip and its derivative: c / (1 + |a c'|), d/da = 1 / (1 + |a c'|)^2
 template <typename T> MF_D T clip_val(T a, T c, int clip) { return clip ? a / ((T)1 + fabs_(a * c)) : a; }
@@ -38,6 +78,23 @@ template <typename T> MF_D T clip_der(T a, T c, int clip) { if (!clip) return (T
 template <typename T> MF_D T bw_exp(T a, T m, const RqsConst<T>& C) { return exp_(clip_val(a, C.two_over_L, C.clip) - m); }
 template <> MF_D float bw_exp<float>(float a, float m, const RqsConst<float>& C) {
     return C.clip ? exp_clip_w(a, C) : FastMath<float>::exp(a - m);
+}
+
+// d clip(a) / da recovered from e = exp(clip(a) - m): with u = clip(a) = a / (1 + c|a|), 1 / (1 + c|a|) = 1 - c|u|, so
+// the derivative is (1 - c |ln e|)^2 (m = 0 whenever the clip is on in fp32; in fp64 m is added back). This lets the
+// kernels overwrite each parameter by its exponential once and never exponentiate it again: one MUFU.LG2 per
+// element in the gradient pass instead of a reciprocal, an exponential and a division.
+template <typename T> MF_D T clip_der_from_e(T e, T m, const RqsConst<T>& C) {
+    if (!C.clip) return (T)1;
+    const T t = (T)1 - fabs_(C.two_over_L) * fabs_(log_(e) + m);
+    return t * t;
+}
+template <> MF_D float clip_der_from_e<float>(float e, float, const RqsConst<float>& C) {
+    if (!C.clip) return 1.0f;
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(e));
+    const float t = fmaf(-C.k1w, fabsf(l), 1.0f);   // k1w = |2 / log slope| ln 2
+    return t * t;
 }
 
 // Row gradient, in place: on entry r[0..3K-2] = parameters of the row, on exit = their gradients. Returns g_v.
@@ -56,9 +113,12 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
         }
     }
     T Sw = (T)0, Sh = (T)0;
-    for (int k = 0; k < K; ++k) {
-        Sw += bw_exp(r[k], mw, C);
-        Sh += bw_exp(r[K + k], mh, C);
+    for (int k = 0; k < K; ++k) {   // each parameter is replaced by its exponential, reused by every later pass
+        const T ew = bw_exp(r[k], mw, C), eh = bw_exp(r[K + k], mh, C);
+        r[k] = ew;
+        r[K + k] = eh;
+        Sw += ew;
+        Sh += eh;
     }
     const T iSw = (T)1 / Sw, iSh = (T)1 / Sh;
     // ---- pass 2: searchsorted on the searched coordinate (X forward / Y inverse) with the knots as the forward builds
@@ -66,12 +126,12 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
     T cs_lo = (T)0, cs_hi = (T)0;
     int cnt = ((T)-B < v) ? 1 : 0;
     {
-        const T ms = INV ? mh : mw, is = INV ? iSh : iSw;
+        const T is = INV ? iSh : iSw;
         T c = (T)0;
         bool found = false;
         for (int k = 0; k < K; ++k) {
             const T cprev = c;
-            c += bw_exp(r[(INV ? K : 0) + k], ms, C) * is;
+            c += r[(INV ? K : 0) + k] * is;
             const bool below = B * ((T)2 * c - (T)1) < v;
             cnt += below ? 1 : 0;
             if (!below && !found) { cs_lo = cprev; cs_hi = c; found = true; }
@@ -84,11 +144,11 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
     }
     T co_lo = (T)0, co_hi = (T)0;
     {
-        const T mo = INV ? mw : mh, io = INV ? iSw : iSh;
+        const T io = INV ? iSw : iSh;
         T c = (T)0;
         for (int k = 0; k <= bin; ++k) {
             if (k == bin) co_lo = c;
-            c += bw_exp(r[(INV ? 0 : K) + k], mo, C) * io;
+            c += r[(INV ? 0 : K) + k] * io;
         }
         co_hi = c;
     }
@@ -98,44 +158,17 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
     const T d0v = bin > 0 ? exp_(clip_val(r[2 * K + bin - 1], C.one_over_L, C.clip)) : (T)1;
     const T d1v = bin < K - 1 ? exp_(clip_val(r[2 * K + bin], C.one_over_L, C.clip)) : (T)1;
     // ---- local partials by forward-mode duals: variables 0..6 = x0, x1, y0, y1, d0, d1, v ----
-    const Dual<T> x0 = dvar(x0v, 0), x1 = dvar(x1v, 1), y0 = dvar(y0v, 2), y1 = dvar(y1v, 3), d0 = dvar(d0v, 4),
-                  d1 = dvar(d1v, 5), vv = dvar(v, 6);
-    const Dual<T> dx = x1 - x0, dy = y1 - y0;
-    const Dual<T> s = dy / dx;
-    const Dual<T> dd = d0 + d1 - (T)2 * s;
-    const Dual<T> one = dconst((T)1);
-    Dual<T> z, out;
-    if constexpr (!INV) {
-        z = (vv - x0) / dx;
-        const Dual<T> zz = z * (one - z);
-        out = y0 + dy * (s * (z * z) + d0 * zz) / (s + dd * zz);
-    } else {
-        const Dual<T> y_ = vv - y0;
-        const Dual<T> a = dy * (s - d0) + y_ * dd;
-        const Dual<T> b = dy * d0 - y_ * dd;
-        const Dual<T> c = -(s * y_);
-        z = ((T)2 * c) / (-b - dsqrt(b * b - (T)4 * (a * c)));
-        out = x0 + z * dx;
-    }
-    const Dual<T> zz = z * (one - z);
-    const Dual<T> den = s + dd * zz;
-    const Dual<T> omz = one - z;
-    const Dual<T> jac = (s * s) * ((T)2 * (s * zz) + d0 * (omz * omz) + d1 * (z * z)) / (den * den);
-    const Dual<T> ladj = dlog(jac);
     T adj[7];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) adj[i] = go * out.d[i] + gl * ladj.d[i];
+    rq_adjoints<T, INV, 7>(0, x0v, x1v, y0v, y1v, d0v, d1v, v, go, gl, adj);
     // ---- pass 2: parameter gradients, overwriting the parameters ----
     const T twoB = (T)2 * B;
     const T gd0 = bin > 0 ? adj[4] * d0v * clip_der(r[2 * K + bin - 1], C.one_over_L, C.clip) : (T)0;
     const T gd1 = bin < K - 1 ? adj[5] * d1v * clip_der(r[2 * K + bin], C.one_over_L, C.clip) : (T)0;
     for (int i = 0; i < K; ++i) {
-        const T aw = r[i], ah = r[K + i];
-        const T pw = bw_exp(aw, mw, C) * iSw;
-        const T ph = bw_exp(ah, mh, C) * iSh;
+        const T ew = r[i], eh = r[K + i];
         const T iw_hi = (i <= bin) ? (T)1 : (T)0, iw_lo = (i < bin) ? (T)1 : (T)0;
-        r[i] = clip_der(aw, C.two_over_L, C.clip) * pw * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
-        r[K + i] = clip_der(ah, C.two_over_L, C.clip) * ph * twoB * (adj[3] * (iw_hi - ch_hi) + adj[2] * (iw_lo - ch_lo));
+        r[i] = clip_der_from_e(ew, mw, C) * (ew * iSw) * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
+        r[K + i] = clip_der_from_e(eh, mh, C) * (eh * iSh) * twoB * (adj[3] * (iw_hi - ch_hi) + adj[2] * (iw_lo - ch_lo));
     }
     for (int i = 0; i < K - 1; ++i) r[2 * K + i] = (i == bin - 1) ? gd0 : ((i == bin) ? gd1 : (T)0);
     return adj[6];
@@ -199,6 +232,220 @@ rqs_backward_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const 
     if (tid == 0) bulk_store_wait_read();
 }
 
+// ---- cooperative variant for long rows: LANES threads share a row ----
+// One thread per row needs its whole row in shared memory, so a 3K-1 = 191-word row leaves room for only 8 warps per
+// SM and every pass is a serial chain over K elements: the one-row-per-thread kernel above runs at 36 % issue
+// utilisation for K = 64. Here a CTA of 256 threads owns 256 / LANES rows; the LANES threads of a row sit in DIFFERENT
+// warps (warp = chunk of the row, lane = row), so a warp's 32 threads read 32 different rows at the same offset
+// (row pitch 3K-1 words is odd: conflict-free) and the threads of a row meet through a few words of shared memory:
+//   S1 chunk sums of exp      -> totals and the chunk's prefix offset
+//   S2 chunk count of knots below v -> bin
+//   S3 the chunk that holds the bin rebuilds its four knots
+//   S4 the seven local adjoints are split over the row's threads (rq_adjoints with NT = ceil(7 / LANES) tangents)
+//   S5 every thread writes the gradients of its chunk in place
+// Knots are offset + running sum inside the chunk, so they may differ from the sequential cumsum in the last bit;
+// the spline and its parameter gradients are continuous across a knot, so a bin flipped by that is harmless.
+template <typename T, bool INV, int LANES>
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 4 : 2)
+rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const T* __restrict__ g_out,
+                         const T* __restrict__ g_ladj, int64_t rows, int K, RqsConst<T> C, int bulk_ok,
+                         T* __restrict__ g_phi, T* __restrict__ g_v) {
+    constexpr int RPT = 256 / LANES;               // rows per tile
+    constexpr int NT = (7 + LANES - 1) / LANES;    // tangents per thread in S4
+    constexpr int SLOTS = 4 * LANES + 12;          // [2 LANES max | cnt] [2 LANES sums] [4 knots] [8 adjoints]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int PW = 3 * K - 1;
+    const size_t tile_elems = (size_t)RPT * PW;
+    T* sm = reinterpret_cast<T*>(smem_raw);
+    T* sc = reinterpret_cast<T*>(smem_raw + (tile_elems * sizeof(T) + 127) / 128 * 128);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sc + (size_t)SLOTS * RPT);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int chunk = wid % LANES, rr = (wid / LANES) * 32 + lane;
+    const int CH = (K + LANES - 1) / LANES;
+    const int k0 = min(K, chunk * CH), k1 = min(K, k0 + CH);
+    T* const r = sm + (size_t)rr * PW;
+    T* const scM = sc + rr;                          // slot s at scM[s * RPT]
+    T* const scS = sc + (size_t)2 * LANES * RPT + rr;
+    T* const scK = sc + (size_t)4 * LANES * RPT + rr;
+    T* const scA = sc + (size_t)(4 * LANES + 4) * RPT + rr;
+    const T B = C.bound;
+    const int64_t num_tiles = (rows + RPT - 1) / RPT;
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    uint32_t parity = 0u;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * RPT;
+        const int nrows = (int)((rows - row0) < RPT ? (rows - row0) : RPT);
+        const bool bulk = bulk_ok && nrows == RPT;
+        const T* src = phi + (size_t)row0 * PW;
+        T* dst = g_phi + (size_t)row0 * PW;
+        if (bulk) {
+            if (tid == 0) {
+                bulk_store_wait_read();  // the previous tile's store has finished reading the buffer
+                const uint32_t bytes = (uint32_t)(tile_elems * sizeof(T));
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(sm, src, bytes, bar);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            if (tid == 0) bulk_store_wait_read();
+            __syncthreads();
+            const size_t ne = (size_t)nrows * PW;
+            for (size_t i = tid; i < ne; i += 256) sm[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        const bool valid = rr < nrows;
+        const int64_t row = row0 + rr;
+        const T v = valid ? vin[row] : (T)0;
+        const T go = (valid && g_out) ? g_out[row] : (T)0, gl = (valid && g_ladj) ? g_ladj[row] : (T)0;
+        // ---- S0 (only without the soft clip): row maxima, as torch.softmax subtracts them ----
+        T mw = (T)0, mh = (T)0;
+        if (!C.clip) {
+            T a = -INFINITY, b = -INFINITY;
+            for (int k = k0; k < k1; ++k) { a = fmax_(a, r[k]); b = fmax_(b, r[K + k]); }
+            scM[(2 * chunk) * RPT] = a;
+            scM[(2 * chunk + 1) * RPT] = b;
+            __syncthreads();
+            mw = scM[0]; mh = scM[RPT];
+#pragma unroll
+            for (int c = 1; c < LANES; ++c) { mw = fmax_(mw, scM[(2 * c) * RPT]); mh = fmax_(mh, scM[(2 * c + 1) * RPT]); }
+        }
+        // ---- S1: chunk sums -> totals, prefix offsets ----
+        {
+            T a = (T)0, b = (T)0;
+            for (int k = k0; k < k1; ++k) {   // each parameter is replaced by its exponential (see clip_der_from_e)
+                const T ew = bw_exp(r[k], mw, C), eh = bw_exp(r[K + k], mh, C);
+                r[k] = ew;
+                r[K + k] = eh;
+                a += ew;
+                b += eh;
+            }
+            scS[(2 * chunk) * RPT] = a;
+            scS[(2 * chunk + 1) * RPT] = b;
+        }
+        __syncthreads();
+        T Sw = (T)0, Sh = (T)0, offw = (T)0, offh = (T)0;
+#pragma unroll
+        for (int c = 0; c < LANES; ++c) {
+            if (c == chunk) { offw = Sw; offh = Sh; }
+            Sw += scS[(2 * c) * RPT];
+            Sh += scS[(2 * c + 1) * RPT];
+        }
+        const T iSw = (T)1 / Sw, iSh = (T)1 / Sh;
+        const int sb = INV ? K : 0, ob = INV ? 0 : K;              // searched / other coordinate
+        const T is = INV ? iSh : iSw, io = INV ? iSw : iSh;
+        const T cs0 = (INV ? offh : offw) * is, co0 = (INV ? offw : offh) * io;
+        // ---- S2: knots of this chunk below v ----
+        {
+            T c = cs0;
+            int cnt = 0;
+            for (int k = k0; k < k1; ++k) {
+                c += r[sb + k] * is;
+                cnt += (B * ((T)2 * c - (T)1) < v) ? 1 : 0;
+            }
+            scM[chunk * RPT] = (T)cnt;   // the max slots are dead by now (read before the S1 barrier)
+        }
+        __syncthreads();
+        int bin = ((T)-B < v) ? 0 : -1;
+#pragma unroll
+        for (int c = 0; c < LANES; ++c) bin += (int)scM[c * RPT];
+        const bool inside = bin >= 0 && bin < K;
+        // ---- S3: the chunk that holds the bin rebuilds the four knots around it ----
+        if (inside && bin >= k0 && bin < k1) {
+            T cs = cs0, co = co0;
+            for (int k = k0; k < bin; ++k) { cs += r[sb + k] * is; co += r[ob + k] * io; }
+            const T cs_hi = cs + r[sb + bin] * is, co_hi = co + r[ob + bin] * io;
+            scK[0] = INV ? co : cs;            // cw_lo
+            scK[RPT] = INV ? co_hi : cs_hi;    // cw_hi
+            scK[2 * RPT] = INV ? cs : co;      // ch_lo
+            scK[3 * RPT] = INV ? cs_hi : co_hi;  // ch_hi
+        }
+        __syncthreads();
+        const T cw_lo = scK[0], cw_hi = scK[RPT], ch_lo = scK[2 * RPT], ch_hi = scK[3 * RPT];
+        // ---- S4: seven local adjoints, NT per thread. The two derivative words of the bin are read here by every
+        //      thread of the row and rewritten in S5 by their owners: all reads are done before the barrier ----
+        T f0 = (T)0, f1 = (T)0;
+        if (inside) {
+            T d0v = (T)1, d1v = (T)1;
+            if (bin > 0) {
+                const T a = r[2 * K + bin - 1];
+                d0v = exp_(clip_val(a, C.one_over_L, C.clip));
+                f0 = d0v * clip_der(a, C.one_over_L, C.clip);
+            }
+            if (bin < K - 1) {
+                const T a = r[2 * K + bin];
+                d1v = exp_(clip_val(a, C.one_over_L, C.clip));
+                f1 = d1v * clip_der(a, C.one_over_L, C.clip);
+            }
+            if (chunk * NT < 7) {
+                T part[NT];
+                rq_adjoints<T, INV, NT>(chunk * NT, B * ((T)2 * cw_lo - (T)1), B * ((T)2 * cw_hi - (T)1),
+                                        B * ((T)2 * ch_lo - (T)1), B * ((T)2 * ch_hi - (T)1), d0v, d1v, v, go, gl, part);
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+                    if (chunk * NT + j < 7) scA[(chunk * NT + j) * RPT] = part[j];
+            }
+        }
+        __syncthreads();
+        // ---- S5: gradients of this chunk, in place ----
+        if (inside) {
+            T adj[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) adj[j] = scA[j * RPT];
+            const T twoB = (T)2 * B;
+            const T gd0 = adj[4] * f0, gd1 = adj[5] * f1;
+            for (int i = k0; i < k1; ++i) {
+                const T ew = r[i], eh = r[K + i];
+                const T iw_hi = (i <= bin) ? (T)1 : (T)0, iw_lo = (i < bin) ? (T)1 : (T)0;
+                r[i] = clip_der_from_e(ew, mw, C) * (ew * iSw) * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
+                r[K + i] = clip_der_from_e(eh, mh, C) * (eh * iSh) * twoB * (adj[3] * (iw_hi - ch_hi) + adj[2] * (iw_lo - ch_lo));
+            }
+            for (int i = k0; i < min(k1, K - 1); ++i) r[2 * K + i] = (i == bin - 1) ? gd0 : ((i == bin) ? gd1 : (T)0);
+            if (chunk == 0 && valid) g_v[row] = adj[6];
+        } else {  // identity tails: out = v, ladj = 0
+            for (int i = k0; i < k1; ++i) { r[i] = (T)0; r[K + i] = (T)0; }
+            for (int i = k0; i < min(k1, K - 1); ++i) r[2 * K + i] = (T)0;
+            if (chunk == 0 && valid) g_v[row] = go;
+        }
+        fence_proxy_async();  // generic writes of the gradients -> visible to the bulk store
+        __syncthreads();
+        if (bulk) {
+            if (tid == 0) bulk_s2g(dst, sm, (uint32_t)(tile_elems * sizeof(T)));
+        } else {
+            const size_t ne = (size_t)nrows * PW;
+            for (size_t i = tid; i < ne; i += 256) dst[i] = sm[i];
+            __syncthreads();
+        }
+    }
+    if (tid == 0) bulk_store_wait_read();
+}
+
+template <typename T, bool INV, int LANES>
+static int rqs_bwd_coop_launch(const T* phi, const T* vin, const T* g_out, const T* g_ladj, int64_t rows, int K,
+                               const RqsConst<T>& C, T* g_phi, T* g_v, cudaStream_t stream) {
+    constexpr int RPT = 256 / LANES, SLOTS = 4 * LANES + 12;
+    const int PW = 3 * K - 1;
+    const size_t smem = ((size_t)RPT * PW * sizeof(T) + 127) / 128 * 128 + (size_t)SLOTS * RPT * sizeof(T) + 16;
+    int dev = 0, sms = 148, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > (size_t)smem_max) return MF_E_SHAPE;
+    const int bulk_ok = (aligned(phi, 16) && aligned(g_phi, 16)) ? 1 : 0;   // RPT * PW * sizeof(T) is a multiple of 128
+    auto kern = rqs_backward_coop_kernel<T, INV, LANES>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int ctas = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 256, smem);
+    if (ctas < 1) ctas = 1;
+    const int64_t tiles = (rows + RPT - 1) / RPT;
+    int64_t grid = (int64_t)sms * ctas;
+    if (grid > tiles) grid = tiles;
+    kern<<<(unsigned)grid, 256, smem, stream>>>(phi, vin, g_out, g_ladj, rows, K, C, bulk_ok, g_phi, g_v);
+    return launch_status();
+}
+
 template <typename T, bool INV>
 static int rqs_bwd_launch(const T* phi, const T* vin, const T* g_out, const T* g_ladj, int64_t B, int F, int K, T bound,
                           T slope, T* g_phi, T* g_v, cudaStream_t stream) {
@@ -208,6 +455,19 @@ static int rqs_bwd_launch(const T* phi, const T* vin, const T* g_out, const T* g
     if (rows == 0) return MF_OK;
     const RqsConst<T> C = make_rqs_const<T>(bound, slope);
     const int PW = 3 * K - 1;
+    {   // long rows: several threads per row. Thresholds from scripts/rqs_bwd_time.py sweeps on B200 (row bytes decide:
+        // they set how many one-thread-per-row warps fit in shared memory). MF_RQS_BWD_LANES = 1/2/4/8 forces a variant.
+        static const int forced = [] { const char* e = getenv("MF_RQS_BWD_LANES"); return e ? atoi(e) : 0; }();
+        const size_t row_bytes = (size_t)PW * sizeof(T);
+        int lanes = forced ? forced : (row_bytes < 420 ? 1 : (row_bytes < 700 ? 2 : (row_bytes < 2000 ? 4 : 8)));
+        for (; lanes >= 2 && lanes <= 8; lanes *= 2) {   // a tile that does not fit: fewer rows per tile
+            int rc = MF_E_SHAPE;
+            if (lanes == 2) rc = rqs_bwd_coop_launch<T, INV, 2>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
+            if (lanes == 4) rc = rqs_bwd_coop_launch<T, INV, 4>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
+            if (lanes == 8) rc = rqs_bwd_coop_launch<T, INV, 8>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
+            if (rc != MF_E_SHAPE) return rc;
+        }
+    }
     int dev = 0, sms = 148, smem_max = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -100,7 +100,7 @@ def test_defining_properties_without_the_oracle(F, K, bound, slope):
         dev = np.abs(np.log(fd) - ladj.cpu().numpy())[~near]          # O(h^2 / width^2) truncation in narrow bins
         assert np.quantile(dev, 0.99) < 1e-6 and dev.max() < 1e-4
         xi = TR.rqs_inverse(phi.cuda(), y, bound=bound, slope=slope)[0].cpu().numpy()
-        assert np.abs(xi - x[..., j]).max() < 1e-12
+        assert np.abs(xi - x[..., j]).max() < 2e-12 * max(bound, 1.0)   # unclipped slopes amplify the rounding of y
         outside = np.abs(x[..., j]) > bound
         assert np.array_equal(y.cpu().numpy()[outside], x[..., j][outside])
     assert (np.diff(np.stack(ys, -1), axis=-1) > 0).all()              # strictly increasing
@@ -200,7 +200,9 @@ def test_ragged_and_unaligned(oracle):
     assert e[0].shape == (0, 7)
 
 
-@pytest.mark.parametrize("F,K,bound,slope", [(7, 10, 1.0, 1e-3), (4, 33, 1.1, 1e-3), (3, 8, 5.0, None)])
+# K < 12: one thread per row; 12..23 / 24..47 / >= 48: 2 / 4 / 8 threads per row (rqs_backward_coop_kernel)
+@pytest.mark.parametrize("F,K,bound,slope", [(7, 10, 1.0, 1e-3), (4, 33, 1.1, 1e-3), (3, 8, 5.0, None), (5, 16, 1.0, 1e-3),
+                                             (3, 64, 1.1, 1e-3), (2, 50, 2.0, None), (3, 13, 1.0, None)])
 def test_spline_autograd_vs_torch_restatement(F, K, bound, slope):
     """SURVEY 8f-4 for K3/K4: gradients w.r.t. the parameters and the input == torch autograd through the op-for-op
     restatement of zuko (oracle/rqs_torch.py), both directions, cotangents on the output AND on the log-det."""
