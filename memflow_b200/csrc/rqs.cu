@@ -9,6 +9,8 @@
 // the copy of tile i+1 overlaps the math of tile i. LANES threads per (event, feature) row turn the row
 // into knots in place (rqs.cuh); row pitch 3K-1 words is odd for even K -> conflict-free.
 // Algorithmic bytes per event and transform: F(3K-1) s + 2 F s (+ s for ladj_sum).
+#include <cstdlib>
+
 #include "rqs.cuh"
 
 namespace mf {
@@ -280,6 +282,15 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
             default: go(rqs_reg2_kernel<64, INV>); break;
             }
             return launch_status();
+        }
+    }
+    {   // every other shape (all fp64, fp32 with bin counts the register kernels do not cover): several threads per
+        // row (rqs_coop.cu). MF_RQS_COOP=0 keeps the generic kernel below, for A/B timing.
+        static const bool coop = [] { const char* e = getenv("MF_RQS_COOP"); return !(e && e[0] == '0'); }();
+        const bool reg1 = sizeof(T) == 4 && (K == 8 || K == 10 || K == 12 || K == 16);
+        if (coop && !reg1) {
+            const int rc = rqs_coop_launch<T, INV>(phi, vin, B, F, K, bound, slope, vout, ladj, ladj_sum, bin, stream);
+            if (rc != MF_E_SHAPE) return rc;
         }
     }
     // 2 lanes per row when rows are long (more warps for the same shared-memory footprint)

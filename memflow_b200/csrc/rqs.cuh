@@ -338,4 +338,9 @@ MF_D void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0
 MF_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 MF_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// rqs_coop.cu: several threads per row; MF_E_SHAPE when no variant fits the shape
+template <typename T, bool INV>
+int rqs_coop_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bound, T slope, T* vout, T* ladj, T* ladj_sum,
+                    int32_t* bin, cudaStream_t stream);
+
 }  // namespace mf
