@@ -404,6 +404,99 @@ static ChainGeom chain_geometry(const float* phi, int64_t N, int F, int T, int K
 
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
+// ---- launch A, compile-time K (8, 10, 12, 16), single stage: what bench.py times ----
+// Same algorithm as flow_sample_kernel; every thread does ONE row per (tile, transform), so whatever is executed per
+// tile is paid per row. The source-level profile of the generic kernel showed 45 % of its instructions outside the row
+// math: 64-bit tile / transform address arithmetic redone at every use, the runtime stage / K dispatch, and one full
+// Philox4x32-10 (102 instructions) per ROW although it yields four variates. Here the tile base pointer and the
+// bulk / ragged decision are taken once per tile, only thread 0 forms copy addresses, and one thread in four runs
+// Philox and hands the other variates over through shared memory.
+template <int K>
+__global__ void __launch_bounds__(256, 8)
+flow_sample_fast_kernel(const float* __restrict__ phi, int64_t N, int F, int T, RqsConst<float> C, int E, int bulk_ok,
+                        uint64_t seed, uint64_t event_offset, double* __restrict__ u_out, double* __restrict__ logq_out) {
+    constexpr int PW = 3 * K - 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int rows = E * F;
+    const uint32_t tile_elems = (uint32_t)rows * PW;
+    const uint32_t tile_bytes = tile_elems * (uint32_t)sizeof(float);
+    float* const sm = reinterpret_cast<float*>(smem_raw);
+    float* const lsum = reinterpret_cast<float*>(smem_raw + ((size_t)tile_bytes + 127) / 128 * 128);  // [256]
+    uint32_t* const rnd = reinterpret_cast<uint32_t*>(lsum);  // the same words, before the transforms
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(lsum + 256);
+    const int tid = threadIdx.x;
+    const int e = tid / F, f = tid - e * F;
+    float* const rowp = sm + (size_t)tid * PW;
+    const int64_t num_tiles = (N + E - 1) / E, full_tiles = bulk_ok ? N / E : 0;  // tiles below full_tiles come by TMA
+    const size_t pitch = (size_t)N * F * PW;                                       // one transform's parameters
+    const float* const last = phi + (size_t)(T - 1) * pitch;                       // transforms run T-1 ... 0
+    const double inv_2b = 1.0 / (2.0 * (double)C.bound);
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    uint32_t parity = 0u;
+    int64_t tile = blockIdx.x;
+    if (tid == 0 && tile < full_tiles) {
+        mbar_expect_tx(bar, tile_bytes);
+        bulk_g2s(sm, last + (size_t)tile * tile_elems, tile_bytes, bar);
+    }
+    for (; tile < num_tiles; tile += gridDim.x) {
+        const bool bulk = tile < full_tiles;
+        const int64_t ev0 = tile * E;
+        const int nev = (int)((N - ev0) < E ? (N - ev0) : E);
+        const int nrows = nev * F;
+        const bool row_active = tid < nrows;
+        if (row_active && (f & 3) == 0) {   // one Philox call serves features f .. f+3 of the event
+            const uint64_t gev = event_offset + (uint64_t)(ev0 + e);
+            const Philox4 r4 = philox4x32_10((uint32_t)gev, (uint32_t)(gev >> 32), (uint32_t)(f >> 2), 0u, (uint32_t)seed,
+                                             (uint32_t)(seed >> 32));
+            rnd[tid] = r4.x;
+            if (f + 1 < F) rnd[tid + 1] = r4.y;
+            if (f + 2 < F) rnd[tid + 2] = r4.z;
+            if (f + 3 < F) rnd[tid + 3] = r4.w;
+        }
+        __syncthreads();
+        float x = row_active ? C.bound * (2.0f * u01_from_bits(rnd[tid]) - 1.0f) : 0.0f;
+        float ladj_acc = 0.0f;
+        for (int t = T - 1; t >= 0; --t) {
+            if (bulk) {
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+            } else {  // ragged last tile or unaligned phi: plain cooperative copy
+                const float* src = phi + (size_t)t * pitch + (size_t)tile * tile_elems;
+                const uint32_t ne = (uint32_t)nrows * PW;
+                for (uint32_t i = tid; i < ne; i += 256) sm[i] = __ldg(src + i);
+                __syncthreads();
+            }
+            if (row_active) {
+                float out, ladj;
+                int bin;
+                rqs_row_reg<K, true>(rowp, C, x, out, ladj, bin);
+                x = out;
+                ladj_acc += ladj;
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {   // refill the (single) stage: next transform of this tile, else the next tile's first
+                const int64_t nt = t > 0 ? tile : tile + gridDim.x;
+                if (nt < full_tiles) {
+                    mbar_expect_tx(bar, tile_bytes);
+                    bulk_g2s(sm, phi + (size_t)(t > 0 ? t - 1 : T - 1) * pitch + (size_t)nt * tile_elems, tile_bytes, bar);
+                }
+            }
+        }
+        lsum[tid] = ladj_acc;
+        if (row_active) u_out[ev0 * F + tid] = ((double)x + (double)C.bound) * inv_2b;
+        __syncthreads();
+        if (tid < nev) {
+            double lq = 0.0;
+            for (int j = 0; j < F; ++j) lq += (double)lsum[tid * F + j];
+            logq_out[ev0 + tid] = lq;
+        }
+        __syncthreads();
+    }
+}
+
+
 // A: Philox base sample + T spline inverses -> u [N,F] fp64, log q [N]
 static int flow_sample_launch(const float* phi, int64_t N, int F, int T, int K, float bound, float slope, uint64_t seed,
                               uint64_t event_offset, double* u, double* logq, cudaStream_t stream) {
@@ -467,6 +560,24 @@ static int flow_sample_launch(const float* phi, int64_t N, int F, int T, int K, 
     };
     // 32 registers per thread -> 2048 resident threads per SM for every CTA size
     static const int minb = env_int("MF_CHAIN_MINB", 8);
+    static const int fast = env_int("MF_CHAIN_FAST", 1);
+    if (fast && thr == 256 && minb == 8 && stages == 1 && (K == 8 || K == 10 || K == 12 || K == 16)) {
+        auto gof = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            int ctas = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 256, smem);
+            if (ctas < 1) ctas = 1;
+            int64_t grid = (int64_t)g.sms * ctas;
+            if (grid > num_tiles) grid = num_tiles;
+            kern<<<(unsigned)grid, 256, smem, stream>>>(phi, N, F, T, C, g.E, g.bulk_ok, seed, event_offset, u, logq);
+        };
+        if (K == 8) gof(flow_sample_fast_kernel<8>);
+        else if (K == 10) gof(flow_sample_fast_kernel<10>);
+        else if (K == 12) gof(flow_sample_fast_kernel<12>);
+        else gof(flow_sample_fast_kernel<16>);
+        return launch_status();
+    }
     if (thr == 256 && minb == 6) go(flow_sample_kernel<256, 6>);
     else if (thr == 256 && minb == 5) go(flow_sample_kernel<256, 5>);
     else if (thr == 256) go(flow_sample_kernel<256, 8>);
