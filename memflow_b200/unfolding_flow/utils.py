@@ -159,6 +159,38 @@ class Compute_ParticlesTensor:
                                          stream_ptr(dev)), "mf_top_decay_f64")
         return out
 
+    # ---- coordinate conversions used around the kernels by the sampling loss (plain differentiable torch, any device;
+    #      reference memflow/unfolding_flow/utils.py:109-119, :169-187). Inside the kernels the same formulas are fused. ----
+    @staticmethod
+    def get_cartesian_comp(particle, mass):
+        """(pt, eta, phi) [N,3] + mass -> (E, px, py, pz) [N,4]."""
+        px = particle[:, 0] * torch.cos(particle[:, 2])
+        py = particle[:, 0] * torch.sin(particle[:, 2])
+        pz = particle[:, 0] * torch.sinh(particle[:, 1])
+        return torch.stack((torch.sqrt(px ** 2 + py ** 2 + pz ** 2 + mass ** 2), px, py, pz), dim=1)
+
+    @staticmethod
+    def _ptetaphi(E, px, py, pz, dim):
+        pt = (px ** 2 + py ** 2) ** 0.5
+        eta = -torch.log(torch.tan(torch.atan2(pt, pz) / 2))
+        cols = (pt, eta, torch.atan2(py, px))
+        return torch.stack(cols if E is None else (E,) + cols, dim=dim)
+
+    @staticmethod
+    def get_ptetaphi_comp(particle):
+        """(E, px, py, pz) [N,4] -> (E, pt, eta, phi) [N,4]."""
+        return Compute_ParticlesTensor._ptetaphi(particle[:, 0], particle[:, 1], particle[:, 2], particle[:, 3], 1)
+
+    @staticmethod
+    def get_ptetaphi_comp_batch(particles):
+        """(E, px, py, pz) [N,P,4] -> (E, pt, eta, phi) [N,P,4]."""
+        return Compute_ParticlesTensor._ptetaphi(particles[..., 0], particles[..., 1], particles[..., 2], particles[..., 3], 2)
+
+    @staticmethod
+    def get_ptetaphi_comp_noEnergy(particle):
+        """(px, py, pz) [N,3] -> (pt, eta, phi) [N,3]."""
+        return Compute_ParticlesTensor._ptetaphi(None, particle[:, 0], particle[:, 1], particle[:, 2], 1)
+
     @staticmethod
     def get_decayPartons_fromlab_propagators_angles(propagators_kinematics, higgs_angles, thad_b_angles, thad_W_angles,
                                                     tlep_b_angles, tlep_W_angles, boost, log_mean_parton_lab,

@@ -307,9 +307,62 @@ def make_decay_partons():
     print("decay_partons written:", N, "events;", int((np.abs(out["out_default"][:, 11, 0] - 0.001) < 1e-12).sum()), "padded ISR rows")
 
 
+
+def make_sampling_pipeline():
+    """sampling_pipeline.npz: the sampling branch of the training loss, memflow/unfolding_flow/unfolding_flow_withDecay_v2.py
+    :376-417, run with the unmodified reference on CPU in float64: ps -> PhaseSpace.get_momenta_from_ps(requires_grad=True)
+    -> boost to the lab -> (pt, eta, phi) -> log / scaling -> get_decayPartons_fromlab_propagators_angles; stores the
+    12-parton event, the scaled boost, and d(sum(out * g))/d(ps)."""
+    phasespace, _, utils = import_reference()
+    for name in ("vector", "awkward"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    from memflow.unfolding_flow.utils import Compute_ParticlesTensor as CPT
+    E_CM, N = 13000.0, 160
+    masses = torch.tensor([125.25, 172.5, 172.5, 0.0])
+    gen = torch.Generator().manual_seed(77)
+    ps = (torch.rand(N, 10, generator=gen, dtype=torch.float64) * 0.9 + 0.05).requires_grad_(True)
+    mean_prop, std_prop = torch.tensor([4.9, 0.02, 0.01]), torch.tensor([0.8, 1.4, 1.8])
+    mean_lab, std_lab = torch.tensor([3.9, -0.01, 0.02]), torch.tensor([0.9, 1.6, 1.81])
+    mean_boost, std_boost = torch.tensor([6.8, 11.0]), torch.tensor([0.45, 610.0])
+    angles = torch.stack([torch.stack((torch.randn(N, generator=gen, dtype=torch.float64) * 1.3,
+                                       (torch.rand(N, generator=gen, dtype=torch.float64) * 2 - 1) * math.pi), dim=1)
+                          for _ in range(5)])
+    with contextlib.redirect_stdout(io.StringIO()):
+        rambo = phasespace.PhaseSpace(E_CM, [21, 21], [25, 6, -6, 21], final_masses=masses, dev="cpu")
+        mom, _, x1, x2 = rambo.get_momenta_from_ps(ps, requires_grad=True)
+    zeros = torch.zeros_like(x1)
+    boost_Epz = torch.stack((rambo.collider_energy * (x1 + x2) / 2, zeros, zeros, rambo.collider_energy * (x1 - x2) / 2), dim=1)
+    lab = utils.boost_tt(mom[:, -4:-1], utils.boostVector_t(boost_Epz).unsqueeze(dim=1))
+    pep = CPT.get_ptetaphi_comp_batch(lab)
+    prop = pep[..., 1:].clone()
+    prop[..., 0] = torch.log(pep[..., 1] + 1)
+    prop[..., 0:2] = (prop[..., 0:2] - mean_prop[:2]) / std_prop[:2]
+    boost_scaled = boost_Epz[..., [0, 3]].clone()
+    boost_scaled[..., 0] = torch.log(boost_Epz[..., 0] + 1)
+    boost_scaled = (boost_scaled - mean_boost) / std_boost
+    out = CPT.get_decayPartons_fromlab_propagators_angles(
+        prop, higgs_angles=angles[0], thad_b_angles=angles[1], thad_W_angles=angles[2], tlep_b_angles=angles[3],
+        tlep_W_angles=angles[4], boost=boost_scaled[:, None, :], log_mean_parton_lab=mean_lab, log_std_parton_lab=std_lab,
+        log_mean_boost=mean_boost, log_std_boost=std_boost, log_mean_parton_Hthadtlep=mean_prop,
+        log_std_parton_Hthadtlep=std_prop, device=torch.device("cpu"), ptetaphi=True, eps=1e-4, unscale_phi=False,
+        final_scaling=True)
+    g_out = torch.randn(out.shape, generator=gen, dtype=torch.float64)
+    g_boost = torch.randn(boost_scaled.shape, generator=gen, dtype=torch.float64)
+    ((out * g_out).sum() + (boost_scaled * g_boost).sum()).backward()
+    np.savez_compressed(os.path.join(HERE, "sampling_pipeline.npz"), ps=ps.detach().numpy(), masses=masses.numpy(),
+                        e_cm=np.float64(E_CM), angles=angles.numpy(), mean_prop=mean_prop.numpy(), std_prop=std_prop.numpy(),
+                        mean_lab=mean_lab.numpy(), std_lab=std_lab.numpy(), mean_boost=mean_boost.numpy(),
+                        std_boost=std_boost.numpy(), out=out.detach().numpy(), boost_scaled=boost_scaled.detach().numpy(),
+                        g_out=g_out.numpy(), g_boost=g_boost.numpy(), g_ps=ps.grad.numpy())
+    print("sampling pipeline written; |g_ps| columns:", np.abs(ps.grad.numpy()).max(0))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "decay_partons":
         make_decay_partons()
+    elif len(sys.argv) > 1 and sys.argv[1] == "sampling_pipeline":
+        make_sampling_pipeline()
     else:
         main()
         make_decay_partons()
+        make_sampling_pipeline()

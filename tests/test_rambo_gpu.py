@@ -445,6 +445,53 @@ def test_decay_partons_autograd_matches_reference_graph(golden_dir):
     assert np.all(got[2][:, 0, 0] == 0.0)  # only pz of the boost enters the event (:857-862)
 
 
+def test_sampling_loss_pipeline_matches_reference(golden_dir):
+    """The sampling branch of the reference's training loss (unfolding_flow_withDecay_v2.py:376-417) end to end on the
+    drop-in API: ps -> get_momenta_from_ps(requires_grad=True) [K1 + backward kernel] -> boost_tt / pt-eta-phi / scaling
+    [torch glue] -> get_decayPartons_fromlab_propagators_angles [fused kernel + backward kernel]; the 12-parton event, the
+    scaled boost and d(loss)/d(ps) must equal what the unmodified reference produced (golden, CPU float64)."""
+    from memflow_b200.phasespace.phasespace import PhaseSpace
+    from memflow_b200.phasespace import utils as ps_utils
+    from memflow_b200.unfolding_flow.utils import Compute_ParticlesTensor as CPT
+    g = np.load(os.path.join(golden_dir, "sampling_pipeline.npz"))
+    c = lambda k: torch.from_numpy(g[k]).cuda()
+    rambo = PhaseSpace(float(g["e_cm"]), [21, 21], [25, 6, -6, 21], final_masses=torch.from_numpy(g["masses"]), dev="cuda:0")
+    ps = c("ps").requires_grad_(True)
+    mom, _, x1, x2 = rambo.get_momenta_from_ps(ps, requires_grad=True)
+    zeros = torch.zeros_like(x1)
+    boost_Epz = torch.stack((rambo.collider_energy * (x1 + x2) / 2, zeros, zeros, rambo.collider_energy * (x1 - x2) / 2), dim=1)
+    lab = ps_utils.boost_tt(mom[:, -4:-1], ps_utils.boostVector_t(boost_Epz).unsqueeze(dim=1))
+    pep = CPT.get_ptetaphi_comp_batch(lab)
+    prop = pep[..., 1:].clone()
+    prop[..., 0] = torch.log(pep[..., 1] + 1)
+    prop[..., 0:2] = (prop[..., 0:2] - c("mean_prop")[:2]) / c("std_prop")[:2]
+    boost_scaled = boost_Epz[..., [0, 3]].clone()
+    boost_scaled[..., 0] = torch.log(boost_Epz[..., 0] + 1)
+    boost_scaled = (boost_scaled - c("mean_boost")) / c("std_boost")
+    a = c("angles")
+    out = CPT.get_decayPartons_fromlab_propagators_angles(
+        prop, higgs_angles=a[0], thad_b_angles=a[1], thad_W_angles=a[2], tlep_b_angles=a[3], tlep_W_angles=a[4],
+        boost=boost_scaled[:, None, :], log_mean_parton_lab=c("mean_lab"), log_std_parton_lab=c("std_lab"),
+        log_mean_boost=c("mean_boost"), log_std_boost=c("std_boost"), log_mean_parton_Hthadtlep=c("mean_prop"),
+        log_std_parton_Hthadtlep=c("std_prop"), device=torch.device("cuda"), ptetaphi=True, eps=1e-4, unscale_phi=False,
+        final_scaling=True)
+    ((out * c("g_out")).sum() + (boost_scaled * c("g_boost")).sum()).backward()
+    o, ref = out.detach().cpu().numpy(), g["out"]
+    assert np.array_equal(np.isfinite(o), np.isfinite(ref))
+    # (pt, eta, phi) of a row inherit the event's rounding amplified by E_event / pt_row
+    pt = np.exp(np.abs(ref[..., 1] * np.where(np.isin(np.arange(12), (0, 3, 7)), g["std_prop"][0], g["std_lab"][0])
+                       + np.where(np.isin(np.arange(12), (0, 3, 7)), g["mean_prop"][0], g["mean_lab"][0]))) - 1
+    kappa = np.maximum(float(g["e_cm"]) / np.maximum(pt, 1e-3), 1.0)[..., None]
+    assert np.nanmax(np.abs(o - ref) / (1 + np.abs(ref)) / kappa) < TOL64
+    assert np.nanmax(np.abs(boost_scaled.detach().cpu().numpy() - g["boost_scaled"])) < 1e-12
+    gp, gr = ps.grad.cpu().numpy(), g["g_ps"]
+    fin = np.isfinite(gr).all(axis=1)
+    assert fin.sum() > 100 and np.isfinite(gp[fin]).all()
+    assert np.all(gp[fin][:, :2] == 0.0) and np.all(gr[fin][:, :2] == 0.0)   # mass-variable columns: the reference's graph has none
+    rel = np.abs(gp - gr)[fin] / (np.abs(gr[fin]).max(axis=1, keepdims=True) + 1e-300)
+    assert np.median(rel) < 1e-12 and np.quantile(rel, 0.99) < 1e-8 and rel.max() < 1e-5, rel.max()
+
+
 @pytest.mark.parametrize("n", [3, 4, 5])
 def test_autograd_matches_reference_graph(golden_dir, oracle, n):
     """d(loss)/d(points) through get_momenta_from_ps == the reference's autograd (golden), incl. its
