@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmemflow_b200.so")
+#: MEMFLOW_B200_LIB points the loader at another build of the same library (A/B timing of two builds on one box)
+LIB_PATH = os.environ.get("MEMFLOW_B200_LIB") or os.path.join(_HERE, "lib", "libmemflow_b200.so")
 
 #: every symbol include/memflow_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = (

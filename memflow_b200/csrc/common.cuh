@@ -97,7 +97,10 @@ MF_D double sqrt_fast(double x) {
     const double g1 = fma(g, r, g), h1 = fma(h, r, h);
     const double s = fma(fma(-g1, g1, x), h1, g1);
     // outside the fast range: sqrt(+-0) = +-0, sqrt(inf) = inf, sqrt(negative or NaN) = NaN
-    return in_fast_range_pos(x) ? s : ((x >= 0.0) ? x : __longlong_as_double(0x7ff8000000000000LL));
+    // (sign clear, or -0: integer tests, a DSETP would take an fp64 issue slot in every call)
+    const unsigned hi = (unsigned)__double2hiint(x);
+    const bool keep = hi < 0x80000000u || (hi == 0x80000000u && __double2loint(x) == 0);
+    return in_fast_range_pos(x) ? s : (keep ? x : __longlong_as_double(0x7ff8000000000000LL));
 }
 MF_D float sqrt_fast(float x) { return sqrtf(x); }
 

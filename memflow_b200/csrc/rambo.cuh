@@ -66,8 +66,9 @@ template <typename T> MF_D void boost(const T (&p)[4], T bx, T by, T bz, T (&o)[
 //   E >= 2 : v is the CDF of Beta(E,2). Work in the well-conditioned variable: x = u and
 //            target t = v when v < 0.65, else x = 1-u and t = 1-v with
 //            1 - v = x^2 P_E(x)  (polynomial, no cancellation). fp32 asymptotic start + 2 fp32
-//            Newton steps (MUFU log2/exp2), then 2 fp64 Halley steps (cubic): converged to <= 2 ulp of
-//            the exact root for all v in (1e-30, 1), tests/test_massvar_solver.py.
+//            Newton steps (MUFU log2/exp2), then one fp64 Newton and one chord step on a per-lane selected
+//            polynomial (MassVarPoly): within 4 ulp of the exact root for all v in (0, 1),
+//            tests/test_rambo_gpu.py::test_massvar_solver_vs_bisection.
 // Edge semantics follow the bisection: v <= 0 -> 2^-180 (its floor after 180 levels); v >= 1 -> the largest
 // double below 1 (the bisection stalls just below 1, so the reference's weight stays finite there).
 // ---------------------------------------------------------------------------------------------
@@ -110,6 +111,39 @@ template <int E, typename T> struct MassVarFn {
     }
 };
 
+// F and F' as Horner forms over per-lane selected coefficients (fp64 polish of solve_massvar)
+MF_D double rcp_seed_refined(double b) {  // 2^-40 reciprocal: a Newton slope does not need more
+    const double r0 = rcp_seed(b);
+    return fma(r0, fma(-b, r0, 1.0), r0);
+}
+// 0 < x < 1 on the bit pattern (integer pipe; false for 0, negatives, NaN, inf)
+MF_D bool in_open_unit(double x) {
+    const unsigned hi = (unsigned)__double2hiint(x);
+    return hi < 0x3ff00000u && (hi | (unsigned)__double2loint(x)) != 0u;
+}
+template <int E> struct MassVarPoly {
+    double c[E];   // c[j] = coefficient of x^(j+2), j = 0..E-1
+    MF_D explicit MassVarPoly(bool small) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const double a = (j + 2 == E) ? (double)(E + 1) : ((j + 2 == E + 1) ? -(double)E : 0.0);
+            c[j] = small ? a : tail_coef(E, j + 2);
+        }
+    }
+    MF_D double residual(double x, double t) const {   // F(x) - t, F(x) = x^2 (c_0 + c_1 x + ...)
+        double h = c[E - 1];
+#pragma unroll
+        for (int j = E - 2; j >= 0; --j) h = fma(h, x, c[j]);
+        return fma(x * x, h, -t);
+    }
+    MF_D double slope(double x) const {   // F'(x) = x (2 c_0 + 3 c_1 x + ...)
+        double g = (double)(E + 1) * c[E - 1];
+#pragma unroll
+        for (int j = E - 2; j >= 0; --j) g = fma(g, x, (double)(j + 2) * c[j]);
+        return x * g;
+    }
+};
+
 template <int E> MF_D float massvar_start_f32(bool small, float tf) {
     float x;
     if (small) {
@@ -145,13 +179,24 @@ template <int E> MF_D double solve_massvar(double v) {
         } else {
             x = (t == 0.0 || t < 0.0) ? 0.0 : t;  // t <= 0 -> 0, NaN -> NaN
         }
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            double f, d1, d2;
-            MassVarFn<E, double>::eval(small, x, t, f, d1, d2);
-            double xn = x - div_fast(2.0 * f * d1, 2.0 * d1 * d1 - f * d2);
-            x = (xn > 0.0 && xn < 1.0) ? xn : x;
+        // fp64 polish. In either variable F is a polynomial sum_{k=2}^{E+1} c_k x^k (x^E((E+1) - E x), or x^2 P_E(x)):
+        // the coefficients are selected per lane, so a warp with both kinds of lanes runs ONE instruction stream.
+        // One Newton step from the fp32 start (relative error ~1e-6 -> ~1e-12) and one chord step with the same
+        // reciprocal slope (-> ~1e-18): 3E + 7 fp64 operations per root, the previous two Halley steps cost ~85
+        // because both variables' formulas were executed by every diverged warp.
+        const MassVarPoly<E> pl(small);
+        if (!(t > 1e-30)) {  // the fp64 asymptotic start of the (unreachable in practice) tail is coarser: two full steps
+#pragma unroll 1
+            for (int it = 0; it < 2; ++it) {
+                const double xn = x - div_fast(pl.residual(x, t), pl.slope(x));
+                x = in_open_unit(xn) ? xn : x;
+            }
         }
+        const double inv = rcp_seed_refined(pl.slope(x));
+        double xn = fma(-pl.residual(x, t), inv, x);
+        x = in_open_unit(xn) ? xn : x;  // also rejects NaN / inf steps
+        xn = fma(-pl.residual(x, t), inv, x);
+        x = in_open_unit(xn) ? xn : x;
         double u = small ? x : 1.0 - x;
         u = (u > Limits<double>::max_u()) ? Limits<double>::max_u() : u;
         return (u < Limits<double>::tiny_u()) ? Limits<double>::tiny_u() : u;  // NaN stays NaN

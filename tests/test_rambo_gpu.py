@@ -236,11 +236,34 @@ def test_massvar_solver_vs_bisection(oracle):
     v = torch.rand(200_000, n - 2, dtype=torch.float64, generator=g)
     v[:1000] = 10.0 ** (-30 * torch.rand(1000, n - 2, dtype=torch.float64, generator=g))
     v[1000:2000] = 1 - 10.0 ** (-16 * torch.rand(1000, n - 2, dtype=torch.float64, generator=g))
+    v[2000:3000] = 10.0 ** (-30 - 250 * torch.rand(1000, n - 2, dtype=torch.float64, generator=g))   # below the fp32 start's range
+    v[3000:4000] = 0.65 + (torch.rand(1000, n - 2, dtype=torch.float64, generator=g) - 0.5) * 1e-6        # the variable switch
     u = ps.generator.bisect_vec_batch(v.cuda()).cpu()
     e = torch.arange(n - 2, 0, -1, dtype=torch.float64)
     res = ((u ** e) * ((e + 1) - e * u) - v).abs()
     assert float((res / v.clamp_min(1e-300)).max()) < 5e-15 or float(res.max()) < 1e-15
     assert bool(((u >= 0) & (u <= 1)).all())
+    # against the root itself: refined in 80-bit arithmetic in the well-conditioned variable (u for small v, d = 1 - u
+    # with 1 - v = d^2 P_e(d) for large v), the returned u must be within 4 ulp (the residual's own rounding: P_e has
+    # alternating coefficients)
+    from math import comb
+    L = np.longdouble
+    un, vn = u.numpy(), v.numpy()
+    for col, ee in enumerate(range(n - 2, 0, -1)):
+        uc, vc = un[:, col].astype(L), vn[:, col].astype(L)
+        ck = [L(-((-1) ** k) * (comb(ee, k) - ee * comb(ee, k - 1))) for k in range(2, ee + 2)]   # d^2 P_e(d) = sum ck d^k
+        x_small, x_large = uc.copy(), (L(1) - uc)
+        for _ in range(3):
+            F = x_small ** ee * ((ee + 1) - ee * x_small) - vc
+            dF = ee * (ee + 1) * x_small ** (ee - 1) * (1 - x_small)
+            x_small = x_small - np.where(dF != 0, F / np.where(dF != 0, dF, 1), 0)
+            G = sum(c * x_large ** k for c, k in zip(ck, range(2, ee + 2))) - (L(1) - vc)
+            dG = sum(c * k * x_large ** (k - 1) for c, k in zip(ck, range(2, ee + 2)))
+            x_large = x_large - np.where(dG != 0, G / np.where(dG != 0, dG, 1), 0)
+        exact = np.where(vc < 0.65, x_small, L(1) - x_large)
+        ok = (vc > 0) & (vc < 1) & (uc < 1 - 2e-16)         # away from the clamps at the two ends
+        err_ulp = np.abs(uc - exact)[ok] / (np.abs(exact[ok]) * L(2.0) ** -53)
+        assert float(err_ulp.max()) <= 4.0, (ee, float(err_ulp.max()))
 
 
 def test_get_ps_vs_reference_golden(oracle, golden_dir):
