@@ -122,25 +122,29 @@ MF_D bool in_open_unit(double x) {
     return hi < 0x3ff00000u && (hi | (unsigned)__double2loint(x)) != 0u;
 }
 template <int E> struct MassVarPoly {
-    double c[E];   // c[j] = coefficient of x^(j+2), j = 0..E-1
-    MF_D explicit MassVarPoly(bool small) {
-#pragma unroll
-        for (int j = 0; j < E; ++j) {
-            const double a = (j + 2 == E) ? (double)(E + 1) : ((j + 2 == E + 1) ? -(double)E : 0.0);
-            c[j] = small ? a : tail_coef(E, j + 2);
-        }
+    bool small;
+    MF_D explicit MassVarPoly(bool s) : small(s) {}
+    // coefficient of x^(j+2), j = 0..E-1: x^E((E+1) - E x) for the small variable, x^2 P_E(x) for the large one.
+    // Selected at every use from two compile-time constants (integer pipe); an array of selected values ended up in
+    // local memory.
+    template <int J> MF_D double coef(double scale) const {
+        constexpr double a = (J + 2 == E) ? (double)(E + 1) : ((J + 2 == E + 1) ? -(double)E : 0.0);
+        constexpr double b = tail_coef(E, J + 2);
+        return small ? scale * a : scale * b;
+    }
+    template <int J> MF_D double horner_f(double x, double h) const {
+        if constexpr (J < 0) return h;
+        else return horner_f<J - 1>(x, fma(h, x, coef<J>(1.0)));
+    }
+    template <int J> MF_D double horner_d(double x, double g) const {
+        if constexpr (J < 0) return g;
+        else return horner_d<J - 1>(x, fma(g, x, coef<J>((double)(J + 2))));
     }
     MF_D double residual(double x, double t) const {   // F(x) - t, F(x) = x^2 (c_0 + c_1 x + ...)
-        double h = c[E - 1];
-#pragma unroll
-        for (int j = E - 2; j >= 0; --j) h = fma(h, x, c[j]);
-        return fma(x * x, h, -t);
+        return fma(x * x, horner_f<E - 2>(x, coef<E - 1>(1.0)), -t);
     }
     MF_D double slope(double x) const {   // F'(x) = x (2 c_0 + 3 c_1 x + ...)
-        double g = (double)(E + 1) * c[E - 1];
-#pragma unroll
-        for (int j = E - 2; j >= 0; --j) g = fma(g, x, (double)(j + 2) * c[j]);
-        return x * g;
+        return x * horner_d<E - 2>(x, coef<E - 1>((double)(E + 1)));
     }
 };
 

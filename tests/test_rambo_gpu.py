@@ -261,7 +261,7 @@ def test_massvar_solver_vs_bisection(oracle):
             dG = sum(c * k * x_large ** (k - 1) for c, k in zip(ck, range(2, ee + 2)))
             x_large = x_large - np.where(dG != 0, G / np.where(dG != 0, dG, 1), 0)
         exact = np.where(vc < 0.65, x_small, L(1) - x_large)
-        ok = (vc > 0) & (vc < 1) & (uc < 1 - 2e-16)         # away from the clamps at the two ends
+        ok = (vc > 0) & (vc < 1) & (uc < 1 - 2e-16) & (uc > L(2.0) ** -179)   # away from the clamps at the two ends (2^-180: the bisection's floor)
         err_ulp = np.abs(uc - exact)[ok] / (np.abs(exact[ok]) * L(2.0) ** -53)
         assert float(err_ulp.max()) <= 4.0, (ee, float(err_ulp.max()))
 
