@@ -16,7 +16,7 @@ namespace mf {
 // EPILOGUE == false: plain CM-frame output, every 4-momentum is stored the moment it is final (streaming core).
 // EPILOGUE == true : lab-frame output and / or cuts need the whole event first (array interface).
 template <typename T, int NF, bool EPILOGUE>
-__global__ void __launch_bounds__(256, (EPILOGUE ? (NF <= 4 ? 3 : 2) : 3))
+__global__ void __launch_bounds__(256, (EPILOGUE ? (NF <= 4 ? 3 : 2) : (NF <= 4 ? 4 : 3)))
 rambo_forward_kernel(const T* __restrict__ u, int64_t N, const __grid_constant__ RamboParams<T, NF> P,
                      T* __restrict__ momenta, T* __restrict__ weight, T* __restrict__ logweight,
                      T* __restrict__ x1o, T* __restrict__ x2o, int32_t* __restrict__ status) {

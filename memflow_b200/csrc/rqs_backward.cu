@@ -246,7 +246,9 @@ rqs_backward_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const 
 // Knots are offset + running sum inside the chunk, so they may differ from the sequential cumsum in the last bit;
 // the spline and its parameter gradients are continuous across a knot, so a bin flipped by that is harmless.
 template <typename T, bool INV, int LANES>
-__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 4 : 2)
+// fp64: 3 CTAs per SM (<= 85 registers, a few spilled words) beat 2 for LANES >= 4; LANES = 2 carries four tangents
+// per thread in S4 and would spill 200 B
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 4 : (LANES >= 4 ? 3 : 2))
 rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const T* __restrict__ g_out,
                          const T* __restrict__ g_ladj, int64_t rows, int K, RqsConst<T> C, int bulk_ok,
                          T* __restrict__ g_phi, T* __restrict__ g_v) {

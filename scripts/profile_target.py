@@ -1,5 +1,5 @@
 """Small single-GPU program for ncu: a few launches of each kernel at benchmark shapes.
-usage: python scripts/profile_target.py [chain|k1|k2|rqs|all]"""
+usage: python scripts/profile_target.py [chain|k1|k2|rqs|rqs64|all]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -35,5 +35,14 @@ if what in ("rqs", "all"):
     for i in range(3):
         TR.rqs_forward(phi, x, bound=1.1)
         TR.rqs_inverse(phi, x, bound=1.1)
+    torch.cuda.synchronize()
+if what in ("rqs64", "all"):   # the reference's configs run the flows in float64: forward + backward at F=10, K=40
+    B, F, K = 1 << 18, 10, 40
+    phi = torch.randn(B, F, 3 * K - 1, device=dev, dtype=torch.float64, requires_grad=True)
+    x = (torch.rand(B, F, device=dev, dtype=torch.float64) * 2.6 - 1.3) * 1.1
+    for i in range(3):
+        y, l, ls = TR.rqs_forward(phi, x, bound=1.1)
+        phi.grad = None
+        ls.sum().backward()
     torch.cuda.synchronize()
 print("done")

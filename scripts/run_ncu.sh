@@ -20,7 +20,9 @@ prof() {  # name kernel-regex target launch-skip
 for w in $WHAT; do
   case $w in
     chain)  prof chain  "is_chain_kernel" chain 2 ;;
-    flowA)  prof flowA  "flow_sample_kernel" chain 2 ;;
+    flowA)  prof flowA  "flow_sample_fast_kernel" chain 2 ;;
+    rqs64f) prof rqs64f "rqs_coop_kernel" rqs64 2 ;;
+    rqs64b) prof rqs64b "rqs_backward_coop_kernel" rqs64 2 ;;
     flowB)  prof flowB  "rambo_is_kernel" chain 2 ;;
     k1n3)   prof k1n3   "rambo_forward_kernel" k1 1 ;;
     k1n8)   prof k1n8   "rambo_forward_kernel" k1 4 ;;
