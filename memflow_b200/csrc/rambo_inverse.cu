@@ -11,7 +11,7 @@
 namespace mf {
 
 template <typename T, int NF>
-__global__ void __launch_bounds__(256, (NF <= 4 ? 3 : 2))
+__global__ void __launch_bounds__(256, (NF <= 3 ? 4 : (NF <= 4 ? 3 : 2)))
 rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const T* __restrict__ x1a,
                      const T* __restrict__ x2a, int64_t N, const __grid_constant__ RamboParams<T, NF> P,
                      T* __restrict__ ps, T* __restrict__ prob, T* __restrict__ logprob,
