@@ -320,7 +320,7 @@ def main():
     t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop() if sampler else None
     t_dev = evs[0].elapsed_time(end) * 1e-3
-    kern_ms = sorted(evs[i].elapsed_time(mids[i]) for i in range(K))          # launch A (flow_sample_kernel)
+    kern_ms = sorted(evs[i].elapsed_time(mids[i]) for i in range(K))          # launch A (flow_sample_fast_kernel)
     kern_b_ms = sorted(mids[i].elapsed_time(evs[i + 1]) for i in range(K))    # launch B (rambo_is_kernel)
     t = torch.tensor([t_dev], dtype=torch.float64, device=dev)
     if world > 1:
@@ -392,7 +392,7 @@ def main():
                 "note": "spline parameters start in pinned host memory; H2D double-buffered against the kernel"},
         "gpu_launches": 2 * K * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic, "kernel": "flow_sample_kernel (launch A of each step)", "peak_source": peak_src,
+                     "traffic": traffic, "kernel": "flow_sample_fast_kernel<10> (launch A of each step)", "peak_source": peak_src,
                      "algorithmic_bytes_per_event": BYTES_PER_EVENT, "events_per_launch": CHUNK,
                      "kernel_ms_avg": avg_kernel_s * 1e3, "kernel_ms_median": med_kernel_s * 1e3,
                      "second_kernel": {"name": "rambo_is_kernel<3> (launch B)", "ms_avg": sum(kern_b_ms) / len(kern_b_ms),
