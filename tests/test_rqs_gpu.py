@@ -198,6 +198,30 @@ def test_ragged_and_unaligned(oracle):
     assert y1 is not None and torch.equal(y1, y0)
     e = TR.rqs_forward(torch.empty(0, 7, 29, device="cuda"), torch.empty(0, 7, device="cuda"), bound=1.0)
     assert e[0].shape == (0, 7)
+    # the cooperative kernels (several threads per row: every fp64 call, fp32 with other bin counts; forward, inverse and
+    # backward): row counts that are not a multiple of the tile, and a base address that rules the bulk copy out
+    for dt, F, K, bound in ((torch.float64, 10, 40, 1.1), (torch.float64, 3, 10, 1.0), (torch.float64, 2, 100, 1.0),
+                            (torch.float32, 5, 24, 1.0)):
+        tol = 1e-12 if dt == torch.float64 else 1e-4
+        for B in (1, 7, 53, 200):
+            phi, x = make(B, F, K, dt, bound, seed=B + K)
+            buf = torch.empty(phi.numel() + 1, dtype=dt, device="cuda")
+            view = buf[1:].view(phi.shape); view.copy_(phi)
+            for fn, ofn in ((TR.rqs_forward, oracle.rqs_forward), (TR.rqs_inverse, oracle.rqs_inverse)):
+                y, l, ls = fn(phi.cuda(), x.cuda(), bound=bound)
+                y1, l1, ls1 = fn(view, x.cuda(), bound=bound)
+                oy, ol, _ = ofn(phi.numpy(), x.numpy(), bound=bound)
+                assert torch.equal(y, y1) and torch.equal(l, l1) and torch.equal(ls, ls1)
+                assert np.abs(y.cpu().numpy() - oy).max() < tol * 100 and np.quantile(np.abs(y.cpu().numpy() - oy), 0.9) < tol
+                assert torch.allclose(ls, l.sum(1), rtol=0, atol=1e-9 if dt == torch.float64 else 1e-3)
+            # backward: the gradient of the aligned and of the unaligned copy must be the same bits
+            grads = []
+            for p in (phi.cuda(), view):
+                p = p.detach().requires_grad_(True)
+                yy, ll, _ = TR.rqs_forward(p, x.cuda(), bound=bound)
+                (yy.sum() + 0.5 * ll.sum()).backward()
+                grads.append(p.grad.clone())
+            assert torch.equal(grads[0], grads[1]) and bool(torch.isfinite(grads[0]).all())
 
 
 # K < 12: one thread per row; 12..23 / 24..47 / >= 48: 2 / 4 / 8 threads per row (rqs_backward_coop_kernel)
