@@ -255,6 +255,10 @@ int mf_decay_partons_bwd_f64(const double* propagators, const double* higgs_angl
  *                         (cells [50-54]); optional momenta / weight / x1 / x2 outputs. */
 int mf_flow_sample_f32(const float* phi, int64_t N, int F, int T, int K, float bound, float slope, uint64_t seed,
                        uint64_t event_offset, double* u, double* logq, mf_stream_t stream);
+/* A with float64 flow parameters (phi [T, N, F, 3K-1] double: the dtype of MEMFlow's configs). Same base point and
+ * outputs as mf_flow_sample_f32; built from the fp64 spline kernel (one launch per transform). */
+int mf_flow_sample_f64(const double* phi, int64_t N, int F, int T, int K, double bound, double slope, uint64_t seed,
+                       uint64_t event_offset, double* u, double* logq, mf_stream_t stream);
 int mf_rambo_is_f64(const double* u, const double* logq, int64_t N, int n_final, const double* masses,
                     double e_collider, uint32_t flags, double* acc, void* workspace, double* momenta, double* weight,
                     double* x1, double* x2, mf_stream_t stream);

@@ -689,6 +689,66 @@ extern "C" int mf_flow_sample_f32(const float* phi, int64_t N, int F, int T, int
     return mf::flow_sample_launch(phi, N, F, T, K, bound, slope, seed, event_offset, u, logq, (cudaStream_t)stream);
 }
 
+// ---- launch A with float64 flow parameters (the dtype of every MEMFlow config): the same chain built from the fp64
+// spline kernel. Philox base point (the fp32 chain's draw, widened) -> T x rqs_coop_kernel<double, inverse> in place on
+// the u buffer, the per-row log-dets summed per event in feature order and accumulated over the transforms
+// (deterministic) -> u = (x + B) / 2B. FP64-latency bound at ~2.6 TB/s of parameters (profiles/: rqs64f). ----
+namespace mf {
+__global__ void __launch_bounds__(256)
+philox_base_f64_kernel(int64_t N, int F, double bound, uint64_t seed, uint64_t event_offset, double* __restrict__ x,
+                       double* __restrict__ logq) {
+    const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ev >= N) return;
+    const uint64_t gev = event_offset + (uint64_t)ev;
+    for (int blk = 0; 4 * blk < F; ++blk) {
+        const Philox4 r4 = philox4x32_10((uint32_t)gev, (uint32_t)(gev >> 32), (uint32_t)blk, 0u, (uint32_t)seed,
+                                         (uint32_t)(seed >> 32));
+        const uint32_t b[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (4 * blk + j < F)  // the fp32 chain's base point bound * (2 u01 - 1), rounded in fp32 like there
+                x[ev * F + 4 * blk + j] = (double)((float)bound * (2.0f * u01_from_bits(b[j]) - 1.0f));
+    }
+    logq[ev] = 0.0;
+}
+__global__ void __launch_bounds__(256)
+ladj_accumulate_kernel(const double* __restrict__ ladj, int64_t N, int F, double* __restrict__ logq) {
+    const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ev >= N) return;
+    double s = 0.0;
+    for (int f = 0; f < F; ++f) s += ladj[ev * F + f];
+    logq[ev] += s;
+}
+__global__ void __launch_bounds__(256) to_unit_kernel(double* __restrict__ x, int64_t n, double bound, double inv_2b) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = (x[i] + bound) * inv_2b;
+}
+}  // namespace mf
+
+extern "C" int mf_flow_sample_f64(const double* phi, int64_t N, int F, int T, int K, double bound, double slope,
+                                  uint64_t seed, uint64_t event_offset, double* u, double* logq, mf_stream_t stream) {
+    if (N < 0 || T < 1 || F < 1 || (N > 0 && (!phi || !u || !logq))) return MF_E_BADARG;
+    if (K < 1 || K > 128) return MF_E_SHAPE;
+    if (N == 0) return MF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((N + 255) / 256);
+    mf::philox_base_f64_kernel<<<grid, 256, 0, st>>>(N, F, bound, seed, event_offset, u, logq);
+    double* ladj = nullptr;
+    if (cudaMallocAsync((void**)&ladj, (size_t)N * F * sizeof(double), st) != cudaSuccess) return -(int)cudaErrorMemoryAllocation;
+    const size_t pitch = (size_t)N * F * (3 * K - 1);
+    int rc = MF_OK;
+    for (int t = T - 1; t >= 0 && rc == MF_OK; --t) {
+        // in place: every thread of a row reads its input before the tile's first barrier, the owner writes after the last
+        rc = mf::rqs_coop_launch<double, true>(phi + (size_t)t * pitch, u, N, F, K, bound, slope, u, ladj, nullptr, nullptr, st);
+        if (rc == MF_OK) mf::ladj_accumulate_kernel<<<grid, 256, 0, st>>>(ladj, N, F, logq);
+    }
+    cudaFreeAsync(ladj, st);
+    if (rc != MF_OK) return rc;
+    const int64_t n = N * (int64_t)F;
+    mf::to_unit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(u, n, bound, 1.0 / (2.0 * bound));
+    return mf::launch_status();
+}
+
 extern "C" int mf_rambo_is_f64(const double* u, const double* logq, int64_t N, int n_final, const double* masses,
                                double e_collider, uint32_t flags, double* acc, void* workspace, double* momenta,
                                double* weight, double* x1, double* x2, mf_stream_t stream) {

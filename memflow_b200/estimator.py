@@ -62,15 +62,16 @@ class ImportanceSampler:
 
     def _check_phi(self, phi):
         require_cuda(phi, "phi")
-        if phi.dtype != torch.float32 or phi.dim() != 4:
-            raise AssertionError("phi must be float32 [T, N, F, 3K-1]")
+        if phi.dtype not in (torch.float32, torch.float64) or phi.dim() != 4:
+            raise AssertionError("phi must be float32 or float64 [T, N, F, 3K-1]")
         T, N, F, PW = phi.shape
         if F != 3 * self.n_final - 2 or (PW + 1) % 3 != 0:
             raise AssertionError("phi shape does not match n_final (F must be 3n-2, last dim 3K-1)")
         return T, N, F, (PW + 1) // 3
 
     def sample_flow(self, phi, event_offset=0, u=None, logq=None):
-        """Stage A alone (mf_flow_sample_f32): u [N, F] float64 in [0,1] and log q(u) [N] of the flow's samples."""
+        """Stage A alone (mf_flow_sample_f32 / _f64 by the dtype of phi): u [N, F] float64 in [0,1] and log q(u) [N] of the
+        flow's samples."""
         T, N, F, K = self._check_phi(phi)
         phi = phi.contiguous()
         dev = phi.device
@@ -78,37 +79,36 @@ class ImportanceSampler:
             u = torch.empty((N, F), dtype=torch.float64, device=dev)
         if logq is None:
             logq = torch.empty(N, dtype=torch.float64, device=dev)
+        f64 = phi.dtype == torch.float64   # MEMFlow's configs run the flows in float64: same chain on the fp64 spline kernel
+        fn = lib().mf_flow_sample_f64 if f64 else lib().mf_flow_sample_f32
+        ct = ctypes.c_double if f64 else ctypes.c_float
         with torch.cuda.device(dev):
-            rc = lib().mf_flow_sample_f32(
-                ptr(phi), ctypes.c_int64(N), ctypes.c_int(F), ctypes.c_int(T), ctypes.c_int(K), ctypes.c_float(self.bound),
-                ctypes.c_float(self.slope if self.slope is not None else 0.0), ctypes.c_uint64(self.seed),
-                ctypes.c_uint64(int(event_offset)), ptr(u), ptr(logq), stream_ptr(dev))
-        check(rc, "mf_flow_sample_f32")
+            rc = fn(ptr(phi), ctypes.c_int64(N), ctypes.c_int(F), ctypes.c_int(T), ctypes.c_int(K), ct(self.bound),
+                    ct(self.slope if self.slope is not None else 0.0), ctypes.c_uint64(self.seed),
+                    ctypes.c_uint64(int(event_offset)), ptr(u), ptr(logq), stream_ptr(dev))
+        check(rc, "mf_flow_sample_f64" if f64 else "mf_flow_sample_f32")
         return u, logq
 
-    def weigh(self, u, logq, acc=None):
-        """Stage B alone (mf_rambo_is_f64): PhaseSpace map of u + weight + accumulation into acc."""
+    def weigh(self, u, logq, acc=None, out=None):
+        """Stage B alone (mf_rambo_is_f64): PhaseSpace map of u + weight + accumulation into acc. `out` (optional dict
+        with momenta / weight / x1 / x2 tensors) receives the per-event values."""
         require_cuda(u, "u")
         dev = u.device
         if acc is None:
             acc = new_accumulator(dev)
         ws = reduce_workspace(dev)
+        out = out or {}
         with torch.cuda.device(dev):
             rc = lib().mf_rambo_is_f64(ptr(u), ptr(logq), ctypes.c_int64(u.shape[0]), ctypes.c_int(self.n_final),
                                        host_array(self.masses, ctypes.c_double), ctypes.c_double(self.collider_energy),
-                                       ctypes.c_uint32(0), ptr(acc), ptr(ws), None, None, None, None, stream_ptr(dev))
+                                       ctypes.c_uint32(0), ptr(acc), ptr(ws), ptr(out.get("momenta")), ptr(out.get("weight")),
+                                       ptr(out.get("x1")), ptr(out.get("x2")), stream_ptr(dev))
         check(rc, "mf_rambo_is_f64")
         return acc
 
     def run_chunk(self, phi, event_offset=0, acc=None, debug_outputs=False):
-        require_cuda(phi, "phi")
-        if phi.dtype != torch.float32 or phi.dim() != 4:
-            raise AssertionError("phi must be float32 [T, N, F, 3K-1]")
-        T, N, F, PW = phi.shape
+        T, N, F, K = self._check_phi(phi)
         n = self.n_final
-        if F != 3 * n - 2 or (PW + 1) % 3 != 0:
-            raise AssertionError("phi shape does not match n_final (F must be 3n-2, last dim 3K-1)")
-        K = (PW + 1) // 3
         phi = phi.contiguous()
         dev = phi.device
         if acc is None:
@@ -122,6 +122,10 @@ class ImportanceSampler:
                        weight=torch.empty(N, dtype=torch.float64, device=dev),
                        x1=torch.empty(N, dtype=torch.float64, device=dev),
                        x2=torch.empty(N, dtype=torch.float64, device=dev))
+        if phi.dtype == torch.float64:   # float64 flow parameters: stage A on the fp64 spline kernel, then stage B
+            u, logq = self.sample_flow(phi, event_offset=event_offset, u=out.get("u"), logq=out.get("logq"))
+            self.weigh(u, logq, acc=acc, out=out)
+            return (acc, out) if debug_outputs else acc
         with torch.cuda.device(dev):
             rc = lib().mf_is_chain_f64(
                 ptr(phi), ctypes.c_int64(N), ctypes.c_int(n), ctypes.c_int(T), ctypes.c_int(K),

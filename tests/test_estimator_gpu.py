@@ -70,6 +70,42 @@ def test_chain_vs_oracle_composition(oracle, n, T, K):
     np.testing.assert_allclose(a[:2], ref[:2], rtol=1e-11)
 
 
+@pytest.mark.parametrize("n,T,K", [(3, 2, 10), (4, 3, 40)])
+def test_chain_with_float64_flow_parameters(oracle, n, T, K):
+    """MEMFlow's configs run the flows in float64: the same chain on the fp64 spline kernel (mf_flow_sample_f64) against
+    the step-by-step oracle composition, at fp64 tolerances; chunk / offset invariant like the fp32 chain."""
+    from memflow_b200 import estimator as ES
+    from oracle import philox as OP
+    F = 3 * n - 2
+    N = 10_000 + 7
+    g = torch.Generator().manual_seed(5)
+    phi = torch.randn(T, N, F, 3 * K - 1, generator=g, dtype=torch.float64)
+    smp = ES.ImportanceSampler(MASSES[n], E, bound=1.0, seed=99, device="cuda:0")
+    acc, out = smp.run_chunk(phi.cuda(), event_offset=5, debug_outputs=True)
+    xcur = OP.base_sample(N, F, 1.0, 99, 5).astype(np.float64)
+    lsum = np.zeros(N)
+    for t in range(T - 1, -1, -1):
+        xcur, l, _ = oracle.rqs_inverse(phi[t].numpy(), xcur, bound=1.0)
+        lsum += l.sum(1)
+    uo = (xcur + 1.0) / 2.0
+    ug = out["u"].cpu().numpy()
+    # T chained inverses: each amplifies the previous one's rounding by its slope (soft-clipped to <= 1e3)
+    assert np.median(np.abs(ug - uo)) < 1e-15 and np.quantile(np.abs(ug - uo), 0.999) < 1e-11
+    dq = np.abs(out["logq"].cpu().numpy() - lsum)
+    assert np.median(dq) < 1e-12 and np.quantile(dq, 0.999) < 1e-9   # a sum of T F log-dets of O(1..10)
+    om, ow, ox1, ox2 = oracle.rambo_forward(ug, MASSES[n], E)
+    tgt = 1.0 / (2 * E * E) / (ox1 * ox2)
+    ref = oracle.is_reduce(tgt, out["weight"].cpu().numpy(), out["logq"].cpu().numpy())
+    a = acc.cpu().numpy()
+    assert a[2] == ref[2]
+    np.testing.assert_allclose(a[:2], ref[:2], rtol=1e-11)
+    # two half-chunks == one chunk, per event
+    h = N // 2
+    u1, q1 = smp.sample_flow(phi[:, :h].contiguous().cuda(), event_offset=5)
+    u2, q2 = smp.sample_flow(phi[:, h:].contiguous().cuda(), event_offset=5 + h)
+    assert torch.equal(torch.cat((u1, u2)), out["u"]) and torch.equal(torch.cat((q1, q2)), out["logq"])
+
+
 def test_chain_is_chunk_and_offset_invariant():
     """Philox counter = global event index: splitting a range into chunks gives the same per-event values,
     and the accumulators add up (what makes the multi-GPU shards reproducible)."""
