@@ -18,6 +18,8 @@
 namespace mf {
 
 template <typename T> MF_D T fw_exp(T a, T m, const RqsConst<T>& C);
+// (library exp: a hand-written Cody-Waite + degree-13 Estrin exp with an integer exponent add was 12 % SLOWER here,
+//  scripts/fastmath_check.cu keeps it for the record)
 template <> MF_D double fw_exp<double>(double a, double m, const RqsConst<double>& C) {
     if (C.clip) a = div_fast(a, 1.0 + fabs(a * C.two_over_L));
     return exp(a - m);

@@ -54,6 +54,24 @@ __device__ double sqrt_g(double x) {  // coupled (Goldschmidt) form: 7 fp64 oper
     const double g1 = fma(g, r, g), h1 = fma(h, r, h);
     return fma(fma(-g1, g1, x), h1, g1);
 }
+__device__ double exp_bounded(double x) {  // rqs.cuh: Cody-Waite reduction, degree-13 Taylor in Estrin form, exponent add
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double p01 = 1.0 + r, p23 = fma(r, 1.0 / 6, 0.5), p45 = fma(r, 1.0 / 120, 1.0 / 24), p67 = fma(r, 1.0 / 5040, 1.0 / 720);
+    const double p89 = fma(r, 1.0 / 362880, 1.0 / 40320), pab = fma(r, 1.0 / 39916800, 1.0 / 3628800);
+    const double pcd = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600);
+    const double q0 = fma(r2, p23, p01), q1 = fma(r2, p67, p45), q2 = fma(r2, pab, p89);
+    const double o0 = fma(r4, q1, q0), o1 = fma(r4, pcd, q2);
+    const double p = fma(r8, o1, o0);
+    const unsigned hi = (unsigned)__double2hiint(x);
+    const bool under = hi > 0xC0862000u && (hi < 0xFFF00000u || (hi == 0xFFF00000u && __double2loint(x) == 0));
+    const double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return under ? 0.0 : res;
+}
 __device__ double ulps(double a, double ref) {
     if (a == ref) return 0.0;
     int ex; frexp(ref, &ex);
@@ -61,10 +79,10 @@ __device__ double ulps(double a, double ref) {
 }
 __device__ uint64_t splitmix(uint64_t& s) { uint64_t z = (s += 0x9e3779b97f4a7c15ULL); z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL; return z ^ (z >> 31); }
 
-__global__ void check(double* out /* [gridDim*blockDim][12] */, int per_thread) {
+__global__ void check(double* out /* [gridDim*blockDim][16] */, int per_thread) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t s = 0x1234567ULL * (t + 1);
-    double m[12] = {0};
+    double m[16] = {0};
     double mr = 0;
     for (int i = 0; i < per_thread; ++i) {
         const uint64_t bits = splitmix(s);
@@ -79,27 +97,33 @@ __global__ void check(double* out /* [gridDim*blockDim][12] */, int per_thread) 
         const double a = ldexp(1.0 + (double)(splitmix(s) >> 12) * (1.0 / 4503599627370496.0), (int)(splitmix(s) % 41) - 20);
         m[11] = fmax(m[11], ulps(div_v<1>(a, x), a / x));
         mr = fmax(mr, ulps(rsqrt_r(x), rs));
-        m[7] = fmax(m[7], ulps(sqrt_g(x), sq));   // (slot of rcp with 2 steps, exact)
+        {   // exp on the spline's argument ranges: soft-clipped [-3.5, 3.5] (and the derivative's [-7, 7]), max-subtracted [-700, 0]
+            const double a = -7.0 + 14.0 * ((double)(splitmix(s) >> 11) * (1.0 / 9007199254740992.0));
+            const double b = -700.0 * ((double)(splitmix(s) >> 11) * (1.0 / 9007199254740992.0));
+            m[13] = fmax(m[13], fmax(ulps(exp_bounded(a), exp(a)), ulps(exp_bounded(b), exp(b))));
+        }
+        m[12] = fmax(m[12], ulps(sqrt_g(x), sq));
         m[9] = fmax(m[9], fabs(rsqrt_seed(x) * sq - 1.0)); m[10] = fmax(m[10], fabs(rcp_seed(x) * x - 1.0));
     }
-    m[8] = mr;  // (rcp with 3 steps is exact like 2: slot reused)
-    for (int k = 0; k < 12; ++k) out[t * 12 + k] = m[k];
+    m[14] = mr;
+    for (int k = 0; k < 16; ++k) out[t * 16 + k] = m[k];
 }
 
 int main() {
     const int blocks = 592, threads = 256, per = 4096;
-    double* d; cudaMalloc(&d, sizeof(double) * blocks * threads * 12);
+    double* d; cudaMalloc(&d, sizeof(double) * blocks * threads * 16);
     check<<<blocks, threads>>>(d, per);
-    double* h = new double[blocks * threads * 12];
-    if (cudaMemcpy(h, d, sizeof(double) * blocks * threads * 12, cudaMemcpyDeviceToHost) != cudaSuccess) { printf("cuda error\n"); return 1; }
-    double m[12] = {0};
-    for (int t = 0; t < blocks * threads; ++t) for (int k = 0; k < 12; ++k) m[k] = fmax(m[k], h[t * 12 + k]);
+    double* h = new double[blocks * threads * 16];
+    if (cudaMemcpy(h, d, sizeof(double) * blocks * threads * 16, cudaMemcpyDeviceToHost) != cudaSuccess) { printf("cuda error\n"); return 1; }
+    double m[16] = {0};
+    for (int t = 0; t < blocks * threads; ++t) for (int k = 0; k < 16; ++k) m[k] = fmax(m[k], h[t * 16 + k]);
     printf("samples %lld\n", (long long)blocks * threads * per);
     printf("sqrt  max ulp, 1/2/3 Newton steps on the rsqrt seed + residual step: %.3f %.3f %.3f\n", m[0], m[1], m[2]);
     printf("rsqrt max ulp, 1/2/3 Newton steps:                                   %.3f %.3f %.3f\n", m[3], m[4], m[5]);
     printf("rcp   max ulp, 1/2/3 Newton steps:                                   %.3f %.3f %.3f\n", m[6], m[7], m[8]);
-    printf("rsqrt max ulp, 1 standard + 1 residual-form step:                    %.3f\n", m[8]);
-    printf("sqrt  max ulp, coupled form (7 operations):                          %.3f\n", m[7]);
+    printf("rsqrt max ulp, 1 standard + 1 residual-form step:                    %.3f\n", m[14]);
+    printf("sqrt  max ulp, coupled form (7 operations):                          %.3f\n", m[12]);
+    printf("exp   max ulp, Estrin degree 13 on [-7, 7] and [-700, 0]:            %.3f\n", m[13]);
     printf("div   max ulp, 1 Newton step on the rcp seed + residual step:        %.3f\n", m[11]);
     printf("seed relative error: rsqrt %.3g (2^%.1f), rcp %.3g (2^%.1f)\n", m[9], log2(m[9]), m[10], log2(m[10]));
     return 0;
