@@ -1,7 +1,7 @@
 """A/B timing of the flow-sample kernel variants inside ONE process per variant, interleaved and repeated, to
 beat run-to-run clock noise: prints the per-variant median of launch A (ms) over several rounds."""
 import os, sys, subprocess, json
-VARIANTS = [dict(MF_CHAIN_FAST="1"), dict(MF_CHAIN_FAST="0")]  # or dict(MEMFLOW_B200_LIB=<other build of the .so>)
+VARIANTS = [dict(MF_CHAIN_FAST="1"), dict(MF_CHAIN_FAST="0")]  # or dict(MF_CHAIN_FAST="0", MF_CHAIN_MINB="6"), dict(MEMFLOW_B200_LIB=<other build of the .so>)
 if len(sys.argv) > 1:
     import torch
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
