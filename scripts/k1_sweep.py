@@ -5,7 +5,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from memflow_b200._lib import lib, ptr, host_array, stream_ptr
 dev = torch.device("cuda:0")
 E = 13000.0
-CASES = {3: [125.25, 172.5, 172.5], 4: [125.25, 172.5, 172.5, 1e-5], 8: [4.7, 4.7, 4.7, 4.7, 0.1, 0.0, 0.3, 0.3]}
+CASES = {3: [125.25, 172.5, 172.5], 4: [125.25, 172.5, 172.5, 1e-5], 5: [125.25, 172.5, 172.5, 1e-5, 0.0],
+         6: [4.7, 4.7, 80.4, 172.5, 0.0, 1e-5], 7: [4.7, 4.7, 4.7, 0.1, 0.0, 0.3, 172.5], 8: [4.7, 4.7, 4.7, 4.7, 0.1, 0.0, 0.3, 0.3]}
+if len(sys.argv) > 1:
+    CASES = {int(a): CASES[int(a)] for a in sys.argv[1:]}
+else:
+    CASES = {n: CASES[n] for n in (3, 4, 8)}
 N = 1 << 24
 L = lib()
 def timeit(f, n=10):
