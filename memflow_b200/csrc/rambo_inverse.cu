@@ -6,6 +6,8 @@
 // event pitch is a parameter so that the `momenta[:, 2:]` slice of a forward output is read in
 // place (the reference clones it, :628, and again per particle, :680).
 // Algorithmic bytes per event: (4n + 2 + 3n-2 + 1) * sizeof(T).
+#include <cstdlib>
+
 #include "rambo.cuh"
 
 namespace mf {
@@ -174,6 +176,115 @@ rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming form for n >= 5 (fp64, not the get_PS / float32-quirk modes). The kernel above holds the whole event: 4n
+// momenta, M[n], K[n] and the 3n-2 outputs, 124-128 registers at n = 7, 8, i.e. 2 CTAs per SM, and its FP64 chains
+// stall on their own latency with 4 warps per scheduler. Everything the inverse needs at step j is the running sum
+// Q_j = p_{n-1} + ... + p_j, p_j itself and (M, K) of step j+1, so here particles are consumed last to first, each
+// loaded when its turn comes, the weight is accumulated on the way (the same pieces as rambo_weight) and every
+// unit-cube coordinate goes straight into the CTA's shared-memory staging row (coalesced 128-bit stores at the end).
+// Difference to the array form: M_j^2 comes from Q_j (summed last to first) instead of a separate first-to-last sum
+// (the reference's torch.sum, :656): a rounding-level change of an ill-conditioned quantity, inside the
+// conditioning-aware bound of tests/parity.py (gamma^2 of the system).
+// ---------------------------------------------------------------------------------------------
+template <int NF>
+__global__ void __launch_bounds__(256, 3)
+rambo_inverse_stream_kernel(const double* __restrict__ momenta, int64_t event_stride, const double* __restrict__ x1a,
+                            const double* __restrict__ x2a, int64_t N, const __grid_constant__ RamboParams<double, NF> P,
+                            double* __restrict__ ps, double* __restrict__ prob, double* __restrict__ logprob,
+                            int32_t* __restrict__ status) {
+    using T = double;
+    constexpr int D = 3 * NF - 4, W = D + 2;
+    __shared__ __align__(16) T stage[256 * W];
+    const int64_t ev_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = ev_raw < N;
+    const int64_t ev = valid ? ev_raw : N - 1;  // threads past the end redo the last event and write nothing
+    T* const row = stage + threadIdx.x * W;
+    const T* base = momenta + ev * event_stride;
+    const T x1 = x1a[ev], x2 = x2a[ev];
+
+    T Q[4] = {(T)0, (T)0, (T)0, (T)0};
+    T Mn = (T)0, Kn = (T)0;                    // M_{j+1}, K_{j+1}
+    T num = (T)1, den = (T)1, f8 = (T)1, pw = (T)1;
+    [&]<int... I>(std::integer_sequence<int, I...>) {
+        ((void)[&] {
+            constexpr int j = NF - 1 - I;      // NF-1, ..., 0
+            T p[4];
+            ld4(base + 4 * P.order[j], p[0], p[1], p[2], p[3]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Q[c] = (j == NF - 1) ? p[c] : Q[c] + p[c];
+            const T sq = sub_rn(sub_rn(sub_rn(mul_rn(Q[0], Q[0]), mul_rn(Q[1], Q[1])), mul_rn(Q[2], Q[2])), mul_rn(Q[3], Q[3]));
+            const T Mj = sqrt_fast(sq);
+            const T Kj = Mj - P.msum_rev[j];
+            if constexpr (j <= NF - 2) {
+                if constexpr (j < NF - 2) {    // mass variable (:665-672), exponent n-2-j
+                    const T uu = div_fast(Kn, Kj);
+                    row[j] = (T)(NF - 1 - j) * ipow<NF - 2 - j>(uu) - (T)(NF - 2 - j) * ipow<NF - 1 - j>(uu);
+                }
+                T pb[4];                       // p_j in the rest frame of Q_j -> (cos theta, phi) (:680-696)
+                const T niq = -rcp_fast(Q[0]);
+                boost(p, Q[1] * niq, Q[2] * niq, Q[3] * niq, pb);
+                row[NF + 2 * j - 2] = ((pb[3] * rsqrt_fast(rho2_3(pb[1], pb[2], pb[3]))) + (T)1) * (T)0.5;
+                T phi = atan_(div_fast(pb[2], pb[1]));
+                T dphi = (pb[2] < (T)0 && pb[1] > (T)0) ? (T)6.283185307179586 : (T)0;
+                dphi += (pb[1] < (T)0) ? (T)3.141592653589793 : (T)0;
+                row[NF + 2 * j - 1] = (phi + dphi) * (T)0.15915494309189535;  // 1 / (2 pi)
+                // weight pieces of the pair (j, j+1), see rambo_weight(); :709-713 uses m_{n-1}, not M_{n-1}
+                const T sM = rho_num(Mj, (j == NF - 2) ? P.m[NF - 1] : Mn, P.m[j]);
+                const T invM = rcp_fast(Mj);
+                if constexpr (j == NF - 2) {
+                    f8 = sM * (invM * invM);
+                } else {
+                    num *= (sM * (invM * invM)) * ((Kj * Kj) * Mn);
+                    den *= fabs_(sub_rn(mul_rn(Kj, Kj), mul_rn(Kn, Kn))) * Kn;
+                }
+                if constexpr (j == 0) pw = ipow<2 * NF - 4>(Kj * invM);
+            }
+            Mn = Mj;
+            Kn = Kj;
+        }(), ...);
+    }(std::make_integer_sequence<int, NF>{});
+
+    if (!(P.flags & MF_FLAG_NO_CM_CHECK) && status != nullptr) {  // :630-635: Q_0 is the summed final state
+        const T r2 = (Q[1] * Q[1] + Q[2] * Q[2]) + Q[3] * Q[3];
+        if (valid && !(r2 < (T)1e-3)) atomicOr(status, MF_ST_NOT_CM);
+    }
+    T jacinv;  // x1, x2 -> uniforms (utils.py:287-309)
+    if (P.flags & MF_FLAG_X1X2_DIRECT) {
+        row[D] = x1; row[D + 1] = x2; jacinv = (T)1;
+    } else {
+        const T ml1 = -log_(x1), ml2 = -log_(x2);
+        row[D] = ((T)(-0.5) * (ml1 * ml1) + P.q * ml1) * P.inv_A;
+        row[D + 1] = div_fast(ml2, P.q - ml1);
+        jacinv = rcp_fast((P.A * x1) * x2);
+    }
+    const T E_cm = sqrt_fast(x1 * x2) * P.e_collider;
+    T w = P.flat_c * (ipow<NF - 2>(E_cm * E_cm) / P.flat_ff);
+    w *= f8;
+    w *= div_fast(num, den);
+    w *= pw;
+    if (valid) {
+        const T pr = rcp_fast(w) * jacinv;
+        prob[ev] = pr;
+        if (logprob != nullptr) logprob[ev] = log_(pr);
+    }
+    // the CTA's rows are contiguous in memory: coalesced 128-bit stores
+    __syncthreads();
+    const int64_t ev0 = (int64_t)blockIdx.x * blockDim.x;
+    const int nrows = (int)((N - ev0) < (int64_t)blockDim.x ? (N - ev0) : (int64_t)blockDim.x);
+    T* g = ps + ev0 * W;
+    const int total = nrows * W;
+    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+        const int nv = total / 2;
+        const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+        uint4* g4 = reinterpret_cast<uint4*>(g);
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) g4[i] = s4[i];
+        for (int i = nv * 2 + threadIdx.x; i < total; i += blockDim.x) g[i] = stage[i];
+    } else {
+        for (int i = threadIdx.x; i < total; i += blockDim.x) g[i] = stage[i];
+    }
+}
+
 template <typename T, int NF>
 static int launch_inverse(const T* momenta, int64_t event_stride, const T* x1, const T* x2, int64_t N,
                           const int32_t* order, const T* masses, const T* target_mass, T e_collider,
@@ -224,6 +335,15 @@ static int launch_inverse(const T* momenta, int64_t event_stride, const T* x1, c
     if (N == 0) return MF_OK;
     const int threads = 256;
     const int64_t blocks = (N + threads - 1) / threads;
+    if constexpr (sizeof(T) == 8 && NF >= 5 && NF != 6) {   // measured: n = 5 +6 %, n = 7 +1 %, n = 8 +10 %, n = 6 -4 %
+        // MF_K2_STREAM=0 keeps the array-form kernel (A/B timing)
+        static const bool stream_form = [] { const char* e = getenv("MF_K2_STREAM"); return !(e && e[0] == '0'); }();
+        if (stream_form && boost == nullptr && !(flags & MF_FLAG_REF_FP32_QUIRKS)) {
+            rambo_inverse_stream_kernel<NF><<<(unsigned)blocks, threads, 0, stream>>>(momenta, event_stride, x1, x2, N, P, ps,
+                                                                                      prob, logprob, status);
+            return launch_status();
+        }
+    }
     rambo_inverse_kernel<T, NF><<<(unsigned)blocks, threads, 0, stream>>>(momenta, event_stride, x1, x2, N, P, ps,
                                                                           prob, logprob, status, boost, mask, logit_out);
     return launch_status();
