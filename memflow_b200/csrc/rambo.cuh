@@ -168,6 +168,19 @@ template <int E> MF_D float massvar_start_f32(bool small, float tf) {
     return x;
 }
 
+// t <= 1e-30: fp64 asymptotic start (library pow) and two full Newton steps. Kept OUT OF LINE: inlined into the five
+// solver instances of an n = 8 event it was a quarter of the kernel's instructions, all of them dead weight in the
+// instruction cache (ncu: no_instruction stalls).
+template <int E> __device__ __noinline__ double massvar_tiny_target(bool small, double t) {
+    double x = small ? pow(t / (double)(E + 1), 1.0 / (double)E) : sqrt(2.0 * t / (double)(E * (E + 1)));
+    const MassVarPoly<E> pl(small);
+    for (int it = 0; it < 2; ++it) {
+        const double xn = x - div_fast(pl.residual(x, t), pl.slope(x));
+        x = in_open_unit(xn) ? xn : x;
+    }
+    return x;
+}
+
 template <int E> MF_D double solve_massvar(double v) {
     if constexpr (E == 1) {
         double u = div_fast(v, 1.0 + sqrt_fast(1.0 - v));
@@ -178,8 +191,8 @@ template <int E> MF_D double solve_massvar(double v) {
         double x;
         if (t > 1e-30) {
             x = (double)massvar_start_f32<E>(small, (float)t);
-        } else if (t > 0.0) {  // outside fp32 range: fp64 asymptotic start (never taken for u in [1e-10, 1-1e-10])
-            x = small ? pow(t / (double)(E + 1), 1.0 / (double)E) : sqrt(2.0 * t / (double)(E * (E + 1)));
+        } else if (t > 0.0) {  // outside fp32 range (never taken for u in [1e-10, 1-1e-10]): out of line, see below
+            x = massvar_tiny_target<E>(small, t);
         } else {
             x = (t == 0.0 || t < 0.0) ? 0.0 : t;  // t <= 0 -> 0, NaN -> NaN
         }
@@ -189,13 +202,6 @@ template <int E> MF_D double solve_massvar(double v) {
         // reciprocal slope (-> ~1e-18): 3E + 7 fp64 operations per root, the previous two Halley steps cost ~85
         // because both variables' formulas were executed by every diverged warp.
         const MassVarPoly<E> pl(small);
-        if (!(t > 1e-30)) {  // the fp64 asymptotic start of the (unreachable in practice) tail is coarser: two full steps
-#pragma unroll 1
-            for (int it = 0; it < 2; ++it) {
-                const double xn = x - div_fast(pl.residual(x, t), pl.slope(x));
-                x = in_open_unit(xn) ? xn : x;
-            }
-        }
         const double inv = rcp_seed_refined(pl.slope(x));
         double xn = fma(-pl.residual(x, t), inv, x);
         x = in_open_unit(xn) ? xn : x;  // also rejects NaN / inf steps
