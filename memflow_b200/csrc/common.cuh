@@ -29,6 +29,8 @@ MF_D double exp_(double x) { return exp(x); }
 MF_D float exp_(float x) { return expf(x); }
 MF_D double log_(double x) { return log(x); }
 MF_D float log_(float x) { return logf(x); }
+MF_D double cospi_(double x) { return cospi(x); }
+MF_D float cospi_(float x) { return cospif(x); }
 MF_D double cos_(double x) { return cos(x); }
 MF_D float cos_(float x) { return cosf(x); }
 MF_D double atan_(double x) { return atan(x); }

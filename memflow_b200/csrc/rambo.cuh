@@ -316,8 +316,12 @@ MF_D void rambo_decay_step(const RamboParams<T, NF>& P, Load& load, Emit& emit, 
     const T qk = sM * ((T)0.5 * invM);  // 4 M_k rho(M_k, M_{k+1}, m_k)
     const T ct = (T)2 * load(NE + 2 * k) - (T)1;
     const T st = sqrt_fast(sub_rn((T)1, mul_rn(ct, ct)));
-    const T phi = (T)6.283185307179586 * load(NE + 2 * k + 1);
-    const T cp = cos_(phi);
+    // cos(2 pi u) as cospi(2u): exact range reduction and no large-argument slow path (the library cos carries a
+    // Payne-Hanek branch that is never taken for phi in [0, 2 pi] but was inlined once per decay: instruction-cache
+    // weight). Differs from cos(fl(2 pi u)) by <= 1e-15 |sin phi|: the rounding of phi itself.
+    const T uphi = load(NE + 2 * k + 1);
+    const T phi = (T)6.283185307179586 * uphi;
+    const T cp = cospi_((T)2 * uphi);
     const T sq = sqrt_fast(sub_rn((T)1, mul_rn(cp, cp)));
     const T sp = (phi > (T)3.141592653589793) ? -sq : sq;
     T p2[4], pb[4];
