@@ -26,7 +26,7 @@ for w in $WHAT; do
     flowB)  prof flowB  "rambo_is_kernel" chain 2 ;;
     k1n3)   prof k1n3   "rambo_forward_kernel" k1 1 ;;
     k1n8)   prof k1n8   "rambo_forward_kernel" k1 4 ;;
-    k2n8)   prof k2n8   "rambo_inverse_kernel" k2 4 ;;
+    k2n8)   prof k2n8   "rambo_inverse_stream_kernel" k2 1 ;;
     rqsfwd) prof rqsfwd "rqs_reg2_kernel" rqs 2 ;;
     rqsinv) prof rqsinv "rqs_reg2_kernel" rqs 3 ;;
     launches) ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_$TAG.csv python scripts/profile_target.py all > /dev/null 2>&1 ;;
