@@ -206,11 +206,13 @@ rambo_inverse_stream_kernel(const double* __restrict__ momenta, int64_t event_st
     T Q[4] = {(T)0, (T)0, (T)0, (T)0};
     T Mn = (T)0, Kn = (T)0;                    // M_{j+1}, K_{j+1}
     T num = (T)1, den = (T)1, f8 = (T)1, pw = (T)1;
+    T pn[4];                                   // the next particle is requested one step ahead of its use
+    ld4(base + 4 * P.order[NF - 1], pn[0], pn[1], pn[2], pn[3]);
     [&]<int... I>(std::integer_sequence<int, I...>) {
         ((void)[&] {
             constexpr int j = NF - 1 - I;      // NF-1, ..., 0
-            T p[4];
-            ld4(base + 4 * P.order[j], p[0], p[1], p[2], p[3]);
+            const T p[4] = {pn[0], pn[1], pn[2], pn[3]};
+            if constexpr (j > 0) ld4(base + 4 * P.order[j - 1], pn[0], pn[1], pn[2], pn[3]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) Q[c] = (j == NF - 1) ? p[c] : Q[c] + p[c];
             const T sq = sub_rn(sub_rn(sub_rn(mul_rn(Q[0], Q[0]), mul_rn(Q[1], Q[1])), mul_rn(Q[2], Q[2])), mul_rn(Q[3], Q[3]));
