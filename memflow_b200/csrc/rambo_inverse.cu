@@ -177,7 +177,7 @@ rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Streaming form for n >= 5 (fp64, not the get_PS / float32-quirk modes). The kernel above holds the whole event: 4n
+// Streaming form (fp64, every n but 4; not the get_PS / float32-quirk modes). The kernel above holds the whole event: 4n
 // momenta, M[n], K[n] and the 3n-2 outputs, 124-128 registers at n = 7, 8, i.e. 2 CTAs per SM, and its FP64 chains
 // stall on their own latency with 4 warps per scheduler. Everything the inverse needs at step j is the running sum
 // Q_j = p_{n-1} + ... + p_j, p_j itself and (M, K) of step j+1, so here particles are consumed last to first, each
@@ -337,7 +337,7 @@ static int launch_inverse(const T* momenta, int64_t event_stride, const T* x1, c
     if (N == 0) return MF_OK;
     const int threads = 256;
     const int64_t blocks = (N + threads - 1) / threads;
-    if constexpr (sizeof(T) == 8 && NF >= 5 && NF != 6) {   // measured: n = 5 +6 %, n = 7 +1 %, n = 8 +10 %, n = 6 -4 %
+    if constexpr (sizeof(T) == 8 && NF != 4) {   // measured vs the array form: n = 3 +3 %, 4 -3 %, 5 +17 %, 6 +1 %, 7 +16 %, 8 +23 %
         // MF_K2_STREAM=0 keeps the array-form kernel (A/B timing)
         static const bool stream_form = [] { const char* e = getenv("MF_K2_STREAM"); return !(e && e[0] == '0'); }();
         if (stream_form && boost == nullptr && !(flags & MF_FLAG_REF_FP32_QUIRKS)) {
