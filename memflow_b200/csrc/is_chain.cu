@@ -359,15 +359,20 @@ rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, i
     double cnt = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ev < N; ev += stride) {
-        const double* __restrict__ urow = u + ev * F;
+        // all of the event's inputs are requested up front: the map's dependency chains would otherwise wait for each
+        // global load where it is first used
+        double uc[F];
+#pragma unroll
+        for (int i = 0; i < F; ++i) uc[i] = ld1(u + ev * F + i);
+        const double lq = __ldg(logq + ev);
         double* mo = momenta ? momenta + ev * (NP * 4) : nullptr;
         double jac, x1, x2;
         // streaming core (rambo.cuh): O(1) live state; momenta leave the registers only if they were asked for
         rambo_forward_stream<double, NF>(
-            P, [&](int i) { return ld1(urow + i); },
+            P, [&](int i) { return uc[i]; },
             [&](int j, const double (&p)[4]) { if (mo) st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, jac, x1, x2);
         const double target = inv_2s * rcp_fast(x1 * x2);  // 1 / (2 x1 x2 s): ME = pdf = 1
-        const double w = target * jac * exp(-__ldg(logq + ev));
+        const double w = target * jac * exp(-lq);
         if (target > 0.0 && jac == jac) { k1.add(w); k2.add(w * w); cnt += 1.0; }
         if (weight) weight[ev] = jac;
         if (x1o) x1o[ev] = x1;
