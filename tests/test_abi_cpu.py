@@ -49,6 +49,35 @@ def test_error_strings_and_host_side_validation():
     assert L.mf_is_reduce_workspace_bytes() >= 64 + 2048 * 24
 
 
+def test_header_is_plain_c_and_struct_layout_matches_the_binding(tmp_path):
+    """include/memflow_b200.h compiles as C (no C++ / CUDA types in the boundary) and mf_decay_partons_cfg has the
+    layout the ctypes binding assumes; the new entry points reject bad arguments on the host."""
+    import subprocess
+    from memflow_b200 import _lib
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "memflow_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu\\n", sizeof(mf_decay_partons_cfg), '
+                   'offsetof(mf_decay_partons_cfg, mean_boost), offsetof(mf_decay_partons_cfg, higgs_mass), '
+                   'offsetof(mf_decay_partons_cfg, ptetaphi)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    size, o_boost, o_mass, o_flags = map(int, subprocess.check_output([str(exe)]).split())
+    C = _lib.DecayPartonsCfg
+    assert (size, o_boost, o_mass, o_flags) == (ctypes.sizeof(C), C.mean_boost.offset, C.higgs_mass.offset, C.ptetaphi.offset)
+    L = _lib.lib()
+    null = ctypes.c_void_p(0)
+    cfg = C()
+    cfg.ptetaphi, cfg.final_scaling = 0, 1   # the reference's cartesian final scaling reads an undefined name
+    assert L.mf_decay_partons_f64(null, null, null, null, null, null, null, ctypes.c_int64(0), ctypes.byref(cfg), null, null) == 1
+    cfg.ptetaphi = 1
+    assert L.mf_decay_partons_f64(null, null, null, null, null, null, null, ctypes.c_int64(0), ctypes.byref(cfg), null, null) == 0
+    assert L.mf_decay_partons_f64(null, null, null, null, null, null, null, ctypes.c_int64(3), ctypes.byref(cfg), null, null) == 1
+    assert L.mf_flow_sample_f64(null, ctypes.c_int64(0), ctypes.c_int(7), ctypes.c_int(2), ctypes.c_int(10), ctypes.c_double(1.0),
+                                ctypes.c_double(1e-3), ctypes.c_uint64(1), ctypes.c_uint64(0), null, null, null) == 0
+    assert L.mf_flow_sample_f64(null, ctypes.c_int64(5), ctypes.c_int(7), ctypes.c_int(2), ctypes.c_int(10), ctypes.c_double(1.0),
+                                ctypes.c_double(1e-3), ctypes.c_uint64(1), ctypes.c_uint64(0), null, null, null) == 1
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from memflow_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
