@@ -59,6 +59,35 @@ def test_no_cpu_fallback():
         rqs_forward(torch.randn(2, 3, 29), torch.rand(2, 3))
 
 
+def test_parton_event_surface_on_cpu():
+    """get_decayPartons_fromlab_propagators_angles: the reference's argument list, its NameError for the cartesian final
+    scaling (utils.py:913), no CPU fallback; the coordinate helpers are plain torch and invert each other."""
+    import inspect
+    import numpy as np
+    from memflow_b200._lib import MemflowB200Error
+    from memflow_b200.unfolding_flow.utils import Compute_ParticlesTensor as CPT
+    names = list(inspect.signature(CPT.get_decayPartons_fromlab_propagators_angles).parameters)
+    assert names[:13] == ["propagators_kinematics", "higgs_angles", "thad_b_angles", "thad_W_angles", "tlep_b_angles",
+                          "tlep_W_angles", "boost", "log_mean_parton_lab", "log_std_parton_lab", "log_mean_boost",
+                          "log_std_boost", "log_mean_parton_Hthadtlep", "log_std_parton_Hthadtlep"]
+    N = 4
+    z3, z2 = torch.zeros(3), torch.ones(2)
+    args = [torch.zeros(N, 3, 3)] + [torch.zeros(N, 2)] * 5 + [torch.zeros(N, 1, 2), z3, z3 + 1, z2, z2, z3, z3 + 1]
+    with pytest.raises(NameError):
+        CPT.get_decayPartons_fromlab_propagators_angles(*args, ptetaphi=False, final_scaling=True)
+    with pytest.raises(MemflowB200Error):
+        CPT.get_decayPartons_fromlab_propagators_angles(*args)
+    g = torch.Generator().manual_seed(2)
+    pep = torch.stack((torch.rand(50, generator=g, dtype=torch.float64) * 100 + 1, torch.randn(50, generator=g, dtype=torch.float64),
+                       (torch.rand(50, generator=g, dtype=torch.float64) * 2 - 1) * 3.1), dim=1)
+    cart = CPT.get_cartesian_comp(pep, 4.7)
+    back = CPT.get_ptetaphi_comp(cart)
+    assert torch.allclose(back[:, 1:], pep, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(back[:, 0] ** 2 - (cart[:, 1:] ** 2).sum(1), torch.full((50,), 4.7 ** 2, dtype=torch.float64), rtol=1e-9)
+    assert torch.equal(CPT.get_ptetaphi_comp_batch(cart[:, None, :])[:, 0], back)
+    assert torch.equal(CPT.get_ptetaphi_comp_noEnergy(cart[:, 1:]), back[:, 1:])
+
+
 def test_small_closed_forms_against_oracle(oracle):
     """get_flatWeights / rho / massless_map keep the reference's formulas (:111-149)."""
     ps = make_ps(3)
