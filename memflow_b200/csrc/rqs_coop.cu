@@ -117,7 +117,7 @@ rqs_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t ro
         {
             T a = (T)0, b = (T)0;
             if (valid) {
-#pragma unroll 2   // four independent exponentials in flight: the fp64 pipe stalls on its own latency otherwise
+#pragma unroll 4   // eight independent exponentials in flight: the fp64 pipe stalls on its own latency otherwise
                 for (int k = k0; k < k1; ++k) {
                     const T ew = fw_exp(r[k], mw, C), eh = fw_exp(r[K + k], mh, C);
                     r[k] = ew;
