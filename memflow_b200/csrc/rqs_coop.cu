@@ -8,7 +8,8 @@
 // threads of a row meet through a few words of shared memory:
 //   S0 (no soft clip only) chunk maxima                         S1 chunk sums of exp, each exp stored in place
 //   S2 chunk count of knots below v (offset + running sum) -> bin
-//   S3 the thread whose chunk holds the bin rebuilds the four knots around it and evaluates the rational quadratic
+//   S3 the row's chunk-0 thread rebuilds the four knots around the bin (the row is in shared memory) and evaluates the
+//      rational quadratic: one fully occupied warp per 32 rows instead of every warp at 1 / LANES lane occupancy
 // Knots are chunk offset + running sum, so they can differ from a sequential cumsum in the last bit (torch's CUDA
 // cumsum is a parallel scan with the same property); searchsorted on given knots (mf_searchsorted_*) stays exact.
 #include <cstdlib>
@@ -140,7 +141,7 @@ rqs_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t ro
         const T iSw = FastMath<T>::rcp(Sw), iSh = FastMath<T>::rcp(Sh);
         const int sb = INV ? K : 0, ob = INV ? 0 : K;              // searched / other coordinate
         const T is = INV ? iSh : iSw, io = INV ? iSw : iSh;
-        const T cs0 = (INV ? offh : offw) * is, co0 = (INV ? offw : offh) * io;
+        const T cs0 = (INV ? offh : offw) * is;
         // ---- S2: knots of this chunk below v ----
         {
             T c = cs0;
@@ -156,12 +157,24 @@ rqs_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t ro
 #pragma unroll
         for (int c = 0; c < LANES; ++c) bin += (int)scM[c * RPT];
         const bool inside = bin >= 0 && bin < K;
-        // ---- S3: the owner of the bin evaluates; chunk 0 handles the identity tails ----
-        if (valid && (inside ? (bin >= k0 && bin < k1) : (chunk == 0))) {
+        // ---- S3: evaluation, by the row's chunk-0 thread only: the whole row is in shared memory, so any thread can
+        //      rebuild the four knots around the bin (prefix of the chunk that holds it + running sum, the same values
+        //      the search used). Leaving it to the thread whose chunk holds the bin would run this, the most expensive
+        //      and divergent part, in every warp of the row group at 1 / LANES lane occupancy. ----
+        if (valid && chunk == 0) {
             T out = v, ladj = (T)0;
             if (inside) {
-                T cs = cs0, co = co0;
-                for (int k = k0; k < bin; ++k) { cs += r[sb + k] * is; co += r[ob + k] * io; }
+                const int oc = bin / CH;                      // chunk that holds the bin
+                T offs = (T)0, offo = (T)0;
+#pragma unroll
+                for (int c = 0; c < LANES; ++c) {
+                    if (c < oc) {
+                        offs += scS[(2 * c + (INV ? 1 : 0)) * RPT];
+                        offo += scS[(2 * c + (INV ? 0 : 1)) * RPT];
+                    }
+                }
+                T cs = offs * is, co = offo * io;
+                for (int k = oc * CH; k < bin; ++k) { cs += r[sb + k] * is; co += r[ob + k] * io; }
                 const T cs_hi = cs + r[sb + bin] * is, co_hi = co + r[ob + bin] * io;
                 const T cw_lo = INV ? co : cs, cw_hi = INV ? co_hi : cs_hi, ch_lo = INV ? cs : co, ch_hi = INV ? cs_hi : co_hi;
                 T d0 = (T)1, d1 = (T)1;  // D_0 = D_K = exp(0)
