@@ -254,6 +254,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    import __graft_entry__
+    __graft_entry__.ensure_built()   # fresh checkout: compile the C-ABI library (and the CPU port of the reference arm) first
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -17,10 +17,8 @@ def pytest_configure(config):
 def pytest_sessionstart(session):
     """Built artefacts are not in git: on a fresh checkout compile the C-ABI library (nvcc cross-compiles sm_100a
     without a GPU) and the oracle before the first test needs them."""
-    lib = os.path.join(ROOT, "memflow_b200", "lib", "libmemflow_b200.so")
-    if not os.path.exists(lib):
-        import __graft_entry__
-        __graft_entry__.build()
+    import __graft_entry__
+    __graft_entry__.ensure_built()
 
 
 def pytest_collection_modifyitems(config, items):
