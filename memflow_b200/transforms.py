@@ -179,30 +179,35 @@ class MonotonicRQSTransform(Transform):
         return (self.phi.shape[-1] + 1) // 3
 
     def _rows(self, x):
+        """x as rows [R, 1] plus the parameter rows [R, 1, 3K-1] they go with. Per-element parameters (what a
+        hyper-network emits) are used in place; parameters shared along some dimension of x (an unconditional
+        transform) are expanded to one row per element, as torch broadcasting would."""
         shape = torch.broadcast_shapes(self.lead, x.shape)
+        phi = self.phi
         if tuple(shape) != tuple(self.lead):
-            raise MemflowB200Error("parameters must broadcast to the shape of x (per-element parameters)")
-        return x.expand(shape).reshape(-1, 1), shape
+            PW = phi.shape[-1]
+            phi = phi.reshape(*self.lead, PW).expand(*shape, PW).reshape(-1, 1, PW)
+        return x.expand(shape).reshape(-1, 1), shape, phi
 
     def _call(self, x):
-        v, shape = self._rows(x)
-        y, _, _, _ = _run("forward", self.phi, v, self.bound, self.slope, want_ladj=False)
+        v, shape, phi = self._rows(x)
+        y, _, _, _ = _run("forward", phi, v, self.bound, self.slope, want_ladj=False)
         return y.reshape(shape).to(x.dtype)
 
     def _inverse(self, y):
-        v, shape = self._rows(y)
-        x, _, _, _ = _run("inverse", self.phi, v, self.bound, self.slope, want_ladj=False)
+        v, shape, phi = self._rows(y)
+        x, _, _, _ = _run("inverse", phi, v, self.bound, self.slope, want_ladj=False)
         return x.reshape(shape).to(y.dtype)
 
     def call_and_ladj(self, x):
-        v, shape = self._rows(x)
-        y, ladj, _, _ = _run("forward", self.phi, v, self.bound, self.slope)
+        v, shape, phi = self._rows(x)
+        y, ladj, _, _ = _run("forward", phi, v, self.bound, self.slope)
         return y.reshape(shape).to(x.dtype), ladj.reshape(shape).to(x.dtype)
 
     def inverse_and_ladj(self, y):
         """(x, forward ladj at x): lets a sampler get log q without a second pass."""
-        v, shape = self._rows(y)
-        x, ladj, _, _ = _run("inverse", self.phi, v, self.bound, self.slope)
+        v, shape, phi = self._rows(y)
+        x, ladj, _, _ = _run("inverse", phi, v, self.bound, self.slope)
         return x.reshape(shape).to(y.dtype), ladj.reshape(shape).to(y.dtype)
 
     def log_abs_det_jacobian(self, x, y=None):

@@ -175,6 +175,14 @@ def test_transform_api_and_golden(golden_dir):
     assert torch.equal(t2(x), y)
     t3 = MonotonicRQSTransform(w, h, d, bound=float(g["bound"]), slope=None)              # zuko <= 0.1: no soft clip
     assert not torch.equal(t3(x), y)
+    # parameters shared along the batch (an unconditional transform: phi [F, 3K-1], x [S, B, F]) broadcast like torch
+    ts = MonotonicRQSTransform(w[3], h[3], d[3], bound=float(g["bound"]))
+    xs = x[:24].reshape(2, 12, -1)
+    ys, ls = ts.call_and_ladj(xs)
+    tr = MonotonicRQSTransform(w[3].expand(2, 12, -1, -1), h[3].expand(2, 12, -1, -1), d[3].expand(2, 12, -1, -1), bound=float(g["bound"]))
+    yr, lr = tr.call_and_ladj(xs)
+    assert ys.shape == xs.shape and torch.equal(ys, yr) and torch.equal(ls, lr)
+    assert torch.allclose(ts.inv(ys), xs, atol=1e-12, rtol=0)
     g32 = np.load(os.path.join(golden_dir, "rqs_f32_F20K64.npz"))
     p32, x32 = torch.from_numpy(g32["phi"]).cuda(), torch.from_numpy(g32["x"]).cuda()
     t = MonotonicRQSTransform(*p32.split([64, 64, 63], dim=-1), bound=float(g32["bound"]))
