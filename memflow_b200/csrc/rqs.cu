@@ -287,8 +287,7 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
     {   // every other shape (all fp64, fp32 with bin counts the register kernels do not cover): several threads per
         // row (rqs_coop.cu). MF_RQS_COOP=0 keeps the generic kernel below, for A/B timing.
         static const bool coop = [] { const char* e = getenv("MF_RQS_COOP"); return !(e && e[0] == '0'); }();
-        const bool reg1 = sizeof(T) == 4 && (K == 8 || K == 10 || K == 12 || K == 16);
-        if (coop && !reg1) {
+        if (coop) {
             const int rc = rqs_coop_launch<T, INV>(phi, vin, B, F, K, bound, slope, vout, ladj, ladj_sum, bin, stream);
             if (rc != MF_E_SHAPE) return rc;
         }

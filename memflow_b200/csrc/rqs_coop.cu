@@ -227,6 +227,78 @@ static int coop_launch_lanes(const T* phi, const T* vin, int64_t rows, int K, co
     return launch_status();
 }
 
+// ---- fp32, K = 8, 10, 12, 16: one thread per row with the row in registers (rqs_row_reg, the row math of the chain's
+// launch A), 256-row single-stage TMA tiles, 8 CTAs per SM. The generic rqs_kernel serves these shapes with 128-thread
+// double-buffered CTAs (28 warps per SM) and whole-event tiles: 81 % of the HBM roofline at F = 7, K = 10. ----
+template <int K, bool INV>
+__global__ void __launch_bounds__(256, 8)
+rqs_small_kernel(const float* __restrict__ phi, const float* __restrict__ vin, int64_t rows, RqsConst<float> C, int bulk_ok,
+                 float* __restrict__ vout, float* __restrict__ ladj_out, int32_t* __restrict__ bin_out) {
+    constexpr int PW = 3 * K - 1, RPT = 256;
+    constexpr uint32_t tile_bytes = RPT * PW * (uint32_t)sizeof(float);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* const sm = reinterpret_cast<float*>(smem_raw);
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + (tile_bytes + 127) / 128 * 128);
+    const int tid = threadIdx.x;
+    float* const rowp = sm + (size_t)tid * PW;
+    const int64_t num_tiles = (rows + RPT - 1) / RPT, full_tiles = bulk_ok ? rows / RPT : 0;
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    uint32_t parity = 0u;
+    int64_t tile = blockIdx.x;
+    if (tid == 0 && tile < full_tiles) {
+        mbar_expect_tx(bar, tile_bytes);
+        bulk_g2s(sm, phi + (size_t)tile * RPT * PW, tile_bytes, bar);
+    }
+    for (; tile < num_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * RPT;
+        const int nrows = (int)((rows - row0) < RPT ? (rows - row0) : RPT);
+        if (tile < full_tiles) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {  // ragged last tile or unaligned phi: plain cooperative copy
+            const float* src = phi + (size_t)row0 * PW;
+            for (int i = tid; i < nrows * PW; i += RPT) sm[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        if (tid < nrows) {
+            float out, ladj;
+            int bin;
+            rqs_row_reg<K, INV>(rowp, C, __ldg(vin + row0 + tid), out, ladj, bin);
+            vout[row0 + tid] = out;
+            if (ladj_out) ladj_out[row0 + tid] = ladj;
+            if (bin_out) bin_out[row0 + tid] = bin;
+        }
+        fence_proxy_async();  // in-place generic writes to the tile happen-before the next TMA refill
+        __syncthreads();
+        if (tid == 0 && tile + gridDim.x < full_tiles) {
+            mbar_expect_tx(bar, tile_bytes);
+            bulk_g2s(sm, phi + (size_t)(tile + gridDim.x) * RPT * PW, tile_bytes, bar);
+        }
+    }
+}
+
+template <int K, bool INV>
+static int small_launch(const float* phi, const float* vin, int64_t rows, const RqsConst<float>& C, float* vout, float* ladj,
+                        int32_t* bin, cudaStream_t stream) {
+    constexpr int PW = 3 * K - 1;
+    const size_t smem = ((size_t)256 * PW * sizeof(float) + 127) / 128 * 128 + 16;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto kern = rqs_small_kernel<K, INV>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int ctas = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 256, smem);
+    if (ctas < 1) ctas = 1;
+    const int64_t num_tiles = (rows + 255) / 256;
+    int64_t grid = (int64_t)sms * ctas;
+    if (grid > num_tiles) grid = num_tiles;
+    kern<<<(unsigned)grid, 256, smem, stream>>>(phi, vin, rows, C, aligned(phi, 16) ? 1 : 0, vout, ladj, bin);
+    return launch_status();
+}
+
 // Returns MF_E_SHAPE when no variant fits (the caller falls back to the generic kernel).
 template <typename T, bool INV>
 int rqs_coop_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bound, T slope, T* vout, T* ladj, T* ladj_sum,
@@ -243,6 +315,14 @@ int rqs_coop_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bound
     }
     const int pref = forced ? forced : (row_bytes < 420 ? 1 : (row_bytes < 700 ? 2 : (row_bytes < 2000 ? 4 : 8)));
     int rc = MF_E_SHAPE;
+    if constexpr (sizeof(T) == 4) {   // register-row kernel for the small bin counts
+        if (!forced) {
+            if (K == 8) rc = small_launch<8, INV>(phi, vin, rows, C, vout, ladj_rows, bin, stream);
+            if (K == 10) rc = small_launch<10, INV>(phi, vin, rows, C, vout, ladj_rows, bin, stream);
+            if (K == 12) rc = small_launch<12, INV>(phi, vin, rows, C, vout, ladj_rows, bin, stream);
+            if (K == 16) rc = small_launch<16, INV>(phi, vin, rows, C, vout, ladj_rows, bin, stream);
+        }
+    }
     for (int pass = 0; pass < 2 && rc == MF_E_SHAPE; ++pass) {  // first try for >= 3 CTAs per SM, then anything that fits
         for (int lanes = pref; lanes <= 8 && rc == MF_E_SHAPE; lanes *= 2) {
             const bool third = pass == 0;

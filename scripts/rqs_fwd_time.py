@@ -4,7 +4,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from memflow_b200 import transforms as TR
 dev = torch.device("cuda:0")
-cases = [(1 << 18, 10, 40, torch.float64), (1 << 20, 7, 10, torch.float64), (1 << 18, 20, 64, torch.float64), (1 << 18, 20, 24, torch.float32)]
+cases = [(1 << 18, 10, 40, torch.float64), (1 << 20, 7, 10, torch.float64), (1 << 18, 20, 64, torch.float64), (1 << 18, 20, 24, torch.float32), (1 << 22, 7, 10, torch.float32), (1 << 21, 10, 16, torch.float32)]
 if len(sys.argv) > 1:
     cases = []
     for k in sys.argv[1:]:
