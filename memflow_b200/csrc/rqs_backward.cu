@@ -99,7 +99,7 @@ template <> MF_D float clip_der_from_e<float>(float e, float, const RqsConst<flo
 
 // Row gradient, in place: on entry r[0..3K-2] = parameters of the row, on exit = their gradients. Returns g_v.
 template <typename T, bool INV>
-MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T go, T gl) {
+MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T go, T gl, int rot0) {
     const int PW = 3 * K - 1;
     const T B = C.bound;
     // ---- pass 1: softmax sums. torch.softmax subtracts the row maximum; with the soft clip the arguments are bounded
@@ -113,7 +113,12 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
         }
     }
     T Sw = (T)0, Sh = (T)0;
-    for (int k = 0; k < K; ++k) {   // each parameter is replaced by its exponential, reused by every later pass
+    // (rot0: where this row starts inside the order-free passes; odd K makes the row pitch even and the rows of a warp
+    //  would otherwise share 2-4 shared-memory banks at a given offset)
+    int kk = rot0;
+    for (int j = 0; j < K; ++j) {   // each parameter is replaced by its exponential, reused by every later pass
+        const int k = kk;
+        kk = (kk + 1 == K) ? 0 : kk + 1;
         const T ew = bw_exp(r[k], mw, C), eh = bw_exp(r[K + k], mh, C);
         r[k] = ew;
         r[K + k] = eh;
@@ -164,7 +169,10 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
     const T twoB = (T)2 * B;
     const T gd0 = bin > 0 ? adj[4] * d0v * clip_der(r[2 * K + bin - 1], C.one_over_L, C.clip) : (T)0;
     const T gd1 = bin < K - 1 ? adj[5] * d1v * clip_der(r[2 * K + bin], C.one_over_L, C.clip) : (T)0;
-    for (int i = 0; i < K; ++i) {
+    int ii = rot0;
+    for (int j = 0; j < K; ++j) {
+        const int i = ii;
+        ii = (ii + 1 == K) ? 0 : ii + 1;
         const T ew = r[i], eh = r[K + i];
         const T iw_hi = (i <= bin) ? (T)1 : (T)0, iw_lo = (i < bin) ? (T)1 : (T)0;
         r[i] = clip_der_from_e(ew, mw, C) * (ew * iSw) * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
@@ -217,7 +225,7 @@ rqs_backward_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const 
         for (int rr = tid; rr < nrows; rr += 128) {
             const int64_t row = row0 + rr;
             const T go = g_out ? g_out[row] : (T)0, gl = g_ladj ? g_ladj[row] : (T)0;
-            g_v[row] = rqs_row_backward<T, INV>(sm + (size_t)rr * PW, K, C, vin[row], go, gl);
+            g_v[row] = rqs_row_backward<T, INV>(sm + (size_t)rr * PW, K, C, vin[row], go, gl, (PW % 2 == 0) ? rr % K : 0);
         }
         fence_proxy_async();  // generic writes of the gradients -> visible to the bulk store
         __syncthreads();
@@ -265,6 +273,7 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
     const int chunk = wid % LANES, rr = (wid / LANES) * 32 + lane;
     const int CH = (K + LANES - 1) / LANES;
     const int k0 = min(K, chunk * CH), k1 = min(K, k0 + CH);
+    const bool rot = (PW % 2) == 0;
     T* const r = sm + (size_t)rr * PW;
     T* const scM = sc + rr;                          // slot s at scM[s * RPT]
     T* const scS = sc + (size_t)2 * LANES * RPT + rr;
@@ -316,7 +325,12 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
         // ---- S1: chunk sums -> totals, prefix offsets ----
         {
             T a = (T)0, b = (T)0;
-            for (int k = k0; k < k1; ++k) {   // each parameter is replaced by its exponential (see clip_der_from_e)
+            // (odd K: even row pitch, bank conflicts between the rows of a warp; the order inside the chunk is free here,
+            //  so row r starts r elements in and wraps -- see rqs_coop.cu)
+            int kk = (rot && k1 > k0) ? k0 + rr % (k1 - k0) : k0;
+            for (int j = k0; j < k1; ++j) {   // each parameter is replaced by its exponential (see clip_der_from_e)
+                const int k = kk;
+                kk = (kk + 1 == k1) ? k0 : kk + 1;
                 const T ew = bw_exp(r[k], mw, C), eh = bw_exp(r[K + k], mh, C);
                 r[k] = ew;
                 r[K + k] = eh;
@@ -397,7 +411,10 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
             for (int j = 0; j < 7; ++j) adj[j] = scA[j * RPT];
             const T twoB = (T)2 * B;
             const T gd0 = adj[4] * f0, gd1 = adj[5] * f1;
-            for (int i = k0; i < k1; ++i) {
+            int ii = (rot && k1 > k0) ? k0 + rr % (k1 - k0) : k0;
+            for (int j = k0; j < k1; ++j) {
+                const int i = ii;
+                ii = (ii + 1 == k1) ? k0 : ii + 1;
                 const T ew = r[i], eh = r[K + i];
                 const T iw_hi = (i <= bin) ? (T)1 : (T)0, iw_lo = (i < bin) ? (T)1 : (T)0;
                 r[i] = clip_der_from_e(ew, mw, C) * (ew * iSw) * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));

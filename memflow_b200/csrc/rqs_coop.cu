@@ -72,6 +72,7 @@ rqs_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t ro
     const int chunk = wid % LANES, rr = (wid / LANES) * 32 + lane;
     const int CH = (K + LANES - 1) / LANES;
     const int k0 = min(K, chunk * CH), k1 = min(K, k0 + CH);
+    const bool rot = (PW % 2) == 0;
     T* const scM = sc + rr;
     T* const scS = sc + (size_t)2 * LANES * RPT + rr;
     const T Bd = C.bound;
@@ -118,8 +119,16 @@ rqs_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t ro
         {
             T a = (T)0, b = (T)0;
             if (valid) {
+                // Odd K makes the row pitch 3K-1 even: the 32 rows of a warp then share 2-4 banks at a given offset
+                // (K = 35, the most common bin count of MEMFlow's configs: 8-way conflicts, -26 % in fp64, 2x in fp32).
+                // This pass does not care about the order inside the chunk, so row r starts r elements in and
+                // wraps: the effective stride is 3K, odd.
+                const int len = k1 - k0;
+                int kk = (rot && len > 0) ? k0 + rr % len : k0;
 #pragma unroll 4   // eight independent exponentials in flight: the fp64 pipe stalls on its own latency otherwise
-                for (int k = k0; k < k1; ++k) {
+                for (int j = 0; j < len; ++j) {
+                    const int k = kk;
+                    kk = (kk + 1 == k1) ? k0 : kk + 1;
                     const T ew = fw_exp(r[k], mw, C), eh = fw_exp(r[K + k], mh, C);
                     r[k] = ew;
                     r[K + k] = eh;
