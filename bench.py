@@ -225,6 +225,15 @@ def extras(torch, dev, hbm_peak):
         out["K3_rqs_backward_F10_K40_f64_256k"] = {"points_per_s": B / tb, "GBps": byb * B / tb / 1e9, "frac_hbm": byb * B / tb / 1e9 / hbm_peak}
         del phi, x, loss
         torch.cuda.empty_cache()
+        # the most common flow shape of the reference's configs: float64, 10 features, 35 bins (odd K: even row pitch)
+        B, F, K = 1 << 18, 10, 35
+        phi = torch.randn(B, F, 3 * K - 1, device=dev, dtype=torch.float64)
+        x = (torch.rand(B, F, device=dev, dtype=torch.float64) * 2.6 - 1.3) * 1.1
+        by = (F * (3 * K - 1) + 2 * F + 1) * 8
+        tf = timeit(lambda: TR.rqs_forward(phi, x, bound=1.1))
+        out["K3_rqs_forward_F10_K35_f64_256k"] = {"points_per_s": B / tf, "GBps": by * B / tf / 1e9, "frac_hbm": by * B / tf / 1e9 / hbm_peak}
+        del phi, x
+        torch.cuda.empty_cache()
         # BASELINE config 5 shape on this GPU: tt-bar-H + 1 jet (n=4), production flow F=10, K=40, T=6
         from memflow_b200 import estimator as ES
         T5, N5, F5, K5 = 6, 1 << 19, 10, 40
