@@ -116,6 +116,8 @@ rqs_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t ro
             for (int c = 1; c < LANES; ++c) { mw = fmax_(mw, scM[(2 * c) * RPT]); mh = fmax_(mh, scM[(2 * c + 1) * RPT]); }
         }
         // ---- S1: chunk sums; each parameter is replaced by its exponential ----
+        T pre_s = (T)0;          // searched array: unnormalised sum of the chunk's elements before this row's start
+        int start = k0;
         {
             T a = (T)0, b = (T)0;
             if (valid) {
@@ -124,16 +126,29 @@ rqs_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t ro
                 // This pass does not care about the order inside the chunk, so row r starts r elements in and
                 // wraps: the effective stride is 3K, odd.
                 const int len = k1 - k0;
-                int kk = (rot && len > 0) ? k0 + rr % len : k0;
+                if (rot && len > 0) {   // (uniform branch: even K pays nothing for the rotation)
+                    start = k0 + rr % len;
+                    int kk = start;
+#pragma unroll 4
+                    for (int j = 0; j < len; ++j) {
+                        const int k = kk;
+                        kk = (kk + 1 == k1) ? k0 : kk + 1;
+                        const T ew = fw_exp(r[k], mw, C), eh = fw_exp(r[K + k], mh, C);
+                        r[k] = ew;
+                        r[K + k] = eh;
+                        a += ew;
+                        b += eh;
+                        pre_s += (k < start) ? (INV ? eh : ew) : (T)0;
+                    }
+                } else {
 #pragma unroll 4   // eight independent exponentials in flight: the fp64 pipe stalls on its own latency otherwise
-                for (int j = 0; j < len; ++j) {
-                    const int k = kk;
-                    kk = (kk + 1 == k1) ? k0 : kk + 1;
-                    const T ew = fw_exp(r[k], mw, C), eh = fw_exp(r[K + k], mh, C);
-                    r[k] = ew;
-                    r[K + k] = eh;
-                    a += ew;
-                    b += eh;
+                    for (int k = k0; k < k1; ++k) {
+                        const T ew = fw_exp(r[k], mw, C), eh = fw_exp(r[K + k], mh, C);
+                        r[k] = ew;
+                        r[K + k] = eh;
+                        a += ew;
+                        b += eh;
+                    }
                 }
             }
             scS[(2 * chunk) * RPT] = a;
@@ -152,12 +167,23 @@ rqs_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t ro
         const T is = INV ? iSh : iSw, io = INV ? iSw : iSh;
         const T cs0 = (INV ? offh : offw) * is;
         // ---- S2: knots of this chunk below v ----
-        {
-            T c = cs0;
+        {   // same rotated walk as S1 (conflict-free for odd K): from the row's start to the end of the chunk on the running
+            // sum that begins at offset + pre_s, then from the chunk's first element on the one that begins at offset
             int cnt = 0;
-            for (int k = k0; k < k1; ++k) {
-                c += r[sb + k] * is;
-                cnt += (Bd * ((T)2 * c - (T)1) < v) ? 1 : 0;
+            if (rot) {
+                T c = cs0 + pre_s * is;
+                int kk = start;
+                for (int j = k0; j < k1; ++j) {
+                    c += r[sb + kk] * is;
+                    cnt += (Bd * ((T)2 * c - (T)1) < v) ? 1 : 0;
+                    if (++kk == k1) { kk = k0; c = cs0; }
+                }
+            } else {
+                T c = cs0;
+                for (int k = k0; k < k1; ++k) {
+                    c += r[sb + k] * is;
+                    cnt += (Bd * ((T)2 * c - (T)1) < v) ? 1 : 0;
+                }
             }
             scM[chunk * RPT] = (T)cnt;   // the max slots are dead by now (read before the S1 barrier)
         }
