@@ -113,17 +113,20 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
         }
     }
     T Sw = (T)0, Sh = (T)0;
-    // (rot0: where this row starts inside the order-free passes; odd K makes the row pitch even and the rows of a warp
-    //  would otherwise share 2-4 shared-memory banks at a given offset)
-    int kk = rot0;
-    for (int j = 0; j < K; ++j) {   // each parameter is replaced by its exponential, reused by every later pass
-        const int k = kk;
-        kk = (kk + 1 == K) ? 0 : kk + 1;
+    // (rot0 >= 0: where this row starts inside the order-free passes; odd K makes the row pitch even and the rows of a
+    //  warp would otherwise share 2-4 shared-memory banks at a given offset; -1: plain order)
+    auto exp_at = [&](int k) {   // each parameter is replaced by its exponential, reused by every later pass
         const T ew = bw_exp(r[k], mw, C), eh = bw_exp(r[K + k], mh, C);
         r[k] = ew;
         r[K + k] = eh;
         Sw += ew;
         Sh += eh;
+    };
+    if (rot0 >= 0) {   // uniform per launch: even K runs the plain loop
+        int kk = rot0;
+        for (int j = 0; j < K; ++j) { exp_at(kk); kk = (kk + 1 == K) ? 0 : kk + 1; }
+    } else {
+        for (int k = 0; k < K; ++k) exp_at(k);
     }
     const T iSw = (T)1 / Sw, iSh = (T)1 / Sh;
     // ---- pass 2: searchsorted on the searched coordinate (X forward / Y inverse) with the knots as the forward builds
@@ -169,14 +172,17 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
     const T twoB = (T)2 * B;
     const T gd0 = bin > 0 ? adj[4] * d0v * clip_der(r[2 * K + bin - 1], C.one_over_L, C.clip) : (T)0;
     const T gd1 = bin < K - 1 ? adj[5] * d1v * clip_der(r[2 * K + bin], C.one_over_L, C.clip) : (T)0;
-    int ii = rot0;
-    for (int j = 0; j < K; ++j) {
-        const int i = ii;
-        ii = (ii + 1 == K) ? 0 : ii + 1;
+    auto grad_at = [&](int i) {
         const T ew = r[i], eh = r[K + i];
         const T iw_hi = (i <= bin) ? (T)1 : (T)0, iw_lo = (i < bin) ? (T)1 : (T)0;
         r[i] = clip_der_from_e(ew, mw, C) * (ew * iSw) * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
         r[K + i] = clip_der_from_e(eh, mh, C) * (eh * iSh) * twoB * (adj[3] * (iw_hi - ch_hi) + adj[2] * (iw_lo - ch_lo));
+    };
+    if (rot0 >= 0) {
+        int ii = rot0;
+        for (int j = 0; j < K; ++j) { grad_at(ii); ii = (ii + 1 == K) ? 0 : ii + 1; }
+    } else {
+        for (int i = 0; i < K; ++i) grad_at(i);
     }
     for (int i = 0; i < K - 1; ++i) r[2 * K + i] = (i == bin - 1) ? gd0 : ((i == bin) ? gd1 : (T)0);
     return adj[6];
@@ -225,7 +231,7 @@ rqs_backward_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const 
         for (int rr = tid; rr < nrows; rr += 128) {
             const int64_t row = row0 + rr;
             const T go = g_out ? g_out[row] : (T)0, gl = g_ladj ? g_ladj[row] : (T)0;
-            g_v[row] = rqs_row_backward<T, INV>(sm + (size_t)rr * PW, K, C, vin[row], go, gl, (PW % 2 == 0) ? rr % K : 0);
+            g_v[row] = rqs_row_backward<T, INV>(sm + (size_t)rr * PW, K, C, vin[row], go, gl, (PW % 2 == 0) ? rr % K : -1);
         }
         fence_proxy_async();  // generic writes of the gradients -> visible to the bulk store
         __syncthreads();
@@ -323,19 +329,33 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
             for (int c = 1; c < LANES; ++c) { mw = fmax_(mw, scM[(2 * c) * RPT]); mh = fmax_(mh, scM[(2 * c + 1) * RPT]); }
         }
         // ---- S1: chunk sums -> totals, prefix offsets ----
+        T pre_s = (T)0;
+        int start = k0;
         {
             T a = (T)0, b = (T)0;
             // (odd K: even row pitch, bank conflicts between the rows of a warp; the order inside the chunk is free here,
             //  so row r starts r elements in and wraps -- see rqs_coop.cu)
-            int kk = (rot && k1 > k0) ? k0 + rr % (k1 - k0) : k0;
-            for (int j = k0; j < k1; ++j) {   // each parameter is replaced by its exponential (see clip_der_from_e)
-                const int k = kk;
-                kk = (kk + 1 == k1) ? k0 : kk + 1;
-                const T ew = bw_exp(r[k], mw, C), eh = bw_exp(r[K + k], mh, C);
-                r[k] = ew;
-                r[K + k] = eh;
-                a += ew;
-                b += eh;
+            if (rot && k1 > k0) {   // uniform branch: even K runs the plain loops
+                start = k0 + rr % (k1 - k0);
+                int kk = start;
+                for (int j = k0; j < k1; ++j) {   // each parameter is replaced by its exponential (see clip_der_from_e)
+                    const int k = kk;
+                    kk = (kk + 1 == k1) ? k0 : kk + 1;
+                    const T ew = bw_exp(r[k], mw, C), eh = bw_exp(r[K + k], mh, C);
+                    r[k] = ew;
+                    r[K + k] = eh;
+                    a += ew;
+                    b += eh;
+                    pre_s += (k < start) ? (INV ? eh : ew) : (T)0;   // searched array, elements before the row's start
+                }
+            } else {
+                for (int k = k0; k < k1; ++k) {
+                    const T ew = bw_exp(r[k], mw, C), eh = bw_exp(r[K + k], mh, C);
+                    r[k] = ew;
+                    r[K + k] = eh;
+                    a += ew;
+                    b += eh;
+                }
             }
             scS[(2 * chunk) * RPT] = a;
             scS[(2 * chunk + 1) * RPT] = b;
@@ -353,12 +373,23 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
         const T is = INV ? iSh : iSw, io = INV ? iSw : iSh;
         const T cs0 = (INV ? offh : offw) * is, co0 = (INV ? offw : offh) * io;
         // ---- S2: knots of this chunk below v ----
-        {
-            T c = cs0;
+        {   // the same rotated walk as S1: from the row's start to the chunk's end on the running sum that begins at
+            // offset + pre_s, then from the chunk's first element on the one that begins at the offset
             int cnt = 0;
-            for (int k = k0; k < k1; ++k) {
-                c += r[sb + k] * is;
-                cnt += (B * ((T)2 * c - (T)1) < v) ? 1 : 0;
+            if (rot) {
+                T c = cs0 + pre_s * is;
+                int kk = start;
+                for (int j = k0; j < k1; ++j) {
+                    c += r[sb + kk] * is;
+                    cnt += (B * ((T)2 * c - (T)1) < v) ? 1 : 0;
+                    if (++kk == k1) { kk = k0; c = cs0; }
+                }
+            } else {
+                T c = cs0;
+                for (int k = k0; k < k1; ++k) {
+                    c += r[sb + k] * is;
+                    cnt += (B * ((T)2 * c - (T)1) < v) ? 1 : 0;
+                }
             }
             scM[chunk * RPT] = (T)cnt;   // the max slots are dead by now (read before the S1 barrier)
         }
@@ -411,14 +442,17 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
             for (int j = 0; j < 7; ++j) adj[j] = scA[j * RPT];
             const T twoB = (T)2 * B;
             const T gd0 = adj[4] * f0, gd1 = adj[5] * f1;
-            int ii = (rot && k1 > k0) ? k0 + rr % (k1 - k0) : k0;
-            for (int j = k0; j < k1; ++j) {
-                const int i = ii;
-                ii = (ii + 1 == k1) ? k0 : ii + 1;
+            auto grad_at = [&](int i) {
                 const T ew = r[i], eh = r[K + i];
                 const T iw_hi = (i <= bin) ? (T)1 : (T)0, iw_lo = (i < bin) ? (T)1 : (T)0;
                 r[i] = clip_der_from_e(ew, mw, C) * (ew * iSw) * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
                 r[K + i] = clip_der_from_e(eh, mh, C) * (eh * iSh) * twoB * (adj[3] * (iw_hi - ch_hi) + adj[2] * (iw_lo - ch_lo));
+            };
+            if (rot) {
+                int ii = start;
+                for (int j = k0; j < k1; ++j) { grad_at(ii); ii = (ii + 1 == k1) ? k0 : ii + 1; }
+            } else {
+                for (int i = k0; i < k1; ++i) grad_at(i);
             }
             for (int i = k0; i < min(k1, K - 1); ++i) r[2 * K + i] = (i == bin - 1) ? gd0 : ((i == bin) ? gd1 : (T)0);
             if (chunk == 0 && valid) g_v[row] = adj[6];
