@@ -28,3 +28,21 @@ off = N - 777
 us, ls = smp.sample_flow(phi[:, off:].contiguous(), event_offset=off)
 assert torch.equal(ub[off:], us) and torch.equal(lb[off:], ls)
 print("chain launch A at 2^25 events (1.4e10 parameters): tail identical to a small launch")
+del phi, ub, lb
+torch.cuda.empty_cache()
+from memflow_b200 import transforms as TR
+for dt, B, F, K in ((torch.float32, 1 << 21, 20, 64), (torch.float64, 1 << 21, 10, 35), (torch.float32, 1 << 25, 7, 10)):
+    phi = torch.randn(B, F, 3 * K - 1, device=dev, dtype=dt)
+    x = (torch.rand(B, F, device=dev, dtype=dt) * 2.6 - 1.3)
+    y, l, ls = TR.rqs_forward(phi, x, bound=1.1)
+    t = slice(B - 333, B)
+    y2, l2, ls2 = TR.rqs_forward(phi[t].contiguous(), x[t].contiguous(), bound=1.1)
+    if K % 2 == 0:
+        assert torch.equal(y[t], y2) and torch.equal(l[t], l2) and torch.equal(ls[t], ls2), (dt, K)
+    else:  # odd K: the softmax sums start at a tile-position dependent element (bank conflicts): last-bit differences
+        tol = 1e-13 if dt == torch.float64 else 1e-4
+        assert (y[t] - y2).abs().max().item() < tol and (ls[t] - ls2).abs().max().item() < 100 * tol, (dt, K)
+    print("spline %s F=%d K=%d at %d events (%.1e parameters): tail %s a small launch" % (
+        str(dt)[6:], F, K, B, phi.numel(), "identical to" if K % 2 == 0 else "equal within rounding to"))
+    del phi, x, y, l, ls
+    torch.cuda.empty_cache()
