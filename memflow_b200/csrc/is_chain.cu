@@ -744,7 +744,8 @@ extern "C" int mf_flow_sample_f64(const double* phi, int64_t N, int F, int T, in
     int rc = MF_OK;
     for (int t = T - 1; t >= 0 && rc == MF_OK; --t) {
         // in place: every thread of a row reads its input before the tile's first barrier, the owner writes after the last
-        rc = mf::rqs_coop_launch<double, true>(phi + (size_t)t * pitch, u, N, F, K, bound, slope, u, ladj, nullptr, nullptr, st);
+        rc = mf::rqs_coop_launch<double, true>(phi + (size_t)t * pitch, u, N, F, K, bound, slope, u, ladj, nullptr, nullptr, st,
+                                                (int64_t)event_offset * F);
         if (rc == MF_OK) mf::ladj_accumulate_kernel<<<grid, 256, 0, st>>>(ladj, N, F, logq);
     }
     cudaFreeAsync(ladj, st);

@@ -341,6 +341,6 @@ MF_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;
 // rqs_coop.cu: several threads per row; MF_E_SHAPE when no variant fits the shape
 template <typename T, bool INV>
 int rqs_coop_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bound, T slope, T* vout, T* ladj, T* ladj_sum,
-                    int32_t* bin, cudaStream_t stream);
+                    int32_t* bin, cudaStream_t stream, int64_t row_offset = 0);
 
 }  // namespace mf

@@ -59,7 +59,7 @@ MF_D void rq_on_knots(T x0, T x1, T y0, T y1, T d0, T d1, T v, T& out, T& ladj) 
 template <typename T, bool INV, int LANES>
 __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 4 : 3)
 rqs_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t rows, int K, RqsConst<T> C, int bulk_ok,
-                T* __restrict__ vout, T* __restrict__ ladj_out, int32_t* __restrict__ bin_out) {
+                T* __restrict__ vout, T* __restrict__ ladj_out, int32_t* __restrict__ bin_out, int64_t rot_base) {
     constexpr int RPT = 256 / LANES;         // rows per tile
     constexpr int SLOTS = 4 * LANES;         // [2 LANES max | cnt] [2 LANES sums]
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -127,7 +127,9 @@ rqs_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t ro
                 // wraps: the effective stride is 3K, odd.
                 const int len = k1 - k0;
                 if (rot && len > 0) {   // (uniform branch: even K pays nothing for the rotation)
-                    start = k0 + rr % len;
+                    // (the start depends on the row's GLOBAL index, rot_base + row: the chain passes its event offset, so
+                    //  a row is summed in the same order whatever chunk it arrives in)
+                    start = k0 + (int)((rot_base + gi) % len);
                     int kk = start;
 #pragma unroll 4
                     for (int j = 0; j < len; ++j) {
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(256) ladj_sum_kernel(const T* __restrict__ lad
 
 template <typename T, bool INV, int LANES>
 static int coop_launch_lanes(const T* phi, const T* vin, int64_t rows, int K, const RqsConst<T>& C, T* vout, T* ladj,
-                             int32_t* bin, cudaStream_t stream, bool must_fit_third) {
+                             int32_t* bin, cudaStream_t stream, bool must_fit_third, int64_t rot_base) {
     constexpr int RPT = 256 / LANES, SLOTS = 4 * LANES;
     const size_t row_bytes = (size_t)(3 * K - 1) * sizeof(T);
     int dev = 0, sms = 148, smem_max = 0;
@@ -258,7 +260,7 @@ static int coop_launch_lanes(const T* phi, const T* vin, int64_t rows, int K, co
     const int64_t num_tiles = (rows + RPT - 1) / RPT;
     int64_t grid = (int64_t)sms * ctas;
     if (grid > num_tiles) grid = num_tiles;
-    kern<<<(unsigned)grid, 256, smem, stream>>>(phi, vin, rows, K, C, bulk_ok, vout, ladj, bin);
+    kern<<<(unsigned)grid, 256, smem, stream>>>(phi, vin, rows, K, C, bulk_ok, vout, ladj, bin, rot_base);
     return launch_status();
 }
 
@@ -337,7 +339,7 @@ static int small_launch(const float* phi, const float* vin, int64_t rows, const 
 // Returns MF_E_SHAPE when no variant fits (the caller falls back to the generic kernel).
 template <typename T, bool INV>
 int rqs_coop_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bound, T slope, T* vout, T* ladj, T* ladj_sum,
-                    int32_t* bin, cudaStream_t stream) {
+                    int32_t* bin, cudaStream_t stream, int64_t row_offset) {
     static const int forced = [] { const char* e = getenv("MF_RQS_LANES"); return e ? atoi(e) : 0; }();
     const RqsConst<T> C = make_rqs_const<T>(bound, slope);
     const size_t row_bytes = (size_t)(3 * K - 1) * sizeof(T);
@@ -361,10 +363,10 @@ int rqs_coop_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bound
     for (int pass = 0; pass < 2 && rc == MF_E_SHAPE; ++pass) {  // first try for >= 3 CTAs per SM, then anything that fits
         for (int lanes = pref; lanes <= 8 && rc == MF_E_SHAPE; lanes *= 2) {
             const bool third = pass == 0;
-            if (lanes == 1) rc = coop_launch_lanes<T, INV, 1>(phi, vin, rows, K, C, vout, ladj_rows, bin, stream, third);
-            if (lanes == 2) rc = coop_launch_lanes<T, INV, 2>(phi, vin, rows, K, C, vout, ladj_rows, bin, stream, third);
-            if (lanes == 4) rc = coop_launch_lanes<T, INV, 4>(phi, vin, rows, K, C, vout, ladj_rows, bin, stream, third);
-            if (lanes == 8) rc = coop_launch_lanes<T, INV, 8>(phi, vin, rows, K, C, vout, ladj_rows, bin, stream, third);
+            if (lanes == 1) rc = coop_launch_lanes<T, INV, 1>(phi, vin, rows, K, C, vout, ladj_rows, bin, stream, third, row_offset);
+            if (lanes == 2) rc = coop_launch_lanes<T, INV, 2>(phi, vin, rows, K, C, vout, ladj_rows, bin, stream, third, row_offset);
+            if (lanes == 4) rc = coop_launch_lanes<T, INV, 4>(phi, vin, rows, K, C, vout, ladj_rows, bin, stream, third, row_offset);
+            if (lanes == 8) rc = coop_launch_lanes<T, INV, 8>(phi, vin, rows, K, C, vout, ladj_rows, bin, stream, third, row_offset);
         }
     }
     if (rc == MF_OK && ladj_sum) {
@@ -375,9 +377,9 @@ int rqs_coop_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bound
     return rc;
 }
 
-template int rqs_coop_launch<float, false>(const float*, const float*, int64_t, int, int, float, float, float*, float*, float*, int32_t*, cudaStream_t);
-template int rqs_coop_launch<float, true>(const float*, const float*, int64_t, int, int, float, float, float*, float*, float*, int32_t*, cudaStream_t);
-template int rqs_coop_launch<double, false>(const double*, const double*, int64_t, int, int, double, double, double*, double*, double*, int32_t*, cudaStream_t);
-template int rqs_coop_launch<double, true>(const double*, const double*, int64_t, int, int, double, double, double*, double*, double*, int32_t*, cudaStream_t);
+template int rqs_coop_launch<float, false>(const float*, const float*, int64_t, int, int, float, float, float*, float*, float*, int32_t*, cudaStream_t, int64_t);
+template int rqs_coop_launch<float, true>(const float*, const float*, int64_t, int, int, float, float, float*, float*, float*, int32_t*, cudaStream_t, int64_t);
+template int rqs_coop_launch<double, false>(const double*, const double*, int64_t, int, int, double, double, double*, double*, double*, int32_t*, cudaStream_t, int64_t);
+template int rqs_coop_launch<double, true>(const double*, const double*, int64_t, int, int, double, double, double*, double*, double*, int32_t*, cudaStream_t, int64_t);
 
 }  // namespace mf
