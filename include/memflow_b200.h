@@ -63,7 +63,7 @@ int mf_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * K1  rambo_forward : unit hypercube -> CM-frame 4-momenta + Jacobian weight
  * replaces FlatInvertiblePhasespace.generateKinematics_batch, rambo_generator.py:168-398
  * (with get_x1x2_from_uniform utils.py:260-284, bisect_vec_batch :400-446 -> closed form /
- * Halley root solve, generateIntermediatesMassive_batch :475-509, setInitialStateMomenta_batch
+ * Newton root solve, generateIntermediatesMassive_batch :475-509, setInitialStateMomenta_batch
  * :511-551, boost_t utils.py:88-118).
  *   u        [N, 3n-2]    3n-4 RAMBO variables, then (u_x1, u_x2)
  *   masses   host [n]     final-state masses

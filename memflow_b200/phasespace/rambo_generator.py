@@ -186,7 +186,7 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
 
     def bisect_vec_batch(self, v_t, target=1.0e-16, maxLevel=600):
         """Solve v = u^e ((e+1) - e u), e = n-2-column, for u (:400-446). The reference bisects the whole
-        batch for up to 180 levels; the kernel uses a closed form (e=1) / fp32-seeded Halley iteration.
+        batch for up to 180 levels; the kernel uses a closed form (e=1) / an fp32-seeded Newton + chord step in fp64.
         `target` / `maxLevel` are accepted for signature compatibility and ignored."""
         if v_t.size(1) == 0:
             return None
