@@ -736,23 +736,35 @@ extern "C" int mf_flow_sample_f64(const double* phi, int64_t N, int F, int T, in
     if (K < 1 || K > 128) return MF_E_SHAPE;
     if (N == 0) return MF_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    {   // one launch: Philox base point -> T inverses -> u, log q (rqs_f64.cu)
+        const int rc1 = mf::rqs64_launch(true, true, phi, nullptr, N, F, K, T, bound, slope, seed, event_offset, u, nullptr, logq,
+                                         nullptr, st);
+        if (rc1 != MF_E_SHAPE) return rc1;
+    }
+    // shapes outside that kernel (no soft clip, very wide events): one launch per transform on the general kernels,
+    // ping-ponging between u and a scratch buffer (the kernels' input and output pointers are __restrict__)
     const unsigned grid = (unsigned)((N + 255) / 256);
-    mf::philox_base_f64_kernel<<<grid, 256, 0, st>>>(N, F, bound, seed, event_offset, u, logq);
-    double* ladj = nullptr;
-    if (cudaMallocAsync((void**)&ladj, (size_t)N * F * sizeof(double), st) != cudaSuccess) return -(int)cudaErrorMemoryAllocation;
+    const int64_t n = N * (int64_t)F;
+    double* scratch = nullptr;
+    if (cudaMallocAsync((void**)&scratch, (size_t)2 * n * sizeof(double), st) != cudaSuccess) return -(int)cudaErrorMemoryAllocation;
+    double* ladj = scratch + n;
+    double* cur = (T % 2 == 0) ? u : scratch;   // T swaps later the result sits in u
+    double* nxt = (T % 2 == 0) ? scratch : u;
+    mf::philox_base_f64_kernel<<<grid, 256, 0, st>>>(N, F, bound, seed, event_offset, cur, logq);
     const size_t pitch = (size_t)N * F * (3 * K - 1);
     int rc = MF_OK;
     for (int t = T - 1; t >= 0 && rc == MF_OK; --t) {
-        // in place: every thread of a row reads its input before the tile's first barrier, the owner writes after the last
-        rc = mf::rqs_coop_launch<double, true>(phi + (size_t)t * pitch, u, N, F, K, bound, slope, u, ladj, nullptr, nullptr, st,
+        rc = mf::rqs_coop_launch<double, true>(phi + (size_t)t * pitch, cur, N, F, K, bound, slope, nxt, ladj, nullptr, nullptr, st,
                                                 (int64_t)event_offset * F);
         if (rc == MF_OK) mf::ladj_accumulate_kernel<<<grid, 256, 0, st>>>(ladj, N, F, logq);
+        double* tmp = cur; cur = nxt; nxt = tmp;
     }
-    cudaFreeAsync(ladj, st);
-    if (rc != MF_OK) return rc;
-    const int64_t n = N * (int64_t)F;
-    mf::to_unit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(u, n, bound, 1.0 / (2.0 * bound));
-    return mf::launch_status();
+    if (rc == MF_OK) {   // cur == u
+        mf::to_unit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(u, n, bound, 1.0 / (2.0 * bound));
+        rc = mf::launch_status();
+    }
+    cudaFreeAsync(scratch, st);
+    return rc;
 }
 
 extern "C" int mf_rambo_is_f64(const double* u, const double* logq, int64_t N, int n_final, const double* masses,

@@ -21,7 +21,9 @@ MF_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, 
     return Philox4{c0, c1, c2, c3};
 }
 
-// uniform in (0,1) from 24 random bits, exactly representable in fp32: (k + 0.5) / 2^24
-MF_HD float u01_from_bits(uint32_t b) { return ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// uniform in (0,1) from the top 23 random bits: (k + 0.5) / 2^23 = (2k + 1) / 2^24, an odd 24-bit numerator, so the sum
+// is exact in fp32 and the variate lies strictly inside (0, 1) for every bit pattern (k = 2^23 - 1 gives 1 - 2^-24).
+// (24 bits would need 25 significand bits for k >= 2^23: round-to-even then returns exactly 1.0 for b = 0xFFFFFFFF.)
+MF_HD float u01_from_bits(uint32_t b) { return ((float)(b >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
 }  // namespace mf

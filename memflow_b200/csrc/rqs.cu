@@ -284,7 +284,11 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
             return launch_status();
         }
     }
-    {   // every other shape (all fp64, fp32 with bin counts the register kernels do not cover): several threads per
+    if constexpr (sizeof(T) == 8) {   // float64 with the soft clip: rqs_f64.cu
+        const int rc = rqs64_launch(INV, false, phi, vin, B, F, K, 1, bound, slope, 0, 0, vout, ladj, ladj_sum, bin, stream);
+        if (rc != MF_E_SHAPE) return rc;
+    }
+    {   // every other shape (fp64 without the clip, fp32 with bin counts the register kernels do not cover): several threads per
         // row (rqs_coop.cu). MF_RQS_COOP=0 keeps the generic kernel below, for A/B timing.
         static const bool coop = [] { const char* e = getenv("MF_RQS_COOP"); return !(e && e[0] == '0'); }();
         if (coop) {

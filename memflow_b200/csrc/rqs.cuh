@@ -343,4 +343,11 @@ template <typename T, bool INV>
 int rqs_coop_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bound, T slope, T* vout, T* ladj, T* ladj_sum,
                     int32_t* bin, cudaStream_t stream, int64_t row_offset = 0);
 
+
+// rqs_f64.cu: float64 with the soft clip (every MEMFlow production flow): K3 / K4 (T = 1) and the chain's whole flow stage
+// (chain = true: Philox base point -> T inverses -> u in [0,1], log q) in one launch; MF_E_SHAPE when the shape is outside it
+int rqs64_launch(bool inverse, bool chain, const double* phi, const double* vin, int64_t B, int F, int K, int T, double bound,
+                 double slope, uint64_t seed, uint64_t event_offset, double* vout, double* ladj, double* ladj_sum,
+                 int32_t* bin, cudaStream_t stream);
+
 }  // namespace mf

@@ -24,6 +24,11 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
+def u01_from_bits(bits):
+    """(k + 0.5) / 2^23 from the top 23 bits: exact in float32 and strictly inside (0, 1) (philox.cuh)."""
+    return ((np.asarray(bits, dtype=np.uint32) >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
+
+
 def base_sample(n_events, F, bound, seed, event_offset=0):
     """z[e, f] in (-bound, bound), float32: counter = (global event, f >> 2), key = seed."""
     gev = np.arange(n_events, dtype=np.uint64) + np.uint64(event_offset)
@@ -36,6 +41,5 @@ def base_sample(n_events, F, bound, seed, event_offset=0):
         for j in range(4):
             f = 4 * blk + j
             if f < F:
-                u01 = ((r[j] >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
-                z[:, f] = np.float32(bound) * (np.float32(2.0) * u01 - np.float32(1.0))
+                z[:, f] = np.float32(bound) * (np.float32(2.0) * u01_from_bits(r[j]) - np.float32(1.0))
     return z

@@ -45,4 +45,25 @@ if what in ("rqs64", "all"):   # the reference's configs run the flows in float6
         phi.grad = None
         ls.sum().backward()
     torch.cuda.synchronize()
+if what in ("rqs64k40", "rqs64k35", "rqs64k33", "rqs64k64", "rqs64k10"):   # float64 forward / inverse alone (csrc/rqs_f64.cu)
+    K = int(what[6:])
+    F = {40: 10, 35: 10, 33: 10, 64: 20, 10: 7}[K]
+    B = (1 << 18) if K >= 33 else (1 << 20)
+    if K == 64:
+        B = 1 << 17
+    phi = torch.randn(B, F, 3 * K - 1, device=dev, dtype=torch.float64)
+    x = (torch.rand(B, F, device=dev, dtype=torch.float64) * 2.6 - 1.3) * 1.1
+    for i in range(3):
+        TR.rqs_forward(phi, x, bound=1.1)
+        TR.rqs_inverse(phi, x, bound=1.1)
+    torch.cuda.synchronize()
+if what in ("chain64", "chain64k35"):   # float64 flow stage of the chain at the config-5 shape (n=4: F=10, T=6)
+    K = 35 if what.endswith("k35") else 40
+    N, T, F = 1 << 17, 6, 10
+    phi = torch.randn(T, N, F, 3 * K - 1, device=dev, dtype=torch.float64)
+    smp = ES.ImportanceSampler([125.25, 172.5, 172.5, 1e-5], E, seed=3, device=dev)
+    acc = ES.new_accumulator(dev)
+    for i in range(3):
+        smp.run_chunk(phi, event_offset=i * N, acc=acc)
+    torch.cuda.synchronize()
 print("done")

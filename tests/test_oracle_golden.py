@@ -171,6 +171,20 @@ def test_philox_known_answer():
     assert [int(v[0]) for v in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
 
 
+def test_base_variate_is_strictly_inside_the_unit_interval():
+    """(k + 0.5) / 2^23 from the top 23 bits: exact in float32 for every bit pattern, never 0 or 1 (a 24-bit k would
+    round to 1.0 for bits = 0xFFFFFFFF and put the base point exactly on the spline's bound)."""
+    from oracle import philox as P
+    bits = np.array([0, 1, 0x1FF, 0x200, 0x7FFFFFFF, 0x80000000, 0xFFFFFDFF, 0xFFFFFE00, 0xFFFFFFFF], dtype=np.uint32)
+    u = P.u01_from_bits(bits)
+    assert u.dtype == np.float32 and (u > 0).all() and (u < 1).all()
+    exact = ((bits >> 9).astype(np.float64) + 0.5) / 2.0 ** 23
+    assert np.array_equal(u.astype(np.float64), exact)
+    assert float(u[-1]) == 1.0 - 2.0 ** -24 and float(u[0]) == 2.0 ** -24
+    z = np.float32(1.0) * (np.float32(2.0) * u - np.float32(1.0))
+    assert (np.abs(z) < 1).all()
+
+
 def test_get_ps_matches_reference(oracle, golden_dir):
     """Compute_ParticlesTensor.get_PS (memflow/unfolding_flow/utils.py:1056-1152), incl. the problem mask."""
     g = np.load(os.path.join(golden_dir, "get_ps_n4.npz"))
