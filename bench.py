@@ -148,16 +148,77 @@ def cpu_leg(steps, warmup, budget_s):
     return steps * n / dt, cores, "%d steps x %d points of the same chain (oracle port: C, pthreads)" % (steps, n), dt / steps * 1e3
 
 
+def reference_torch_leg(steps, warmup, budget_s):
+    """The reference's OWN torch CPU path on the host cores (oracle/_ref = the unmodified memflow/phasespace files staged by
+    oracle/make_ref.py; zuko is absent from the reference tree, so the spline step is the torch restatement
+    oracle/rqs_torch.py): the same chain on a bounded sample. Returns None when oracle/_ref is not staged."""
+    from oracle import ref_torch as R
+    if not R.available():
+        return None
+    import numpy as np
+    import torch
+    from oracle import philox as OP
+    ps_mod, _, _ = R.load()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ps = ps_mod.PhaseSpace(E_CM, [21, 21], [25, 6, -6], final_masses=torch.tensor(MASSES, dtype=torch.float64), dev="cpu")
+    g = torch.Generator().manual_seed(0)
+
+    def run(n, off):
+        phi = torch.randn(T_FLOW, n, F_DIM, PW, generator=g, dtype=torch.float32)
+        z = torch.from_numpy(OP.base_sample(n, F_DIM, 1.0, 1, off))
+        t0 = time.perf_counter()
+        R.chain_step(phi, z, MASSES, E_CM, ps=ps)
+        return time.perf_counter() - t0
+
+    probe = 1 << 14
+    run(probe, 0)
+    per_ev = run(probe, 0) / probe
+    n = int(budget_s / max(steps + warmup, 1) / per_ev)
+    n = max(1 << 12, min(n, 1 << 20))
+    for i in range(warmup):
+        run(n, i * n)
+    dt = sum(run(n, (warmup + i) * n) for i in range(steps))
+    return {"value": steps * n / dt, "cores": cores, "ms_per_step": dt / steps * 1e3, "cpu": R.cpu_model(),
+            "sample": "%d steps x %d points of the same chain: torch CPU, %d threads; phase space = unmodified reference "
+                      "PhaseSpace.get_momenta_from_ps (oracle/_ref), spline = torch restatement of zuko (zuko is absent)"
+                      % (steps, n, cores)}
+
+
+def cpu_baseline_block(steps, warmup, budget_s, with_phase_space=True):
+    """cpu_baseline of the JSON line: the reference torch path when it is staged (kind "reference"), with the C port's number
+    next to it; the port alone (kind "port") otherwise."""
+    v, cores, sample, ms = cpu_leg(steps, warmup, budget_s=min(budget_s, 20.0))
+    port = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    ref = None
+    try:
+        ref = reference_torch_leg(steps, warmup, budget_s)
+    except Exception as e:  # the reference leg must never break the line
+        port["reference_error"] = repr(e)
+    if ref is None:
+        return port, ms
+    block = {"value": ref["value"], "unit": UNIT, "cores": ref["cores"], "kind": "reference", "sample": ref["sample"],
+             "cpu": ref["cpu"], "port": port}
+    if with_phase_space:
+        try:
+            from oracle import ref_torch as R
+            block["reference_torch"] = R.time_phase_space(1_000_000, reps=2)
+        except Exception as e:
+            block["reference_torch"] = {"error": repr(e)}
+    return block, ref["ms_per_step"]
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's algorithm on the host cores (oracle port; the Python reference cannot
-    travel to the GPU box). Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (oracle/_ref: its torch
+    phase-space files, unmodified; the spline step is the torch restatement of the absent zuko). Falls back to the C port
+    when oracle/_ref is not staged. Rank 0 only."""
     if rank != 0:
         return
-    v, cores, sample, ms = cpu_leg(args.steps, args.warmup, budget_s=100.0)
+    block, ms = cpu_baseline_block(args.steps, args.warmup, budget_s=100.0, with_phase_space=False)
+    v = block["value"]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": CONFIG,
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "dtype": "f64", "data": "synthetic", "config": CONFIG, "cpu_baseline": block,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
 
@@ -254,6 +315,65 @@ def extras(torch, dev, hbm_peak):
     return out
 
 
+def config5_block(torch, dist, dev, rank, world, hbm_peak, barrier):
+    """BASELINE configs[4] ("Sharded MEM integral ... ttH+1j ... across 2/4/8 B200") at its own shape: n = 4 with
+    masses (125.25, 172.5, 172.5, 1e-5), the production flow F = 10, K = 40, T = 6
+    (configs/flow_pretrain_labframe_sampling/flow_config_forEnric.yaml), float32 parameters (the notebook's dtype) and
+    float64 parameters (`.double()`, transfer_flow_paper.py:116-127). Device-resident parameters, whole job = all ranks,
+    time = max over ranks of the CUDA-event time. Roofline: algorithmic bytes = T F (3K-1) s per event."""
+    from memflow_b200 import estimator as ES
+    from memflow_b200.distributed import allreduce_accumulators
+    out = {"workload": "is_chain_ttH+1j: philox -> 6x RQS inverse (F=10,K=40) -> RAMBO n=4 fp64 -> weight -> sum w, sum w^2",
+           "n_final": 4, "masses": [125.25, 172.5, 172.5, 1e-5], "flow": {"T": 6, "F": 10, "K": 40, "bound": 1.0}, "n_gpus": world}
+    try:
+        T5, F5, K5 = 6, 10, 40
+        smp = ES.ImportanceSampler([125.25, 172.5, 172.5, 1e-5], E_CM, seed=3, device=dev)
+        for name, dt, N5, steps in (("phi_f32", torch.float32, 1 << 19, 6), ("phi_f64", torch.float64, 1 << 18, 6)):
+            g = torch.Generator(device=dev).manual_seed(77 + rank)
+            phi5 = torch.randn(T5, N5, F5, 3 * K5 - 1, device=dev, dtype=dt, generator=g)
+            u5 = torch.empty(N5, F5, dtype=torch.float64, device=dev)
+            lq5 = torch.empty(N5, dtype=torch.float64, device=dev)
+            acc5 = ES.new_accumulator(dev)
+            base = rank * (steps + 2) * N5
+            for i in range(2):
+                smp.sample_flow(phi5, event_offset=base + i * N5, u=u5, logq=lq5)
+                smp.weigh(u5, lq5, acc=acc5)
+            acc5.zero_()
+            a, m, b = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            ta = 0.0
+            barrier()
+            a.record()
+            for i in range(steps):
+                if i == steps - 1:
+                    m.record()
+                smp.sample_flow(phi5, event_offset=base + (2 + i) * N5, u=u5, logq=lq5)
+                if i == steps - 1:
+                    lastA = torch.cuda.Event(enable_timing=True)
+                    lastA.record()
+                smp.weigh(u5, lq5, acc=acc5)
+            allreduce_accumulators(acc5)
+            b.record()
+            barrier()
+            ta = m.elapsed_time(lastA) * 1e-3      # launch A of the last step alone
+            t = torch.tensor([a.elapsed_time(b) * 1e-3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            by = T5 * F5 * (3 * K5 - 1) * phi5.element_size()
+            I, sigma, nv = ES.mc_estimate(acc5, world * steps * N5)
+            out[name] = {"value": world * steps * N5 / float(t.item()), "unit": UNIT, "events_per_step_per_gpu": N5, "steps": steps,
+                         "ms_per_step": float(t.item()) / steps * 1e3,
+                         "roofline": {"bound": "hbm", "achieved": by * N5 / ta / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": by * N5 / ta / 1e9 / hbm_peak, "algorithmic_bytes_per_event": by,
+                                      "kernel": "flow_sample_reg2_kernel<40>" if dt == torch.float32 else "rqs64_kernel<inverse, 4, chain>",
+                                      "kernel_ms": ta * 1e3, "rank": 0},
+                         "estimate": {"I": I, "sigma": sigma, "n_valid": nv}}
+            del phi5, u5, lq5
+            torch.cuda.empty_cache()
+    except Exception as e:  # must never break the headline line
+        out["error"] = repr(e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -342,43 +462,42 @@ def main():
     acc_host = acc.cpu().tolist()
     I, sigma, nvalid = ES.mc_estimate(acc_host, total_events)
 
-    # ---- e2e: host parameters in pinned memory -> H2D -> chain -> D2H accumulators, every step ----
+    # ---- e2e: host parameters in pinned memory -> H2D -> chain -> D2H accumulators, every step, through the package's
+    #      host-buffer call (memflow_b200.distributed.HostPipeline: double-buffered, 2 copy streams) ----
+    from memflow_b200.distributed import HostPipeline, bind_to_gpu_cpus
+    numa = bind_to_gpu_cpus(local_rank)          # before the pinned allocation: first touch on the GPU's NUMA node
     e2e_chunk = 1 << 20
     e2e_steps = max(3, min(K, 12))
-    host = torch.empty((T_FLOW, e2e_chunk, F_DIM, PW), dtype=torch.float32).pin_memory()
+    pipe = HostPipeline(smp, (T_FLOW, e2e_chunk, F_DIM, PW), dtype=torch.float32, n_copy_streams=2, device=dev)
+    host = pipe.pinned_chunk()
     host.copy_(phi[:, :e2e_chunk].cpu())
     res_host = torch.empty(3, dtype=torch.float64).pin_memory()
-    bufs = [torch.empty_like(host, device=dev) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    main_stream = torch.cuda.current_stream(dev)
     acc2 = ES.new_accumulator(dev)
-    copied = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
 
     def e2e_pass(nsteps, off0):
         for i in range(nsteps):
-            b = i & 1
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[b])
-                bufs[b].copy_(host, non_blocking=True)
-                copied[b].record(copy_stream)
-            main_stream.wait_event(copied[b])
-            smp.run_chunk(bufs[b], event_offset=off0 + i * e2e_chunk, acc=acc2)
-            consumed[b].record(main_stream)
+            pipe.submit(host, off0 + i * e2e_chunk, acc2)
             res_host.copy_(acc2, non_blocking=True)   # the step's result goes back to the host
         torch.cuda.synchronize()
 
-    for b in range(2):
-        consumed[b].record(main_stream)
     e2e_pass(2, 0)
     barrier()
     t0 = time.perf_counter()
     e2e_pass(e2e_steps, 2 * e2e_chunk)
     barrier()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    h2d_gbps = torch.tensor([host.numel() * 4 * e2e_steps / float(te.item()) / 1e9], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(h2d_gbps, op=dist.ReduceOp.MIN)
     e2e_value = world * e2e_steps * e2e_chunk / float(te.item())
+    del pipe
+
+    # ---- BASELINE configs[4] at its own shape on every N: n = 4 (H, t, tbar, j), production flow F = 10, K = 40, T = 6,
+    #      float32 and float64 parameters, events sharded, max over ranks ----
+    del phi
+    torch.cuda.empty_cache()
+    config5 = config5_block(torch, dist, dev, rank, world, hbm_peak, barrier)
 
     if rank != 0:
         if world > 1:
@@ -399,8 +518,12 @@ def main():
         "ms_per_step": t_max / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": CONFIG,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": 24,
-                "steps": e2e_steps, "chunk_events": e2e_chunk,
-                "note": "spline parameters start in pinned host memory; H2D double-buffered against the kernel"},
+                "steps": e2e_steps, "chunk_events": e2e_chunk, "api": "memflow_b200.distributed.HostPipeline.submit",
+                "h2d_GBps_per_rank_min": float(h2d_gbps.item()), "copy_streams": 2,
+                "cpu_binding": {"numa_node": numa[0], "cpus": numa[1]},
+                "note": "spline parameters start in pinned host memory (1624 B/event): PCIe-bound by construction; "
+                        "H2D double-buffered against the kernels on 2 copy streams"},
+        "config5": config5,
         "gpu_launches": 2 * K * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "kernel": "flow_sample_fast_kernel<10> (launch A of each step)", "peak_source": peak_src,
@@ -415,10 +538,8 @@ def main():
         "wall_s_timed_region": t_wall,
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, sample, _ = cpu_leg(3, 1, budget_s=20.0)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line["cpu_baseline"], _ = cpu_baseline_block(3, 1, budget_s=20.0)
     if world == 1 and not args.no_extras:
-        del phi, bufs
         torch.cuda.empty_cache()
         line["extra"] = extras(torch, dev, hbm_peak)
     emit(line)

@@ -302,6 +302,44 @@ MF_D void rqs_row_reg(float* __restrict__ row, const RqsConst<float>& C, float v
     rqs_eval_fast<INV>(row + 2 * K, K, C, bin, x0, x1, y0, y1, v, out, ladj);
 }
 
+// ---------------------------------------------------------------------------------------------
+// float64 exp(soft_clip(a)) = 2^(a / (ln2 + |a| k1)), k1 = |f / log slope| ln2 (f = 2 widths / heights, 1 derivatives), as ONE
+// branch-free sequence of 18 FP64 instructions (the library's exp + a range-checked division cost ~95 issued instructions
+// per parameter in round 1): the log2(e) factor is folded into the divisor, the reciprocal is MUFU.RCP64H (2^-20) with a
+// cubic correction r0 (1 + e + e^2) (2^-60 before rounding), 2^q = 2^k P11(q - k) with a degree-11 minimax polynomial
+// (|error| <= 3.2e-18, Chebyshev fit in 60-digit arithmetic) and an integer add into the exponent field. The soft clip
+// bounds |q| <= |log2 slope| / 2 (5 for slope = 1e-3), so there is no range check; callers track the largest |a| (one
+// integer max per element) and take an exact out-of-line path for non-finite / astronomically large parameters.
+// Relative error <= ~6e-16 (tests compare against exp() of the IEEE quotient).
+// ---------------------------------------------------------------------------------------------
+static __constant__ double kExp2[12] = {1.0, 6.9314718055994530925e-1, 2.4022650695910159567e-1, 5.5504108664821627039e-2,
+                                        9.6181291075872566681e-3, 1.3333558146406470697e-3, 1.5403530463724354209e-4,
+                                        1.5252733841556772589e-5, 1.3215432535912376166e-6, 1.0178057087733941105e-7,
+                                        7.0741942972885210056e-9, 4.455817908336064493e-10};
+// parameters at or above 2^993 in magnitude, inf and NaN leave the fast sequence's domain
+constexpr int kHiAbsLimit = 0x7e000000;
+// 2^q for |q| < 1000: q = k + r, |r| <= 1/2
+MF_D double exp2_of_q(double q) {
+    const double tk = q + 6755399441055744.0;       // 1.5 * 2^52: rint(q) in the low word
+    const double kd = tk - 6755399441055744.0;
+    const double r = q - kd;                        // exact
+    double p = kExp2[11];
+#pragma unroll
+    for (int i = 10; i >= 0; --i) p = fma(p, r, kExp2[i]);
+    return __hiloint2double(__double2hiint(p) + (__double2loint(tk) << 20), __double2loint(p));
+}
+// q = a / (ln2 + |a| k1) = log2 of exp(soft_clip(a)); hi_abs_max tracks the largest exponent field seen
+MF_D double clip_log2(double a, double k1, double ln2, int& hi_abs_max) {
+    hi_abs_max = max(hi_abs_max, __double2hiint(a) & 0x7fffffff);
+    const double bq = fma(fabs(a), k1, ln2);
+    const double r0 = rcp_seed(bq);                 // MUFU.RCP64H: 2^-20
+    const double e = fma(-bq, r0, 1.0);
+    const double t = fma(e, e, e);
+    const double s = fma(r0, t, r0);                // 1 / bq
+    return a * s;
+}
+MF_D double exp2_clip(double a, double k1, double ln2, int& hi_abs_max) { return exp2_of_q(clip_log2(a, k1, ln2, hi_abs_max)); }
+
 // Bulk async copy (TMA, 1-D) global -> shared with mbarrier completion.
 MF_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 MF_D void mbar_init(uint64_t* bar, uint32_t count) {

@@ -29,12 +29,12 @@ MF_DUAL operator-(const RDual<T, NT>& a) { RDual<T, NT> r; r.v = -a.v; MF_DLOOP 
 MF_DUAL operator*(const RDual<T, NT>& a, const RDual<T, NT>& b) { RDual<T, NT> r; r.v = a.v * b.v; MF_DLOOP r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
 MF_DUAL operator*(T a, const RDual<T, NT>& b) { RDual<T, NT> r; r.v = a * b.v; MF_DLOOP r.d[i] = a * b.d[i]; return r; }
 MF_DUAL operator/(const RDual<T, NT>& a, const RDual<T, NT>& b) {
-    RDual<T, NT> r; const T ib = (T)1 / b.v; r.v = a.v * ib;
+    RDual<T, NT> r; const T ib = rcp_fast(b.v); r.v = a.v * ib;   // fp64: MUFU seed + 2 Newton steps (common.cuh), <= 1 ulp
     MF_DLOOP r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
     return r;
 }
-MF_DUAL dsqrt(const RDual<T, NT>& a) { RDual<T, NT> r; r.v = sqrt_(a.v); const T h = (T)0.5 / r.v; MF_DLOOP r.d[i] = a.d[i] * h; return r; }
-MF_DUAL dlog(const RDual<T, NT>& a) { RDual<T, NT> r; r.v = log_(a.v); const T ia = (T)1 / a.v; MF_DLOOP r.d[i] = a.d[i] * ia; return r; }
+MF_DUAL dsqrt(const RDual<T, NT>& a) { RDual<T, NT> r; r.v = sqrt_fast(a.v); const T h = (T)0.5 * rcp_fast(r.v); MF_DLOOP r.d[i] = a.d[i] * h; return r; }
+MF_DUAL dlog(const RDual<T, NT>& a) { RDual<T, NT> r; r.v = log_(a.v); const T ia = rcp_fast(a.v); MF_DLOOP r.d[i] = a.d[i] * ia; return r; }
 
 // Adjoints of go * out + gl * ladj w.r.t. variables [base, base + NT) of (x0, x1, y0, y1, d0, d1, v): one evaluation
 // of the rational quadratic (forward: out = y, inverse: out = x; ladj = forward log|dy/dx| at x either way) on dual
@@ -97,15 +97,51 @@ template <> MF_D float clip_der_from_e<float>(float e, float, const RqsConst<flo
     return t * t;
 }
 
+// ---- float64 with the soft clip (every MEMFlow production flow): the lean sequence of rqs.cuh. The first pass stores
+// q = log2(exp(clip(a))) = a / (ln2 + |a| k1) in place instead of the exponential: 2^q is 14 FP64 instructions away
+// (exp2_of_q) wherever the exponential is needed again, and the clip's derivative is (1 - k1 |q|)^2 -- no log, no division.
+// Round 1 (library exp + IEEE division in the first pass, library log per element in the gradient pass): ~105 FP64-pipe
+// instructions per parameter; now ~52. Non-finite / astronomically large parameters poison the row with NaN. ----
+template <bool LEAN, typename T> MF_D T lean_store(T a, T m, const RqsConst<T>& C, T& e, int& hmax) {
+    if constexpr (LEAN) {
+        const double q = clip_log2(a, C.k1w, C.ln2, hmax);
+        e = exp2_of_q(q);
+        return q;
+    } else {
+        e = bw_exp(a, m, C);
+        return e;
+    }
+}
+template <bool LEAN, typename T> MF_D T lean_exp(T stored) {
+    if constexpr (LEAN) return exp2_of_q(stored); else return stored;
+}
+template <bool LEAN, typename T> MF_D T lean_clip_der(T stored, T e, T m, const RqsConst<T>& C) {
+    if constexpr (LEAN) { const double t = fma(-C.k1w, fabs(stored), 1.0); return t * t; }
+    else return clip_der_from_e(e, m, C);
+}
+// exp(clip(d)) and d clip / dd for a derivative parameter of the selected bin
+template <bool LEAN, typename T> MF_D void lean_deriv(T a, const RqsConst<T>& C, T& dv, T& f) {
+    if constexpr (LEAN) {
+        int hm = 0;
+        const double q = clip_log2(a, C.k1d, C.ln2, hm);
+        const double t = fma(-C.k1d, fabs(q), 1.0);
+        dv = hm >= kHiAbsLimit ? __longlong_as_double(0x7ff8000000000000LL) : exp2_of_q(q);
+        f = dv * (t * t);
+    } else {
+        dv = exp_(clip_val(a, C.one_over_L, C.clip));
+        f = dv * clip_der(a, C.one_over_L, C.clip);
+    }
+}
+
 // Row gradient, in place: on entry r[0..3K-2] = parameters of the row, on exit = their gradients. Returns g_v.
-template <typename T, bool INV>
+template <typename T, bool INV, bool LEAN>
 MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T go, T gl, int rot0) {
     const int PW = 3 * K - 1;
     const T B = C.bound;
     // ---- pass 1: softmax sums. torch.softmax subtracts the row maximum; with the soft clip the arguments are bounded
     //      by |log slope| / 2, so in fp32 the subtraction is skipped (same value up to rounding) ----
     T mw = (T)0, mh = (T)0;
-    if (!(C.clip && sizeof(T) == 4)) {
+    if (!LEAN && !(C.clip && sizeof(T) == 4)) {
         mw = clip_val(r[0], C.two_over_L, C.clip); mh = clip_val(r[K], C.two_over_L, C.clip);
         for (int k = 1; k < K; ++k) {
             mw = fmax_(mw, clip_val(r[k], C.two_over_L, C.clip));
@@ -115,10 +151,11 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
     T Sw = (T)0, Sh = (T)0;
     // (rot0 >= 0: where this row starts inside the order-free passes; odd K makes the row pitch even and the rows of a
     //  warp would otherwise share 2-4 shared-memory banks at a given offset; -1: plain order)
-    auto exp_at = [&](int k) {   // each parameter is replaced by its exponential, reused by every later pass
-        const T ew = bw_exp(r[k], mw, C), eh = bw_exp(r[K + k], mh, C);
-        r[k] = ew;
-        r[K + k] = eh;
+    int hmax = 0;
+    auto exp_at = [&](int k) {   // each parameter is replaced by its exponential (LEAN: by its log2), reused by every later pass
+        T ew, eh;
+        r[k] = lean_store<LEAN>(r[k], mw, C, ew, hmax);
+        r[K + k] = lean_store<LEAN>(r[K + k], mh, C, eh, hmax);
         Sw += ew;
         Sh += eh;
     };
@@ -127,6 +164,10 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
         for (int j = 0; j < K; ++j) { exp_at(kk); kk = (kk + 1 == K) ? 0 : kk + 1; }
     } else {
         for (int k = 0; k < K; ++k) exp_at(k);
+    }
+    if (LEAN && hmax >= kHiAbsLimit) {   // non-finite / astronomically large parameter: outside the lean sequence's domain
+        for (int i = 0; i < PW; ++i) r[i] = (T)NAN;
+        return (T)NAN;
     }
     const T iSw = (T)1 / Sw, iSh = (T)1 / Sh;
     // ---- pass 2: searchsorted on the searched coordinate (X forward / Y inverse) with the knots as the forward builds
@@ -139,7 +180,7 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
         bool found = false;
         for (int k = 0; k < K; ++k) {
             const T cprev = c;
-            c += r[(INV ? K : 0) + k] * is;
+            c += lean_exp<LEAN>(r[(INV ? K : 0) + k]) * is;
             const bool below = B * ((T)2 * c - (T)1) < v;
             cnt += below ? 1 : 0;
             if (!below && !found) { cs_lo = cprev; cs_hi = c; found = true; }
@@ -156,27 +197,28 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
         T c = (T)0;
         for (int k = 0; k <= bin; ++k) {
             if (k == bin) co_lo = c;
-            c += r[(INV ? 0 : K) + k] * io;
+            c += lean_exp<LEAN>(r[(INV ? 0 : K) + k]) * io;
         }
         co_hi = c;
     }
     const T cw_lo = INV ? co_lo : cs_lo, cw_hi = INV ? co_hi : cs_hi, ch_lo = INV ? cs_lo : co_lo, ch_hi = INV ? cs_hi : co_hi;
     const T x0v = B * ((T)2 * cw_lo - (T)1), x1v = B * ((T)2 * cw_hi - (T)1);
     const T y0v = B * ((T)2 * ch_lo - (T)1), y1v = B * ((T)2 * ch_hi - (T)1);
-    const T d0v = bin > 0 ? exp_(clip_val(r[2 * K + bin - 1], C.one_over_L, C.clip)) : (T)1;
-    const T d1v = bin < K - 1 ? exp_(clip_val(r[2 * K + bin], C.one_over_L, C.clip)) : (T)1;
+    T d0v = (T)1, d1v = (T)1, f0 = (T)0, f1 = (T)0;
+    if (bin > 0) lean_deriv<LEAN>(r[2 * K + bin - 1], C, d0v, f0);
+    if (bin < K - 1) lean_deriv<LEAN>(r[2 * K + bin], C, d1v, f1);
     // ---- local partials by forward-mode duals: variables 0..6 = x0, x1, y0, y1, d0, d1, v ----
     T adj[7];
     rq_adjoints<T, INV, 7>(0, x0v, x1v, y0v, y1v, d0v, d1v, v, go, gl, adj);
     // ---- pass 2: parameter gradients, overwriting the parameters ----
     const T twoB = (T)2 * B;
-    const T gd0 = bin > 0 ? adj[4] * d0v * clip_der(r[2 * K + bin - 1], C.one_over_L, C.clip) : (T)0;
-    const T gd1 = bin < K - 1 ? adj[5] * d1v * clip_der(r[2 * K + bin], C.one_over_L, C.clip) : (T)0;
+    const T gd0 = adj[4] * f0, gd1 = adj[5] * f1;
     auto grad_at = [&](int i) {
-        const T ew = r[i], eh = r[K + i];
+        const T sw = r[i], sh = r[K + i];
+        const T ew = lean_exp<LEAN>(sw), eh = lean_exp<LEAN>(sh);
         const T iw_hi = (i <= bin) ? (T)1 : (T)0, iw_lo = (i < bin) ? (T)1 : (T)0;
-        r[i] = clip_der_from_e(ew, mw, C) * (ew * iSw) * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
-        r[K + i] = clip_der_from_e(eh, mh, C) * (eh * iSh) * twoB * (adj[3] * (iw_hi - ch_hi) + adj[2] * (iw_lo - ch_lo));
+        r[i] = lean_clip_der<LEAN>(sw, ew, mw, C) * (ew * iSw) * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
+        r[K + i] = lean_clip_der<LEAN>(sh, eh, mh, C) * (eh * iSh) * twoB * (adj[3] * (iw_hi - ch_hi) + adj[2] * (iw_lo - ch_lo));
     };
     if (rot0 >= 0) {
         int ii = rot0;
@@ -191,7 +233,7 @@ MF_D T rqs_row_backward(T* __restrict__ r, int K, const RqsConst<T>& C, T v, T g
 // Persistent CTAs; a tile of `rpt` rows comes in by one TMA bulk load, every thread turns its row into its gradient in
 // place, and the tile leaves by one TMA bulk store (cp.async.bulk.global.shared::cta): parameters and gradients each
 // cross HBM exactly once, fully coalesced.
-template <typename T, bool INV>
+template <typename T, bool INV, bool LEAN>
 __global__ void __launch_bounds__(128)
 rqs_backward_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const T* __restrict__ g_out,
                     const T* __restrict__ g_ladj, int64_t rows, int K, RqsConst<T> C, int rpt, int bulk_ok,
@@ -231,7 +273,7 @@ rqs_backward_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const 
         for (int rr = tid; rr < nrows; rr += 128) {
             const int64_t row = row0 + rr;
             const T go = g_out ? g_out[row] : (T)0, gl = g_ladj ? g_ladj[row] : (T)0;
-            g_v[row] = rqs_row_backward<T, INV>(sm + (size_t)rr * PW, K, C, vin[row], go, gl, (PW % 2 == 0) ? rr % K : -1);
+            g_v[row] = rqs_row_backward<T, INV, LEAN>(sm + (size_t)rr * PW, K, C, vin[row], go, gl, (PW % 2 == 0) ? rr % K : -1);
         }
         fence_proxy_async();  // generic writes of the gradients -> visible to the bulk store
         __syncthreads();
@@ -259,7 +301,7 @@ rqs_backward_kernel(const T* __restrict__ phi, const T* __restrict__ vin, const 
 //   S5 every thread writes the gradients of its chunk in place
 // Knots are offset + running sum inside the chunk, so they may differ from the sequential cumsum in the last bit;
 // the spline and its parameter gradients are continuous across a knot, so a bin flipped by that is harmless.
-template <typename T, bool INV, int LANES>
+template <typename T, bool INV, int LANES, bool LEAN>
 // fp64: 3 CTAs per SM (<= 85 registers, a few spilled words) beat 2 for LANES >= 4; LANES = 2 carries four tangents
 // per thread in S4 and would spill 200 B
 __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 4 : (LANES >= 4 ? 3 : 2))
@@ -332,6 +374,7 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
         T pre_s = (T)0;
         int start = k0;
         {
+            int hmax = 0;
             T a = (T)0, b = (T)0;
             // (odd K: even row pitch, bank conflicts between the rows of a warp; the order inside the chunk is free here,
             //  so row r starts r elements in and wraps -- see rqs_coop.cu)
@@ -341,22 +384,24 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
                 for (int j = k0; j < k1; ++j) {   // each parameter is replaced by its exponential (see clip_der_from_e)
                     const int k = kk;
                     kk = (kk + 1 == k1) ? k0 : kk + 1;
-                    const T ew = bw_exp(r[k], mw, C), eh = bw_exp(r[K + k], mh, C);
-                    r[k] = ew;
-                    r[K + k] = eh;
+                    T ew, eh;
+                    r[k] = lean_store<LEAN>(r[k], mw, C, ew, hmax);
+                    r[K + k] = lean_store<LEAN>(r[K + k], mh, C, eh, hmax);
                     a += ew;
                     b += eh;
                     pre_s += (k < start) ? (INV ? eh : ew) : (T)0;   // searched array, elements before the row's start
                 }
             } else {
+#pragma unroll 2
                 for (int k = k0; k < k1; ++k) {
-                    const T ew = bw_exp(r[k], mw, C), eh = bw_exp(r[K + k], mh, C);
-                    r[k] = ew;
-                    r[K + k] = eh;
+                    T ew, eh;
+                    r[k] = lean_store<LEAN>(r[k], mw, C, ew, hmax);
+                    r[K + k] = lean_store<LEAN>(r[K + k], mh, C, eh, hmax);
                     a += ew;
                     b += eh;
                 }
             }
+            if (LEAN && hmax >= kHiAbsLimit) a = b = (T)NAN;   // outside the lean sequence's domain: NaN gradients for the row
             scS[(2 * chunk) * RPT] = a;
             scS[(2 * chunk + 1) * RPT] = b;
         }
@@ -380,14 +425,15 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
                 T c = cs0 + pre_s * is;
                 int kk = start;
                 for (int j = k0; j < k1; ++j) {
-                    c += r[sb + kk] * is;
+                    c += lean_exp<LEAN>(r[sb + kk]) * is;
                     cnt += (B * ((T)2 * c - (T)1) < v) ? 1 : 0;
                     if (++kk == k1) { kk = k0; c = cs0; }
                 }
             } else {
                 T c = cs0;
+#pragma unroll 2
                 for (int k = k0; k < k1; ++k) {
-                    c += r[sb + k] * is;
+                    c += lean_exp<LEAN>(r[sb + k]) * is;
                     cnt += (B * ((T)2 * c - (T)1) < v) ? 1 : 0;
                 }
             }
@@ -401,8 +447,8 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
         // ---- S3: the chunk that holds the bin rebuilds the four knots around it ----
         if (inside && bin >= k0 && bin < k1) {
             T cs = cs0, co = co0;
-            for (int k = k0; k < bin; ++k) { cs += r[sb + k] * is; co += r[ob + k] * io; }
-            const T cs_hi = cs + r[sb + bin] * is, co_hi = co + r[ob + bin] * io;
+            for (int k = k0; k < bin; ++k) { cs += lean_exp<LEAN>(r[sb + k]) * is; co += lean_exp<LEAN>(r[ob + k]) * io; }
+            const T cs_hi = cs + lean_exp<LEAN>(r[sb + bin]) * is, co_hi = co + lean_exp<LEAN>(r[ob + bin]) * io;
             scK[0] = INV ? co : cs;            // cw_lo
             scK[RPT] = INV ? co_hi : cs_hi;    // cw_hi
             scK[2 * RPT] = INV ? cs : co;      // ch_lo
@@ -415,16 +461,8 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
         T f0 = (T)0, f1 = (T)0;
         if (inside) {
             T d0v = (T)1, d1v = (T)1;
-            if (bin > 0) {
-                const T a = r[2 * K + bin - 1];
-                d0v = exp_(clip_val(a, C.one_over_L, C.clip));
-                f0 = d0v * clip_der(a, C.one_over_L, C.clip);
-            }
-            if (bin < K - 1) {
-                const T a = r[2 * K + bin];
-                d1v = exp_(clip_val(a, C.one_over_L, C.clip));
-                f1 = d1v * clip_der(a, C.one_over_L, C.clip);
-            }
+            if (bin > 0) lean_deriv<LEAN>(r[2 * K + bin - 1], C, d0v, f0);
+            if (bin < K - 1) lean_deriv<LEAN>(r[2 * K + bin], C, d1v, f1);
             if (chunk * NT < 7) {
                 T part[NT];
                 rq_adjoints<T, INV, NT>(chunk * NT, B * ((T)2 * cw_lo - (T)1), B * ((T)2 * cw_hi - (T)1),
@@ -442,16 +480,24 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
             for (int j = 0; j < 7; ++j) adj[j] = scA[j * RPT];
             const T twoB = (T)2 * B;
             const T gd0 = adj[4] * f0, gd1 = adj[5] * f1;
+            // (the bracket takes three values per array: i < bin, i == bin, i > bin)
+            const T gw_lt = twoB * iSw * (adj[1] * ((T)1 - cw_hi) + adj[0] * ((T)1 - cw_lo));
+            const T gw_eq = twoB * iSw * (adj[1] * ((T)1 - cw_hi) - adj[0] * cw_lo);
+            const T gw_gt = -twoB * iSw * (adj[1] * cw_hi + adj[0] * cw_lo);
+            const T gh_lt = twoB * iSh * (adj[3] * ((T)1 - ch_hi) + adj[2] * ((T)1 - ch_lo));
+            const T gh_eq = twoB * iSh * (adj[3] * ((T)1 - ch_hi) - adj[2] * ch_lo);
+            const T gh_gt = -twoB * iSh * (adj[3] * ch_hi + adj[2] * ch_lo);
             auto grad_at = [&](int i) {
-                const T ew = r[i], eh = r[K + i];
-                const T iw_hi = (i <= bin) ? (T)1 : (T)0, iw_lo = (i < bin) ? (T)1 : (T)0;
-                r[i] = clip_der_from_e(ew, mw, C) * (ew * iSw) * twoB * (adj[1] * (iw_hi - cw_hi) + adj[0] * (iw_lo - cw_lo));
-                r[K + i] = clip_der_from_e(eh, mh, C) * (eh * iSh) * twoB * (adj[3] * (iw_hi - ch_hi) + adj[2] * (iw_lo - ch_lo));
+                const T sw = r[i], sh = r[K + i];
+                const T ew = lean_exp<LEAN>(sw), eh = lean_exp<LEAN>(sh);
+                r[i] = lean_clip_der<LEAN>(sw, ew, mw, C) * ew * (i < bin ? gw_lt : (i == bin ? gw_eq : gw_gt));
+                r[K + i] = lean_clip_der<LEAN>(sh, eh, mh, C) * eh * (i < bin ? gh_lt : (i == bin ? gh_eq : gh_gt));
             };
             if (rot) {
                 int ii = start;
                 for (int j = k0; j < k1; ++j) { grad_at(ii); ii = (ii + 1 == k1) ? k0 : ii + 1; }
             } else {
+#pragma unroll 2
                 for (int i = k0; i < k1; ++i) grad_at(i);
             }
             for (int i = k0; i < min(k1, K - 1); ++i) r[2 * K + i] = (i == bin - 1) ? gd0 : ((i == bin) ? gd1 : (T)0);
@@ -474,7 +520,7 @@ rqs_backward_coop_kernel(const T* __restrict__ phi, const T* __restrict__ vin, c
     if (tid == 0) bulk_store_wait_read();
 }
 
-template <typename T, bool INV, int LANES>
+template <typename T, bool INV, int LANES, bool LEAN>
 static int rqs_bwd_coop_launch(const T* phi, const T* vin, const T* g_out, const T* g_ladj, int64_t rows, int K,
                                const RqsConst<T>& C, T* g_phi, T* g_v, cudaStream_t stream) {
     constexpr int RPT = 256 / LANES, SLOTS = 4 * LANES + 12;
@@ -486,7 +532,7 @@ static int rqs_bwd_coop_launch(const T* phi, const T* vin, const T* g_out, const
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (smem > (size_t)smem_max) return MF_E_SHAPE;
     const int bulk_ok = (aligned(phi, 16) && aligned(g_phi, 16)) ? 1 : 0;   // RPT * PW * sizeof(T) is a multiple of 128
-    auto kern = rqs_backward_coop_kernel<T, INV, LANES>;
+    auto kern = rqs_backward_coop_kernel<T, INV, LANES, LEAN>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int ctas = 1;
@@ -508,6 +554,9 @@ static int rqs_bwd_launch(const T* phi, const T* vin, const T* g_out, const T* g
     if (rows == 0) return MF_OK;
     const RqsConst<T> C = make_rqs_const<T>(bound, slope);
     const int PW = 3 * K - 1;
+    // float64 with the soft clip: the lean exp2 sequence (MF_RQS64=0 keeps the library path, for A/B timing)
+    static const bool lean_on = [] { const char* e = getenv("MF_RQS64"); return !(e && e[0] == '0'); }();
+    const bool lean = sizeof(T) == 8 && lean_on && C.clip && (double)C.k1w < 1048576.0;
     {   // long rows: several threads per row. Thresholds from scripts/rqs_bwd_time.py sweeps on B200 (row bytes decide:
         // they set how many one-thread-per-row warps fit in shared memory). MF_RQS_BWD_LANES = 1/2/4/8 forces a variant.
         static const int forced = [] { const char* e = getenv("MF_RQS_BWD_LANES"); return e ? atoi(e) : 0; }();
@@ -515,9 +564,18 @@ static int rqs_bwd_launch(const T* phi, const T* vin, const T* g_out, const T* g
         int lanes = forced ? forced : (row_bytes < 420 ? 1 : (row_bytes < 700 ? 2 : (row_bytes < 2000 ? 4 : 8)));
         for (; lanes >= 2 && lanes <= 8; lanes *= 2) {   // a tile that does not fit: fewer rows per tile
             int rc = MF_E_SHAPE;
-            if (lanes == 2) rc = rqs_bwd_coop_launch<T, INV, 2>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
-            if (lanes == 4) rc = rqs_bwd_coop_launch<T, INV, 4>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
-            if (lanes == 8) rc = rqs_bwd_coop_launch<T, INV, 8>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
+            if constexpr (sizeof(T) == 8) {
+                if (lean) {
+                    if (lanes == 2) rc = rqs_bwd_coop_launch<T, INV, 2, true>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
+                    if (lanes == 4) rc = rqs_bwd_coop_launch<T, INV, 4, true>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
+                    if (lanes == 8) rc = rqs_bwd_coop_launch<T, INV, 8, true>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
+                    if (rc != MF_E_SHAPE) return rc;
+                    continue;
+                }
+            }
+            if (lanes == 2) rc = rqs_bwd_coop_launch<T, INV, 2, false>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
+            if (lanes == 4) rc = rqs_bwd_coop_launch<T, INV, 4, false>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
+            if (lanes == 8) rc = rqs_bwd_coop_launch<T, INV, 8, false>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
             if (rc != MF_E_SHAPE) return rc;
         }
     }
@@ -533,15 +591,20 @@ static int rqs_bwd_launch(const T* phi, const T* vin, const T* g_out, const T* g
     const int bulk_ok = (aligned(phi, 16) && aligned(g_phi, 16) && ((size_t)rpt * PW * sizeof(T)) % 16 == 0) ? 1 : 0;
     const size_t smem = need(rpt);
     const int64_t tiles = (rows + rpt - 1) / rpt;
-    auto kern = rqs_backward_kernel<T, INV>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    int ctas = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 128, smem);
-    if (ctas < 1) ctas = 1;
-    int64_t grid = (int64_t)sms * ctas;
-    if (grid > tiles) grid = tiles;
-    kern<<<(unsigned)grid, 128, smem, stream>>>(phi, vin, g_out, g_ladj, rows, K, C, rpt, bulk_ok, g_phi, g_v);
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int ctas = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 128, smem);
+        if (ctas < 1) ctas = 1;
+        int64_t grid = (int64_t)sms * ctas;
+        if (grid > tiles) grid = tiles;
+        kern<<<(unsigned)grid, 128, smem, stream>>>(phi, vin, g_out, g_ladj, rows, K, C, rpt, bulk_ok, g_phi, g_v);
+    };
+    if constexpr (sizeof(T) == 8) {
+        if (lean) { go(rqs_backward_kernel<T, INV, true>); return launch_status(); }
+    }
+    go(rqs_backward_kernel<T, INV, false>);
     return launch_status();
 }
 

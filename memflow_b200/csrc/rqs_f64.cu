@@ -30,35 +30,6 @@
 
 namespace mf {
 
-// ---- exp(soft_clip(a)) = 2^(a / (ln2 + |a| k1)), k1 = |f / log slope| ln2 (f = 2 widths / heights, 1 derivatives) ----
-// Error budget: reciprocal r0 (1 + e + e^2) is 2^-60 before its rounding, q = a * s carries <= 1 ulp, |q| <= 5 for
-// slope = 1e-3: relative error of the result <= ~6e-16 (measured against exp() of the IEEE quotient: tests).
-// 2^r on [-1/2, 1/2]: degree-11 minimax (Chebyshev fit in 60-digit arithmetic, |error| <= 3.2e-18), constant bank operands
-__constant__ double kExp2[12] = {1.0, 6.9314718055994530925e-1, 2.4022650695910159567e-1, 5.5504108664821627039e-2,
-                                 9.6181291075872566681e-3, 1.3333558146406470697e-3, 1.5403530463724354209e-4,
-                                 1.5252733841556772589e-5, 1.3215432535912376166e-6, 1.0178057087733941105e-7,
-                                 7.0741942972885210056e-9, 4.455817908336064493e-10};
-MF_D double exp2_clip(double a, double k1, double ln2, int& hi_abs_max) {
-    const int hi = __double2hiint(a) & 0x7fffffff;
-    hi_abs_max = max(hi_abs_max, hi);
-    const double bq = fma(fabs(a), k1, ln2);
-    const double r0 = rcp_seed(bq);                 // MUFU.RCP64H: 2^-20
-    const double e = fma(-bq, r0, 1.0);
-    const double t = fma(e, e, e);
-    const double s = fma(r0, t, r0);                // 1 / bq
-    const double q = a * s;
-    const double tk = q + 6755399441055744.0;       // 1.5 * 2^52: rint(q) in the low word
-    const double kd = tk - 6755399441055744.0;
-    const double r = q - kd;                        // exact, |r| <= 0.5
-    double p = kExp2[11];
-#pragma unroll
-    for (int i = 10; i >= 1; --i) p = fma(p, r, kExp2[i]);
-    p = fma(p, r, 1.0);
-    return __hiloint2double(__double2hiint(p) + (__double2loint(tk) << 20), __double2loint(p));
-}
-// parameters at or above 2^993 in magnitude, inf and NaN leave the fast sequence's domain
-constexpr int kHiAbsLimit = 0x7e000000;
-
 // exact path for such a segment, from the untouched global copy of the row (never taken for sane parameters)
 static __device__ __noinline__ double segment_exact(const double* __restrict__ g, double* __restrict__ r, int lo, int hi,
                                                     double two_over_L) {
@@ -117,7 +88,10 @@ struct Rqs64Args {
     size_t transform_pitch; // elements between phi[t] and phi[t+1]
     uint64_t seed, event_offset;
     RqsConst<double> C;
-    int F, K, T, ept, pitch /*shared-memory row pitch in elements*/, bulk_ok, chw /*chunk length*/, nsteps /*binary search*/;
+    int F, K, T;
+    int rows_per_tile;      // whole events (a multiple of F: per-event sums in the kernel) or any even count <= 256 / LANES
+    int whole_events;
+    int pitch /*shared-memory row pitch in elements*/, bulk_ok, chw /*chunk length*/, nsteps /*binary search*/;
 };
 
 template <bool INV, int LANES, bool PAIR, bool CHAIN>
@@ -136,14 +110,15 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int chunk = wid % LANES, group = wid / LANES, rr = group * 32 + lane;
     const bool evaluator = chunk == (group % LANES);   // the thread of the row that searches and evaluates (spread over the schedulers)
-    const int rows_per_tile = A.ept * F;
-    const int64_t num_tiles = (A.B + A.ept - 1) / A.ept;
-    const int64_t full_tiles = A.bulk_ok ? A.B / A.ept : 0;
+    const int rows_per_tile = A.rows_per_tile;
+    const int64_t total_rows = A.B * (int64_t)F;
+    const int64_t num_tiles = (total_rows + rows_per_tile - 1) / rows_per_tile;
+    const int64_t full_tiles = A.bulk_ok ? total_rows / rows_per_tile : 0;
     const size_t tile_elems = (size_t)rows_per_tile * PW;
     const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(double));
     const double Bd = C.bound, half_over_B = 0.5 / Bd;
     double* const r = sm + (size_t)rr * PWP;
-    const bool want_sum = A.ladj_sum != nullptr;
+    const bool want_sum = A.ladj_sum != nullptr && A.whole_events;
 
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncthreads();
@@ -155,10 +130,13 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
                 mbar_expect_tx(bar, tile_bytes);
                 bulk_g2s(sm, src, tile_bytes, bar);
             }
-        } else if (wid == 0) {
-            if (lane == 0) mbar_expect_tx(bar, tile_bytes);
-            __syncwarp();
-            for (int row = lane; row < rows_per_tile; row += 32)
+        } else {
+            // (a bulk copy is issued from uniform registers: the lanes of a warp take turns, so the rows are spread over
+            //  all 8 warps; complete_tx may overtake thread 0's expect_tx, the pending arrival keeps the phase open)
+            if (tid == 0) mbar_expect_tx(bar, tile_bytes);
+            const int per = (rows_per_tile + 7) >> 3;
+            const int row = wid * per + lane;
+            if (lane < per && row < rows_per_tile)
                 bulk_g2s(sm + (size_t)row * PWP, src + (size_t)row * PW, (uint32_t)(PW * sizeof(double)), bar);
         }
     };
@@ -167,16 +145,16 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
     if (tile < full_tiles) issue(tile, T - 1);
     for (; tile < num_tiles; tile += gridDim.x) {
         const bool bulk = tile < full_tiles;
-        const int64_t ev0 = tile * A.ept;
-        const int nev = (int)((A.B - ev0) < A.ept ? (A.B - ev0) : A.ept);
-        const int nrows = nev * F;
+        const int64_t row0 = tile * rows_per_tile;
+        const int nrows = (int)((total_rows - row0) < rows_per_tile ? (total_rows - row0) : rows_per_tile);
         const bool valid = rr < nrows;
-        const int64_t gi = ev0 * F + rr;
+        const int64_t gi = row0 + rr;
         double v = 0.0, ladj_acc = 0.0;
         if (evaluator && valid) {
             if constexpr (CHAIN) {   // base point: Philox counter = (global event index, feature block), key = seed
-                const int e = rr / F, f = rr - e * F;
-                const uint64_t gev = A.event_offset + (uint64_t)(ev0 + e);
+                const int64_t e = gi / F;
+                const int f = (int)(gi - e * F);
+                const uint64_t gev = A.event_offset + (uint64_t)e;
                 const Philox4 r4 = philox4x32_10((uint32_t)gev, (uint32_t)(gev >> 32), (uint32_t)(f >> 2), 0u, (uint32_t)A.seed,
                                                  (uint32_t)(A.seed >> 32));
                 const uint32_t bits = (f & 3) == 0 ? r4.x : ((f & 3) == 1 ? r4.y : ((f & 3) == 2 ? r4.z : r4.w));
@@ -305,7 +283,10 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
                 if constexpr (CHAIN) {
                     v = out;           // the next transform's input stays in this thread's register
                     ladj_acc += ladj;
-                    if (t == 0) A.vout[gi] = (out + Bd) * half_over_B;   // u = (x + B) / 2B
+                    if (t == 0) {
+                        A.vout[gi] = (out + Bd) * half_over_B;   // u = (x + B) / 2B
+                        if (A.ladj_out) A.ladj_out[gi] = ladj_acc;  // row tiles: the per-event sum is a second, tiny launch
+                    }
                 } else {
                     A.vout[gi] = out;
                     if (A.ladj_out) A.ladj_out[gi] = ladj;
@@ -317,16 +298,25 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
         if (want_sum) {   // sum over the F features of each event (AutoregressiveTransform), in feature order: deterministic
             if (evaluator && valid) lad[rr] = ladj_acc;
             __syncthreads();
-            if (tid < nev) {
+            if (tid * F < nrows) {
                 double s = 0.0;
                 for (int f = 0; f < F; ++f) s += lad[tid * F + f];
-                A.ladj_sum[ev0 + tid] = s;
+                A.ladj_sum[row0 / F + tid] = s;
             }
             // lad is rewritten only after the next tile's barriers
         }
     }
 }
 
+
+// sum over the F features of each event, in feature order (row tiles: events straddle tiles)
+__global__ void __launch_bounds__(256) rqs64_event_sum_kernel(const double* __restrict__ ladj, int64_t B, int F, double* __restrict__ out) {
+    const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ev >= B) return;
+    double s = 0.0;
+    for (int f = 0; f < F; ++f) s += __ldg(ladj + ev * F + f);
+    out[ev] = s;
+}
 
 template <bool INV, int LANES, bool PAIR, bool CHAIN>
 static int rqs64_go(Rqs64Args& A, size_t smem, int sms, cudaStream_t stream) {
@@ -336,7 +326,8 @@ static int rqs64_go(Rqs64Args& A, size_t smem, int sms, cudaStream_t stream) {
     int ctas = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 256, smem);
     if (ctas < 1) ctas = 1;
-    const int64_t num_tiles = (A.B + A.ept - 1) / A.ept;
+    const int64_t total_rows = A.B * (int64_t)A.F;
+    const int64_t num_tiles = (total_rows + A.rows_per_tile - 1) / A.rows_per_tile;
     int64_t grid = (int64_t)sms * ctas;
     if (grid > num_tiles) grid = num_tiles;
     kern<<<(unsigned)grid, 256, smem, stream>>>(A);
@@ -355,13 +346,14 @@ static int rqs64_pick(Rqs64Args& A, int lanes, bool pair, size_t smem, int sms, 
 #undef MF_GO
 }
 
-// Returns MF_E_SHAPE when the shape is outside this kernel (no soft clip, an event wider than a tile, a row that does
-// not fit shared memory): the caller then takes the general kernels of rqs_coop.cu / rqs.cu.
+// Returns MF_E_SHAPE when the shape is outside this kernel (no soft clip, a row that does not fit shared memory): the
+// caller then takes the general kernels of rqs_coop.cu / rqs.cu.
 int rqs64_launch(bool inverse, bool chain, const double* phi, const double* vin, int64_t B, int F, int K, int T, double bound,
                  double slope, uint64_t seed, uint64_t event_offset, double* vout, double* ladj, double* ladj_sum,
                  int32_t* bin, cudaStream_t stream) {
     static const bool enabled = [] { const char* e = getenv("MF_RQS64"); return !(e && e[0] == '0'); }();
     static const int forced = [] { const char* e = getenv("MF_RQS64_LANES"); return e ? atoi(e) : 0; }();
+    static const int tiles_env = [] { const char* e = getenv("MF_RQS64_TILES"); return e ? atoi(e) : 0; }();  // 1: whole events, 2: row tiles
     if (!enabled || !(slope > 0.0) || K < 1 || F < 1 || T < 1) return MF_E_SHAPE;
     Rqs64Args A{};
     A.C = make_rqs_const<double>(bound, slope);
@@ -382,27 +374,50 @@ int rqs64_launch(bool inverse, bool chain, const double* phi, const double* vin,
     int lanes = 0;
     for (int pass = 0; pass < 2 && !lanes; ++pass)   // first aim at 3 CTAs per SM, then at anything that fits
         for (int l = pref; l <= 8 && !lanes; l *= 2)
-            if (F <= 256 / l && need(l) <= (size_t)smem_max / (pass == 0 ? 3 : 1)) lanes = l;
+            if (need(l) <= (size_t)smem_max / (pass == 0 ? 3 : 1)) lanes = l;
     if (!lanes) return MF_E_SHAPE;
     const int rpt = 256 / lanes, hc = lanes >= 2 ? lanes / 2 : 1;
+    // Tiles of whole events keep the per-event log-det sum in the kernel; when the events pack a tile badly (F = 20 in
+    // 32 rows: 37 % of the lanes idle) or no sum is asked for, tiles are plain runs of rows and the sum is a second,
+    // tiny launch over 8 B per row.
+    const bool want_sum = ladj_sum != nullptr;
     int ept = rpt / F;
+    bool whole = want_sum && ept >= 1 && (double)(ept * F) >= 0.9 * rpt;
+    if (tiles_env == 1 && ept >= 1) whole = true;
+    if (tiles_env == 2) whole = false;
     A.transform_pitch = (size_t)B * F * PW;
     int bulk_ok = aligned(phi, 16) && (T == 1 || (A.transform_pitch * sizeof(double)) % 16 == 0) ? 1 : 0;
-    if (bulk_ok && pitch == PW && ((size_t)ept * F * PW * sizeof(double)) % 16 != 0) {  // one copy per tile: 16-byte multiples
-        int e = ept;
-        while (e > 0 && ((size_t)e * F * PW * sizeof(double)) % 16 != 0) --e;
-        if (e > 0) ept = e; else bulk_ok = 0;
+    int rows_per_tile = whole ? ept * F : rpt;
+    if (bulk_ok && pitch == PW && ((size_t)rows_per_tile * PW * sizeof(double)) % 16 != 0) {  // one copy per tile: 16-byte multiples
+        if (whole) {
+            int e = ept;
+            while (e > 0 && ((size_t)e * F * PW * sizeof(double)) % 16 != 0) --e;
+            if (e > 0) rows_per_tile = e * F; else bulk_ok = 0;
+        } else {
+            rows_per_tile -= 1;   // rpt is even
+        }
     }
-    A.phi = phi; A.vin = vin; A.vout = vout; A.ladj_out = ladj; A.ladj_sum = ladj_sum; A.bin_out = bin;
+    double* ladj_rows = ladj;
+    if (want_sum && !whole && !ladj_rows) {
+        if (cudaMallocAsync((void**)&ladj_rows, (size_t)B * F * sizeof(double), stream) != cudaSuccess) return -(int)cudaErrorMemoryAllocation;
+    }
+    A.phi = phi; A.vin = vin; A.vout = vout; A.ladj_out = ladj_rows; A.ladj_sum = ladj_sum; A.bin_out = bin;
     A.B = B; A.seed = seed; A.event_offset = event_offset;
-    A.F = F; A.K = K; A.T = T; A.ept = ept; A.pitch = pitch; A.bulk_ok = bulk_ok;
+    A.F = F; A.K = K; A.T = T; A.rows_per_tile = rows_per_tile; A.whole_events = whole ? 1 : 0; A.pitch = pitch; A.bulk_ok = bulk_ok;
     A.chw = (K + hc - 1) / hc;
     A.nsteps = 0;
     while ((1 << A.nsteps) < A.chw + 1) ++A.nsteps;
     const size_t smem = need(lanes);
-    if (chain) return rqs64_pick<true, true>(A, lanes, pair, smem, sms, stream);
-    return inverse ? rqs64_pick<true, false>(A, lanes, pair, smem, sms, stream)
-                   : rqs64_pick<false, false>(A, lanes, pair, smem, sms, stream);
+    int rc;
+    if (chain) rc = rqs64_pick<true, true>(A, lanes, pair, smem, sms, stream);
+    else rc = inverse ? rqs64_pick<true, false>(A, lanes, pair, smem, sms, stream)
+                      : rqs64_pick<false, false>(A, lanes, pair, smem, sms, stream);
+    if (rc == MF_OK && want_sum && !whole) {
+        rqs64_event_sum_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(ladj_rows, B, F, ladj_sum);
+        rc = launch_status();
+    }
+    if (ladj_rows != ladj) cudaFreeAsync(ladj_rows, stream);
+    return rc;
 }
 
 }  // namespace mf

@@ -47,6 +47,21 @@ if what in ("time", "all"):
             tag, n, T, F, K, N, ta, by * N / ta / 1e6, by * N / ta / 1e6 / HBM, tb, N / (ta + tb) * 1e3), flush=True)
         del phi
 
+if what in ("bwd", "all"):
+    tag = "rqs64=%s" % os.environ.get("MF_RQS64", "1")
+    for (B, F, K) in ((1 << 18, 10, 40), (1 << 18, 10, 35), (1 << 17, 20, 64), (1 << 20, 7, 10)):
+        phi = torch.randn(B, F, 3 * K - 1, device=dev, dtype=torch.float64, requires_grad=True)
+        x = (torch.rand(B, F, device=dev, dtype=torch.float64) * 2.6 - 1.3) * 1.1
+        y, l, ls = TR.rqs_forward(phi, x, bound=1.1)
+        loss = ls.sum()
+        def bwd():
+            phi.grad = None
+            loss.backward(retain_graph=True)
+        ms = timeit(bwd)
+        by = 2 * F * (3 * K - 1) * 8
+        print("bwd %s f64 F=%d K=%d B=%d: %.3f ms  %.0f GB/s  frac %.3f" % (tag, F, K, B, ms, by * B / ms / 1e6, by * B / ms / 1e6 / HBM), flush=True)
+        del phi, x, y, l, ls, loss
+
 if what in ("acc", "all"):
     from oracle import oracle as O
     O.build()
