@@ -49,6 +49,8 @@ typedef struct CUstream_st* mf_stream_t; /* == cudaStream_t */
 #define MF_FLAG_CUTS 4u            /* forward: apply cuts[3] = {pT_min, dR_min, |eta|_max} (:350-393) */
 #define MF_FLAG_X1X2_DIRECT 8u     /* uniform_x1x2=False: last two columns ARE x1,x2, no Jacobian (:229-234) */
 #define MF_FLAG_NO_CM_CHECK 16u    /* inverse: ensure_CM=False (:630) */
+#define MF_FLAG_ZERO_STATUS 32u    /* forward / inverse: *status is cleared (cudaMemsetAsync on the call's stream) before the \
+                                      launch, so the caller may hand in uninitialised memory */
 
 /* status bits written with atomicOr into *status (device int32, may be NULL) */
 #define MF_ST_NAN_INPUT 1 /* forward: a random variable was NaN (:191-199 raises) */

@@ -3,7 +3,7 @@ importance-sampling hot path, behind the reference's own Python API.
 
     from memflow_b200.phasespace.phasespace import PhaseSpace          # memflow.phasespace.phasespace
     from memflow_b200.transforms import MonotonicRQSTransform          # zuko.transforms
-    from memflow_b200.estimator import importance_weights, mc_estimate, ImportanceSampler
+    from memflow_b200.estimator import accumulate_weights, mc_estimate, ImportanceSampler
 
 All compute goes through hand-written CUDA kernels (memflow_b200/csrc) via the C ABI of
 include/memflow_b200.h. There is no CPU or PyTorch fallback.

@@ -123,7 +123,7 @@ is_chain_kernel(const float* __restrict__ phi, int64_t N, int T, int K, RqsConst
             rambo_forward_event<double, NF>(r, P, out, jac, x1, x2);
             const double target = inv_2s / (x1 * x2);  // 1 / (2 x1 x2 s): ME = pdf = 1
             const double w = target * jac / exp(logq);
-            if (target > 0.0 && jac == jac) { k1.add(w); k2.add(w * w); cnt += 1.0; }
+            if (target > 0.0 && jac == jac && isfinite(w)) { k1.add(w); k2.add(w * w); cnt += 1.0; }
             const int64_t ge = ev0 + tid;
             if (u_out) {
 #pragma unroll
@@ -373,7 +373,7 @@ rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, i
             [&](int j, const double (&p)[4]) { if (mo) st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, jac, x1, x2);
         const double target = inv_2s * rcp_fast(x1 * x2);  // 1 / (2 x1 x2 s): ME = pdf = 1
         const double w = target * jac * exp(-lq);
-        if (target > 0.0 && jac == jac) { k1.add(w); k2.add(w * w); cnt += 1.0; }
+        if (target > 0.0 && jac == jac && isfinite(w)) { k1.add(w); k2.add(w * w); cnt += 1.0; }
         if (weight) weight[ev] = jac;
         if (x1o) x1o[ev] = x1;
         if (x2o) x2o[ev] = x2;

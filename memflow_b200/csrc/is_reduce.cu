@@ -18,7 +18,9 @@ is_reduce_kernel(const double* __restrict__ target, const double* __restrict__ j
         const double t = target ? __ldg(target + i) : 1.0;
         const double j = __ldg(jac + i);
         const double w = t * j / exp(__ldg(logq + i));
-        if (t > 0.0 && j == j) {
+        // mask of notebook cells [35,43] (target > 0, Jacobian not NaN) and a FINITE weight: one NaN / inf log q must not
+        // poison the accumulators of a whole sharded run (n_valid would still look healthy)
+        if (t > 0.0 && j == j && isfinite(w)) {
             k1.add(w);
             k2.add(w * w);
             cnt += 1.0;

@@ -103,6 +103,7 @@ static int forward_dispatch(const T* u, int64_t N, int n, const T* masses, T e_c
     const size_t row_align = (W % 4 == 0) ? 4 * sizeof(T) : ((W % 2 == 0) ? 2 * sizeof(T) : sizeof(T));
     if (!aligned(u, row_align) || !aligned(momenta, 4 * sizeof(T))) return MF_E_ALIGN;
     if (N > (int64_t)0x7fffffff * 256) return MF_E_BADARG;
+    if ((flags & MF_FLAG_ZERO_STATUS) && status != nullptr) cudaMemsetAsync(status, 0, sizeof(int32_t), stream);
     switch (n) {
 #define MF_CASE(NF) \
     case NF: return launch_forward<T, NF>(u, N, masses, e_collider, cuts, flags, momenta, weight, logweight, x1, x2, status, stream);

@@ -363,6 +363,7 @@ static int inverse_dispatch(const T* momenta, int64_t event_stride, const T* x1,
     const size_t row_align = (W % 4 == 0) ? 4 * sizeof(T) : ((W % 2 == 0) ? 2 * sizeof(T) : sizeof(T));
     if (!aligned(momenta, 4 * sizeof(T)) || !aligned(ps, row_align)) return MF_E_ALIGN;
     if (N > (int64_t)0x7fffffff * 256) return MF_E_BADARG;
+    if ((flags & MF_FLAG_ZERO_STATUS) && status != nullptr) cudaMemsetAsync(status, 0, sizeof(int32_t), stream);
     switch (n) {
 #define MF_CASE(NF) \
     case NF: return launch_inverse<T, NF>(momenta, event_stride, x1, x2, N, order, masses, target_mass, e_collider, flags, ps, prob, logprob, status, stream);

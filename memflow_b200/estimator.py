@@ -1,6 +1,6 @@
 """Importance-sampling weight, Monte-Carlo estimator and the fused sampling chain (K5 + chain kernel).
 
-Reference: notebooks/TestFlows_ImportanceSampling.ipynb cells [50-54] (weights, I, sigma), mask of cells
+Reference: notebooks/TestFlows_ImportanceSampling.ipynb cells [50-54] (weights, I; sigma as in cell [54]), mask of cells
 [35,43]; notebooks/TestMadgraphChain.ipynb [19-24]. The reference has no module for this -- only notebook
 cells -- so the function names here are ours; the arithmetic is the notebook's.
 """
@@ -18,8 +18,9 @@ def new_accumulator(device):
 
 
 def accumulate_weights(target, rambo_jac, logq, acc=None):
-    """acc += (sum w, sum w^2, n_valid) with w = target * rambo_jac / exp(logq); valid = target > 0 and
-    rambo_jac not NaN. `target=None` means 1. Returns acc (device tensor; no host sync)."""
+    """acc += (sum w, sum w^2, n_valid) with w = target * rambo_jac / exp(logq); valid = target > 0, rambo_jac not
+    NaN (notebook cells [35,43]) and w finite (one bad log q must not turn a whole run's sums into NaN).
+    `target=None` means 1. Returns acc (device tensor; no host sync)."""
     require_cuda(rambo_jac, "rambo_jac")
     dev = rambo_jac.device
     jac = rambo_jac.detach().double().contiguous()

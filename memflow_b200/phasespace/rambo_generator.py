@@ -29,6 +29,7 @@ MF_FLAG_LAB_FRAME = 2
 MF_FLAG_CUTS = 4
 MF_FLAG_X1X2_DIRECT = 8
 MF_FLAG_NO_CM_CHECK = 16
+MF_FLAG_ZERO_STATUS = 32
 MF_ST_NAN_INPUT = 1
 MF_ST_NOT_CM = 2
 
@@ -118,6 +119,8 @@ class VirtualPhaseSpaceGenerator(object):
 
     def __init__(self, initial_masses, final_masses, collider_energy, pdf=None, pdf_active=False,
                  uniform_x1x2=True, lhapdf_dir=None, dev=None):
+        # `last_status` (device int32, bit-or of MF_ST_*) belongs to the most recent call made through THIS generator object:
+        # use one generator per stream / thread when calls overlap
         if dev is None:
             dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
         self.dev = torch.device(dev)
@@ -200,6 +203,43 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
                                              stream_ptr(v.device)), "mf_massvar_solve_f64")
         return u
 
+    def generateIntermediatesMassless_batch(self, M_t, E_cm, random_variables):
+        """Intermediate masses of a MASSLESS final state, on their own (:448-473): K_i = K_0 prod_{j<i} u_j with
+        u = bisect_vec_batch(random_variables[:, :n-2]) (the mass-variable kernel, mf_massvar_solve_f64), and the massless
+        volume get_flatWeights(E_cm, n). Returns (weight [N], K [N, n-1]). K1 has this fused in; the method exists for
+        callers of the reference's API. The volume stays float64 (the reference's tensor branch is float32, :132)."""
+        require_cuda(random_variables, "random_variables")
+        n = self.n_final
+        u = self.bisect_vec_batch(random_variables[:, : n - 2])
+        N = random_variables.shape[0]
+        ones = torch.ones(N, 1, dtype=torch.float64, device=M_t.device)
+        prod_u = torch.cumprod(torch.cat((ones, u), dim=1) if u is not None else ones, dim=1)
+        K = M_t[:, 0].unsqueeze(1).to(torch.float64) * prod_u
+        if not torch.is_tensor(E_cm) or E_cm.dim() == 0:
+            w = torch.full((N,), float(self.get_flatWeights(float(E_cm), n)), dtype=torch.float64, device=random_variables.device)
+        else:
+            w = self.get_flatWeights(E_cm.to(torch.float64), n)
+        return w, K
+
+    def generateIntermediatesMassive_batch(self, M, E_cm, random_variables):
+        """Intermediate masses of the MASSIVE final state and the massive / massless volume ratio (:475-509):
+        M_i = K_i + sum_{j>=i} m_j, weight = V_n(E) 8 rho(M_{n-2}, m_{n-1}, m_{n-2})
+        prod_{i<=n-3} [rho(M_i, M_{i+1}, m_i) / rho(K_i, K_{i+1}, 0)] (M_{i+1} / K_{i+1}) (K_0 / M_0)^(2n-4).
+        Returns (weight [N], M [N, n-1]); float64 throughout (the reference's in-place chain runs in float32)."""
+        n = self.n_final
+        masses = self.masses_t.to(device=M.device, dtype=torch.float64)
+        Mc = M.clone().to(torch.float64)
+        Mc[:, 0] -= masses.sum()
+        weight, K = self.generateIntermediatesMassless_batch(Mc, E_cm, random_variables)
+        weight = weight.clone()
+        msum = torch.flip(torch.cumsum(torch.flip(masses, (-1,)), -1), (-1,))
+        Mi = K + msum[:-1]
+        weight = weight * 8.0 * self.rho(Mi[:, n - 2], masses[n - 1], masses[n - 2])
+        weight = weight * torch.prod((self.rho(Mi[:, : n - 2], Mi[:, 1:], masses[: n - 2]) / self.rho(K[:, : n - 2], K[:, 1:], 0.0))
+                                     * (Mi[:, 1: n - 1] / K[:, 1: n - 1]), -1)
+        weight = weight * torch.pow(K[:, 0] / Mi[:, 0], 2 * n - 4)
+        return weight, Mi
+
     # ------------------------------------------------------------------ K1
     def generateKinematics_batch(self, random_variables_full, pT_mincut=-1, delR_mincut=-1, rap_maxcut=-1,
                                  pdgs=[0, 0], requires_grad=False, lab_frame=False, return_logweight=False):
@@ -245,8 +285,8 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         x1 = torch.empty(N, dtype=dt, device=dev)
         x2 = torch.empty(N, dtype=dt, device=dev)
         logw = torch.empty(N, dtype=dt, device=dev) if return_logweight else None
-        status = torch.zeros(1, dtype=torch.int32, device=dev)
-        flags = 0
+        status = torch.empty(1, dtype=torch.int32, device=dev)   # cleared inside the call (no fill launch)
+        flags = MF_FLAG_ZERO_STATUS
         if self.ref_fp32_quirks:
             flags |= MF_FLAG_REF_FP32_QUIRKS
         if not self.uniform_x1x2:
@@ -330,8 +370,8 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         ps = torch.empty((N, 3 * n - 2), dtype=dt, device=dev)
         prob = torch.empty(N, dtype=dt, device=dev)
         logp = torch.empty(N, dtype=dt, device=dev) if return_logprob else None
-        status = torch.zeros(1, dtype=torch.int32, device=dev)
-        flags = 0
+        status = torch.empty(1, dtype=torch.int32, device=dev)   # cleared inside the call (no fill launch)
+        flags = MF_FLAG_ZERO_STATUS
         if self.ref_fp32_quirks:
             flags |= MF_FLAG_REF_FP32_QUIRKS
         if not self.uniform_x1x2:

@@ -9,6 +9,7 @@ on-disk names as keys.
 import torch
 
 from ..phasespace.phasespace import PhaseSpace
+from ..phasespace.rambo_generator import MF_ST_NOT_CM
 
 M_HIGGS = 125.25
 M_TOP = 172.5
@@ -39,6 +40,11 @@ def phasespace_products(momenta_HttISR, boost, on_shell=True, E_CM=13000, masses
         x1 = (b[:, 0] + b[:, 3]) / E_CM
         x2 = (b[:, 0] - b[:, 3]) / E_CM
     ps, detjinv = ps_gen.get_ps_from_momenta(momenta_HttISR, x1, x2)
+    # The reference raises when the batch is not in the CM frame (rambo_generator.py:630-635); the kernel only sets a status
+    # bit. This is the offline caching path: one host sync is harmless, and lab-frame or mis-ordered momenta must not end up
+    # silently in cached ps / detjac tensors.
+    if int(ps_gen.generator.last_status.item()) & MF_ST_NOT_CM:
+        raise Exception("Momenta batch not in the CM, failing to convert back to PS point")
     out = {"phasespace_intermediateParticles" + suffix: ps,
            "phasespace_rambo_detjacobian" + suffix: detjinv}
     if on_shell:

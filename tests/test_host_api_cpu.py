@@ -142,6 +142,58 @@ def test_shard_and_chunk_ranges():
         shard_range(10, 2, 2)
 
 
+class _OracleSampler:
+    """CPU stand-in for ImportanceSampler.run_chunk (the oracle's estimator as the per-chunk engine): lets the host logic of
+    ShardedIntegrator (chunking, checkpoint / resume) run without a GPU."""
+
+    def __init__(self, jac, lq, seed=7):
+        self.jac, self.lq, self.seed, self.device, self.calls = jac, lq, seed, torch.device("cpu"), []
+
+    def run_chunk(self, phi, event_offset=0, acc=None):
+        from oracle import oracle as O
+        b, e = event_offset, event_offset + phi
+        self.calls.append((b, e))
+        acc += torch.from_numpy(O.is_reduce(None, self.jac[b:e], self.lq[b:e]))
+        return acc
+
+
+def test_restartable_accumulator(tmp_path, oracle):
+    """SURVEY section 5, checkpoint row: a run killed after some chunks and resumed from its state file processes every
+    chunk exactly once and ends on bit-identical accumulators; a state file of another run is refused."""
+    from memflow_b200.distributed import ShardedIntegrator
+    rng = np.random.default_rng(3)
+    n = 1000
+    jac, lq = rng.random(n) * 3, rng.standard_normal(n)
+    full = ShardedIntegrator(_OracleSampler(jac, lq), n, 128).run(lambda b, e: e - b, acc=torch.zeros(3, dtype=torch.float64))
+    path = str(tmp_path / "state.json")
+
+    class Killed(Exception):
+        pass
+
+    smp = _OracleSampler(jac, lq)
+
+    def provider(b, e):
+        if len(smp.calls) == 5:
+            raise Killed()
+        return e - b
+
+    it = ShardedIntegrator(smp, n, 128)
+    with pytest.raises(Killed):
+        it.run(provider, acc=torch.zeros(3, dtype=torch.float64), state_path=path, save_every=2)
+    assert os.path.exists(path) and len(smp.calls) == 5          # chunks 0..4 done, the last save was after chunk 3
+    smp2 = _OracleSampler(jac, lq)
+    res = ShardedIntegrator(smp2, n, 128).run(lambda b, e: e - b, acc=torch.zeros(3, dtype=torch.float64), state_path=path, save_every=2)
+    assert smp2.calls[0] == (512, 640) and smp2.calls[-1] == (896, 1000)   # resumed after the last SAVED chunk
+    assert torch.equal(res, full)                                   # bit-identical (hex-encoded doubles in the state file)
+    done = ShardedIntegrator(_OracleSampler(jac, lq), n, 128)
+    s3 = done.sampler
+    assert torch.equal(done.run(lambda b, e: e - b, acc=torch.zeros(3, dtype=torch.float64), state_path=path), full) and s3.calls == []
+    with pytest.raises(ValueError):                                 # another chunking: not this run's checkpoint
+        ShardedIntegrator(_OracleSampler(jac, lq), n, 100).run(lambda b, e: e - b, acc=torch.zeros(3, dtype=torch.float64), state_path=path)
+    with pytest.raises(ValueError):                                 # another seed
+        ShardedIntegrator(_OracleSampler(jac, lq, seed=8), n, 128).run(lambda b, e: e - b, acc=torch.zeros(3, dtype=torch.float64), state_path=path)
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

@@ -230,3 +230,34 @@ def test_decay_partons_match_reference(oracle, golden_dir):
         assert np.nanmax(decay_partons_scaled_err(out, ref, g["out_cart"], pep)) < 1e-12, name
     padded = np.abs(g["out_noscale"][:, 11, 0] - 0.001) < 1e-15
     assert padded.sum() >= 32 and (~padded).sum() >= 100  # both branches of :897-905 are in the fixture
+
+
+def test_spline_oracles_vs_high_precision_known_answers(oracle, golden_dir):
+    """Best-effort pin of the spline restatement (zuko is absent: "parity unpinned"): the C oracle and the torch restatement
+    against 50-digit mpmath evaluations of the closed form (Durkan et al. 2019 eqs. 4-8 + zuko's parameterisation),
+    tests/golden/make_rqs_known_answers.py. Bins exact; values to the conditioning of the case."""
+    import json
+    import torch
+    from oracle import rqs_torch
+    ka = json.load(open(os.path.join(golden_dir, "rqs_known_answers.json")))
+    assert len(ka["cases"]) == 4
+    for c in ka["cases"]:
+        K = len(c["widths"])
+        phi = np.array(c["widths"] + c["heights"] + c["derivatives"], dtype=np.float64)
+        P = len(c["points"])
+        x = np.array([p["x"] for p in c["points"]])
+        phib = np.broadcast_to(phi, (P, 1, 3 * K - 1)).copy()
+        ry, rl, rx, rli = (np.array([float(p[k]) for p in c["points"]]) for k in ("y", "ladj", "x_inv", "ladj_at_x_inv"))
+        rb, rbi = (np.array([p[k] for p in c["points"]]) for k in ("bin", "bin_inv"))
+        tol = 1e-14 if c["name"] != "K8_bound5_large_parameters" else 2e-12     # bins 1e-4 wide: 1 / width conditioning
+        t = rqs_torch.MonotonicRQSTransform(torch.from_numpy(phib[..., :K]), torch.from_numpy(phib[..., K:2 * K]),
+                                            torch.from_numpy(phib[..., 2 * K:]), bound=c["bound"], slope=c["slope"])
+        y, l = t.call_and_ladj(torch.from_numpy(x[:, None]))
+        xi = t._inverse(torch.from_numpy(x[:, None]))
+        assert np.abs(y.numpy()[:, 0] - ry).max() < tol and np.abs(l.numpy()[:, 0] - rl).max() < tol
+        assert np.abs(xi.numpy()[:, 0] - rx).max() < tol
+        oy, ol, ob = oracle.rqs_forward(phib, x[:, None], bound=c["bound"], slope=c["slope"])
+        ox, oli, obi = oracle.rqs_inverse(phib, x[:, None], bound=c["bound"], slope=c["slope"])
+        assert np.array_equal(ob[:, 0], rb) and np.array_equal(obi[:, 0], rbi)
+        assert np.abs(oy[:, 0] - ry).max() < tol and np.abs(ol[:, 0] - rl).max() < tol
+        assert np.abs(ox[:, 0] - rx).max() < tol and np.abs(oli[:, 0] - rli).max() < tol

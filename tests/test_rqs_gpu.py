@@ -106,6 +106,35 @@ def test_defining_properties_without_the_oracle(F, K, bound, slope):
     assert (np.diff(np.stack(ys, -1), axis=-1) > 0).all()              # strictly increasing
 
 
+def test_kernels_vs_high_precision_known_answers(golden_dir):
+    """The kernels against 50-digit mpmath evaluations of the closed form (tests/golden/make_rqs_known_answers.py):
+    independent of the oracle's arithmetic. Bins exact; fp64 to the conditioning of the case, fp32 at 1e-5."""
+    import json
+    from memflow_b200 import transforms as TR
+    ka = json.load(open(os.path.join(golden_dir, "rqs_known_answers.json")))
+    for c in ka["cases"]:
+        K = len(c["widths"])
+        phi = torch.tensor(c["widths"] + c["heights"] + c["derivatives"], dtype=torch.float64)
+        P = len(c["points"])
+        x = torch.tensor([p["x"] for p in c["points"]], dtype=torch.float64)
+        phib = phi.expand(P, 1, 3 * K - 1).contiguous()
+        ry, rl, rx, rli = (np.array([float(p[k]) for p in c["points"]]) for k in ("y", "ladj", "x_inv", "ladj_at_x_inv"))
+        rb, rbi = (np.array([p[k] for p in c["points"]]) for k in ("bin", "bin_inv"))
+        narrow = c["name"] == "K8_bound5_large_parameters"      # bins down to 1e-4 wide: 1 / width conditioning
+        y, l, _, b = TR.rqs_forward(phib.cuda(), x[:, None].cuda(), bound=c["bound"], slope=c["slope"], return_bins=True)
+        xi, li, _, bi = TR.rqs_inverse(phib.cuda(), x[:, None].cuda(), bound=c["bound"], slope=c["slope"], return_bins=True)
+        tol = 5e-12 if narrow else 2e-14
+        assert np.array_equal(b.cpu().numpy()[:, 0], rb) and np.array_equal(bi.cpu().numpy()[:, 0], rbi), c["name"]
+        assert np.abs(y.cpu().numpy()[:, 0] - ry).max() < tol and np.abs(l.cpu().numpy()[:, 0] - rl).max() < tol, c["name"]
+        assert np.abs(xi.cpu().numpy()[:, 0] - rx).max() < tol and np.abs(li.cpu().numpy()[:, 0] - rli).max() < tol, c["name"]
+        if narrow:
+            continue
+        y32, l32, _ = TR.rqs_forward(phib.float().cuda(), x[:, None].float().cuda(), bound=c["bound"], slope=c["slope"])
+        x64 = x.float().double().numpy()                        # the fp32 kernel sees the rounded input
+        moved = np.abs(x64 - x.numpy()) > 0
+        assert np.abs(y32.cpu().numpy()[:, 0] - ry)[~moved].max() < 1e-5 and np.abs(l32.cpu().numpy()[:, 0] - rl)[~moved].max() < 1e-4
+
+
 @pytest.mark.parametrize("F,K,bound", [(20, 64, 1.1), (7, 10, 1.0), (10, 40, 1.1)])
 def test_fp32_forward_inverse(oracle, F, K, bound):
     from memflow_b200 import transforms as TR
