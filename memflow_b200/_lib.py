@@ -41,6 +41,43 @@ class DecayPartonsCfg(ctypes.Structure):
 
 _lib = None
 
+#: C type -> ctypes type of the scalar arguments of the ABI; every pointer (device or host array, struct, stream) travels as
+#: c_void_p, which accepts None, integers, c_void_p, ctypes arrays and byref() results
+_CTYPES = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint32_t": ctypes.c_uint32,
+           "uint64_t": ctypes.c_uint64, "double": ctypes.c_double, "float": ctypes.c_float, "mf_stream_t": ctypes.c_void_p}
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "memflow_b200.h")
+
+
+def header_signatures(path=None):
+    """{symbol: (restype, [argtypes])} parsed from the declarations of include/memflow_b200.h -- the ONE table of the
+    boundary: the binding sets argtypes from it (a wrong argument count or width is a TypeError / ArgumentError instead of
+    silent memory corruption) and tests/test_abi_cpu.py checks the exports against it."""
+    import re
+    src = open(path or HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    src = re.sub(r"typedef\s+struct[^{;]*\{.*?\}[^;]*;", " ", src, flags=re.S)
+    src = " ".join(l for l in src.splitlines() if not l.lstrip().startswith("#") and "\\" not in l[-2:])
+    out = {}
+    for stmt in src.split(";"):
+        stmt = stmt.strip()
+        m = re.search(r"(mf_[a-z0-9_]+)\s*\((.*)\)\s*$", stmt, flags=re.S)
+        if not m:
+            continue
+        name, args = m.group(1), m.group(2)
+        ret = stmt[: m.start(1)]
+        restype = ctypes.c_char_p if "char" in ret else (ctypes.c_int64 if "int64_t" in ret else ctypes.c_int)
+        argtypes = []
+        for a in (x.strip() for x in args.split(",")):
+            if a in ("", "void"):
+                continue
+            if "*" in a:
+                argtypes.append(ctypes.c_void_p)
+                continue
+            toks = a.replace("const", " ").split()
+            argtypes.append(_CTYPES[toks[0]])
+        out[name] = (restype, argtypes)
+    return out
+
 
 def lib():
     """Load the shared library (once). Raises if it has not been built: there is no fallback path."""
@@ -57,6 +94,10 @@ def lib():
         for s in SYMBOLS:
             if s not in ("mf_error_string", "mf_is_reduce_workspace_bytes"):
                 getattr(L, s).restype = ctypes.c_int
+        if os.path.exists(HEADER_PATH):   # argument types of every entry point, from the header itself
+            for name, (restype, argtypes) in header_signatures().items():
+                f = getattr(L, name)
+                f.restype, f.argtypes = restype, argtypes
         _lib = L
     return _lib
 

@@ -9,6 +9,7 @@ import math
 
 import torch
 
+from . import ops  # noqa: F401  (registers torch.ops.memflow_b200.*)
 from ._lib import check, host_array, lib, ptr, reduce_workspace, require_cuda, stream_ptr
 
 
@@ -22,16 +23,9 @@ def accumulate_weights(target, rambo_jac, logq, acc=None):
     NaN (notebook cells [35,43]) and w finite (one bad log q must not turn a whole run's sums into NaN).
     `target=None` means 1. Returns acc (device tensor; no host sync)."""
     require_cuda(rambo_jac, "rambo_jac")
-    dev = rambo_jac.device
-    jac = rambo_jac.detach().double().contiguous()
-    lq = logq.detach().double().contiguous()
-    tg = None if target is None else target.detach().double().contiguous()
     if acc is None:
-        acc = new_accumulator(dev)
-    ws = reduce_workspace(dev)
-    with torch.cuda.device(dev):
-        check(lib().mf_is_reduce_f64(ptr(tg), ptr(jac), ptr(lq), ctypes.c_int64(jac.shape[0]), ptr(acc), ptr(ws),
-                                     stream_ptr(dev)), "mf_is_reduce_f64")
+        acc = new_accumulator(rambo_jac.device)
+    torch.ops.memflow_b200.is_reduce_(None if target is None else target.detach(), rambo_jac.detach(), logq.detach(), acc)
     return acc
 
 
@@ -74,6 +68,9 @@ class ImportanceSampler:
         """Stage A alone (mf_flow_sample_f32 / _f64 by the dtype of phi): u [N, F] float64 in [0,1] and log q(u) [N] of the
         flow's samples."""
         T, N, F, K = self._check_phi(phi)
+        if u is None and logq is None:   # the registered op (memflow_b200/ops.py) allocates the two outputs
+            return torch.ops.memflow_b200.flow_sample(phi.detach(), self.seed, int(event_offset), self.bound,
+                                                      float(self.slope) if self.slope is not None else 0.0)
         phi = phi.contiguous()
         dev = phi.device
         if u is None:
@@ -97,8 +94,10 @@ class ImportanceSampler:
         dev = u.device
         if acc is None:
             acc = new_accumulator(dev)
+        if not out:
+            torch.ops.memflow_b200.rambo_is_(u, logq, self.masses, self.collider_energy, acc)
+            return acc
         ws = reduce_workspace(dev)
-        out = out or {}
         with torch.cuda.device(dev):
             rc = lib().mf_rambo_is_f64(ptr(u), ptr(logq), ctypes.c_int64(u.shape[0]), ctypes.c_int(self.n_final),
                                        host_array(self.masses, ctypes.c_double), ctypes.c_double(self.collider_energy),

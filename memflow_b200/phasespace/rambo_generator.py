@@ -9,8 +9,9 @@ Deviations from the reference, all deliberate (DESIGN.md "Reference quirks"):
   * data-dependent raises (NaN scan :191-199, CM check :630-635) cost host syncs in the reference. Here
     they set bits in `generator.last_status` (device int32); `sync_errors=True` restores the raises.
   * CUDA tensors only: there is no CPU fallback.
-  * autograd: an input that requires grad goes through `_RamboForwardFn` (backward kernel with the reference graph's
-    gradient semantics); the inverse map (`getPSpoint_batch`, `get_PS`) is differentiable in `ps` (not in `prob`).
+  * autograd: K1 and K2 run as registered ops (torch.ops.memflow_b200.rambo_forward / rambo_inverse, memflow_b200/ops.py)
+    whose autograd formulas call the backward kernels: the forward map has the reference graph's gradient semantics; the
+    inverse map (`getPSpoint_batch`, `get_PS`) is differentiable in `ps` (not in `prob`).
 """
 import ctypes
 import math
@@ -18,6 +19,7 @@ import math
 import torch
 
 from .. import _lib
+from .. import ops  # noqa: F401  (registers torch.ops.memflow_b200.*)
 from .._lib import MemflowB200Error, check, host_array, lib, ptr, require_cuda, stream_ptr
 
 M_HIGGS = 125.25
@@ -38,40 +40,6 @@ class PhaseSpaceGeneratorError(Exception):
     pass
 
 
-class _RamboForwardFn(torch.autograd.Function):
-    """K1 with a backward (mf_rambo_forward_bwd_f64) that reproduces the gradient of the reference's autograd graph
-    (SURVEY 8f-4): zero for the mass-variable columns, the true Jacobian for the angle columns, and x1/x2 columns that
-    reach x1, x2, the weight and the incoming rows only."""
-
-    @staticmethod
-    def forward(ctx, points, gen):
-        u = points.detach().to(torch.float64).contiguous()
-        momenta, weight, x1, x2, _ = gen._launch_forward(u, torch.float64, -1, -1, -1, False, False)
-        ctx.save_for_backward(u, momenta, weight, x1, x2)
-        ctx.gen = gen
-        ctx.in_dtype = points.dtype
-        return momenta, weight, x1, x2
-
-    @staticmethod
-    def backward(ctx, g_mom, g_w, g_x1, g_x2):
-        u, momenta, weight, x1, x2 = ctx.saved_tensors
-        gen = ctx.gen
-
-        def c(t):
-            return None if t is None else t.detach().to(torch.float64).contiguous()
-
-        g_mom, g_w, g_x1, g_x2 = c(g_mom), c(g_w), c(g_x1), c(g_x2)
-        grad_u = torch.empty_like(u)
-        flags = 0 if gen.uniform_x1x2 else MF_FLAG_X1X2_DIRECT
-        with torch.cuda.device(u.device):
-            rc = lib().mf_rambo_forward_bwd_f64(
-                ptr(u), ptr(momenta), ptr(weight), ptr(x1), ptr(x2), ptr(g_mom), ptr(g_w), ptr(g_x1), ptr(g_x2),
-                ctypes.c_int64(u.shape[0]), ctypes.c_int(gen.n_final), host_array(gen._masses_host, ctypes.c_double),
-                ctypes.c_double(float(gen.collider_energy)), ctypes.c_uint32(flags), ptr(grad_u), stream_ptr(u.device))
-        check(rc, "mf_rambo_forward_bwd_f64")
-        return grad_u.to(ctx.in_dtype), None
-
-
 def _inverse_vjp(mom, x1, x2, g_ps, n, order, masses_host, target_host, permute_target, e_collider, flags, want_x):
     """mf_rambo_inverse_bwd_f64 on contiguous fp64 tensors; returns (g_momenta [N,n,4], g_x1, g_x2)."""
     dev = mom.device
@@ -88,30 +56,6 @@ def _inverse_vjp(mom, x1, x2, g_ps, n, order, masses_host, target_host, permute_
             ptr(g_x1), ptr(g_x2), stream_ptr(dev))
     check(rc, "mf_rambo_inverse_bwd_f64")
     return g_mom, g_x1, g_x2
-
-
-class _RamboInverseFn(torch.autograd.Function):
-    """K2 with a backward for `ps` (mf_rambo_inverse_bwd_f64); `prob` is returned as non-differentiable."""
-
-    @staticmethod
-    def forward(ctx, momenta, x1, x2, gen, order, target_host, ensure_CM):
-        mom = momenta.detach().to(torch.float64).contiguous()
-        x1c, x2c = x1.detach().to(torch.float64).contiguous(), x2.detach().to(torch.float64).contiguous()
-        ps, prob, _ = gen._launch_inverse(mom, x1c, x2c, order, target_host, ensure_CM, False)
-        ctx.save_for_backward(mom, x1c, x2c)
-        ctx.gen, ctx.order, ctx.target_host = gen, order, target_host
-        ctx.dtypes = (momenta.dtype, x1.dtype, x2.dtype)
-        ctx.mark_non_differentiable(prob)
-        return ps, prob
-
-    @staticmethod
-    def backward(ctx, g_ps, _g_prob):
-        mom, x1, x2 = ctx.saved_tensors
-        gen = ctx.gen
-        flags = 0 if gen.uniform_x1x2 else MF_FLAG_X1X2_DIRECT
-        g_mom, g_x1, g_x2 = _inverse_vjp(mom, x1, x2, g_ps.detach().to(torch.float64).contiguous(), gen.n_final, ctx.order,
-                                         gen._masses_host, ctx.target_host, False, gen.collider_energy, flags, True)
-        return (g_mom.to(ctx.dtypes[0]), g_x1.to(ctx.dtypes[1]), g_x2.to(ctx.dtypes[2]), None, None, None, None)
 
 
 class VirtualPhaseSpaceGenerator(object):
@@ -253,65 +197,36 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         assert random_variables_full.shape[1] - 2 == self.nDimPhaseSpace
         cuts_on = (pT_mincut > 0) or (delR_mincut > 0) or (rap_maxcut > 0)
         dt = self.compute_dtype
-        if torch.is_grad_enabled() and random_variables_full.requires_grad:
-            # differentiable path (the reference's requires_grad=True, scripts/run_model_labframe_sampling.py:432)
-            if cuts_on or lab_frame or dt != torch.float64 or self.ref_fp32_quirks:
-                raise MemflowB200Error("autograd through the phase-space map supports the plain fp64 CM-frame output only "
-                                       "(no cuts, no lab_frame, no fp32 compute / quirks)")
-            momenta, weight, x1, x2 = _RamboForwardFn.apply(random_variables_full, self)
-            if self.sync_errors and int(self.last_status.item()) & MF_ST_NAN_INPUT:
-                raise PhaseSpaceGeneratorError("Some of the random variables passed to the phase-space generator are NaN")
-            if return_logweight:
-                return momenta, weight, x1, x2, weight.log()
-            return momenta, weight, x1, x2
-        u = random_variables_full.detach().to(dt).contiguous()
-        momenta, weight, x1, x2, logw = self._launch_forward(u, dt, pT_mincut, delR_mincut, rap_maxcut, lab_frame,
-                                                             return_logweight)
-        if self.sync_errors and int(self.last_status.item()) & MF_ST_NAN_INPUT:
-            raise PhaseSpaceGeneratorError("Some of the random variables passed to the phase-space generator are NaN")
-        if dt != torch.float64:  # reference contract: outputs are float64
-            momenta, weight, x1, x2 = momenta.double(), weight.double(), x1.double(), x2.double()
-            logw = logw.double() if logw is not None else None
-        if return_logweight:
-            return momenta, weight, x1, x2, logw
-        return momenta, weight, x1, x2
-
-    def _launch_forward(self, u, dt, pT_mincut, delR_mincut, rap_maxcut, lab_frame, return_logweight):
-        """One K1 launch on a contiguous [N, 3n-2] tensor of dtype dt; returns (momenta, weight, x1, x2, logw)."""
-        dev = u.device
-        N, n = u.shape[0], self.n_final
-        momenta = torch.empty((N, n + 2, 4), dtype=dt, device=dev)
-        weight = torch.empty(N, dtype=dt, device=dev)
-        x1 = torch.empty(N, dtype=dt, device=dev)
-        x2 = torch.empty(N, dtype=dt, device=dev)
-        logw = torch.empty(N, dtype=dt, device=dev) if return_logweight else None
-        status = torch.empty(1, dtype=torch.int32, device=dev)   # cleared inside the call (no fill launch)
-        flags = MF_FLAG_ZERO_STATUS
+        if dt not in (torch.float64, torch.float32):
+            raise MemflowB200Error("compute_dtype must be torch.float64 or torch.float32")
+        needs_grad = torch.is_grad_enabled() and random_variables_full.requires_grad
+        if needs_grad and (cuts_on or lab_frame or dt != torch.float64 or self.ref_fp32_quirks):
+            # differentiable path = the reference's requires_grad=True (scripts/run_model_labframe_sampling.py:432)
+            raise MemflowB200Error("autograd through the phase-space map supports the plain fp64 CM-frame output only "
+                                   "(no cuts, no lab_frame, no fp32 compute / quirks)")
+        u = (random_variables_full if needs_grad else random_variables_full.detach()).to(dt)
+        flags = 0
         if self.ref_fp32_quirks:
             flags |= MF_FLAG_REF_FP32_QUIRKS
         if not self.uniform_x1x2:
             flags |= MF_FLAG_X1X2_DIRECT
         if lab_frame:
             flags |= MF_FLAG_LAB_FRAME
-        # the reference evaluates the cuts always; with the default -1 thresholds they cannot fire
-        cuts_on = (pT_mincut > 0) or (delR_mincut > 0) or (rap_maxcut > 0)
-        if cuts_on:
+        if cuts_on:   # the reference evaluates the cuts always; with the default -1 thresholds they cannot fire
             flags |= MF_FLAG_CUTS
-        if dt == torch.float64:
-            fn, ct = lib().mf_rambo_forward_f64, ctypes.c_double
-        elif dt == torch.float32:
-            fn, ct = lib().mf_rambo_forward_f32, ctypes.c_float
-        else:
-            raise MemflowB200Error("compute_dtype must be torch.float64 or torch.float32")
-        masses = host_array(self._masses_host, ct)
-        cuts = host_array([pT_mincut, delR_mincut, rap_maxcut], ct) if cuts_on else None
-        with torch.cuda.device(dev):
-            rc = fn(ptr(u), ctypes.c_int64(N), ctypes.c_int(n), masses, ct(float(self.collider_energy)), cuts,
-                    ctypes.c_uint32(flags), ptr(momenta), ptr(weight), ptr(logw), ptr(x1), ptr(x2), ptr(status),
-                    stream_ptr(dev))
-        check(rc, "mf_rambo_forward")
+        # ONE launch through the registered op (memflow_b200/ops.py): K1, its status word, autograd via the backward kernel
+        momenta, weight, x1, x2, logw, status = torch.ops.memflow_b200.rambo_forward(
+            u, self._masses_host, float(self.collider_energy),
+            [float(pT_mincut), float(delR_mincut), float(rap_maxcut)] if cuts_on else [], flags, bool(return_logweight))
         self.last_status = status
-        return momenta, weight, x1, x2, logw
+        if self.sync_errors and int(status.item()) & MF_ST_NAN_INPUT:
+            raise PhaseSpaceGeneratorError("Some of the random variables passed to the phase-space generator are NaN")
+        if dt != torch.float64:  # reference contract: outputs are float64
+            momenta, weight, x1, x2 = momenta.double(), weight.double(), x1.double(), x2.double()
+            logw = logw.double()
+        if return_logweight:
+            return momenta, weight, x1, x2, logw
+        return momenta, weight, x1, x2
 
     # ------------------------------------------------------------------ K2
     def getPSpoint_batch(self, momenta_batch, x1, x2, order=None, target_mass=None, ensure_CM=True,
@@ -334,63 +249,36 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
             if len(target_host) != n:
                 raise AssertionError("target_mass must hold n_final=%d masses ([n] or [1,n])" % n)
         dt = self.compute_dtype
-        needs_grad = torch.is_grad_enabled() and (momenta_batch.requires_grad or
-                                                  (torch.is_tensor(x1) and x1.requires_grad) or
-                                                  (torch.is_tensor(x2) and x2.requires_grad))
-        if needs_grad:
-            if dt != torch.float64 or self.ref_fp32_quirks:
-                raise MemflowB200Error("autograd through the inverse map supports fp64 compute without quirks only")
-            ps, prob = _RamboInverseFn.apply(momenta_batch, x1, x2, self, order, target_host, ensure_CM)
-            logp = prob.log() if return_logprob else None
-        else:
-            mom = momenta_batch.detach()
-            if mom.dtype != dt:
-                mom = mom.to(dt)
-            ps, prob, logp = self._launch_inverse(mom, x1.detach().to(dt).contiguous(), x2.detach().to(dt).contiguous(), order,
-                                                  target_host, ensure_CM, return_logprob)
-        if ensure_CM and self.sync_errors and int(self.last_status.item()) & MF_ST_NOT_CM:
-            raise Exception("Momenta batch not in the CM, failing to convert back to PS point")
-        if dt != torch.float64:
-            ps, prob = ps.double(), prob.double()
-            logp = logp.double() if logp is not None else None
-        if return_logprob:
-            return ps, prob, logp
-        return ps, prob
-
-    def _launch_inverse(self, mom, x1c, x2c, order, target_host, ensure_CM, return_logprob):
-        """One K2 launch; mom may be a strided [N, n, 4] view (e.g. forward_output[:, 2:]) that is read in place."""
-        dev = mom.device
-        n = self.n_final
-        dt = mom.dtype
-        esz = mom.element_size()
-        if not (mom.stride(2) == 1 and mom.stride(1) == 4 and mom.stride(0) % 4 == 0 and mom.stride(0) >= 4 * n
-                and mom.data_ptr() % (4 * esz) == 0):
-            mom = mom.contiguous()
-        N = mom.shape[0]
-        ps = torch.empty((N, 3 * n - 2), dtype=dt, device=dev)
-        prob = torch.empty(N, dtype=dt, device=dev)
-        logp = torch.empty(N, dtype=dt, device=dev) if return_logprob else None
-        status = torch.empty(1, dtype=torch.int32, device=dev)   # cleared inside the call (no fill launch)
-        flags = MF_FLAG_ZERO_STATUS
+        x1 = torch.as_tensor(x1, device=momenta_batch.device)
+        x2 = torch.as_tensor(x2, device=momenta_batch.device)
+        needs_grad = torch.is_grad_enabled() and (momenta_batch.requires_grad or x1.requires_grad or x2.requires_grad)
+        if needs_grad and (dt != torch.float64 or self.ref_fp32_quirks):
+            raise MemflowB200Error("autograd through the inverse map supports fp64 compute without quirks only")
+        mom = momenta_batch if needs_grad else momenta_batch.detach()
+        if mom.dtype != dt:
+            mom = mom.to(dt)
+        flags = 0
         if self.ref_fp32_quirks:
             flags |= MF_FLAG_REF_FP32_QUIRKS
         if not self.uniform_x1x2:
             flags |= MF_FLAG_X1X2_DIRECT
         if not ensure_CM:
             flags |= MF_FLAG_NO_CM_CHECK
-        if dt == torch.float64:
-            fn, ct = lib().mf_rambo_inverse_f64, ctypes.c_double
-        else:
-            fn, ct = lib().mf_rambo_inverse_f32, ctypes.c_float
-        masses = host_array(self._masses_host, ct)
-        tm = host_array(target_host, ct) if target_host is not None else None
-        with torch.cuda.device(dev):
-            rc = fn(ptr(mom), ctypes.c_int64(mom.stride(0)), ptr(x1c), ptr(x2c), ctypes.c_int64(N), ctypes.c_int(n),
-                    host_array(order, ctypes.c_int32), masses, tm, ct(float(self.collider_energy)),
-                    ctypes.c_uint32(flags), ptr(ps), ptr(prob), ptr(logp), ptr(status), stream_ptr(dev))
-        check(rc, "mf_rambo_inverse")
+        # ONE launch through the registered op: a strided [N, n, 4] view (e.g. forward_output[:, 2:]) is read in place;
+        # `ps` is differentiable w.r.t. the momenta and x1, x2 (backward kernel), `prob` carries no gradient
+        ps, prob, logp, status = torch.ops.memflow_b200.rambo_inverse(
+            mom, x1 if needs_grad else x1.detach(), x2 if needs_grad else x2.detach(), order, self._masses_host, target_host,
+            float(self.collider_energy), flags, bool(return_logprob))
+        if needs_grad:
+            prob, logp = prob.detach(), logp.detach()
         self.last_status = status
-        return ps, prob, logp
+        if ensure_CM and self.sync_errors and int(status.item()) & MF_ST_NOT_CM:
+            raise Exception("Momenta batch not in the CM, failing to convert back to PS point")
+        if dt != torch.float64:
+            ps, prob, logp = ps.double(), prob.double(), logp.double()
+        if return_logprob:
+            return ps, prob, logp
+        return ps, prob
 
     def setInitialStateMomenta_batch(self, output_momenta, E_cm):
         """Rows 0,1 <- (E/2, 0, 0, +-E/2) for massless beams (:511-551); in place, like the reference."""

@@ -7,95 +7,30 @@ memflow/unfolding_flow/custom_spline_flow_ps.py:16-33): `t(x)`, `t.inv(y)`, `t.c
 `t.log_abs_det_jacobian(x, y)`. The functional forms `rqs_forward / rqs_inverse` take the hyper-network
 output row `phi[B, F, 3K-1]` directly and also return the per-event sum of log-dets.
 
-Differentiable: when phi / the input require grad the calls go through `_RqsFn` (backward kernels
-mf_rqs_{forward,inverse}_bwd). CUDA tensors only.
+Every call goes through the registered op `torch.ops.memflow_b200.rqs` (memflow_b200/ops.py): differentiable in phi and in
+the input through the backward kernels (mf_rqs_{forward,inverse}_bwd), traceable with fake tensors. CUDA tensors
+only.
 """
 import ctypes
 
 import torch
 from torch.distributions import Transform, constraints
 
+from . import ops
 from ._lib import MemflowB200Error, check, lib, ptr, require_cuda, stream_ptr
 
 
-def _fn(direction, dtype):
-    if dtype == torch.float32:
-        return getattr(lib(), "mf_rqs_%s_f32" % direction), ctypes.c_float
-    if dtype == torch.float64:
-        return getattr(lib(), "mf_rqs_%s_f64" % direction), ctypes.c_double
-    raise MemflowB200Error("spline kernels support float32 / float64, got %s" % dtype)
-
-
-class _RqsFn(torch.autograd.Function):
-    """K3 / K4 with their backward kernels (mf_rqs_{forward,inverse}_bwd): differentiable in phi and in the input."""
-
-    @staticmethod
-    def forward(ctx, phi, v, direction, bound, slope):
-        phi_c = phi.detach().contiguous()
-        v_c = v.detach().to(phi_c.dtype).contiguous()
-        out, ladj, _, _ = _launch(direction, phi_c, v_c, bound, slope, True, False, False)
-        ctx.save_for_backward(phi_c, v_c)
-        ctx.cfg = (direction, bound, slope, v.dtype)
-        return out, ladj
-
-    @staticmethod
-    def backward(ctx, g_out, g_ladj):
-        phi, v = ctx.saved_tensors
-        direction, bound, slope, vdt = ctx.cfg
-        B, F, PW = phi.shape
-        K = (PW + 1) // 3
-        g_phi = torch.empty_like(phi)
-        g_v = torch.empty_like(v)
-        go = None if g_out is None else g_out.detach().to(phi.dtype).contiguous()
-        gl = None if g_ladj is None else g_ladj.detach().to(phi.dtype).contiguous()
-        suffix = "f32" if phi.dtype == torch.float32 else "f64"
-        ct = ctypes.c_float if phi.dtype == torch.float32 else ctypes.c_double
-        fn = getattr(lib(), "mf_rqs_%s_bwd_%s" % (direction, suffix))
-        with torch.cuda.device(phi.device):
-            rc = fn(ptr(phi), ptr(v), ptr(go), ptr(gl), ctypes.c_int64(B), ctypes.c_int(F), ctypes.c_int(K), ct(float(bound)),
-                    ct(float(slope) if slope is not None else 0.0), ptr(g_phi), ptr(g_v), stream_ptr(phi.device))
-        check(rc, "mf_rqs_%s_bwd" % direction)
-        return g_phi, g_v.to(vdt), None, None, None
-
-
 def _run(direction, phi, v, bound, slope, want_ladj=True, want_sum=False, want_bin=False):
+    """One call of the registered op memflow_b200::rqs (memflow_b200/ops.py: schema, fake implementation, autograd through
+    the backward kernels). CUDA tensors only."""
     require_cuda(phi, "phi")
     require_cuda(v, "x")
-    if torch.is_grad_enabled() and (phi.requires_grad or v.requires_grad):
-        if phi.dim() != 3 or v.shape != phi.shape[:2]:
-            raise AssertionError("phi must be [B, F, 3K-1] and x [B, F]")
-        out, ladj = _RqsFn.apply(phi, v, direction, bound, slope)
-        lsum = ladj.sum(dim=1) if want_sum else None
-        bins = None
-        if want_bin:
-            bins = _launch(direction, phi.detach().contiguous(), v.detach().to(phi.dtype).contiguous(), bound, slope, False,
-                           False, True)[3]
-        return out, (ladj if want_ladj else None), lsum, bins
-    return _launch(direction, phi.detach(), v.detach(), bound, slope, want_ladj, want_sum, want_bin)
-
-
-def _launch(direction, phi, v, bound, slope, want_ladj=True, want_sum=False, want_bin=False):
-    if phi.dim() != 3:
-        raise AssertionError("phi must be [B, F, 3K-1]")
-    B, F, PW = phi.shape
-    if (PW + 1) % 3 != 0:
-        raise AssertionError("last dim of phi must be 3K-1")
-    K = (PW + 1) // 3
-    if v.shape != (B, F):
-        raise AssertionError("x must be [B, F] = %s, got %s" % ((B, F), tuple(v.shape)))
-    phi = phi.detach().contiguous()
-    v = v.detach().to(phi.dtype).contiguous()
-    fn, ct = _fn(direction, phi.dtype)
-    out = torch.empty_like(v)
-    ladj = torch.empty_like(v) if want_ladj else None
-    lsum = torch.empty(B, dtype=phi.dtype, device=phi.device) if want_sum else None
-    bins = torch.empty((B, F), dtype=torch.int32, device=phi.device) if want_bin else None
-    with torch.cuda.device(phi.device):
-        rc = fn(ptr(phi), ptr(v), ctypes.c_int64(B), ctypes.c_int(F), ctypes.c_int(K), ct(float(bound)),
-                ct(float(slope) if slope is not None else 0.0), ptr(out), ptr(ladj), ptr(lsum), ptr(bins),
-                stream_ptr(phi.device))
-    check(rc, "mf_rqs_%s" % direction)
-    return out, ladj, lsum, bins
+    if phi.dtype not in (torch.float32, torch.float64):
+        raise MemflowB200Error("spline kernels support float32 / float64, got %s" % phi.dtype)
+    outputs = (ops.RQS_LADJ if want_ladj else 0) | (ops.RQS_SUM if want_sum else 0) | (ops.RQS_BINS if want_bin else 0)
+    out, ladj, lsum, bins = torch.ops.memflow_b200.rqs(phi, v, float(bound), float(slope) if slope is not None else 0.0,
+                                                       direction == "inverse", outputs)
+    return out, (ladj if want_ladj else None), (lsum if want_sum else None), (bins if want_bin else None)
 
 
 def rqs_forward(phi, x, bound=5.0, slope=1e-3, return_bins=False):
@@ -135,7 +70,7 @@ def _pack(widths, heights, derivatives):
     PW = 3 * K - 1
     es = widths.element_size()
     needs_grad = torch.is_grad_enabled() and (widths.requires_grad or heights.requires_grad or derivatives.requires_grad)
-    same = (not needs_grad and widths.dtype == heights.dtype == derivatives.dtype and widths.shape[:-1] == lead
+    same = (widths.dtype == heights.dtype == derivatives.dtype and widths.shape[:-1] == lead
             and heights.shape[:-1] == lead and derivatives.shape[:-1] == lead
             and widths.stride() == heights.stride() == derivatives.stride()
             and widths.stride(-1) == 1
@@ -153,7 +88,15 @@ def _pack(widths, heights, derivatives):
             rows = 1
             for s in lead:
                 rows *= s
-            return torch.as_strided(widths, (rows, 1, PW), (PW, PW, 1)), lead
+            if not needs_grad:
+                return torch.as_strided(widths, (rows, 1, PW), (PW, PW, 1)), lead
+            # under autograd the three tensors are views of ONE hyper-network output (zuko: unflatten + split): a view
+            # of that common base is the same memory and differentiable, so no concatenation copy on the way in and no
+            # split of the gradient on the way back
+            base = widths._base
+            if (base is not None and heights._base is base and derivatives._base is base and base.is_contiguous()
+                    and base.data_ptr() == widths.data_ptr() and base.numel() == rows * PW):
+                return base.view(rows, 1, PW), lead
     w = widths.expand(*lead, K)
     h = heights.expand(*lead, K)
     d = derivatives.expand(*lead, K - 1)

@@ -52,6 +52,15 @@ def conditioning(u, mom_ref, n, masses=None):
     return np.maximum(g2, 1.0) * k_angle * k_mass * k_thr
 
 
+def conditioning_fp32_weight(kappa, x1_ref, x2_ref, masses, e_collider):
+    """Extra factor for the LOG-WEIGHT in float32: x1, x2 = exp(-a) carry eps32 |a| relative error, so the available energy
+    K_0 = E_cm - sum m inherits eps32 |a| E_cm / K_0 and the weight ~ K_0^(2n-4) multiplies it by its exponent. (The same
+    factor exists in float64, where it stays far below 1e-12.)"""
+    ecm = np.sqrt(x1_ref * x2_ref) * e_collider
+    k0 = np.maximum(ecm - float(np.sum(masses)), 1e-300)
+    return kappa * (1.0 + ecm / k0)
+
+
 def summarize(err, tol, kappa=None):
     out = {"max": float(np.nanmax(err)), "p50": float(np.nanquantile(err, 0.5)),
            "p99": float(np.nanquantile(err, 0.99)), "frac_gt_tol": float((err > tol).mean())}

@@ -26,6 +26,28 @@ def test_library_exports_every_declared_symbol():
     assert L.mf_abi_version() == 1
 
 
+def test_argtypes_come_from_the_header():
+    """Every entry point carries argtypes parsed from include/memflow_b200.h (one table for the binding and this test): a
+    wrong argument count is a TypeError, a wrong kind an ArgumentError, instead of silent memory corruption."""
+    from memflow_b200 import _lib
+    L = _lib.lib()
+    sig = _lib.header_signatures()
+    assert sorted(sig) == header_symbols() == sorted(_lib.SYMBOLS)
+    for name, (restype, argtypes) in sig.items():
+        f = getattr(L, name)
+        assert f.restype is restype and list(f.argtypes or []) == argtypes, name
+    assert sig["mf_is_reduce_workspace_bytes"] == (ctypes.c_int64, [])
+    assert sig["mf_error_string"] == (ctypes.c_char_p, [ctypes.c_int])
+    assert sig["mf_rqs_forward_f32"][1] == [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                            ctypes.c_float] + [ctypes.c_void_p] * 5
+    assert sig["mf_is_chain_f64"][1][7:9] == [ctypes.c_uint64, ctypes.c_uint64]
+    with pytest.raises(TypeError):           # one argument short
+        L.mf_rqs_forward_f32(None, None, 0, 4, 500, 1.0, 1e-3, None, None, None, None)
+    with pytest.raises(ctypes.ArgumentError):  # a float where the event count goes
+        L.mf_rqs_forward_f32(None, None, 1.5, 4, 500, 1.0, 1e-3, None, None, None, None, None)
+    assert L.mf_rqs_forward_f32(None, None, 0, 4, 500, 1.0, 1e-3, None, None, None, None, None) == 4   # plain Python values
+
+
 def test_error_strings_and_host_side_validation():
     from memflow_b200 import _lib
     L = _lib.lib()

@@ -121,8 +121,13 @@ def test_config3_spline_fp32_1M_rows(oracle):
         e_l = np.abs(ladj.cpu().numpy() - l64)
         lim_out = 1e-5 + 8 * c_out
         # log J = 2 log s + ...: relative rounding of dx, dy (each a difference of two fp32-accurate cumulative sums) and of z
-        lim_l = 1e-5 + np.where(inside, 64 * eps32 * bound * (1 / dx + 1 / dy), 0.0)
+        # (a K-term float32 running sum carries up to ~K/2 eps32 of rounding into each knot, and log J has 2 log(dy / dx))
+        lim_l = 1e-5 + np.where(inside, 8 * K * eps32 * bound * (1 / dx + 1 / dy), 0.0)
         r_out, r_l = (e_out / lim_out)[ok], (e_l / lim_l)[ok]
+        o32, l32, b32 = orc(phi.numpy(), x.numpy(), bound=bound)        # the fp32 ORACLE (sequential float32, as torch computes)
+        ok32 = b32 == b64
+        print("config 3 inv=%s: fp32 oracle itself: ladj max/limit %.2f, out max/limit %.2f" % (
+            inverse, (np.abs(l32 - l64) / lim_l)[ok32].max(), (np.abs(o32 - o64) / lim_out)[ok32].max()))
         print("config 3 inv=%s: out p50 %.1e max %.1e (max/limit %.2f) | ladj p50 %.1e p99 %.1e max %.1e (max/limit %.2f, frac>1e-5 %.1e)"
               % (inverse, np.median(e_out), e_out[ok].max(), r_out.max(), np.median(e_l), np.quantile(e_l, 0.99), e_l[ok].max(),
                  r_l.max(), (e_l[ok] > 1e-5).mean()))
@@ -159,7 +164,9 @@ def test_config4_chain_1M_events(oracle):
         np.median(du), np.quantile(du, 0.999), du.max(), np.median(dq), np.quantile(dq, 0.99), dq.max()))
     assert np.median(du) < 2e-7 and np.quantile(du, 0.999) < 1e-4      # fp32 spline on both sides
     assert np.median(dq) < 2e-5 and np.quantile(dq, 0.99) < 2e-3
-    assert bool(((ug > 0) & (ug < 1)).all())
+    # the float32 spline may round a sample onto the edge of its domain (as the reference's float32 flow does): such
+    # events give a degenerate phase-space point whose weight the estimator's mask drops
+    assert bool(((ug >= 0) & (ug <= 1)).all()) and ((ug == 0) | (ug == 1)).any(axis=1).mean() < 1e-4
     om, ow, ox1, ox2 = oracle.rambo_forward(ug, masses, E)             # fp64 part: the oracle on the kernel's own u
     kappa = parity.conditioning(ug, om, n, masses)
     err = parity.momenta_error(out["momenta"].cpu().numpy(), om, ox1, ox2, E)

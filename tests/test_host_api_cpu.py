@@ -129,6 +129,56 @@ def test_utils_match_oracle_math(oracle):
     assert float(U.mass_t(lab[:, 2])) == pytest.approx(float(U.mass_t(mom[:, 2])), rel=1e-12)
 
 
+def test_registered_ops_have_schemas_fake_kernels_and_no_cpu_backend():
+    """torch.library layer (memflow_b200/ops.py): every op carries a schema and a fake implementation (shape propagation on
+    meta tensors, no GPU needed), the differentiable ones an autograd formula, and there is NO CPU kernel to fall back to."""
+    from memflow_b200 import ops
+    for name in ops.OPS:
+        assert hasattr(torch.ops.memflow_b200, name)
+    phi = torch.empty(4, 3, 29, device="meta")
+    x = torch.empty(4, 3, device="meta")
+    out, ladj, lsum, bins = torch.ops.memflow_b200.rqs(phi, x, 1.0, 1e-3, False, ops.RQS_LADJ | ops.RQS_SUM | ops.RQS_BINS)
+    assert out.shape == ladj.shape == bins.shape == (4, 3) and lsum.shape == (4,) and bins.dtype == torch.int32
+    out, ladj, lsum, bins = torch.ops.memflow_b200.rqs(phi, x, 1.0, 1e-3, True, 0)
+    assert out.shape == (4, 3) and ladj.numel() == lsum.numel() == bins.numel() == 0
+    u = torch.empty(5, 7, device="meta", dtype=torch.float64)
+    mom, w, x1, x2, lw, st = torch.ops.memflow_b200.rambo_forward(u, [125.25, 172.5, 172.5], 13000.0, [], 0, True)
+    assert mom.shape == (5, 5, 4) and w.shape == x1.shape == x2.shape == lw.shape == (5,) and st.dtype == torch.int32
+    ps, prob, lp, st = torch.ops.memflow_b200.rambo_inverse(mom[:, 2:], x1, x2, [0, 1, 2], [125.25, 172.5, 172.5], None, 13000.0, 0, False)
+    assert ps.shape == (5, 7) and prob.shape == (5,) and lp.numel() == 0
+    uu, lq = torch.ops.memflow_b200.flow_sample(torch.empty(2, 8, 7, 29, device="meta"), 1, 0, 1.0, 1e-3)
+    assert uu.shape == (8, 7) and lq.shape == (8,) and uu.dtype == torch.float64
+    # autograd formulas are registered: gradients propagate through the fake kernels
+    phi_g = torch.empty(4, 3, 29, device="meta", requires_grad=True)
+    out, ladj, lsum, _ = torch.ops.memflow_b200.rqs(phi_g, x, 1.0, 1e-3, False, ops.RQS_LADJ | ops.RQS_SUM)
+    (out.sum() + lsum.sum()).backward()
+    assert phi_g.grad.shape == phi_g.shape
+    ug = torch.empty(5, 7, device="meta", dtype=torch.float64, requires_grad=True)
+    mom = torch.ops.memflow_b200.rambo_forward(ug, [125.25, 172.5, 172.5], 13000.0, [], 0, False)[0]
+    mom.sum().backward()
+    assert ug.grad.shape == ug.shape
+    # no CPU backend: the dispatcher refuses
+    with pytest.raises(NotImplementedError, match="CPU"):
+        torch.ops.memflow_b200.rqs(torch.zeros(4, 3, 29), torch.zeros(4, 3), 1.0, 1e-3, False, 0)
+    with pytest.raises(NotImplementedError, match="CPU"):
+        torch.ops.memflow_b200.rambo_forward(torch.zeros(5, 7, dtype=torch.float64), [1.0, 2.0, 3.0], 13000.0, [], 0, False)
+
+
+def test_transform_packing_is_zero_copy_also_under_autograd():
+    """zuko hands the univariate transform three split views of ONE hyper-network output: the parameter block is used in
+    place, with and without autograd (a view of the common base: no torch.cat on the way in, no gradient split back)."""
+    from memflow_b200 import transforms as TR
+    B, F, K = 6, 3, 5
+    hyper = torch.randn(B, F * (3 * K - 1), requires_grad=True) * 1.0        # non-leaf, like a network output
+    w, h, d = hyper.unflatten(-1, (F, 3 * K - 1)).split([K, K, K - 1], dim=-1)
+    p, lead = TR._pack(w, h, d)
+    assert p.shape == (B * F, 1, 3 * K - 1) and tuple(lead) == (B, F) and p.data_ptr() == hyper.data_ptr() and p.requires_grad
+    p2, _ = TR._pack(w.detach(), h.detach(), d.detach())
+    assert p2.data_ptr() == hyper.data_ptr() and not p2.requires_grad
+    p3, _ = TR._pack(w.clone(), h.clone(), d.clone())                          # separate tensors: one concatenation
+    assert p3.data_ptr() != hyper.data_ptr() and p3.requires_grad and torch.equal(p3.detach().reshape(B, F, -1), hyper.detach().reshape(B, F, -1))
+
+
 def test_shard_and_chunk_ranges():
     from memflow_b200.distributed import chunk_ranges, shard_range
     for n_total in (0, 1, 7, 10 ** 10, 12345678901):

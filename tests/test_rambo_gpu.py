@@ -301,7 +301,8 @@ def test_fp32_kernels(oracle):
         print("fp32 forward n=%d momenta" % n, s)
         assert s["max_over_kappa"] < 1e-5 and s["p99"] < 1e-5 and s["p50"] < 2e-7, s
         dl = np.abs(np.log(w.cpu().numpy()) - np.log(ow))
-        sl = parity.summarize(dl, 1e-5, kappa)
+        # log-weight: the float32 rounding of x1, x2 is amplified by E_cm / (E_cm - sum m) (parity.conditioning_fp32_weight)
+        sl = parity.summarize(dl, 1e-5, parity.conditioning_fp32_weight(kappa, ox1, ox2, MASSES[n], E))
         print("fp32 forward n=%d ln w" % n, sl)
         assert sl["max_over_kappa"] < 1e-5 and sl["p50"] < 1e-5 and sl["frac_gt_tol"] < 0.05, sl
         for a, b in ((x1, ox1), (x2, ox2)):
