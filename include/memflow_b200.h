@@ -161,6 +161,21 @@ int mf_rqs_inverse_f32(const float* phi, const float* y, int64_t B, int F, int K
                        float* x, float* ladj, float* ladj_sum, int32_t* bin, mf_stream_t stream);
 int mf_rqs_inverse_f64(const double* phi, const double* y, int64_t B, int F, int K, double bound, double slope,
                        double* x, double* ladj, double* ladj_sum, int32_t* bin, mf_stream_t stream);
+/* K3 / K4 on a FEATURE SUBSET of a wider parameter tensor, read in place: phi points at the subset's first row, the F rows of
+ * an event are contiguous and consecutive events are event_stride ELEMENTS apart (event_stride >= F (3K-1); equality = the
+ * calls above). This is what an autoregressive sampler needs: pass j of zuko's MaskedAutoregressiveTransform inverse
+ * (call sites memflow/unfolding_flow/unfolding_flow.py:97,186) determines feature j only, so it has to read 3K-1 of the
+ * event's F_total (3K-1) parameters -- phi + j (3K-1), F = 1, event_stride = F_total (3K-1) -- instead of all of them.
+ * x / y / ladj / bin are packed [B, F]. */
+int mf_rqs_forward_strided_f32(const float* phi, int64_t event_stride, const float* x, int64_t B, int F, int K, float bound,
+                               float slope, float* y, float* ladj, float* ladj_sum, int32_t* bin, mf_stream_t stream);
+int mf_rqs_forward_strided_f64(const double* phi, int64_t event_stride, const double* x, int64_t B, int F, int K, double bound,
+                               double slope, double* y, double* ladj, double* ladj_sum, int32_t* bin, mf_stream_t stream);
+int mf_rqs_inverse_strided_f32(const float* phi, int64_t event_stride, const float* y, int64_t B, int F, int K, float bound,
+                               float slope, float* x, float* ladj, float* ladj_sum, int32_t* bin, mf_stream_t stream);
+int mf_rqs_inverse_strided_f64(const double* phi, int64_t event_stride, const double* y, int64_t B, int F, int K, double bound,
+                               double slope, double* x, double* ladj, double* ladj_sum, int32_t* bin, mf_stream_t stream);
+
 /* Vector-Jacobian products of K3 / K4: from the cotangents g_out [B,F] of the output and g_ladj [B,F] of the
  * per-element log-det (either may be NULL = zero; for a cotangent of ladj_sum broadcast it over F), the gradients
  * g_phi [B,F,3K-1] w.r.t. the unconstrained parameters and g_in [B,F] w.r.t. the input, through soft clip, softmax, cumsum,

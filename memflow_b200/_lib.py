@@ -16,6 +16,7 @@ SYMBOLS = (
     "mf_abi_version", "mf_error_string", "mf_device_info",
     "mf_rambo_forward_f64", "mf_rambo_forward_f32", "mf_massvar_solve_f64", "mf_rambo_forward_bwd_f64", "mf_rambo_inverse_bwd_f64", "mf_rambo_inverse_f64", "mf_rambo_inverse_f32", "mf_get_ps_f64",
     "mf_rqs_forward_f32", "mf_rqs_forward_f64", "mf_rqs_inverse_f32", "mf_rqs_inverse_f64",
+    "mf_rqs_forward_strided_f32", "mf_rqs_forward_strided_f64", "mf_rqs_inverse_strided_f32", "mf_rqs_inverse_strided_f64",
     "mf_searchsorted_f32", "mf_searchsorted_f64",
     "mf_rqs_forward_bwd_f32", "mf_rqs_forward_bwd_f64", "mf_rqs_inverse_bwd_f32", "mf_rqs_inverse_bwd_f64",
     "mf_is_reduce_workspace_bytes", "mf_is_reduce_f64", "mf_is_chain_f64", "mf_flow_sample_f32", "mf_flow_sample_f64", "mf_rambo_is_f64", "mf_higgs_decay_f64", "mf_top_decay_f64",
@@ -94,10 +95,12 @@ def lib():
         for s in SYMBOLS:
             if s not in ("mf_error_string", "mf_is_reduce_workspace_bytes"):
                 getattr(L, s).restype = ctypes.c_int
-        if os.path.exists(HEADER_PATH):   # argument types of every entry point, from the header itself
-            for name, (restype, argtypes) in header_signatures().items():
-                f = getattr(L, name)
-                f.restype, f.argtypes = restype, argtypes
+        if not os.path.exists(HEADER_PATH):
+            raise MemflowB200Error("memflow_b200: %s not found: the binding takes the argument types of every entry point from "
+                                   "the header (device pointers travel as plain integers)" % HEADER_PATH)
+        for name, (restype, argtypes) in header_signatures().items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = restype, argtypes
         _lib = L
     return _lib
 
@@ -108,17 +111,56 @@ def check(rc, what):
 
 
 def ptr(t):
-    """Device pointer of a CUDA tensor (None -> NULL)."""
+    """Device pointer of a CUDA tensor (None -> NULL), as the int / None the c_void_p argtypes of the binding accept."""
     if t is None:
-        return ctypes.c_void_p(0)
+        return None
     if not t.is_cuda:
         raise MemflowB200Error("memflow_b200 kernels need CUDA tensors (got device %s); there is no CPU fallback"
                                % t.device)
-    return ctypes.c_void_p(t.data_ptr())
+    return t.data_ptr()
 
 
 def stream_ptr(device):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """Raw cudaStream_t of torch's current stream on `device` (an int: the bound argtype is c_void_p)."""
+    idx = device.index
+    return torch._C._cuda_getCurrentRawStream(idx if idx is not None else torch.cuda.current_device())
+
+
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device):
+    """`with device_guard(dev):` makes `dev` the current CUDA device for the launch -- a no-op object when it already is
+    (torch.cuda.device costs several microseconds per call; training calls the kernels with B ~ 1e3)."""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
+def needs_dispatcher(*tensors):
+    """True when a call has to go through the registered torch op (memflow_b200/ops.py) rather than straight to the C ABI:
+    autograd is recording for one of the tensors, torch.compile is tracing, or a tensor is not a plain torch.Tensor
+    (FakeTensor, functorch wrappers...). Plain eager inference calls skip the dispatcher's ~15 us."""
+    if torch.compiler.is_compiling():
+        return True
+    grad = torch.is_grad_enabled()
+    for t in tensors:
+        if t is None:
+            continue
+        if type(t) is not torch.Tensor and type(t) is not torch.nn.Parameter:
+            return True
+        if grad and t.requires_grad:
+            return True
+    return False
 
 
 def host_array(values, ctype):

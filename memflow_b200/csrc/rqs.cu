@@ -21,7 +21,7 @@ template <typename T, bool INV, int LANES>
 __global__ void __launch_bounds__(kRqsThreads)
 rqs_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t B, int F, int K, RqsConst<T> C,
            int ept /*events per tile*/, int stages, int bulk_ok, T* __restrict__ vout, T* __restrict__ ladj_out,
-           T* __restrict__ ladj_sum, int32_t* __restrict__ bin_out) {
+           T* __restrict__ ladj_sum, int32_t* __restrict__ bin_out, int64_t event_stride /*elements between events*/) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int PW = 3 * K - 1;
     const int rows_per_tile = ept * F;
@@ -63,10 +63,18 @@ rqs_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t B, int 
         if (tile_is_bulk(tile)) {
             mbar_wait(&bars[st], st ? parity1 : parity0);
             if (st) parity1 ^= 1u; else parity0 ^= 1u;
-        } else {  // ragged last tile or unaligned phi: plain cooperative copy
+        } else if (event_stride == (int64_t)F * PW) {  // ragged last tile or unaligned phi: plain cooperative copy
             const T* src = phi + (size_t)tile * tile_elems;
             const size_t ne = (size_t)nrows * PW;
             for (size_t i = tid; i < ne; i += kRqsThreads) sm[i] = __ldg(src + i);
+            __syncthreads();
+        } else {  // a feature subset of a wider parameter tensor (autoregressive sampling passes): the F rows of an event are
+                  // contiguous, events are event_stride elements apart
+            const int epw = F * PW;
+            for (int e = 0; e < nev; ++e) {
+                const T* src = phi + (size_t)(ev0 + e) * event_stride;
+                for (int i = tid; i < epw; i += kRqsThreads) sm[e * epw + i] = __ldg(src + i);
+            }
             __syncthreads();
         }
 
@@ -238,15 +246,18 @@ searchsorted_kernel(const T* __restrict__ knots, const T* __restrict__ v, int64_
 
 template <typename T, bool INV>
 static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bound, T slope, T* vout, T* ladj,
-                      T* ladj_sum, int32_t* bin, cudaStream_t stream) {
+                      T* ladj_sum, int32_t* bin, cudaStream_t stream, int64_t event_stride = 0) {
     if (B < 0 || F < 1 || K < 1) return MF_E_SHAPE;
     if (K > 128) return MF_E_SHAPE;
     if (B > 0 && (!phi || !vin || !vout)) return MF_E_BADARG;
     if (B == 0) return MF_OK;
     const int PW = 3 * K - 1;
     const size_t row_bytes = (size_t)PW * sizeof(T);
+    if (event_stride == 0) event_stride = (int64_t)F * PW;
+    if (event_stride < (int64_t)F * PW) return MF_E_SHAPE;
+    const bool strided = event_stride != (int64_t)F * PW;   // a feature subset: only the kernels with a row-wise copy path
     if constexpr (sizeof(T) == 4) {
-        if ((K == 32 || K == 40 || K == 48 || K == 64) && F <= 64) {
+        if (!strided && (K == 32 || K == 40 || K == 48 || K == 64) && F <= 64) {
             int dev = 0, sms = 148, smem_max = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -285,10 +296,11 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
         }
     }
     if constexpr (sizeof(T) == 8) {   // float64 with the soft clip: rqs_f64.cu
-        const int rc = rqs64_launch(INV, false, phi, vin, B, F, K, 1, bound, slope, 0, 0, vout, ladj, ladj_sum, bin, stream);
+        const int rc = rqs64_launch(INV, false, phi, vin, B, F, K, 1, bound, slope, 0, 0, vout, ladj, ladj_sum, bin, stream,
+                                    event_stride);
         if (rc != MF_E_SHAPE) return rc;
     }
-    {   // every other shape (fp64 without the clip, fp32 with bin counts the register kernels do not cover): several threads per
+    if (!strided) {   // every other shape (fp64 without the clip, fp32 with bin counts the register kernels do not cover): several threads per
         // row (rqs_coop.cu). MF_RQS_COOP=0 keeps the generic kernel below, for A/B timing.
         static const bool coop = [] { const char* e = getenv("MF_RQS_COOP"); return !(e && e[0] == '0'); }();
         if (coop) {
@@ -313,7 +325,7 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
     if (need(ept, 2) > (size_t)smem_max) stages = 1;
     if (need(ept, stages) > (size_t)smem_max) return MF_E_SHAPE;
     // tile byte size must be a multiple of 16 for the bulk copy; shrink ept until it is (or give up bulk)
-    int bulk_ok = aligned(phi, 16) ? 1 : 0;
+    int bulk_ok = (aligned(phi, 16) && !strided) ? 1 : 0;
     if (bulk_ok) {
         int e = ept;
         while (e > 0 && ((size_t)e * F * row_bytes) % 16 != 0) --e;
@@ -331,7 +343,7 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         kern<<<(unsigned)grid, kRqsThreads, smem, stream>>>(phi, vin, B, F, K, C, ept, stages, bulk_ok, vout, ladj,
-                                                            ladj_sum, bin);
+                                                            ladj_sum, bin, event_stride);
     };
     if (lanes == 2) go(rqs_kernel<T, INV, 2>); else go(rqs_kernel<T, INV, 1>);
     return launch_status();
@@ -362,6 +374,25 @@ extern "C" int mf_rqs_inverse_f32(const float* phi, const float* y, int64_t B, i
 extern "C" int mf_rqs_inverse_f64(const double* phi, const double* y, int64_t B, int F, int K, double bound,
                                   double slope, double* x, double* ladj, double* ladj_sum, int32_t* bin, mf_stream_t s) {
     return mf::rqs_launch<double, true>(phi, y, B, F, K, bound, slope, x, ladj, ladj_sum, bin, (cudaStream_t)s);
+}
+// K3 / K4 on a FEATURE SUBSET of a wider parameter tensor: the F rows of an event are contiguous, consecutive events are
+// event_stride elements apart (phi points at the subset's first row). What an autoregressive sampler needs: pass j of
+// MaskedAutoregressiveTransform._inverse determines feature j only, i.e. 3K-1 of the event's F_total (3K-1) parameters.
+extern "C" int mf_rqs_forward_strided_f32(const float* phi, int64_t event_stride, const float* x, int64_t B, int F, int K, float bound,
+                                          float slope, float* y, float* ladj, float* ladj_sum, int32_t* bin, mf_stream_t s) {
+    return mf::rqs_launch<float, false>(phi, x, B, F, K, bound, slope, y, ladj, ladj_sum, bin, (cudaStream_t)s, event_stride);
+}
+extern "C" int mf_rqs_forward_strided_f64(const double* phi, int64_t event_stride, const double* x, int64_t B, int F, int K, double bound,
+                                          double slope, double* y, double* ladj, double* ladj_sum, int32_t* bin, mf_stream_t s) {
+    return mf::rqs_launch<double, false>(phi, x, B, F, K, bound, slope, y, ladj, ladj_sum, bin, (cudaStream_t)s, event_stride);
+}
+extern "C" int mf_rqs_inverse_strided_f32(const float* phi, int64_t event_stride, const float* y, int64_t B, int F, int K, float bound,
+                                          float slope, float* x, float* ladj, float* ladj_sum, int32_t* bin, mf_stream_t s) {
+    return mf::rqs_launch<float, true>(phi, y, B, F, K, bound, slope, x, ladj, ladj_sum, bin, (cudaStream_t)s, event_stride);
+}
+extern "C" int mf_rqs_inverse_strided_f64(const double* phi, int64_t event_stride, const double* y, int64_t B, int F, int K, double bound,
+                                          double slope, double* x, double* ladj, double* ladj_sum, int32_t* bin, mf_stream_t s) {
+    return mf::rqs_launch<double, true>(phi, y, B, F, K, bound, slope, x, ladj, ladj_sum, bin, (cudaStream_t)s, event_stride);
 }
 extern "C" int mf_searchsorted_f32(const float* knots, const float* v, int64_t BF, int len, int32_t* idx, mf_stream_t s) {
     return mf::search_launch<float>(knots, v, BF, len, idx, (cudaStream_t)s);

@@ -386,6 +386,6 @@ int rqs_coop_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bound
 // (chain = true: Philox base point -> T inverses -> u in [0,1], log q) in one launch; MF_E_SHAPE when the shape is outside it
 int rqs64_launch(bool inverse, bool chain, const double* phi, const double* vin, int64_t B, int F, int K, int T, double bound,
                  double slope, uint64_t seed, uint64_t event_offset, double* vout, double* ladj, double* ladj_sum,
-                 int32_t* bin, cudaStream_t stream);
+                 int32_t* bin, cudaStream_t stream, int64_t event_stride = 0);
 
 }  // namespace mf

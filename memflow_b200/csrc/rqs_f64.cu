@@ -86,6 +86,7 @@ struct Rqs64Args {
     int32_t* bin_out;       // [B][F] or null
     int64_t B;
     size_t transform_pitch; // elements between phi[t] and phi[t+1]
+    int64_t event_stride;   // elements between consecutive events (F (3K-1) unless the rows are a feature subset of a wider tensor)
     uint64_t seed, event_offset;
     RqsConst<double> C;
     int F, K, T;
@@ -163,14 +164,23 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
                 v = __ldg(A.vin + gi);
             }
         }
+        const bool packed = A.event_stride == (int64_t)F * PW;
+        // global address of tile row `row` (packed: rows follow each other; feature subset: events are event_stride apart)
+        auto row_src = [&](const double* base, int row) {
+            if (packed) return base + (size_t)(row0 + row) * PW;
+            const int64_t g = row0 + row, e = g / F;
+            return base + (size_t)e * A.event_stride + (size_t)(g - e * F) * PW;
+        };
         for (int t = T - 1; t >= 0; --t) {   // sampling applies the transforms in reverse order (T = 1 for K3 / K4)
-            const double* src = A.phi + (size_t)t * A.transform_pitch + (size_t)tile * tile_elems;
+            const double* tbase = A.phi + (size_t)t * A.transform_pitch;
             if (bulk) {
                 mbar_wait(bar, parity);
                 parity ^= 1u;
             } else {  // ragged last tile or unaligned phi: plain cooperative copy into the same (padded) rows
-                for (int row = wid; row < nrows; row += 8)
-                    for (int i = lane; i < PW; i += 32) sm[(size_t)row * PWP + i] = __ldg(src + (size_t)row * PW + i);
+                for (int row = wid; row < nrows; row += 8) {
+                    const double* src = row_src(tbase, row);
+                    for (int i = lane; i < PW; i += 32) sm[(size_t)row * PWP + i] = __ldg(src + i);
+                }
                 __syncthreads();
             }
             // ---- S1: running sums of exp(clip(.)) over this thread's segment(s), in place ----
@@ -181,7 +191,7 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
                     const int lo = arr * K + min(K, ch * A.chw), hi = arr * K + min(K, (ch + 1) * A.chw);
                     int hmax = 0;
                     double total = scan_segment<PAIR>(r, lo, hi, C, hmax);
-                    if (hmax >= kHiAbsLimit) total = segment_exact(src + (size_t)rr * PW, r, lo, hi, C.two_over_L);
+                    if (hmax >= kHiAbsLimit) total = segment_exact(row_src(tbase, rr), r, lo, hi, C.two_over_L);
                     tot[s * RPT + rr] = total;
                 }
             }
@@ -350,7 +360,7 @@ static int rqs64_pick(Rqs64Args& A, int lanes, bool pair, size_t smem, int sms, 
 // caller then takes the general kernels of rqs_coop.cu / rqs.cu.
 int rqs64_launch(bool inverse, bool chain, const double* phi, const double* vin, int64_t B, int F, int K, int T, double bound,
                  double slope, uint64_t seed, uint64_t event_offset, double* vout, double* ladj, double* ladj_sum,
-                 int32_t* bin, cudaStream_t stream) {
+                 int32_t* bin, cudaStream_t stream, int64_t event_stride) {
     static const bool enabled = [] { const char* e = getenv("MF_RQS64"); return !(e && e[0] == '0'); }();
     static const int forced = [] { const char* e = getenv("MF_RQS64_LANES"); return e ? atoi(e) : 0; }();
     static const int tiles_env = [] { const char* e = getenv("MF_RQS64_TILES"); return e ? atoi(e) : 0; }();  // 1: whole events, 2: row tiles
@@ -386,7 +396,10 @@ int rqs64_launch(bool inverse, bool chain, const double* phi, const double* vin,
     if (tiles_env == 1 && ept >= 1) whole = true;
     if (tiles_env == 2) whole = false;
     A.transform_pitch = (size_t)B * F * PW;
-    int bulk_ok = aligned(phi, 16) && (T == 1 || (A.transform_pitch * sizeof(double)) % 16 == 0) ? 1 : 0;
+    A.event_stride = event_stride > 0 ? event_stride : (int64_t)F * PW;
+    const bool strided = A.event_stride != (int64_t)F * PW;   // feature subset: rows are gathered by plain loads, no bulk copy
+    if (strided && (chain || T != 1)) return MF_E_SHAPE;
+    int bulk_ok = !strided && aligned(phi, 16) && (T == 1 || (A.transform_pitch * sizeof(double)) % 16 == 0) ? 1 : 0;
     int rows_per_tile = whole ? ept * F : rpt;
     if (bulk_ok && pitch == PW && ((size_t)rows_per_tile * PW * sizeof(double)) % 16 != 0) {  // one copy per tile: 16-byte multiples
         if (whole) {

@@ -10,7 +10,7 @@ import math
 import torch
 
 from . import ops  # noqa: F401  (registers torch.ops.memflow_b200.*)
-from ._lib import check, host_array, lib, ptr, reduce_workspace, require_cuda, stream_ptr
+from ._lib import check, device_guard, host_array, lib, ptr, reduce_workspace, require_cuda, stream_ptr
 
 
 def new_accumulator(device):
@@ -80,7 +80,7 @@ class ImportanceSampler:
         f64 = phi.dtype == torch.float64   # MEMFlow's configs run the flows in float64: same chain on the fp64 spline kernel
         fn = lib().mf_flow_sample_f64 if f64 else lib().mf_flow_sample_f32
         ct = ctypes.c_double if f64 else ctypes.c_float
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             rc = fn(ptr(phi), ctypes.c_int64(N), ctypes.c_int(F), ctypes.c_int(T), ctypes.c_int(K), ct(self.bound),
                     ct(self.slope if self.slope is not None else 0.0), ctypes.c_uint64(self.seed),
                     ctypes.c_uint64(int(event_offset)), ptr(u), ptr(logq), stream_ptr(dev))
@@ -98,7 +98,7 @@ class ImportanceSampler:
             torch.ops.memflow_b200.rambo_is_(u, logq, self.masses, self.collider_energy, acc)
             return acc
         ws = reduce_workspace(dev)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             rc = lib().mf_rambo_is_f64(ptr(u), ptr(logq), ctypes.c_int64(u.shape[0]), ctypes.c_int(self.n_final),
                                        host_array(self.masses, ctypes.c_double), ctypes.c_double(self.collider_energy),
                                        ctypes.c_uint32(0), ptr(acc), ptr(ws), ptr(out.get("momenta")), ptr(out.get("weight")),
@@ -126,7 +126,7 @@ class ImportanceSampler:
             u, logq = self.sample_flow(phi, event_offset=event_offset, u=out.get("u"), logq=out.get("logq"))
             self.weigh(u, logq, acc=acc, out=out)
             return (acc, out) if debug_outputs else acc
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             rc = lib().mf_is_chain_f64(
                 ptr(phi), ctypes.c_int64(N), ctypes.c_int(n), ctypes.c_int(T), ctypes.c_int(K),
                 ctypes.c_float(self.bound), ctypes.c_float(self.slope if self.slope is not None else 0.0),

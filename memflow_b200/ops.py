@@ -23,7 +23,7 @@ argument types taken from that header (_lib.header_signatures).
 import torch
 from torch.library import Library
 
-from ._lib import MemflowB200Error, check, host_array, lib, ptr, reduce_workspace, stream_ptr
+from ._lib import check, device_guard, host_array, lib, MemflowB200Error, ptr, reduce_workspace, stream_ptr
 import ctypes
 
 _NS = "memflow_b200"
@@ -34,6 +34,17 @@ def _register(name, schema, cuda_impl, fake_impl):
     _DEF.define(name + schema)
     _DEF.impl(name, cuda_impl, "CUDA")
     torch.library.register_fake(_NS + "::" + name, fake_impl)
+
+
+_FN = {}
+
+
+def _abi(name):
+    """cached attribute lookup on the loaded library"""
+    f = _FN.get(name)
+    if f is None:
+        f = _FN[name] = getattr(lib(), name)
+    return f
 
 
 def _suffix(dtype):
@@ -61,18 +72,30 @@ def _rqs_shapes(phi, v):
 RQS_LADJ, RQS_SUM, RQS_BINS = 1, 2, 4   # `outputs` bit mask: which of ladj [B,F], ladj_sum [B], bins [B,F] are produced
 
 
+def _rqs_rows(phi):
+    """(phi usable in place, event stride in elements): a [B, F, 3K-1] view whose rows are contiguous and whose events are
+    a constant number of elements apart -- e.g. phi_all[:, j:j+1] in an autoregressive sampling pass -- is read in place by
+    the strided entry points; anything else is packed first."""
+    B, F, PW = phi.shape
+    es = phi.element_size()
+    if phi.stride(2) == 1 and (F == 1 or phi.stride(1) == PW) and phi.stride(0) >= F * PW and phi.data_ptr() % es == 0 and B > 0:
+        return phi, int(phi.stride(0)) if B > 1 else F * PW
+    phi = phi.contiguous()
+    return phi, F * PW
+
+
 def _rqs_cuda(phi, v, bound, slope, inverse, outputs):
     B, F, K = _rqs_shapes(phi, v)
-    phi = phi.contiguous()
+    phi, ev_stride = _rqs_rows(phi)
     v = v.to(phi.dtype).contiguous()
     dev = phi.device
     out = torch.empty_like(v)
     ladj = torch.empty((B, F) if outputs & RQS_LADJ else (0,), dtype=phi.dtype, device=dev)
     lsum = torch.empty((B,) if outputs & RQS_SUM else (0,), dtype=phi.dtype, device=dev)
     bins = torch.empty((B, F) if outputs & RQS_BINS else (0,), dtype=torch.int32, device=dev)
-    fn = getattr(lib(), "mf_rqs_%s_%s" % ("inverse" if inverse else "forward", _suffix(phi.dtype)))
-    with torch.cuda.device(dev):
-        rc = fn(ptr(phi), ptr(v), B, F, K, bound, slope, ptr(out), ptr(ladj) if outputs & RQS_LADJ else None,
+    fn = _abi(("mf_rqs_inverse_strided_" if inverse else "mf_rqs_forward_strided_") + _suffix(phi.dtype))
+    with device_guard(dev):
+        rc = fn(ptr(phi), ev_stride, ptr(v), B, F, K, bound, slope, ptr(out), ptr(ladj) if outputs & RQS_LADJ else None,
                 ptr(lsum) if outputs & RQS_SUM else None, ptr(bins) if outputs & RQS_BINS else None, stream_ptr(dev))
     check(rc, "mf_rqs_%s" % ("inverse" if inverse else "forward"))
     return out, ladj, lsum, bins
@@ -94,7 +117,7 @@ def _rqs_bwd_cuda(phi, v, g_out, g_ladj, bound, slope, inverse):
     g_phi = torch.empty_like(phi)
     g_v = torch.empty_like(v)
     fn = getattr(lib(), "mf_rqs_%s_bwd_%s" % ("inverse" if inverse else "forward", _suffix(phi.dtype)))
-    with torch.cuda.device(phi.device):
+    with device_guard(phi.device):
         rc = fn(ptr(phi), ptr(v), ptr(go), ptr(gl), B, F, K, bound, slope, ptr(g_phi), ptr(g_v), stream_ptr(phi.device))
     check(rc, "mf_rqs_bwd")
     return g_phi, g_v
@@ -153,8 +176,8 @@ def _k1_cuda(u, masses, e_collider, cuts, flags, want_logw):
     x2 = torch.empty(N, dtype=dt, device=dev)
     logw = torch.empty(N if want_logw else 0, dtype=dt, device=dev)
     status = torch.empty(1, dtype=torch.int32, device=dev)   # cleared inside the call (MF_FLAG_ZERO_STATUS): no fill launch
-    fn = getattr(lib(), "mf_rambo_forward_" + _suffix(dt))
-    with torch.cuda.device(dev):
+    fn = _abi("mf_rambo_forward_" + _suffix(dt))
+    with device_guard(dev):
         rc = fn(ptr(u), N, n, host_array(masses, ct), e_collider, host_array(cuts, ct) if (flags & MF_FLAG_CUTS) else None,
                 flags | MF_FLAG_ZERO_STATUS, ptr(momenta), ptr(weight), ptr(logw) if want_logw else None, ptr(x1), ptr(x2),
                 ptr(status), stream_ptr(dev))
@@ -174,7 +197,7 @@ def _k1_bwd_cuda(u, momenta, weight, x1, x2, g_mom, g_w, g_x1, g_x2, masses, e_c
 
     g_mom, g_w, g_x1, g_x2 = c(g_mom), c(g_w), c(g_x1), c(g_x2)
     grad_u = torch.empty_like(u)
-    with torch.cuda.device(u.device):
+    with device_guard(u.device):
         rc = lib().mf_rambo_forward_bwd_f64(ptr(u), ptr(momenta), ptr(weight), ptr(x1), ptr(x2), ptr(g_mom), ptr(g_w), ptr(g_x1),
                                             ptr(g_x2), u.shape[0], len(masses), host_array(masses, ctypes.c_double), e_collider,
                                             flags, ptr(grad_u), stream_ptr(u.device))
@@ -236,8 +259,8 @@ def _k2_cuda(momenta, x1, x2, order, masses, target_mass, e_collider, flags, wan
     prob = torch.empty(N, dtype=dt, device=dev)
     logp = torch.empty(N if want_logp else 0, dtype=dt, device=dev)
     status = torch.empty(1, dtype=torch.int32, device=dev)
-    fn = getattr(lib(), "mf_rambo_inverse_" + _suffix(dt))
-    with torch.cuda.device(dev):
+    fn = _abi("mf_rambo_inverse_" + _suffix(dt))
+    with device_guard(dev):
         rc = fn(ptr(mom), mom.stride(0), ptr(x1c), ptr(x2c), N, n, host_array(order, ctypes.c_int32), host_array(masses, ct),
                 host_array(target_mass, ct) if target_mass is not None else None, e_collider, flags | MF_FLAG_ZERO_STATUS,
                 ptr(ps), ptr(prob), ptr(logp) if want_logp else None, ptr(status), stream_ptr(dev))
@@ -258,7 +281,7 @@ def _k2_bwd_cuda(momenta, x1, x2, g_ps, order, masses, target_mass, permute_targ
     g_mom = torch.empty((N, n, 4), dtype=torch.float64, device=dev)
     g_x1 = torch.empty(N, dtype=torch.float64, device=dev)
     g_x2 = torch.empty(N, dtype=torch.float64, device=dev)
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         rc = lib().mf_rambo_inverse_bwd_f64(ptr(mom), mom.stride(0), ptr(x1.to(torch.float64).contiguous()),
                                             ptr(x2.to(torch.float64).contiguous()), ptr(g_ps.to(torch.float64).contiguous()), N, n,
                                             host_array(order, ctypes.c_int32), host_array(masses, ctypes.c_double),
@@ -306,7 +329,7 @@ def _is_reduce_cuda(target, jac, logq, acc):
     lq = logq.to(torch.float64).contiguous()
     tg = None if target is None else target.to(torch.float64).contiguous()
     ws = reduce_workspace(dev)
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib().mf_is_reduce_f64(ptr(tg), ptr(jac), ptr(lq), jac.shape[0], ptr(acc), ptr(ws), stream_ptr(dev)), "mf_is_reduce_f64")
 
 
@@ -318,7 +341,7 @@ def _flow_sample_cuda(phi, seed, event_offset, bound, slope):
     u = torch.empty((N, F), dtype=torch.float64, device=dev)
     logq = torch.empty(N, dtype=torch.float64, device=dev)
     fn = getattr(lib(), "mf_flow_sample_" + _suffix(phi.dtype))
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         rc = fn(ptr(phi), N, F, T, K, bound, slope, seed, event_offset, ptr(u), ptr(logq), stream_ptr(dev))
     check(rc, "mf_flow_sample")
     return u, logq
@@ -329,7 +352,7 @@ def _rambo_is_cuda(u, logq, masses, e_collider, acc):
     u = u.to(torch.float64).contiguous()
     logq = logq.to(torch.float64).contiguous()
     ws = reduce_workspace(dev)
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         rc = lib().mf_rambo_is_f64(ptr(u), ptr(logq), u.shape[0], len(masses), host_array(masses, ctypes.c_double), e_collider, 0,
                                    ptr(acc), ptr(ws), None, None, None, None, stream_ptr(dev))
     check(rc, "mf_rambo_is_f64")
@@ -339,6 +362,9 @@ _register("is_reduce_", "(Tensor? target, Tensor jac, Tensor logq, Tensor(a!) ac
 _register("flow_sample", "(Tensor phi, int seed, int event_offset, float bound, float slope) -> (Tensor, Tensor)", _flow_sample_cuda,
           lambda phi, *a: (phi.new_empty((phi.shape[1], phi.shape[2]), dtype=torch.float64), phi.new_empty((phi.shape[1],), dtype=torch.float64)))
 _register("rambo_is_", "(Tensor u, Tensor logq, float[] masses, float e_collider, Tensor(a!) acc) -> ()", _rambo_is_cuda, lambda *a: None)
+
+# the CUDA implementations, callable directly by the host classes when neither autograd nor a tracer is involved
+rqs_cuda, rambo_forward_cuda, rambo_inverse_cuda = _rqs_cuda, _k1_cuda, _k2_cuda
 
 OPS = ("rqs", "rqs_bwd", "rambo_forward", "rambo_forward_bwd", "rambo_inverse", "rambo_inverse_bwd", "is_reduce_", "flow_sample",
        "rambo_is_")

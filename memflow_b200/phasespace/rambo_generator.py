@@ -20,7 +20,7 @@ import torch
 
 from .. import _lib
 from .. import ops  # noqa: F401  (registers torch.ops.memflow_b200.*)
-from .._lib import MemflowB200Error, check, host_array, lib, ptr, require_cuda, stream_ptr
+from .._lib import check, device_guard, host_array, lib, MemflowB200Error, needs_dispatcher, ptr, require_cuda, stream_ptr
 
 M_HIGGS = 125.25
 M_TOP = 172.5
@@ -48,7 +48,7 @@ def _inverse_vjp(mom, x1, x2, g_ps, n, order, masses_host, target_host, permute_
     g_x1 = torch.empty(N, dtype=torch.float64, device=dev) if want_x else None
     g_x2 = torch.empty(N, dtype=torch.float64, device=dev) if want_x else None
     tm = host_array(target_host, ctypes.c_double) if target_host is not None else None
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         rc = lib().mf_rambo_inverse_bwd_f64(
             ptr(mom), ctypes.c_int64(mom.stride(0)), ptr(x1), ptr(x2), ptr(g_ps), ctypes.c_int64(N), ctypes.c_int(n),
             host_array(order, ctypes.c_int32), host_array(masses_host, ctypes.c_double), tm,
@@ -142,7 +142,7 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
             raise AssertionError("bisect_vec_batch expects [N, n_final-2]")
         v = v_t.detach().to(torch.float64).contiguous()
         u = torch.empty_like(v)
-        with torch.cuda.device(v.device):
+        with device_guard(v.device):
             check(lib().mf_massvar_solve_f64(ptr(v), ctypes.c_int64(v.shape[0]), ctypes.c_int(self.n_final), ptr(u),
                                              stream_ptr(v.device)), "mf_massvar_solve_f64")
         return u
@@ -215,7 +215,8 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         if cuts_on:   # the reference evaluates the cuts always; with the default -1 thresholds they cannot fire
             flags |= MF_FLAG_CUTS
         # ONE launch through the registered op (memflow_b200/ops.py): K1, its status word, autograd via the backward kernel
-        momenta, weight, x1, x2, logw, status = torch.ops.memflow_b200.rambo_forward(
+        call = torch.ops.memflow_b200.rambo_forward if needs_dispatcher(u) else ops.rambo_forward_cuda
+        momenta, weight, x1, x2, logw, status = call(
             u, self._masses_host, float(self.collider_energy),
             [float(pT_mincut), float(delR_mincut), float(rap_maxcut)] if cuts_on else [], flags, bool(return_logweight))
         self.last_status = status
@@ -266,7 +267,8 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
             flags |= MF_FLAG_NO_CM_CHECK
         # ONE launch through the registered op: a strided [N, n, 4] view (e.g. forward_output[:, 2:]) is read in place;
         # `ps` is differentiable w.r.t. the momenta and x1, x2 (backward kernel), `prob` carries no gradient
-        ps, prob, logp, status = torch.ops.memflow_b200.rambo_inverse(
+        call = torch.ops.memflow_b200.rambo_inverse if needs_dispatcher(mom, x1, x2) else ops.rambo_inverse_cuda
+        ps, prob, logp, status = call(
             mom, x1 if needs_grad else x1.detach(), x2 if needs_grad else x2.detach(), order, self._masses_host, target_host,
             float(self.collider_energy), flags, bool(return_logprob))
         if needs_grad:

@@ -17,7 +17,7 @@ import torch
 from torch.distributions import Transform, constraints
 
 from . import ops
-from ._lib import MemflowB200Error, check, lib, ptr, require_cuda, stream_ptr
+from ._lib import check, device_guard, lib, MemflowB200Error, needs_dispatcher, ptr, require_cuda, stream_ptr
 
 
 def _run(direction, phi, v, bound, slope, want_ladj=True, want_sum=False, want_bin=False):
@@ -28,8 +28,9 @@ def _run(direction, phi, v, bound, slope, want_ladj=True, want_sum=False, want_b
     if phi.dtype not in (torch.float32, torch.float64):
         raise MemflowB200Error("spline kernels support float32 / float64, got %s" % phi.dtype)
     outputs = (ops.RQS_LADJ if want_ladj else 0) | (ops.RQS_SUM if want_sum else 0) | (ops.RQS_BINS if want_bin else 0)
-    out, ladj, lsum, bins = torch.ops.memflow_b200.rqs(phi, v, float(bound), float(slope) if slope is not None else 0.0,
-                                                       direction == "inverse", outputs)
+    # plain eager inference goes straight to the C ABI; autograd / torch.compile / fake tensors go through the dispatcher
+    call = torch.ops.memflow_b200.rqs if needs_dispatcher(phi, v) else ops.rqs_cuda
+    out, ladj, lsum, bins = call(phi, v, float(bound), float(slope) if slope is not None else 0.0, direction == "inverse", outputs)
     return out, (ladj if want_ladj else None), (lsum if want_sum else None), (bins if want_bin else None)
 
 
@@ -54,7 +55,7 @@ def searchsorted(knots, v):
     BF = v.numel()
     idx = torch.empty(v.shape, dtype=torch.int32, device=knots.device)
     fn = lib().mf_searchsorted_f32 if knots.dtype == torch.float32 else lib().mf_searchsorted_f64
-    with torch.cuda.device(knots.device):
+    with device_guard(knots.device):
         check(fn(ptr(knots), ptr(v), ctypes.c_int64(BF), ctypes.c_int(length), ptr(idx), stream_ptr(knots.device)),
               "mf_searchsorted")
     return idx
@@ -76,6 +77,23 @@ def _pack(widths, heights, derivatives):
             and widths.stride(-1) == 1
             and heights.data_ptr() == widths.data_ptr() + K * es
             and derivatives.data_ptr() == widths.data_ptr() + 2 * K * es)
+    if same and not needs_grad:
+        # rows of a CONSTANT pitch P >= PW (one feature's rows out of a [.., F, 3K-1] parameter tensor, as an autoregressive
+        # sampling pass selects them): read in place through the strided entry points, no gather copy
+        sizes = [(size, stride) for size, stride in zip(lead, widths.stride()[:-1]) if size != 1]
+        if sizes:
+            P = sizes[-1][1]
+            exp, okp = P, P >= PW
+            for size, stride in reversed(sizes):
+                if stride != exp:
+                    okp = False
+                    break
+                exp *= size
+            if okp and P != PW:
+                rows = 1
+                for s_ in lead:
+                    rows *= s_
+                return torch.as_strided(widths, (rows, 1, PW), (P, PW, 1)), lead
     if same:
         # contiguous rows of pitch PW?
         exp, ok = PW, True

@@ -12,7 +12,7 @@ import ctypes
 
 import torch
 
-from .._lib import DecayPartonsCfg, check, host_array, lib, ptr, require_cuda, stream_ptr
+from .._lib import check, DecayPartonsCfg, device_guard, host_array, lib, ptr, require_cuda, stream_ptr
 
 M_HIGGS = 125.25
 M_TOP = 172.5
@@ -107,7 +107,7 @@ class Compute_ParticlesTensor:
                 ls = host_array(torch.as_tensor(logit_scale).detach().cpu().double().reshape(-1).tolist(), ctypes.c_double)
             if (lm is not None and len(lm) != W) or (ls is not None and len(ls) != W):
                 raise AssertionError("logit_mean / logit_scale must have 3n-2 = %d entries" % W)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             rc = lib().mf_get_ps_f64(ptr(mom), ctypes.c_int64(mom.stride(0)), ptr(boost), ctypes.c_int64(N), ctypes.c_int(n),
                                      host_array(order, ctypes.c_int32), host_array(tm, ctypes.c_double),
                                      ctypes.c_double(float(E_CM)), ptr(ps), ptr(jac0), ptr(mask),
@@ -135,7 +135,7 @@ class Compute_ParticlesTensor:
         ang = higgs_angles.detach().to(torch.float64).contiguous()
         N = mom.shape[0]
         out = torch.empty((N, 3, 4), dtype=torch.float64, device=dev)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             check(lib().mf_higgs_decay_f64(ptr(mom), ctypes.c_int64(stride), ptr(ang), ctypes.c_int64(N),
                                            ctypes.c_double(float(higgs_mass)), ctypes.c_int(int(bool(ptetaphi))), ptr(out),
                                            stream_ptr(dev)), "mf_higgs_decay_f64")
@@ -152,7 +152,7 @@ class Compute_ParticlesTensor:
         aw = top_W_angles.detach().to(torch.float64).contiguous()
         N = mom.shape[0]
         out = torch.empty((N, 4, 4), dtype=torch.float64, device=dev)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             check(lib().mf_top_decay_f64(ptr(mom), ctypes.c_int64(stride), ptr(ab), ptr(aw), ctypes.c_int64(N),
                                          ctypes.c_double(float(top_mass)), ctypes.c_double(float(W_mass)),
                                          ctypes.c_double(float(b_mass)), ctypes.c_int(int(bool(ptetaphi))), ptr(out),
@@ -247,7 +247,7 @@ class _DecayPartonsFn(torch.autograd.Function):
         d = [t.detach().to(torch.float64).contiguous() for t in ins]
         N = d[0].shape[0]
         out = torch.empty((N, 12, 4), dtype=torch.float64, device=dev)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             check(lib().mf_decay_partons_f64(*[ptr(t) for t in d], ctypes.c_int64(N), ctypes.byref(cfg), ptr(out),
                                              stream_ptr(dev)), "mf_decay_partons_f64")
         ctx.cfg = cfg
@@ -262,7 +262,7 @@ class _DecayPartonsFn(torch.autograd.Function):
         N = d[0].shape[0]
         g = g_out.detach().to(torch.float64).contiguous()
         grads = [torch.empty_like(t) for t in d]
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             check(lib().mf_decay_partons_bwd_f64(*[ptr(t) for t in d], ctypes.c_int64(N), ctypes.byref(ctx.cfg), ptr(g),
                                                  *[ptr(t) for t in grads], stream_ptr(dev)), "mf_decay_partons_bwd_f64")
         outs = [gr.reshape(shape).to(dt) if need else None

@@ -309,3 +309,58 @@ def test_spline_autograd_vs_torch_restatement(F, K, bound, slope):
     y32, l32, _ = TR.rqs_forward(p32, x32, bound=bound, slope=slope)
     (y32 * gy.float().cuda()).sum().backward()
     assert torch.isfinite(p32.grad).all()
+
+
+@pytest.mark.parametrize("dt,F,K", [(torch.float64, 10, 40), (torch.float64, 6, 35), (torch.float32, 10, 40), (torch.float32, 7, 10), (torch.float64, 7, 10)])
+def test_feature_subset_reads_rows_in_place(dt, F, K):
+    """Autoregressive sampling: pass j of zuko's MaskedAutoregressiveTransform inverse determines feature j only, so it
+    should read that feature's 3K-1 parameters, not the event's F (3K-1) (call sites memflow/unfolding_flow/unfolding_flow.py:
+    97,186). The strided entry points take the column view of the parameter tensor in place: same bits as the full call."""
+    from memflow_b200 import ops, transforms as TR
+    B, bound = 3001, 1.1
+    phi, x = make(B, F, K, dt, bound, seed=3)
+    phi, x = phi.cuda(), x.cuda()
+    for fn in (TR.rqs_forward, TR.rqs_inverse):
+        full, lfull, _, bfull = fn(phi, x, bound=bound, return_bins=True)
+        for j0, fc in ((0, 1), (F - 1, 1), (2, 3), (1, F - 1)):
+            sub = phi[:, j0:j0 + fc]                      # a view: events F (3K-1) elements apart, fc rows each
+            assert not sub.is_contiguous() or fc == F
+            kept, stride = ops._rqs_rows(sub)
+            assert kept.data_ptr() == sub.data_ptr() and stride == F * (3 * K - 1)   # read in place, no gather copy
+            o, l, ls, b = fn(sub, x[:, j0:j0 + fc], bound=bound, return_bins=True)
+            assert torch.equal(o, full[:, j0:j0 + fc]) and torch.equal(l, lfull[:, j0:j0 + fc]) and torch.equal(b, bfull[:, j0:j0 + fc])
+            assert torch.allclose(ls, lfull[:, j0:j0 + fc].sum(1), rtol=0, atol=1e-9 if dt == torch.float64 else 1e-3)
+    # F passes, one feature each == one pass over all features (parameters given), through the Transform surface
+    w, h, d = phi.split([K, K, K - 1], dim=-1)
+    t_full = TR.MonotonicRQSTransform(w, h, d, bound=bound)
+    x_full = t_full.inv(x)
+    cols = []
+    for j in range(F):
+        tj = TR.MonotonicRQSTransform(w[:, j], h[:, j], d[:, j], bound=bound)
+        assert tj.phi.data_ptr() == phi[:, j].data_ptr() and tj.phi.stride(0) == F * (3 * K - 1)   # zero-copy column
+        cols.append(tj.inv(x[:, j]))
+    assert torch.equal(torch.stack(cols, dim=1), x_full)
+
+
+def test_registered_ops_opcheck_and_compile():
+    """The torch.library layer on the device: schema / fake kernel / autograd registration are mutually consistent
+    (torch.library.opcheck), the ops trace under torch.compile, and the eager fast path gives the same bits as the op."""
+    from memflow_b200 import ops, transforms as TR
+    phi, x = make(33, 4, 10, torch.float64, 1.0, seed=5)
+    phi, x = phi.cuda(), x.cuda()
+    args = (phi.clone().requires_grad_(True), x.clone().requires_grad_(True), 1.0, 1e-3, False, ops.RQS_LADJ | ops.RQS_SUM)
+    torch.library.opcheck(torch.ops.memflow_b200.rqs, args, test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    u = torch.rand(17, 7, dtype=torch.float64, device="cuda").clamp_(1e-6, 1 - 1e-6)
+    torch.library.opcheck(torch.ops.memflow_b200.rambo_forward, (u.clone().requires_grad_(True), [125.25, 172.5, 172.5], 13000.0, [], 0, True),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    a = torch.ops.memflow_b200.rqs(phi, x, 1.0, 1e-3, False, ops.RQS_LADJ | ops.RQS_SUM)
+    b = ops.rqs_cuda(phi, x, 1.0, 1e-3, False, ops.RQS_LADJ | ops.RQS_SUM)
+    assert all(torch.equal(p, q) for p, q in zip(a, b))
+
+    def f(p, v):
+        y, ladj, lsum = TR.rqs_forward(p, v, bound=1.0)
+        return y * 2.0 + lsum[:, None]
+
+    ref = f(phi, x)
+    got = torch.compile(f, backend="aot_eager", fullgraph=False)(phi, x)
+    assert torch.allclose(got, ref, rtol=0, atol=0)
