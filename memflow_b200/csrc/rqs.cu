@@ -146,7 +146,7 @@ template <int K, bool INV>
 __global__ void __launch_bounds__(128, 4)
 rqs_reg2_kernel(const float* __restrict__ phi, const float* __restrict__ vin, int64_t B, int F, RqsConst<float> C, int ept,
                 int bulk_ok, float* __restrict__ vout, float* __restrict__ ladj_out, float* __restrict__ ladj_sum,
-                int32_t* __restrict__ bin_out) {
+                int32_t* __restrict__ bin_out, int64_t event_stride /*elements between events*/) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int PW = 3 * K - 1;
     const int rows_per_tile = ept * F;
@@ -175,9 +175,16 @@ rqs_reg2_kernel(const float* __restrict__ phi, const float* __restrict__ vin, in
             }
             mbar_wait(bar, parity);
             parity ^= 1u;
-        } else {
+        } else if (event_stride == (int64_t)F * PW) {
             const size_t ne = (size_t)nrows * PW;
             for (size_t i = tid; i < ne; i += 128) sm[i] = __ldg(src + i);
+            __syncthreads();
+        } else {  // a feature subset of a wider parameter tensor: the event's F rows are contiguous, events event_stride apart
+            const int epw = F * PW;
+            for (int i = tid; i < nev * epw; i += 128) {
+                const int e = i / epw;
+                sm[i] = __ldg(phi + (size_t)(ev0 + e) * event_stride + (i - e * epw));
+            }
             __syncthreads();
         }
         const bool active = row < nrows;
@@ -257,7 +264,7 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
     if (event_stride < (int64_t)F * PW) return MF_E_SHAPE;
     const bool strided = event_stride != (int64_t)F * PW;   // a feature subset: only the kernels with a row-wise copy path
     if constexpr (sizeof(T) == 4) {
-        if (!strided && (K == 32 || K == 40 || K == 48 || K == 64) && F <= 64) {
+        if ((K == 32 || K == 40 || K == 48 || K == 64) && F <= 64) {
             int dev = 0, sms = 148, smem_max = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -266,7 +273,7 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
             auto need = [&](int e) { return ((size_t)e * F * row_bytes + 127) / 128 * 128 + extra; };
             int ept = 64 / F;
             while (ept > 1 && need(ept) > (size_t)smem_max / 4) --ept;  // aim for 4 CTAs per SM
-            int bulk_ok = aligned(phi, 16) ? 1 : 0;
+            int bulk_ok = (aligned(phi, 16) && !strided) ? 1 : 0;
             if (bulk_ok) {
                 int e = ept;
                 while (e > 0 && ((size_t)e * F * row_bytes) % 16 != 0) --e;
@@ -284,7 +291,7 @@ static int rqs_launch(const T* phi, const T* vin, int64_t B, int F, int K, T bou
                 int64_t grid = (int64_t)sms * ctas;
                 if (grid > num_tiles) grid = num_tiles;
                 kern<<<(unsigned)grid, 128, smem, stream>>>((const float*)phi, (const float*)vin, B, F, C, ept, bulk_ok,
-                                                            (float*)vout, (float*)ladj, (float*)ladj_sum, bin);
+                                                            (float*)vout, (float*)ladj, (float*)ladj_sum, bin, event_stride);
             };
             switch (K) {
             case 32: go(rqs_reg2_kernel<32, INV>); break;
