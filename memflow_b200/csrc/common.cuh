@@ -106,6 +106,58 @@ MF_D double sqrt_fast(double x) {
 }
 MF_D float sqrt_fast(float x) { return sqrtf(x); }
 
+// ---------------------------------------------------------------------------------------------
+// Primitive policies of the phase-space cores. PrimIEEE = the guarded sequences above (IEEE results for 0 / inf / NaN /
+// denormal operands through a final select). PrimRaw = the same sequences WITHOUT the select: for an in-range operand
+// the result is bit-identical; for 0, a denormal (flushed by the MUFU seed), inf or NaN the Newton residual is
+// 0 * inf or NaN, so the result is NaN -- never a silently wrong finite number. Kernels run the event once on PrimRaw,
+// look at the exponent field of every value they store, and redo the (astronomically rare) event whose outputs are not
+// finite on PrimIEEE, out of line. The guards cost ~7 issued instructions per primitive (exponent extract, compare,
+// BSSY / BRA / BSYNC or two FSEL plus moves): ~560 of the 3250 instructions of an n = 8 event (ncu, profiles/r1).
+// ---------------------------------------------------------------------------------------------
+struct PrimIEEE {
+    template <typename T> static MF_D T rcp(T b) { return rcp_fast(b); }
+    template <typename T> static MF_D T div(T a, T b) { return div_fast(a, b); }
+    template <typename T> static MF_D T sqrt(T x) { return sqrt_fast(x); }
+    template <typename T> static MF_D T rsqrt(T x) { return rsqrt_fast(x); }
+};
+struct PrimRaw {
+    static MF_D double rcp(double b) {
+        const double r0 = rcp_seed(b);
+        double e = fma(-b, r0, 1.0);
+        double r = fma(r0, e, r0);
+        e = fma(-b, r, 1.0);
+        return fma(r, e, r);
+    }
+    static MF_D double div(double a, double b) {
+        const double r0 = rcp_seed(b);
+        const double e = fma(-b, r0, 1.0);
+        const double r = fma(r0, e, r0);
+        const double q = a * r;
+        return fma(fma(-b, q, a), r, q);
+    }
+    static MF_D double rsqrt(double x) {
+        const double y0 = rsqrt_seed(x);
+        const double y1 = y0 * fma(-0.5 * x * y0, y0, 1.5);
+        const double e = fma(-(x * y1), y1, 1.0);
+        return fma(0.5 * y1, e, y1);
+    }
+    static MF_D double sqrt(double x) {
+        const double y0 = rsqrt_seed(x);
+        const double g = x * y0, h = 0.5 * y0;
+        const double r = fma(-g, h, 0.5);
+        const double g1 = fma(g, r, g), h1 = fma(h, r, h);
+        return fma(fma(-g1, g1, x), h1, g1);
+    }
+    static MF_D float rcp(float b) { return 1.0f / b; }
+    static MF_D float div(float a, float b) { return a / b; }
+    static MF_D float rsqrt(float x) { return rsqrtf(x); }
+    static MF_D float sqrt(float x) { return sqrtf(x); }
+};
+// exponent field all ones: NaN or inf (integer pipe)
+MF_D bool not_finite_bits(double x) { return ((unsigned)__double2hiint(x) & 0x7ff00000u) == 0x7ff00000u; }
+MF_D bool not_finite_bits(float x) { return ((unsigned)__float_as_int(x) & 0x7f800000u) == 0x7f800000u; }
+
 template <typename T> struct Limits;
 template <> struct Limits<double> {
     static MF_HD double huge() { return 1.7976931348623157e308; }

@@ -348,6 +348,17 @@ flow_sample_reg2_kernel(const float* __restrict__ phi, int64_t N, int F, int T, 
     }
 }
 
+// The event again on the guarded primitives (PrimIEEE, common.cuh), out of line; taken when the speculative pass of
+// rambo_is_kernel produced a non-finite weight or momentum. Reloads the event's uniforms from global memory.
+template <int NF>
+__device__ __noinline__ void rambo_is_redo(const RamboParams<double, NF>& P, const double* urow, double* mo, double* wx) {
+    double jac, x1, x2;
+    rambo_forward_stream<double, NF, PrimIEEE>(
+        P, [&](int i) { return urow[i]; },
+        [&](int j, const double (&p)[4]) { if (mo) st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, jac, x1, x2);
+    wx[0] = jac; wx[1] = x1; wx[2] = x2;
+}
+
 template <int NF>
 __global__ void __launch_bounds__(256, 3)
 rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, int64_t N,
@@ -368,9 +379,17 @@ rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, i
         double* mo = momenta ? momenta + ev * (NP * 4) : nullptr;
         double jac, x1, x2;
         // streaming core (rambo.cuh): O(1) live state; momenta leave the registers only if they were asked for
-        rambo_forward_stream<double, NF>(
+        // speculative pass on the unguarded primitives (see rambo_forward_kernel)
+        bool redo = false;
+        rambo_forward_stream<double, NF, PrimRaw>(
             P, [&](int i) { return uc[i]; },
-            [&](int j, const double (&p)[4]) { if (mo) st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, jac, x1, x2);
+            [&](int j, const double (&p)[4]) { if (mo) { redo |= not_finite_bits(p[0]); st4(mo + 4 * j, p[0], p[1], p[2], p[3]); } },
+            jac, x1, x2);
+        if (redo | not_finite_bits(jac)) {
+            double wx[3];
+            rambo_is_redo<NF>(P, u + ev * F, mo, wx);
+            jac = wx[0]; x1 = wx[1]; x2 = wx[2];
+        }
         const double target = inv_2s * rcp_fast(x1 * x2);  // 1 / (2 x1 x2 s): ME = pdf = 1
         const double w = target * jac * exp(-lq);
         if (target > 0.0 && jac == jac && isfinite(w)) { k1.add(w); k2.add(w * w); cnt += 1.0; }

@@ -37,20 +37,20 @@ template <typename T> MF_D T rho_f(T M, T N, T m) {
 }
 
 // sqrt((M^2-(N+m)^2)(M^2-(N-m)^2)): numerator of 8 M^2 rho(M,N,m); the products are non-contractible
-template <typename T> MF_D T rho_num(T M, T N, T m) {
+template <typename Pr = PrimIEEE, typename T> MF_D T rho_num(T M, T N, T m) {
     T Msqr = mul_rn(M, M);
     T a = N + m, b = N - m;
-    return sqrt_fast(mul_rn(sub_rn(Msqr, mul_rn(a, a)), sub_rn(Msqr, mul_rn(b, b))));
+    return Pr::sqrt(mul_rn(sub_rn(Msqr, mul_rn(a, a)), sub_rn(Msqr, mul_rn(b, b))));
 }
 
 template <typename T> MF_D T rho2_3(T x, T y, T z) { return (x * x + y * y) + z * z; }
 
 // utils.py:88-118 boost_t: general Lorentz boost by velocity bv
-template <typename T> MF_D void boost(const T (&p)[4], T bx, T by, T bz, T (&o)[4]) {
+template <typename Pr = PrimIEEE, typename T> MF_D void boost(const T (&p)[4], T bx, T by, T bz, T (&o)[4]) {
     T b2 = add_rn(add_rn(mul_rn(bx, bx), mul_rn(by, by)), mul_rn(bz, bz));
-    T gamma = rsqrt_fast(sub_rn((T)1, b2));
+    T gamma = Pr::rsqrt(sub_rn((T)1, b2));
     T bp = (p[1] * bx + p[2] * by) + p[3] * bz;
-    T gamma2 = (b2 > (T)0) ? div_fast(gamma - (T)1, b2) : (T)0;
+    T gamma2 = (b2 > (T)0) ? Pr::div(gamma - (T)1, b2) : (T)0;
     T factor = gamma2 * bp + gamma * p[0];
     o[1] = p[1] + factor * bx;
     o[2] = p[2] + factor * by;
@@ -181,9 +181,9 @@ template <int E> __device__ __noinline__ double massvar_tiny_target(bool small, 
     return x;
 }
 
-template <int E> MF_D double solve_massvar(double v) {
+template <int E, typename Pr = PrimIEEE> MF_D double solve_massvar(double v) {
     if constexpr (E == 1) {
-        double u = div_fast(v, 1.0 + sqrt_fast(1.0 - v));
+        double u = Pr::div(v, 1.0 + Pr::sqrt(1.0 - v));
         return (v <= 0.0) ? Limits<double>::tiny_u() : ((v >= 1.0 || u > Limits<double>::max_u()) ? Limits<double>::max_u() : u);
     } else {
         const bool small = v < 0.65;
@@ -212,7 +212,7 @@ template <int E> MF_D double solve_massvar(double v) {
         return (u < Limits<double>::tiny_u()) ? Limits<double>::tiny_u() : u;  // NaN stays NaN
     }
 }
-template <int E> MF_D float solve_massvar(float v) {
+template <int E, typename Pr = PrimIEEE> MF_D float solve_massvar(float v) {
     if constexpr (E == 1) {
         float u = v / (1.0f + sqrtf(1.0f - v));
         return (v <= 0.0f) ? Limits<float>::tiny_u() : ((v >= 1.0f || u > Limits<float>::max_u()) ? Limits<float>::max_u() : u);
@@ -288,7 +288,7 @@ template <typename T> MF_D T delphi(const T (&a)[4], const T (&b)[4]) {  // util
 //   load(i)    -> the event's i-th uniform (i is a compile-time constant after unrolling)
 //   emit(j, p) -> row j of the output (0,1 incoming; 2.. final), p = (E,px,py,pz)
 // ---------------------------------------------------------------------------------------------
-template <typename T, int NF, int K_IDX, typename Load, typename Emit>
+template <typename T, int NF, int K_IDX, typename Pr, typename Load, typename Emit>
 MF_D void rambo_decay_step(const RamboParams<T, NF>& P, Load& load, Emit& emit, const T K0, T& prod, T& Kk, T& Mk,
                            T (&Q)[4], T& num, T& den, T& f8, T& pw) {
     constexpr int NE = NF - 2;
@@ -296,15 +296,15 @@ MF_D void rambo_decay_step(const RamboParams<T, NF>& P, Load& load, Emit& emit, 
     // next intermediate mass (:448-509): K_{k+1} = K_0 prod_{j<=k} t_j, M_{k+1} = K_{k+1} + sum_{j>k} m_j
     T Kn, Mn;
     if constexpr (k < NF - 2) {
-        prod *= solve_massvar<NF - 2 - k>(load(k));  // exponent of column k is NF-2-k (:405-407)
+        prod *= solve_massvar<NF - 2 - k, Pr>(load(k));  // exponent of column k is NF-2-k (:405-407)
         Kn = K0 * prod;
         Mn = Kn + P.msum_rev[k + 1];
     } else {
         Kn = (T)0;
         Mn = P.m[NF - 1];
     }
-    const T sM = rho_num(Mk, Mn, P.m[k]);
-    const T invM = rcp_fast(Mk);
+    const T sM = rho_num<Pr>(Mk, Mn, P.m[k]);
+    const T invM = Pr::rcp(Mk);
     if constexpr (k == 0) pw = ipow<2 * NF - 4>(K0 * invM);
     if constexpr (k <= NF - 3) {  // weight accumulators, see rambo_weight() for the algebra
         num *= (sM * (invM * invM)) * ((Kk * Kk) * Mn);
@@ -315,37 +315,37 @@ MF_D void rambo_decay_step(const RamboParams<T, NF>& P, Load& load, Emit& emit, 
     // two-body decay M_k -> m_k + M_{k+1} in the rest frame of Q, then boost (:310-343)
     const T qk = sM * ((T)0.5 * invM);  // 4 M_k rho(M_k, M_{k+1}, m_k)
     const T ct = (T)2 * load(NE + 2 * k) - (T)1;
-    const T st = sqrt_fast(sub_rn((T)1, mul_rn(ct, ct)));
+    const T st = Pr::sqrt(sub_rn((T)1, mul_rn(ct, ct)));
     // cos(2 pi u) as cospi(2u): exact range reduction and no large-argument slow path (the library cos carries a
     // Payne-Hanek branch that is never taken for phi in [0, 2 pi] but was inlined once per decay: instruction-cache
     // weight). Differs from cos(fl(2 pi u)) by <= 1e-15 |sin phi|: the rounding of phi itself.
     const T uphi = load(NE + 2 * k + 1);
     const T phi = (T)6.283185307179586 * uphi;
     const T cp = cospi_((T)2 * uphi);
-    const T sq = sqrt_fast(sub_rn((T)1, mul_rn(cp, cp)));
+    const T sq = Pr::sqrt(sub_rn((T)1, mul_rn(cp, cp)));
     const T sp = (phi > (T)3.141592653589793) ? -sq : sq;
     T p2[4], pb[4];
     p2[1] = (qk * st) * cp;
     p2[2] = (qk * st) * sp;
     p2[3] = qk * ct;
     const T m2 = P.m[k] * P.m[k];
-    p2[0] = sqrt_fast(rho2_3(p2[1], p2[2], p2[3]) + m2);
+    p2[0] = Pr::sqrt(rho2_3(p2[1], p2[2], p2[3]) + m2);
     if constexpr (k == 0) {  // Q = (M_0, 0, 0, 0): the boost is the identity (beta = 0 exactly)
 #pragma unroll
         for (int c = 0; c < 4; ++c) pb[c] = p2[c];
     } else {
-        const T iq = rcp_fast(Q[0]);
-        boost(p2, Q[1] * iq, Q[2] * iq, Q[3] * iq, pb);
-        pb[0] = sqrt_fast(rho2_3(pb[1], pb[2], pb[3]) + m2);
+        const T iq = Pr::rcp(Q[0]);
+        boost<Pr>(p2, Q[1] * iq, Q[2] * iq, Q[3] * iq, pb);
+        pb[0] = Pr::sqrt(rho2_3(pb[1], pb[2], pb[3]) + m2);
     }
     emit(2 + k, pb);
     Q[1] -= pb[1]; Q[2] -= pb[2]; Q[3] -= pb[3];
-    Q[0] = sqrt_fast(rho2_3(Q[1], Q[2], Q[3]) + Mn * Mn);
+    Q[0] = Pr::sqrt(rho2_3(Q[1], Q[2], Q[3]) + Mn * Mn);
     Kk = Kn;
     Mk = Mn;
 }
 
-template <typename T, int NF, typename Load, typename Emit>
+template <typename T, int NF, typename Pr = PrimIEEE, typename Load, typename Emit>
 MF_D void rambo_forward_stream(const RamboParams<T, NF>& P, Load&& load, Emit&& emit, T& wgt, T& x1, T& x2) {
     constexpr int D = 3 * NF - 4, NP = NF + 2;
     // ---- x1, x2 from the last two uniforms: utils.py:260-284 ----
@@ -356,19 +356,19 @@ MF_D void rambo_forward_stream(const RamboParams<T, NF>& P, Load&& load, Emit&& 
         T ml1;
         if constexpr (sizeof(T) == 8) {
             // the reference's inverse-CDF expression as written (utils.py:271-272): same operations, same rounding
-            ml1 = (P.t1 + sqrt_fast(P.t1sq + ((T)-2 * load(D)) * P.inv_A)) * P.neg_A;
+            ml1 = (P.t1 + Pr::sqrt(P.t1sq + ((T)-2 * load(D)) * P.inv_A)) * P.neg_A;
         } else {
             // float32: the algebraically identical q (1 - sqrt(1 - u)). The literal form subtracts 2u/A from (q/A)^2, which
             // for u -> 1 loses eps32 / (1 - u) of the radicand: 2.5e-4 relative error on x1 at 1 - u = 1e-6 (measured);
             // 1 - u is exact here and the error stays at eps32 q
-            ml1 = P.q * ((T)1 - sqrt_fast((T)1 - load(D)));
+            ml1 = P.q * ((T)1 - Pr::sqrt((T)1 - load(D)));
         }
         T ml2 = (P.q - ml1) * load(D + 1);
         x1 = exp_(-ml1);
         x2 = exp_(-ml2);
         wx = (P.A * x1) * x2;
     }
-    const T E_cm = sqrt_fast(x1 * x2) * P.e_collider;  // :226
+    const T E_cm = Pr::sqrt(x1 * x2) * P.e_collider;  // :226
     const bool quirks = (P.flags & MF_FLAG_REF_FP32_QUIRKS) != 0;
     {   // incoming partons :511-551
         T h = quirks ? (T)((float)E_cm / 2.0f) : E_cm / (T)2;
@@ -381,11 +381,11 @@ MF_D void rambo_forward_stream(const RamboParams<T, NF>& P, Load&& load, Emit&& 
     T Q[4] = {Mk, (T)0, (T)0, (T)0};
     T num = (T)1, den = (T)1, f8 = (T)1, pw = (T)1;
     [&]<int... I>(std::integer_sequence<int, I...>) {
-        (rambo_decay_step<T, NF, I>(P, load, emit, K0, prod, Kk, Mk, Q, num, den, f8, pw), ...);
+        (rambo_decay_step<T, NF, I, Pr>(P, load, emit, K0, prod, Kk, Mk, Q, num, den, f8, pw), ...);
     }(std::make_integer_sequence<int, NF - 1>{});
     emit(NP - 1, Q);
     // weight: get_flatWeights (:111-140) * massive correction (:489-507), same product order as the reference
-    const T pr = div_fast(num, den);
+    const T pr = Pr::div(num, den);
     T w;
     if (!quirks) {
         w = P.flat_c * (ipow<NF - 2>(E_cm * E_cm) / P.flat_ff);

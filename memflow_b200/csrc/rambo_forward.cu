@@ -14,6 +14,17 @@
 
 namespace mf {
 
+// The event again on the guarded primitives (common.cuh, PrimIEEE), out of line: taken only when the speculative pass below
+// stored a non-finite value (an operand of a reciprocal / square root was 0, denormal, inf or NaN: exact thresholds,
+// cos(theta) = +-1, garbage input). `src` is the event's row of uniforms (generic pointer: shared or global memory).
+template <typename T, int NF>
+__device__ __noinline__ void rambo_forward_redo(const RamboParams<T, NF>& P, const T* src, T* mo, T* wx) {
+    T wgt, x1, x2;
+    rambo_forward_stream<T, NF, PrimIEEE>(
+        P, [&](int i) { return src[i]; }, [&](int j, const T (&p)[4]) { st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, wgt, x1, x2);
+    wx[0] = wgt; wx[1] = x1; wx[2] = x2;
+}
+
 // EPILOGUE == false: plain CM-frame output, every 4-momentum is stored the moment it is final (streaming core).
 // EPILOGUE == true : lab-frame output and / or cuts need the whole event first (array interface).
 template <typename T, int NF, bool EPILOGUE>
@@ -54,10 +65,18 @@ rambo_forward_kernel(const T* __restrict__ u, int64_t N, const __grid_constant__
     T wgt, x1, x2;
     bool bad = false;
     if constexpr (!EPILOGUE) {
+        // speculative pass on the unguarded primitives; every stored energy depends on all components of its row, the
+        // last row on the whole chain: one exponent test per row (+ the weight) sees any operand that left their domain
         const T* __restrict__ srow = su + threadIdx.x * W;
-        rambo_forward_stream<T, NF>(
+        bool redo = false;
+        rambo_forward_stream<T, NF, PrimRaw>(
             P, [&](int i) { T v = PREFETCH ? srow[i] : ld1(urow + i); bad |= (v != v); return v; },
-            [&](int j, const T (&p)[4]) { st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, wgt, x1, x2);
+            [&](int j, const T (&p)[4]) { redo |= not_finite_bits(p[0]); st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, wgt, x1, x2);
+        if (redo | not_finite_bits(wgt)) {
+            T wx[3];
+            rambo_forward_redo<T, NF>(P, PREFETCH ? srow : urow, mo, wx);
+            wgt = wx[0]; x1 = wx[1]; x2 = wx[2];
+        }
     } else {
         T r[W];
         load_row<W>(urow, r);

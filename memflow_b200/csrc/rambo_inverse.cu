@@ -187,6 +187,82 @@ rambo_inverse_kernel(const T* __restrict__ momenta, int64_t event_stride, const 
 // (the reference's torch.sum, :656): a rounding-level change of an ill-conditioned quantity, inside the
 // conditioning-aware bound of tests/parity.py (gamma^2 of the system).
 // ---------------------------------------------------------------------------------------------
+// One event of the streaming form. put(c, value) receives unit-cube coordinate c; returns prob, leaves the summed final
+// state in Q (for the CM check). Pr = primitive policy (common.cuh).
+template <int NF, typename Pr, typename Put>
+MF_D double rambo_inverse_stream_event(const RamboParams<double, NF>& P, const double* __restrict__ base, double x1, double x2,
+                                       Put&& put, double (&Q)[4]) {
+    using T = double;
+    constexpr int D = 3 * NF - 4;
+    T Mn = (T)0, Kn = (T)0;                    // M_{j+1}, K_{j+1}
+    T num = (T)1, den = (T)1, f8 = (T)1, pw = (T)1;
+    T pn[4];                                   // the next particle is requested one step ahead of its use
+    ld4(base + 4 * P.order[NF - 1], pn[0], pn[1], pn[2], pn[3]);
+    [&]<int... I>(std::integer_sequence<int, I...>) {
+        ((void)[&] {
+            constexpr int j = NF - 1 - I;      // NF-1, ..., 0
+            const T p[4] = {pn[0], pn[1], pn[2], pn[3]};
+            if constexpr (j > 0) ld4(base + 4 * P.order[j - 1], pn[0], pn[1], pn[2], pn[3]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Q[c] = (j == NF - 1) ? p[c] : Q[c] + p[c];
+            const T sq = sub_rn(sub_rn(sub_rn(mul_rn(Q[0], Q[0]), mul_rn(Q[1], Q[1])), mul_rn(Q[2], Q[2])), mul_rn(Q[3], Q[3]));
+            const T Mj = Pr::sqrt(sq);
+            const T Kj = Mj - P.msum_rev[j];
+            if constexpr (j <= NF - 2) {
+                if constexpr (j < NF - 2) {    // mass variable (:665-672), exponent n-2-j
+                    const T uu = Pr::div(Kn, Kj);
+                    put(j, (T)(NF - 1 - j) * ipow<NF - 2 - j>(uu) - (T)(NF - 2 - j) * ipow<NF - 1 - j>(uu));
+                }
+                T pb[4];                       // p_j in the rest frame of Q_j -> (cos theta, phi) (:680-696)
+                const T niq = -Pr::rcp(Q[0]);
+                boost<Pr>(p, Q[1] * niq, Q[2] * niq, Q[3] * niq, pb);
+                put(NF + 2 * j - 2, ((pb[3] * Pr::rsqrt(rho2_3(pb[1], pb[2], pb[3]))) + (T)1) * (T)0.5);
+                T phi = atan_(Pr::div(pb[2], pb[1]));
+                T dphi = (pb[2] < (T)0 && pb[1] > (T)0) ? (T)6.283185307179586 : (T)0;
+                dphi += (pb[1] < (T)0) ? (T)3.141592653589793 : (T)0;
+                put(NF + 2 * j - 1, (phi + dphi) * (T)0.15915494309189535);  // 1 / (2 pi)
+                // weight pieces of the pair (j, j+1), see rambo_weight(); :709-713 uses m_{n-1}, not M_{n-1}
+                const T sM = rho_num<Pr>(Mj, (j == NF - 2) ? P.m[NF - 1] : Mn, P.m[j]);
+                const T invM = Pr::rcp(Mj);
+                if constexpr (j == NF - 2) {
+                    f8 = sM * (invM * invM);
+                } else {
+                    num *= (sM * (invM * invM)) * ((Kj * Kj) * Mn);
+                    den *= fabs_(sub_rn(mul_rn(Kj, Kj), mul_rn(Kn, Kn))) * Kn;
+                }
+                if constexpr (j == 0) pw = ipow<2 * NF - 4>(Kj * invM);
+            }
+            Mn = Mj;
+            Kn = Kj;
+        }(), ...);
+    }(std::make_integer_sequence<int, NF>{});
+    T jacinv;  // x1, x2 -> uniforms (utils.py:287-309)
+    if (P.flags & MF_FLAG_X1X2_DIRECT) {
+        put(D, x1); put(D + 1, x2); jacinv = (T)1;
+    } else {
+        const T ml1 = -log_(x1), ml2 = -log_(x2);
+        put(D, ((T)(-0.5) * (ml1 * ml1) + P.q * ml1) * P.inv_A);
+        put(D + 1, Pr::div(ml2, P.q - ml1));
+        jacinv = Pr::rcp((P.A * x1) * x2);
+    }
+    const T E_cm = Pr::sqrt(x1 * x2) * P.e_collider;
+    T w = P.flat_c * (ipow<NF - 2>(E_cm * E_cm) / P.flat_ff);
+    w *= f8;
+    w *= Pr::div(num, den);
+    w *= pw;
+    return Pr::rcp(w) * jacinv;
+}
+
+// The event again on the guarded primitives, out of line (see rambo_forward_redo in rambo_forward.cu)
+template <int NF>
+__device__ __noinline__ double rambo_inverse_stream_redo(const RamboParams<double, NF>& P, const double* base, double x1, double x2,
+                                                         double* row, double* Qout) {
+    double Q[4] = {0.0, 0.0, 0.0, 0.0};
+    const double pr = rambo_inverse_stream_event<NF, PrimIEEE>(P, base, x1, x2, [&](int c, double v) { row[c] = v; }, Q);
+    Qout[0] = Q[1]; Qout[1] = Q[2]; Qout[2] = Q[3];
+    return pr;
+}
+
 template <int NF>
 __global__ void __launch_bounds__(256, 3)
 rambo_inverse_stream_kernel(const double* __restrict__ momenta, int64_t event_stride, const double* __restrict__ x1a,
@@ -203,70 +279,22 @@ rambo_inverse_stream_kernel(const double* __restrict__ momenta, int64_t event_st
     const T* base = momenta + ev * event_stride;
     const T x1 = x1a[ev], x2 = x2a[ev];
 
+    // speculative pass on the unguarded primitives: unit-cube coordinates lie in [0, 1] (exponent field <= 0x3ff), so the OR
+    // of their high words has an all-ones exponent only if one of them is NaN / inf (never a false negative)
     T Q[4] = {(T)0, (T)0, (T)0, (T)0};
-    T Mn = (T)0, Kn = (T)0;                    // M_{j+1}, K_{j+1}
-    T num = (T)1, den = (T)1, f8 = (T)1, pw = (T)1;
-    T pn[4];                                   // the next particle is requested one step ahead of its use
-    ld4(base + 4 * P.order[NF - 1], pn[0], pn[1], pn[2], pn[3]);
-    [&]<int... I>(std::integer_sequence<int, I...>) {
-        ((void)[&] {
-            constexpr int j = NF - 1 - I;      // NF-1, ..., 0
-            const T p[4] = {pn[0], pn[1], pn[2], pn[3]};
-            if constexpr (j > 0) ld4(base + 4 * P.order[j - 1], pn[0], pn[1], pn[2], pn[3]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) Q[c] = (j == NF - 1) ? p[c] : Q[c] + p[c];
-            const T sq = sub_rn(sub_rn(sub_rn(mul_rn(Q[0], Q[0]), mul_rn(Q[1], Q[1])), mul_rn(Q[2], Q[2])), mul_rn(Q[3], Q[3]));
-            const T Mj = sqrt_fast(sq);
-            const T Kj = Mj - P.msum_rev[j];
-            if constexpr (j <= NF - 2) {
-                if constexpr (j < NF - 2) {    // mass variable (:665-672), exponent n-2-j
-                    const T uu = div_fast(Kn, Kj);
-                    row[j] = (T)(NF - 1 - j) * ipow<NF - 2 - j>(uu) - (T)(NF - 2 - j) * ipow<NF - 1 - j>(uu);
-                }
-                T pb[4];                       // p_j in the rest frame of Q_j -> (cos theta, phi) (:680-696)
-                const T niq = -rcp_fast(Q[0]);
-                boost(p, Q[1] * niq, Q[2] * niq, Q[3] * niq, pb);
-                row[NF + 2 * j - 2] = ((pb[3] * rsqrt_fast(rho2_3(pb[1], pb[2], pb[3]))) + (T)1) * (T)0.5;
-                T phi = atan_(div_fast(pb[2], pb[1]));
-                T dphi = (pb[2] < (T)0 && pb[1] > (T)0) ? (T)6.283185307179586 : (T)0;
-                dphi += (pb[1] < (T)0) ? (T)3.141592653589793 : (T)0;
-                row[NF + 2 * j - 1] = (phi + dphi) * (T)0.15915494309189535;  // 1 / (2 pi)
-                // weight pieces of the pair (j, j+1), see rambo_weight(); :709-713 uses m_{n-1}, not M_{n-1}
-                const T sM = rho_num(Mj, (j == NF - 2) ? P.m[NF - 1] : Mn, P.m[j]);
-                const T invM = rcp_fast(Mj);
-                if constexpr (j == NF - 2) {
-                    f8 = sM * (invM * invM);
-                } else {
-                    num *= (sM * (invM * invM)) * ((Kj * Kj) * Mn);
-                    den *= fabs_(sub_rn(mul_rn(Kj, Kj), mul_rn(Kn, Kn))) * Kn;
-                }
-                if constexpr (j == 0) pw = ipow<2 * NF - 4>(Kj * invM);
-            }
-            Mn = Mj;
-            Kn = Kj;
-        }(), ...);
-    }(std::make_integer_sequence<int, NF>{});
-
+    unsigned hi_or = 0u;
+    T pr = rambo_inverse_stream_event<NF, PrimRaw>(
+        P, base, x1, x2, [&](int c, T v) { hi_or |= (unsigned)__double2hiint(v); row[c] = v; }, Q);
+    if ((hi_or & 0x7ff00000u) == 0x7ff00000u || not_finite_bits(pr)) {
+        T q3[3];
+        pr = rambo_inverse_stream_redo<NF>(P, base, x1, x2, row, q3);
+        Q[1] = q3[0]; Q[2] = q3[1]; Q[3] = q3[2];
+    }
     if (!(P.flags & MF_FLAG_NO_CM_CHECK) && status != nullptr) {  // :630-635: Q_0 is the summed final state
         const T r2 = (Q[1] * Q[1] + Q[2] * Q[2]) + Q[3] * Q[3];
         if (valid && !(r2 < (T)1e-3)) atomicOr(status, MF_ST_NOT_CM);
     }
-    T jacinv;  // x1, x2 -> uniforms (utils.py:287-309)
-    if (P.flags & MF_FLAG_X1X2_DIRECT) {
-        row[D] = x1; row[D + 1] = x2; jacinv = (T)1;
-    } else {
-        const T ml1 = -log_(x1), ml2 = -log_(x2);
-        row[D] = ((T)(-0.5) * (ml1 * ml1) + P.q * ml1) * P.inv_A;
-        row[D + 1] = div_fast(ml2, P.q - ml1);
-        jacinv = rcp_fast((P.A * x1) * x2);
-    }
-    const T E_cm = sqrt_fast(x1 * x2) * P.e_collider;
-    T w = P.flat_c * (ipow<NF - 2>(E_cm * E_cm) / P.flat_ff);
-    w *= f8;
-    w *= div_fast(num, den);
-    w *= pw;
     if (valid) {
-        const T pr = rcp_fast(w) * jacinv;
         prob[ev] = pr;
         if (logprob != nullptr) logprob[ev] = log_(pr);
     }
