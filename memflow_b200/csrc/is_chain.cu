@@ -384,7 +384,7 @@ rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, i
         rambo_forward_stream<double, NF, PrimRaw>(
             P, [&](int i) { return uc[i]; },
             [&](int j, const double (&p)[4]) { if (mo) { redo |= not_finite_bits(p[0]); st4(mo + 4 * j, p[0], p[1], p[2], p[3]); } },
-            jac, x1, x2);
+            jac, x1, x2, redo);
         if (redo | not_finite_bits(jac)) {
             double wx[3];
             rambo_is_redo<NF>(P, u + ev * F, mo, wx);

@@ -4,6 +4,7 @@
 // unrolled on the compile-time multiplicity NF).
 #pragma once
 #include <cmath>
+#include <type_traits>
 #include <utility>
 
 #include "common.cuh"
@@ -148,21 +149,62 @@ template <int E> struct MassVarPoly {
     }
 };
 
-template <int E> MF_D float massvar_start_f32(bool small, float tf) {
-    float x;
-    if (small) {
-        const float ie = 1.0f / (float)E;
-        x = exp2f(__log2f(tf * (1.0f / (float)(E + 1))) * ie);
-        x = exp2f(__log2f(__fdividef(tf, (float)(E + 1) - (float)E * x)) * ie);
-    } else {
-        float d0 = sqrtf((2.0f / (float)(E * (E + 1))) * tf);
-        x = d0 * (1.0f + ((float)(E - 1) / 3.0f) * d0);
+// log2 of the asymptote prefactors (compile-time tables, E = 1..7)
+template <int E> MF_HD constexpr float kLog2InvEp1() {   // log2(1 / (E + 1))
+    constexpr float t[8] = {0.0f, -1.0f, -1.5849625007211562f, -2.0f, -2.321928094887362f, -2.584962500721156f,
+                            -2.807354922057604f, -3.0f};
+    return t[E];
+}
+template <int E> MF_HD constexpr float kLog2TwoOverEEp1() {   // log2(2 / (E (E + 1)))
+    constexpr float t[8] = {0.0f, 0.0f, -1.5849625007211562f, -2.584962500721156f, -3.321928094887362f, -3.9068905956085187f,
+                            -4.392317422778761f, -4.807354922057604f};
+    return t[E];
+}
+// MUFU approximations without the denormal / special-case wrappers of exp2f, __log2f, sqrtf (each wrapper is a compare
+// and a branch per call: they cut the event's instruction stream into basic blocks the scheduler cannot interleave)
+MF_D float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+MF_D float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+MF_D float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// fp32 start of the root, BRANCH-FREE: both variables share one instruction stream.
+//   asymptote   x0 = (a t)^p          small variable: a = 1/(E+1), p = 1/E;   large variable: a = 2/(E(E+1)), p = 1/2
+//   refinement  small: (t / ((E+1) - E x0))^(1/E)      large: x0 (1 + (E-1)/3 x0)
+//   2 Newton steps on F(x) - t = x^2 H(x) - t, F'(x) = x G(x), H and G Horner forms over per-lane selected coefficients
+//   (the same polynomial the fp64 polish uses). Valid for 1e-30 < t <= 0.65; callers route everything else elsewhere.
+template <int E> struct MassVarPolyF {
+    bool small;
+    MF_D explicit MassVarPolyF(bool s) : small(s) {}
+    template <int J> MF_D float coef(float scale) const {
+        constexpr float a = (J + 2 == E) ? (float)(E + 1) : ((J + 2 == E + 1) ? -(float)E : 0.0f);
+        constexpr float b = (float)tail_coef(E, J + 2);
+        return small ? scale * a : scale * b;
     }
+    template <int J> MF_D float horner_f(float x, float h) const {
+        if constexpr (J < 0) return h;
+        else return horner_f<J - 1>(x, fmaf(h, x, coef<J>(1.0f)));
+    }
+    template <int J> MF_D float horner_d(float x, float g) const {
+        if constexpr (J < 0) return g;
+        else return horner_d<J - 1>(x, fmaf(g, x, coef<J>((float)(J + 2))));
+    }
+    MF_D float residual(float x, float t) const { return fmaf(x * x, horner_f<E - 2>(x, coef<E - 1>(1.0f)), -t); }
+    MF_D float slope(float x) const { return x * horner_d<E - 2>(x, coef<E - 1>((float)(E + 1))); }
+};
+template <int E> MF_D float massvar_start_f32(bool small, float tf) {
+    constexpr float ie = 1.0f / (float)E;
+    const float lt = lg2_approx(tf);
+    // log2 of the asymptote's prefactor a, times the exponent p
+    const float p = small ? ie : 0.5f;
+    // constants folded at compile time: log2(1/(E+1)) and log2(2/(E(E+1)))
+    const float lga = small ? kLog2InvEp1<E>() : kLog2TwoOverEEp1<E>();
+    const float x0 = ex2_approx((lt + lga) * p);
+    const float xs = ex2_approx((lt - lg2_approx(fmaf(-(float)E, x0, (float)(E + 1)))) * ie);
+    const float xl = x0 * fmaf((float)(E - 1) / 3.0f, x0, 1.0f);
+    float x = small ? xs : xl;
+    const MassVarPolyF<E> pl(small);
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-        float f, d1, d2;
-        MassVarFn<E, float>::eval(small, x, tf, f, d1, d2);
-        float xn = x - __fdividef(f, d1);
+        const float xn = fmaf(-pl.residual(x, tf), rcp_approx(pl.slope(x)), x);
         x = (xn > 0.0f && xn < 1.0f) ? xn : x;  // also rejects NaN/inf steps
     }
     return x;
@@ -181,20 +223,30 @@ template <int E> __device__ __noinline__ double massvar_tiny_target(bool small, 
     return x;
 }
 
-template <int E, typename Pr = PrimIEEE> MF_D double solve_massvar(double v) {
+// `rare` (PrimRaw only): set when the target leaves the fp32 start's domain (t <= 1e-30, t <= 0, NaN): the caller redoes the
+// event on PrimIEEE, whose result is bit-identical for every other t (same start, same polish).
+template <int E, typename Pr = PrimIEEE> MF_D double solve_massvar(double v, bool& rare) {
     if constexpr (E == 1) {
         double u = Pr::div(v, 1.0 + Pr::sqrt(1.0 - v));
         return (v <= 0.0) ? Limits<double>::tiny_u() : ((v >= 1.0 || u > Limits<double>::max_u()) ? Limits<double>::max_u() : u);
     } else {
-        const bool small = v < 0.65;
+        // v < 0.65 on the high word (integer pipe; either variable is fine within 2^-20 of the boundary; negative v -> small,
+        // NaN -> large, both end in the t <= 0 / NaN handling)
+        const bool small = __double2hiint(v) < 0x3fe4cccc;
         const double t = small ? v : 1.0 - v;
+        const float tf = (float)t;
         double x;
-        if (t > 1e-30) {
-            x = (double)massvar_start_f32<E>(small, (float)t);
-        } else if (t > 0.0) {  // outside fp32 range (never taken for u in [1e-10, 1-1e-10]): out of line, see below
-            x = massvar_tiny_target<E>(small, t);
+        if constexpr (std::is_same_v<Pr, PrimRaw>) {
+            rare |= !(tf > 1e-30f);
+            x = (double)massvar_start_f32<E>(small, tf);
         } else {
-            x = (t == 0.0 || t < 0.0) ? 0.0 : t;  // t <= 0 -> 0, NaN -> NaN
+            if (tf > 1e-30f) {
+                x = (double)massvar_start_f32<E>(small, tf);
+            } else if (t > 0.0) {  // outside fp32 range (never taken for u in [1e-10, 1-1e-10]): out of line, see below
+                x = massvar_tiny_target<E>(small, t);
+            } else {
+                x = (t == 0.0 || t < 0.0) ? 0.0 : t;  // t <= 0 -> 0, NaN -> NaN
+            }
         }
         // fp64 polish. In either variable F is a polynomial sum_{k=2}^{E+1} c_k x^k (x^E((E+1) - E x), or x^2 P_E(x)):
         // the coefficients are selected per lane, so a warp with both kinds of lanes runs ONE instruction stream.
@@ -211,6 +263,10 @@ template <int E, typename Pr = PrimIEEE> MF_D double solve_massvar(double v) {
         u = (u > Limits<double>::max_u()) ? Limits<double>::max_u() : u;
         return (u < Limits<double>::tiny_u()) ? Limits<double>::tiny_u() : u;  // NaN stays NaN
     }
+}
+template <int E, typename Pr = PrimIEEE> MF_D double solve_massvar(double v) {
+    bool rare = false;
+    return solve_massvar<E, Pr>(v, rare);
 }
 template <int E, typename Pr = PrimIEEE> MF_D float solve_massvar(float v) {
     if constexpr (E == 1) {
@@ -229,6 +285,8 @@ template <int E, typename Pr = PrimIEEE> MF_D float solve_massvar(float v) {
         return (u < Limits<float>::tiny_u()) ? Limits<float>::tiny_u() : u;
     }
 }
+
+template <int E, typename Pr = PrimIEEE> MF_D float solve_massvar(float v, bool&) { return solve_massvar<E, Pr>(v); }
 
 // get_flatWeights (:111-140) * massive correction (:489-507), from K_i, M_i and the shared pieces
 // sM_i = sqrt((M_i^2-(M_{i+1}+m_i)^2)(M_i^2-(M_{i+1}-m_i)^2)), invM_i = 1/M_i:
@@ -280,6 +338,38 @@ template <typename T> MF_D T delphi(const T (&a)[4], const T (&b)[4]) {  // util
     return r;
 }
 
+// cos(2 pi u) in fp64 without the library's coefficient-table loads (cospi fetches 6 coefficients with 3 LDG.128 per call:
+// ncu showed the dependent DFMAs waiting on them, `long_scoreboard`). Exact reduction u -> quarter turns: k = rint(4u),
+// r = 2u - k/2, |r| <= 1/4; cos(pi r) or sin(pi r) by one degree-7 Horner form in r^2 over per-lane selected minimax
+// coefficients (Remez fit in 60-digit arithmetic: relative error 4e-20 / 2e-21 before rounding); measured <= 1 ulp
+// against 50-digit cos(2 pi u) for u in [0, 1]. Valid for |u| < 2^49 (callers route anything larger to the library).
+MF_D double cos2pi_fast(double u) {
+    const double tk = fma(4.0, u, 6755399441055744.0);   // 1.5 * 2^52: rint(4u) in the low word
+    const double kd = tk - 6755399441055744.0;
+    const int k = __double2loint(tk);
+    const double r = fma(kd, -0.5, u + u);               // exact
+    const bool odd = (k & 1) != 0;
+    const double s = r * r;
+    double p = odd ? -2.1716765487702665e-05 : -0.00010355601112394462;
+    p = fma(p, s, odd ? 0.0004662825901993505 : 0.0019294632268243347);
+    p = fma(p, s, odd ? -0.007370429872719428 : -0.025806885435598757);
+    p = fma(p, s, odd ? 0.08214588657954407 : 0.23533063018157302);
+    p = fma(p, s, odd ? -0.5992645293202866 : -1.3352627688517122);
+    p = fma(p, s, odd ? 2.5501640398773415 : 4.058712126416745);
+    p = fma(p, s, odd ? -5.16771278004997 : -4.934802200544679);
+    p = fma(p, s, odd ? 3.141592653589793 : 1.0);
+    const double res = (odd ? r : 1.0) * p;
+    // cos(pi (k/2 + r)): k mod 4 = 0: cos, 1: -sin, 2: -cos, 3: sin
+    return __hiloint2double(__double2hiint(res) ^ (((k + 1) & 2) << 30), __double2loint(res));
+}
+// |u| >= 2^49, inf, NaN (high word, integer pipe)
+MF_D bool beyond_cos2pi_fast(double u) { return ((unsigned)__double2hiint(u) & 0x7fffffffu) >= 0x43000000u; }
+// u > 1/2 on the bit pattern (false for negative u and -0)
+MF_D bool above_half(double u) {
+    const int hi = __double2hiint(u);
+    return hi > 0x3fe00000 || (hi == 0x3fe00000 && __double2loint(u) != 0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Streaming core of generateKinematics_batch (rambo_generator.py:168-398). The event is produced decay by decay:
 // each iteration solves one mass variable, updates the weight accumulators, builds one two-body decay, boosts it and
@@ -290,13 +380,13 @@ template <typename T> MF_D T delphi(const T (&a)[4], const T (&b)[4]) {  // util
 // ---------------------------------------------------------------------------------------------
 template <typename T, int NF, int K_IDX, typename Pr, typename Load, typename Emit>
 MF_D void rambo_decay_step(const RamboParams<T, NF>& P, Load& load, Emit& emit, const T K0, T& prod, T& Kk, T& Mk,
-                           T (&Q)[4], T& num, T& den, T& f8, T& pw) {
+                           T (&Q)[4], T& num, T& den, T& f8, T& pw, bool& rare) {
     constexpr int NE = NF - 2;
     constexpr int k = K_IDX;
     // next intermediate mass (:448-509): K_{k+1} = K_0 prod_{j<=k} t_j, M_{k+1} = K_{k+1} + sum_{j>k} m_j
     T Kn, Mn;
     if constexpr (k < NF - 2) {
-        prod *= solve_massvar<NF - 2 - k, Pr>(load(k));  // exponent of column k is NF-2-k (:405-407)
+        prod *= solve_massvar<NF - 2 - k, Pr>(load(k), rare);  // exponent of column k is NF-2-k (:405-407)
         Kn = K0 * prod;
         Mn = Kn + P.msum_rev[k + 1];
     } else {
@@ -320,10 +410,23 @@ MF_D void rambo_decay_step(const RamboParams<T, NF>& P, Load& load, Emit& emit, 
     // Payne-Hanek branch that is never taken for phi in [0, 2 pi] but was inlined once per decay: instruction-cache
     // weight). Differs from cos(fl(2 pi u)) by <= 1e-15 |sin phi|: the rounding of phi itself.
     const T uphi = load(NE + 2 * k + 1);
-    const T phi = (T)6.283185307179586 * uphi;
-    const T cp = cospi_((T)2 * uphi);
-    const T sq = Pr::sqrt(sub_rn((T)1, mul_rn(cp, cp)));
-    const T sp = (phi > (T)3.141592653589793) ? -sq : sq;
+    T cp, sp;
+    if constexpr (sizeof(T) == 8) {
+        if constexpr (std::is_same_v<Pr, PrimRaw>) {
+            rare |= beyond_cos2pi_fast(uphi);
+            cp = cos2pi_fast(uphi);
+        } else {
+            cp = beyond_cos2pi_fast(uphi) ? cospi_((T)2 * uphi) : cos2pi_fast(uphi);
+        }
+        const T sq = Pr::sqrt(sub_rn((T)1, mul_rn(cp, cp)));
+        // sin(phi) = -sqrt(..) for phi > pi (:321-322); fl(2 pi u) > fl(pi) <=> u > 1/2
+        sp = above_half(uphi) ? -sq : sq;
+    } else {
+        const T phi = (T)6.283185307179586 * uphi;
+        cp = cospi_((T)2 * uphi);
+        const T sq = Pr::sqrt(sub_rn((T)1, mul_rn(cp, cp)));
+        sp = (phi > (T)3.141592653589793) ? -sq : sq;
+    }
     T p2[4], pb[4];
     p2[1] = (qk * st) * cp;
     p2[2] = (qk * st) * sp;
@@ -346,7 +449,7 @@ MF_D void rambo_decay_step(const RamboParams<T, NF>& P, Load& load, Emit& emit, 
 }
 
 template <typename T, int NF, typename Pr = PrimIEEE, typename Load, typename Emit>
-MF_D void rambo_forward_stream(const RamboParams<T, NF>& P, Load&& load, Emit&& emit, T& wgt, T& x1, T& x2) {
+MF_D void rambo_forward_stream(const RamboParams<T, NF>& P, Load&& load, Emit&& emit, T& wgt, T& x1, T& x2, bool& rare) {
     constexpr int D = 3 * NF - 4, NP = NF + 2;
     // ---- x1, x2 from the last two uniforms: utils.py:260-284 ----
     T wx;
@@ -381,7 +484,7 @@ MF_D void rambo_forward_stream(const RamboParams<T, NF>& P, Load&& load, Emit&& 
     T Q[4] = {Mk, (T)0, (T)0, (T)0};
     T num = (T)1, den = (T)1, f8 = (T)1, pw = (T)1;
     [&]<int... I>(std::integer_sequence<int, I...>) {
-        (rambo_decay_step<T, NF, I, Pr>(P, load, emit, K0, prod, Kk, Mk, Q, num, den, f8, pw), ...);
+        (rambo_decay_step<T, NF, I, Pr>(P, load, emit, K0, prod, Kk, Mk, Q, num, den, f8, pw, rare), ...);
     }(std::make_integer_sequence<int, NF - 1>{});
     emit(NP - 1, Q);
     // weight: get_flatWeights (:111-140) * massive correction (:489-507), same product order as the reference
@@ -402,6 +505,12 @@ MF_D void rambo_forward_stream(const RamboParams<T, NF>& P, Load&& load, Emit&& 
         w = (T)wf;
     }
     wgt = wx * w;
+}
+
+template <typename T, int NF, typename Pr = PrimIEEE, typename Load, typename Emit>
+MF_D void rambo_forward_stream(const RamboParams<T, NF>& P, Load&& load, Emit&& emit, T& wgt, T& x1, T& x2) {
+    bool rare = false;
+    rambo_forward_stream<T, NF, Pr>(P, load, emit, wgt, x1, x2, rare);
 }
 
 // Array interface (chain kernels, lab-frame / cut epilogue): r = the event's 3NF-2 uniforms, out = all rows.

@@ -17,18 +17,26 @@ namespace mf {
 // The event again on the guarded primitives (common.cuh, PrimIEEE), out of line: taken only when the speculative pass below
 // stored a non-finite value (an operand of a reciprocal / square root was 0, denormal, inf or NaN: exact thresholds,
 // cos(theta) = +-1, garbage input). `src` is the event's row of uniforms (generic pointer: shared or global memory).
+// A NaN among the inputs always reaches the outputs, so the NaN-input status bit is raised here as well and the fast
+// path carries no per-input test.
 template <typename T, int NF>
-__device__ __noinline__ void rambo_forward_redo(const RamboParams<T, NF>& P, const T* src, T* mo, T* wx) {
+__device__ __noinline__ void rambo_forward_redo(const RamboParams<T, NF>& P, const T* src, T* mo, T* wx, int32_t* status) {
     T wgt, x1, x2;
+    bool bad = false;
     rambo_forward_stream<T, NF, PrimIEEE>(
-        P, [&](int i) { return src[i]; }, [&](int j, const T (&p)[4]) { st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, wgt, x1, x2);
+        P, [&](int i) { const T v = src[i]; bad |= (v != v); return v; },
+        [&](int j, const T (&p)[4]) { st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, wgt, x1, x2);
+    if (status != nullptr && bad) atomicOr(status, MF_ST_NAN_INPUT);
     wx[0] = wgt; wx[1] = x1; wx[2] = x2;
 }
 
+#ifndef MF_K1_MINB
+#define MF_K1_MINB (NF <= 4 ? 4 : 3)
+#endif
 // EPILOGUE == false: plain CM-frame output, every 4-momentum is stored the moment it is final (streaming core).
 // EPILOGUE == true : lab-frame output and / or cuts need the whole event first (array interface).
 template <typename T, int NF, bool EPILOGUE>
-__global__ void __launch_bounds__(256, (EPILOGUE ? (NF <= 4 ? 3 : 2) : (NF <= 4 ? 4 : 3)))
+__global__ void __launch_bounds__(256, (EPILOGUE ? (NF <= 4 ? 3 : 2) : MF_K1_MINB))
 rambo_forward_kernel(const T* __restrict__ u, int64_t N, const __grid_constant__ RamboParams<T, NF> P,
                      T* __restrict__ momenta, T* __restrict__ weight, T* __restrict__ logweight,
                      T* __restrict__ x1o, T* __restrict__ x2o, int32_t* __restrict__ status) {
@@ -36,7 +44,10 @@ rambo_forward_kernel(const T* __restrict__ u, int64_t N, const __grid_constant__
     // n >= 6, streaming core: the CTA's 256 input rows (contiguous) come in with one TMA bulk copy, so the uniforms the
     // dependency chains wait for are shared-memory reads instead of global loads issued one by one along the chain
     constexpr bool PREFETCH = !EPILOGUE && NF >= 6 && sizeof(T) == 8;  // n = 6: +15 %, n = 7, 8: +4-7 %, n = 5: neutral
-    __shared__ __align__(128) T su[PREFETCH ? 256 * W : 1];
+    // row pitch in shared memory: W = 16 doubles (n = 6) would put every row of a warp in the same banks (32-way conflicts on
+    // each read); those rows come in by one bulk copy per row, 18 doubles apart
+    constexpr int WP = (W % 16 == 0) ? W + 2 : W;
+    __shared__ __align__(128) T su[PREFETCH ? 256 * WP : 1];
     __shared__ uint64_t bar;
     if constexpr (PREFETCH) {
         const int64_t ev0 = (int64_t)blockIdx.x * blockDim.x;
@@ -49,12 +60,15 @@ rambo_forward_kernel(const T* __restrict__ u, int64_t N, const __grid_constant__
                 mbar_init(&bar, 1);
                 fence_mbar_init();
                 mbar_expect_tx(&bar, bytes);
-                bulk_g2s(su, src, bytes, &bar);
+                if constexpr (WP == W) bulk_g2s(su, src, bytes, &bar);
             }
             __syncthreads();
+            if constexpr (WP != W) {
+                if ((int)threadIdx.x < nrows) bulk_g2s(su + threadIdx.x * WP, src + threadIdx.x * W, W * (uint32_t)sizeof(T), &bar);
+            }
             mbar_wait(&bar, 0u);
         } else {
-            for (int i = threadIdx.x; i < nrows * W; i += blockDim.x) su[i] = src[i];
+            for (int i = threadIdx.x; i < nrows * W; i += blockDim.x) su[(i / W) * WP + (i % W)] = src[i];
             __syncthreads();
         }
     }
@@ -67,14 +81,16 @@ rambo_forward_kernel(const T* __restrict__ u, int64_t N, const __grid_constant__
     if constexpr (!EPILOGUE) {
         // speculative pass on the unguarded primitives; every stored energy depends on all components of its row, the
         // last row on the whole chain: one exponent test per row (+ the weight) sees any operand that left their domain
-        const T* __restrict__ srow = su + threadIdx.x * W;
+        const T* __restrict__ srow = su + threadIdx.x * WP;
         bool redo = false;
+        // (Fetching the first decay's five uniforms with plain loads and waiting for the tile's bulk copy only before the
+        // second decay was tried: 2-9 % slower at n = 6, 7, 8 on the same box.)
         rambo_forward_stream<T, NF, PrimRaw>(
-            P, [&](int i) { T v = PREFETCH ? srow[i] : ld1(urow + i); bad |= (v != v); return v; },
-            [&](int j, const T (&p)[4]) { redo |= not_finite_bits(p[0]); st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, wgt, x1, x2);
+            P, [&](int i) { return PREFETCH ? srow[i] : ld1(urow + i); },
+            [&](int j, const T (&p)[4]) { redo |= not_finite_bits(p[0]); st4(mo + 4 * j, p[0], p[1], p[2], p[3]); }, wgt, x1, x2, redo);
         if (redo | not_finite_bits(wgt)) {
             T wx[3];
-            rambo_forward_redo<T, NF>(P, PREFETCH ? srow : urow, mo, wx);
+            rambo_forward_redo<T, NF>(P, PREFETCH ? srow : urow, mo, wx, status);
             wgt = wx[0]; x1 = wx[1]; x2 = wx[2];
         }
     } else {
