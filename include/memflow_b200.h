@@ -265,6 +265,29 @@ int mf_decay_partons_bwd_f64(const double* propagators, const double* higgs_angl
                              double* g_thad_w_angles, double* g_tlep_b_angles, double* g_tlep_w_angles, double* g_boost,
                              mf_stream_t stream);
 
+/* The sampling branch of the reference's training loss as ONE launch (memflow/unfolding_flow/unfolding_flow_withDecay_v2.py:
+ * 376-417: rambo.get_momenta_from_ps(ps, requires_grad=True) -> boost_tt(momenta[:, -4:-1], boostVector_t(boost_Epz)) ->
+ * get_ptetaphi_comp_batch -> log(pt+1) and scaling -> get_decayPartons_fromlab_propagators_angles), n_final >= 4.
+ *   ps [N, 3n-2], the five angle pairs [N,2], cfg as for mf_decay_partons_f64 (mean/std_prop scale the propagators both
+ *   ways, mean/std_boost the boost)  ->  out [N,12,4] (the 12-parton event), boost_scaled [N,2] = scaled (log(E_b+1), pz_b).
+ *   Saved for the backward launch (and returned to the caller like the reference's tensors): momenta [N,n+2,4] (CM frame),
+ *   weight, x1, x2 [N] (K1's outputs), propagators [N,3,3] (scaled lab-frame (log(pt+1), eta, phi) of H, thad, tlep). */
+int mf_sampling_partons_f64(const double* ps, int64_t N, int n_final, const double* masses, double e_collider,
+                            const double* higgs_angles, const double* thad_b_angles, const double* thad_w_angles,
+                            const double* tlep_b_angles, const double* tlep_w_angles, const mf_decay_partons_cfg* cfg,
+                            double* out, double* boost_scaled, double* momenta, double* weight, double* x1, double* x2,
+                            double* propagators, int32_t* status, mf_stream_t stream);
+/* Its vector-Jacobian product, ONE launch: g_out [N,12,4], g_boost_scaled [N,2] (may be NULL) -> g_ps [N,3n-2] and the
+ * gradients of the five angle pairs. Gradient semantics of the reference's autograd graph (see mf_rambo_forward_bwd_f64:
+ * the mass-variable columns of ps receive none). */
+int mf_sampling_partons_bwd_f64(const double* ps, int64_t N, int n_final, const double* masses, double e_collider,
+                                const double* higgs_angles, const double* thad_b_angles, const double* thad_w_angles,
+                                const double* tlep_b_angles, const double* tlep_w_angles, const mf_decay_partons_cfg* cfg,
+                                const double* momenta, const double* weight, const double* x1, const double* x2,
+                                const double* propagators, const double* boost_scaled, const double* g_out,
+                                const double* g_boost_scaled, double* g_ps, double* g_higgs_angles, double* g_thad_b_angles,
+                                double* g_thad_w_angles, double* g_tlep_b_angles, double* g_tlep_w_angles, mf_stream_t stream);
+
 /* The two stages of the chain as separate entry points (mf_is_chain_f64 runs them back to back):
  *  A  mf_flow_sample_f32: Philox base sample + T spline inverses -> u [N,F] (fp64, in [0,1]) and log q [N]
  *                         (flow().sample + flow().log_prob of TestFlows_ImportanceSampling.ipynb [45,50] in one pass)

@@ -20,7 +20,7 @@ SYMBOLS = (
     "mf_searchsorted_f32", "mf_searchsorted_f64",
     "mf_rqs_forward_bwd_f32", "mf_rqs_forward_bwd_f64", "mf_rqs_inverse_bwd_f32", "mf_rqs_inverse_bwd_f64",
     "mf_is_reduce_workspace_bytes", "mf_is_reduce_f64", "mf_is_chain_f64", "mf_flow_sample_f32", "mf_flow_sample_f64", "mf_rambo_is_f64", "mf_higgs_decay_f64", "mf_top_decay_f64",
-    "mf_decay_partons_f64", "mf_decay_partons_bwd_f64",
+    "mf_decay_partons_f64", "mf_decay_partons_bwd_f64", "mf_sampling_partons_f64", "mf_sampling_partons_bwd_f64",
 )
 
 

@@ -66,55 +66,11 @@ decay_partons_kernel(const double* __restrict__ prop, const double* __restrict__
                      double* __restrict__ out) {
     const int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ev >= N) return;
-    const double mass[3] = {C.higgs_mass, C.tlep_mass, C.thad_mass};
-    double P[3][4];
+    double k[9];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double k[3] = {prop[ev * 9 + 3 * i], prop[ev * 9 + 3 * i + 1], prop[ev * 9 + 3 * i + 2]};
-        propagator_cartesian(k, mass[i], C, P[i]);
-    }
-    const double boost_pz = boost[2 * ev + 1] * C.std_boost[1] + C.mean_boost[1];
-    double* o = out + ev * 48;
-    auto emit = [&](int row, const double (&p)[4], bool is_prop, bool is_gluon_pad) {
-        double r[4];
-        finish_row(p, is_prop, is_gluon_pad, C, r);
-        st4(o + 4 * row, r[0], r[1], r[2], r[3]);
-    };
-    {
-        double eta, phi, l1[4], l2[4];
-        ld2(higgs_angles + 2 * ev, eta, phi);
-        higgs_decay_rows(P[0], eta, phi, C.higgs_mass, l1, l2);
-        emit(0, P[0], true, false);
-        emit(1, l1, false, false);
-        emit(2, l2, false, false);
-    }
-    {
-        double eb, pb, ew, pw, bl[4], q1l[4], q2l[4];
-        ld2(thad_b_angles + 2 * ev, eb, pb);
-        ld2(thad_w_angles + 2 * ev, ew, pw);
-        top_decay_rows(P[2], eb, pb, ew, pw, top_Eb(C.thad_mass, C.w_had_mass, C.b_mass), C.w_had_mass, C.b_mass, bl, q1l, q2l);
-        emit(3, P[2], true, false);
-        emit(4, bl, false, false);
-        emit(5, q1l, false, false);
-        emit(6, q2l, false, false);
-    }
-    {
-        double eb, pb, ew, pw, bl[4], q1l[4], q2l[4];
-        ld2(tlep_b_angles + 2 * ev, eb, pb);
-        ld2(tlep_w_angles + 2 * ev, ew, pw);
-        top_decay_rows(P[1], eb, pb, ew, pw, top_Eb(C.tlep_mass, C.w_lep_mass, C.b_mass), C.w_lep_mass, C.b_mass, bl, q1l, q2l);
-        emit(7, P[1], true, false);
-        emit(8, bl, false, false);
-        emit(9, q1l, false, false);
-        emit(10, q2l, false, false);
-    }
-    // ISR gluon = boost - partons (:881-905); the all-soft case is replaced by the reference's padding row
-    double g[4];
-    g[1] = -((P[0][1] + P[2][1]) + P[1][1]);
-    g[2] = -((P[0][2] + P[2][2]) + P[1][2]);
-    g[3] = boost_pz - ((P[0][3] + P[2][3]) + P[1][3]);
-    g[0] = sqrt((g[1] * g[1] + g[2] * g[2]) + g[3] * g[3]) + C.eps;
-    emit(11, g, false, gluon_pad(g, C));
+    for (int i = 0; i < 9; ++i) k[i] = prop[ev * 9 + i];
+    decay_partons_event(k, higgs_angles + 2 * ev, thad_b_angles + 2 * ev, thad_w_angles + 2 * ev, tlep_b_angles + 2 * ev,
+                        tlep_w_angles + 2 * ev, boost[2 * ev + 1], C, out + ev * 48);
 }
 
 }  // namespace mf

@@ -196,4 +196,79 @@ MF_D bool gluon_pad(const S (&g)[4], const mf_decay_partons_cfg& C) {
     return C.ptetaphi && ::fabs(dk::value(g[1])) < 0.1 && ::fabs(dk::value(g[2])) < 0.1 && ::fabs(dk::value(g[3])) < 0.1;
 }
 
+// ---- the whole parton-level event from the three scaled lab-frame propagators k[3][3] = (log(pt+1), eta, phi), the five
+//      decay angle pairs (global memory, this event's) and the scaled boost pz:
+//      Compute_ParticlesTensor.get_decayPartons_fromlab_propagators_angles, memflow/unfolding_flow/utils.py:826-935
+//      (call site: unfolding_flow_withDecay_v2.py:399-417). unscale -> pt = exp|.|-1 -> cartesian -> H->bb, t->bqq',
+//      t->blv -> ISR gluon from the momentum balance -> (E,pt,eta,phi) -> log(pt+1) + scaling.
+//      Output rows: H b1 b2 | thad b q1 q2 | tlep b l nu | ISR. The reference's naming quirk is kept: propagator 1
+//      takes (tlep_mass, tlep angles), propagator 2 takes (thad_mass, thad angles) (:866-873). ----
+MF_D void decay_partons_event(const double (&k)[9], const double* __restrict__ higgs_angles,
+                              const double* __restrict__ thad_b_angles, const double* __restrict__ thad_w_angles,
+                              const double* __restrict__ tlep_b_angles, const double* __restrict__ tlep_w_angles,
+                              double boost_pz_scaled, const mf_decay_partons_cfg& C, double* __restrict__ o) {
+    const double mass[3] = {C.higgs_mass, C.tlep_mass, C.thad_mass};
+    double P[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double ki[3] = {k[3 * i], k[3 * i + 1], k[3 * i + 2]};
+        propagator_cartesian(ki, mass[i], C, P[i]);
+    }
+    const double boost_pz = boost_pz_scaled * C.std_boost[1] + C.mean_boost[1];
+    auto emit = [&](int row, const double (&p)[4], bool is_prop, bool is_gluon_pad) {
+        double r[4];
+        finish_row(p, is_prop, is_gluon_pad, C, r);
+        st4(o + 4 * row, r[0], r[1], r[2], r[3]);
+    };
+    {
+        double eta, phi, l1[4], l2[4];
+        ld2(higgs_angles, eta, phi);
+        higgs_decay_rows(P[0], eta, phi, C.higgs_mass, l1, l2);
+        emit(0, P[0], true, false);
+        emit(1, l1, false, false);
+        emit(2, l2, false, false);
+    }
+    {
+        double eb, pb, ew, pw, bl[4], q1l[4], q2l[4];
+        ld2(thad_b_angles, eb, pb);
+        ld2(thad_w_angles, ew, pw);
+        top_decay_rows(P[2], eb, pb, ew, pw, top_Eb(C.thad_mass, C.w_had_mass, C.b_mass), C.w_had_mass, C.b_mass, bl, q1l, q2l);
+        emit(3, P[2], true, false);
+        emit(4, bl, false, false);
+        emit(5, q1l, false, false);
+        emit(6, q2l, false, false);
+    }
+    {
+        double eb, pb, ew, pw, bl[4], q1l[4], q2l[4];
+        ld2(tlep_b_angles, eb, pb);
+        ld2(tlep_w_angles, ew, pw);
+        top_decay_rows(P[1], eb, pb, ew, pw, top_Eb(C.tlep_mass, C.w_lep_mass, C.b_mass), C.w_lep_mass, C.b_mass, bl, q1l, q2l);
+        emit(7, P[1], true, false);
+        emit(8, bl, false, false);
+        emit(9, q1l, false, false);
+        emit(10, q2l, false, false);
+    }
+    // ISR gluon = boost - partons (:881-905); the all-soft case is replaced by the reference's padding row
+    double g[4];
+    g[1] = -((P[0][1] + P[2][1]) + P[1][1]);
+    g[2] = -((P[0][2] + P[2][2]) + P[1][2]);
+    g[3] = boost_pz - ((P[0][3] + P[2][3]) + P[1][3]);
+    g[0] = ::sqrt((g[1] * g[1] + g[2] * g[2]) + g[3] * g[3]) + C.eps;
+    emit(11, g, false, gluon_pad(g, C));
+}
+
+// ---- the sampling branch's glue between K1 and the decay chain (unfolding_flow_withDecay_v2.py:381-397): one CM-frame
+//      propagator -> lab frame by the event's boost (E_b, 0, 0, pz_b) -> (pt, eta, phi) -> (scaled log(pt+1), scaled eta, phi).
+//      Generic over the scalar like the decay blocks: double in the forward kernel, a dual number in the backward one. ----
+template <typename S>
+MF_D void lab_scaled_propagator(const S (&p_cm)[4], const S& boost_E, const S& boost_pz, const mf_decay_partons_cfg& C, S (&k)[3]) {
+    const S parent[4] = {boost_E, S(0.0), S(0.0), boost_pz};
+    S lab[4], o[4];
+    boost_by_parent(p_cm, parent, lab);   // ps_utils.boost_tt(p, ps_utils.boostVector_t(boost_Epz))  (:384-387)
+    ptetaphi(lab, o);                     // get_ptetaphi_comp_batch (:390)
+    k[0] = (dk::log(o[1] + 1.0) - C.mean_prop[0]) / C.std_prop[0];   // :392-393
+    k[1] = (o[2] - C.mean_prop[1]) / C.std_prop[1];
+    k[2] = o[3];
+}
+
 }  // namespace mf

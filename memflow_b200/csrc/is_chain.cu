@@ -359,8 +359,11 @@ __device__ __noinline__ void rambo_is_redo(const RamboParams<double, NF>& P, con
     wx[0] = jac; wx[1] = x1; wx[2] = x2;
 }
 
+#ifndef MF_CHAINB_MINB
+#define MF_CHAINB_MINB 3
+#endif
 template <int NF>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, MF_CHAINB_MINB)
 rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, int64_t N,
                 const __grid_constant__ RamboParams<double, NF> P, double inv_2s, double* __restrict__ acc,
                 void* workspace, double* __restrict__ momenta, double* __restrict__ weight, double* __restrict__ x1o,

@@ -209,22 +209,9 @@ class Compute_ParticlesTensor:
             raise NameError("name 'log_mean_parton' is not defined (memflow/unfolding_flow/utils.py:913: the cartesian "
                             "final scaling of the reference never worked; use ptetaphi=True or final_scaling=False)")
         require_cuda(propagators_kinematics, "propagators_kinematics")
-        cfg = DecayPartonsCfg()
-        def put(field, t, n):
-            v = [float(x) for x in torch.as_tensor(t).detach().reshape(-1).tolist()]
-            if len(v) < n:
-                raise ValueError("get_decayPartons_fromlab_propagators_angles: scaling vector shorter than %d" % n)
-            for i in range(n):
-                field[i] = v[i]
-        put(cfg.mean_prop, log_mean_parton_Hthadtlep, 3 if unscale_phi else 2)
-        put(cfg.std_prop, log_std_parton_Hthadtlep, 3 if unscale_phi else 2)
-        put(cfg.mean_lab, log_mean_parton_lab, 3 if unscale_phi else 2)
-        put(cfg.std_lab, log_std_parton_lab, 3 if unscale_phi else 2)
-        put(cfg.mean_boost, log_mean_boost, 2)
-        put(cfg.std_boost, log_std_boost, 2)
-        cfg.higgs_mass, cfg.thad_mass, cfg.tlep_mass = float(higgs_mass), float(thad_mass), float(tlep_mass)
-        cfg.w_had_mass, cfg.w_lep_mass, cfg.b_mass, cfg.eps = float(W_had_mass), float(W_lep_mass), float(b_mass), float(eps)
-        cfg.ptetaphi, cfg.unscale_phi, cfg.final_scaling = int(bool(ptetaphi)), int(bool(unscale_phi)), int(bool(final_scaling))
+        cfg = _decay_cfg(log_mean_parton_lab, log_std_parton_lab, log_mean_boost, log_std_boost, log_mean_parton_Hthadtlep,
+                         log_std_parton_Hthadtlep, higgs_mass, thad_mass, tlep_mass, W_had_mass, W_lep_mass, b_mass, ptetaphi,
+                         eps, unscale_phi, final_scaling)
         N = propagators_kinematics.shape[0]
         if tuple(propagators_kinematics.shape) != (N, 3, 3):
             raise ValueError("propagators_kinematics must be [N,3,3] (H, thad, tlep) x (log(pt+1), eta, phi)")
@@ -268,3 +255,114 @@ class _DecayPartonsFn(torch.autograd.Function):
         outs = [gr.reshape(shape).to(dt) if need else None
                 for gr, (shape, dt), need in zip(grads, ctx.in_meta, ctx.needs_input_grad[1:])]
         return (None, *outs)
+
+
+def _decay_cfg(log_mean_parton_lab, log_std_parton_lab, log_mean_boost, log_std_boost, log_mean_parton_Hthadtlep,
+               log_std_parton_Hthadtlep, higgs_mass, thad_mass, tlep_mass, W_had_mass, W_lep_mass, b_mass, ptetaphi, eps,
+               unscale_phi, final_scaling):
+    """mf_decay_partons_cfg from the reference's keyword arguments (memflow/unfolding_flow/utils.py:826-845)."""
+    cfg = DecayPartonsCfg()
+
+    def put(field, t, n):
+        v = [float(x) for x in torch.as_tensor(t).detach().reshape(-1).tolist()]
+        if len(v) < n:
+            raise ValueError("get_decayPartons_fromlab_propagators_angles: scaling vector shorter than %d" % n)
+        for i in range(n):
+            field[i] = v[i]
+    put(cfg.mean_prop, log_mean_parton_Hthadtlep, 3 if unscale_phi else 2)
+    put(cfg.std_prop, log_std_parton_Hthadtlep, 3 if unscale_phi else 2)
+    put(cfg.mean_lab, log_mean_parton_lab, 3 if unscale_phi else 2)
+    put(cfg.std_lab, log_std_parton_lab, 3 if unscale_phi else 2)
+    put(cfg.mean_boost, log_mean_boost, 2)
+    put(cfg.std_boost, log_std_boost, 2)
+    cfg.higgs_mass, cfg.thad_mass, cfg.tlep_mass = float(higgs_mass), float(thad_mass), float(tlep_mass)
+    cfg.w_had_mass, cfg.w_lep_mass, cfg.b_mass, cfg.eps = float(W_had_mass), float(W_lep_mass), float(b_mass), float(eps)
+    cfg.ptetaphi, cfg.unscale_phi, cfg.final_scaling = int(bool(ptetaphi)), int(bool(unscale_phi)), int(bool(final_scaling))
+    return cfg
+
+
+def sampled_decayPartons_from_ps(rambo, ps_samples, higgs_angles, thad_b_angles, thad_W_angles, tlep_b_angles, tlep_W_angles,
+                                 log_mean_parton_lab, log_std_parton_lab, log_mean_boost, log_std_boost,
+                                 log_mean_parton_Hthadtlep, log_std_parton_Hthadtlep, higgs_mass=125.25, thad_mass=172.5,
+                                 tlep_mass=172.5, W_had_mass=80.4, W_lep_mass=80.4, b_mass=0.0, ptetaphi=True, eps=1e-4,
+                                 unscale_phi=False, final_scaling=True):
+    """The sampling branch of the reference's training loss, memflow/unfolding_flow/unfolding_flow_withDecay_v2.py:376-417, as
+    ONE forward launch (`mf_sampling_partons_f64`) and ONE backward launch (`mf_sampling_partons_bwd_f64`):
+
+        momenta, _, x1, x2 = rambo.get_momenta_from_ps(ps_samples, requires_grad=True)
+        boost_Epz = stack(E (x1 + x2) / 2, 0, 0, E (x1 - x2) / 2)
+        lab = ps_utils.boost_tt(momenta[:, -4:-1], ps_utils.boostVector_t(boost_Epz).unsqueeze(1))
+        prop = scaled (log(pt + 1), eta, phi) of get_ptetaphi_comp_batch(lab)
+        boost_scaled = ((log(boost_E + 1), boost_pz) - log_mean_boost) / log_std_boost
+        partons = Compute_ParticlesTensor.get_decayPartons_fromlab_propagators_angles(prop, <angles>, boost_scaled[:, None], ...)
+
+    `rambo` is a memflow_b200 PhaseSpace with n >= 4 final-state bodies (H, thad, tlep, ISR). Returns
+    (partons [N,12,4], boost_scaled [N,2], momenta [N,n+2,4], weight [N], x1 [N], x2 [N]); partons and boost_scaled are
+    differentiable w.r.t. ps_samples (the reference graph's semantics: no gradient through the mass-variable columns) and
+    the five angle pairs; momenta / weight / x1 / x2 are returned detached (differentiate them through
+    `rambo.get_momenta_from_ps` instead)."""
+    if final_scaling and not ptetaphi:
+        raise NameError("name 'log_mean_parton' is not defined (memflow/unfolding_flow/utils.py:913)")
+    require_cuda(ps_samples, "ps_samples")
+    gen = rambo.generator
+    n = gen.n_final
+    if n < 4:
+        raise ValueError("sampled_decayPartons_from_ps needs n >= 4 final-state bodies (momenta[:, -4:-1])")
+    N = ps_samples.shape[0]
+    if tuple(ps_samples.shape) != (N, 3 * n - 2):
+        raise ValueError("ps_samples must be [N, 3n-2]")
+    angles = [higgs_angles, thad_b_angles, thad_W_angles, tlep_b_angles, tlep_W_angles]
+    for a in angles:
+        if tuple(a.shape) != (N, 2):
+            raise ValueError("decay angles must be [N,2] = (eta, phi)")
+    cfg = _decay_cfg(log_mean_parton_lab, log_std_parton_lab, log_mean_boost, log_std_boost, log_mean_parton_Hthadtlep,
+                     log_std_parton_Hthadtlep, higgs_mass, thad_mass, tlep_mass, W_had_mass, W_lep_mass, b_mass, ptetaphi, eps,
+                     unscale_phi, final_scaling)
+    masses = list(gen._masses_host)
+    out, bs, mom, w, x1, x2 = _SamplingPartonsFn.apply(cfg, masses, float(gen.collider_energy), ps_samples, *angles)
+    return out.to(ps_samples.dtype), bs.to(ps_samples.dtype), mom, w, x1, x2
+
+
+class _SamplingPartonsFn(torch.autograd.Function):
+    """mf_sampling_partons_f64 / mf_sampling_partons_bwd_f64."""
+
+    @staticmethod
+    def forward(ctx, cfg, masses, e_collider, ps, *angles):
+        dev = ps.device
+        d = [t.detach().to(torch.float64).contiguous() for t in (ps, *angles)]
+        N, n = d[0].shape[0], len(masses)
+        out = torch.empty((N, 12, 4), dtype=torch.float64, device=dev)
+        bs = torch.empty((N, 2), dtype=torch.float64, device=dev)
+        mom = torch.empty((N, n + 2, 4), dtype=torch.float64, device=dev)
+        w, x1, x2 = (torch.empty(N, dtype=torch.float64, device=dev) for _ in range(3))
+        prop = torch.empty((N, 3, 3), dtype=torch.float64, device=dev)
+        mh = host_array(masses, ctypes.c_double)
+        with device_guard(dev):
+            check(lib().mf_sampling_partons_f64(ptr(d[0]), ctypes.c_int64(N), ctypes.c_int(n), mh, ctypes.c_double(e_collider),
+                                                *[ptr(t) for t in d[1:]], ctypes.byref(cfg), ptr(out), ptr(bs), ptr(mom), ptr(w),
+                                                ptr(x1), ptr(x2), ptr(prop), None, stream_ptr(dev)), "mf_sampling_partons_f64")
+        ctx.cfg, ctx.masses, ctx.e_collider = cfg, masses, e_collider
+        ctx.save_for_backward(*d, mom, w, x1, x2, prop, bs)
+        ctx.in_meta = [(t.shape, t.dtype) for t in (ps, *angles)]
+        ctx.mark_non_differentiable(mom, w, x1, x2)
+        return out, bs, mom, w, x1, x2
+
+    @staticmethod
+    def backward(ctx, g_out, g_bs, _gm, _gw, _gx1, _gx2):
+        *d, mom, w, x1, x2, prop, bs = ctx.saved_tensors
+        dev = d[0].device
+        N, n = d[0].shape[0], len(ctx.masses)
+        g = (torch.zeros((N, 12, 4), dtype=torch.float64, device=dev) if g_out is None
+             else g_out.detach().to(torch.float64).contiguous())
+        gb = None if g_bs is None else g_bs.detach().to(torch.float64).contiguous()
+        grads = [torch.empty_like(t) for t in d]
+        mh = host_array(ctx.masses, ctypes.c_double)
+        with device_guard(dev):
+            check(lib().mf_sampling_partons_bwd_f64(ptr(d[0]), ctypes.c_int64(N), ctypes.c_int(n), mh,
+                                                    ctypes.c_double(ctx.e_collider), *[ptr(t) for t in d[1:]],
+                                                    ctypes.byref(ctx.cfg), ptr(mom), ptr(w), ptr(x1), ptr(x2), ptr(prop), ptr(bs),
+                                                    ptr(g), ptr(gb), *[ptr(t) for t in grads], stream_ptr(dev)),
+                  "mf_sampling_partons_bwd_f64")
+        outs = [gr.reshape(shape).to(dt) if need else None
+                for gr, (shape, dt), need in zip(grads, ctx.in_meta, ctx.needs_input_grad[3:])]
+        return (None, None, None, *outs)

@@ -695,3 +695,81 @@ def test_get_ps_autograd_matches_reference_graph(golden_dir):
     out = Compute_ParticlesTensor.get_PS(mom2, boost.detach(), order=[1, 0, 2, 3], target_mass=torch.from_numpy(g["target_mass"]),
                                          E_CM=float(g["e_cm"]), logit_eps=5e-5)
     assert len(out) == 4 and out[3].requires_grad
+
+
+def test_sampling_branch_fused_one_launch_each_way(golden_dir):
+    """The same branch (unfolding_flow_withDecay_v2.py:376-417) through the fused entry: ONE forward launch
+    (mf_sampling_partons_f64) and ONE backward launch (mf_sampling_partons_bwd_f64), no torch glue in between. Same
+    golden outputs and gradients of the unmodified reference as the test above, and agreement with the unfused path."""
+    from memflow_b200 import _lib
+    from memflow_b200.phasespace.phasespace import PhaseSpace
+    from memflow_b200.unfolding_flow import utils as UU
+    g = np.load(os.path.join(golden_dir, "sampling_pipeline.npz"))
+    c = lambda k: torch.from_numpy(g[k]).cuda()
+    rambo = PhaseSpace(float(g["e_cm"]), [21, 21], [25, 6, -6, 21], final_masses=torch.from_numpy(g["masses"]), dev="cuda:0")
+    ps = c("ps").requires_grad_(True)
+    a = [c("angles")[i].clone().requires_grad_(True) for i in range(5)]
+    L = _lib.lib()
+    calls = []
+    names = [n for n in _lib.SYMBOLS if n not in ("mf_error_string", "mf_abi_version", "mf_device_info", "mf_is_reduce_workspace_bytes")]
+    orig = {n: getattr(L, n) for n in names}
+    try:
+        for n in names:
+            setattr(L, n, (lambda f, n=n: (lambda *args: (calls.append(n), f(*args))[1]))(orig[n]))
+        out, bs, mom, w, x1, x2 = UU.sampled_decayPartons_from_ps(
+            rambo, ps, *a, log_mean_parton_lab=c("mean_lab"), log_std_parton_lab=c("std_lab"), log_mean_boost=c("mean_boost"),
+            log_std_boost=c("std_boost"), log_mean_parton_Hthadtlep=c("mean_prop"), log_std_parton_Hthadtlep=c("std_prop"),
+            ptetaphi=True, eps=1e-4, unscale_phi=False, final_scaling=True)
+        assert calls == ["mf_sampling_partons_f64"], calls
+        ((out * c("g_out")).sum() + (bs * c("g_boost")).sum()).backward()
+        assert calls == ["mf_sampling_partons_f64", "mf_sampling_partons_bwd_f64"], calls
+    finally:
+        for n in names:
+            setattr(L, n, orig[n])
+    o, ref = out.detach().cpu().numpy(), g["out"]
+    assert np.array_equal(np.isfinite(o), np.isfinite(ref))
+    pt = np.exp(np.abs(ref[..., 1] * np.where(np.isin(np.arange(12), (0, 3, 7)), g["std_prop"][0], g["std_lab"][0])
+                       + np.where(np.isin(np.arange(12), (0, 3, 7)), g["mean_prop"][0], g["mean_lab"][0]))) - 1
+    kappa = np.maximum(float(g["e_cm"]) / np.maximum(pt, 1e-3), 1.0)[..., None]
+    assert np.nanmax(np.abs(o - ref) / (1 + np.abs(ref)) / kappa) < TOL64
+    assert np.nanmax(np.abs(bs.detach().cpu().numpy() - g["boost_scaled"])) < 1e-12
+    gp, gr = ps.grad.cpu().numpy(), g["g_ps"]
+    fin = np.isfinite(gr).all(axis=1)
+    assert fin.sum() > 100 and np.isfinite(gp[fin]).all()
+    assert np.all(gp[fin][:, :2] == 0.0)
+    rel = np.abs(gp - gr)[fin] / (np.abs(gr[fin]).max(axis=1, keepdims=True) + 1e-300)
+    print("fused sampling branch: d loss / d ps vs reference: median %.1e q99 %.1e max %.1e" % (np.median(rel), np.quantile(rel, 0.99), rel.max()))
+    assert np.median(rel) < 1e-12 and np.quantile(rel, 0.99) < 1e-8 and rel.max() < 1e-5, rel.max()
+    # the K1 outputs that come back with it are those of the plain call
+    m2, w2, x12, x22 = rambo.get_momenta_from_ps(ps.detach())
+    assert torch.equal(x1, x12) and torch.equal(x2, x22)
+    ok = torch.isfinite(m2).all(dim=(1, 2)) & torch.isfinite(mom).all(dim=(1, 2))
+    assert float((mom[ok] - m2[ok]).abs().max()) <= 1e-9 * float(g["e_cm"])
+    # angle gradients against the unfused path (decay kernel backward on the torch glue)
+    from memflow_b200.phasespace import utils as ps_utils
+    CPT = UU.Compute_ParticlesTensor
+    ps2 = c("ps").requires_grad_(True)
+    a2 = [c("angles")[i].clone().requires_grad_(True) for i in range(5)]
+    mom_, _, x1_, x2_ = rambo.get_momenta_from_ps(ps2, requires_grad=True)
+    zeros = torch.zeros_like(x1_)
+    bE = torch.stack((rambo.collider_energy * (x1_ + x2_) / 2, zeros, zeros, rambo.collider_energy * (x1_ - x2_) / 2), dim=1)
+    lab = ps_utils.boost_tt(mom_[:, -4:-1], ps_utils.boostVector_t(bE).unsqueeze(dim=1))
+    pep = CPT.get_ptetaphi_comp_batch(lab)
+    prop = pep[..., 1:].clone()
+    prop[..., 0] = torch.log(pep[..., 1] + 1)
+    prop[..., 0:2] = (prop[..., 0:2] - c("mean_prop")[:2]) / c("std_prop")[:2]
+    bsc = bE[..., [0, 3]].clone()
+    bsc[..., 0] = torch.log(bE[..., 0] + 1)
+    bsc = (bsc - c("mean_boost")) / c("std_boost")
+    out2 = CPT.get_decayPartons_fromlab_propagators_angles(
+        prop, higgs_angles=a2[0], thad_b_angles=a2[1], thad_W_angles=a2[2], tlep_b_angles=a2[3], tlep_W_angles=a2[4],
+        boost=bsc[:, None, :], log_mean_parton_lab=c("mean_lab"), log_std_parton_lab=c("std_lab"),
+        log_mean_boost=c("mean_boost"), log_std_boost=c("std_boost"), log_mean_parton_Hthadtlep=c("mean_prop"),
+        log_std_parton_Hthadtlep=c("std_prop"), device=torch.device("cuda"), ptetaphi=True, eps=1e-4, unscale_phi=False,
+        final_scaling=True)
+    ((out2 * c("g_out")).sum() + (bsc * c("g_boost")).sum()).backward()
+    for x, y in zip(a, a2):
+        gx, gy = x.grad.cpu().numpy(), y.grad.cpu().numpy()
+        okr = np.isfinite(gy).all(axis=1) & np.isfinite(gx).all(axis=1)
+        assert okr.sum() > 100
+        assert np.max(np.abs(gx - gy)[okr] / (np.abs(gy[okr]).max() + 1e-300)) < 1e-9
