@@ -337,7 +337,13 @@ def extras(torch, dev, hbm_peak):
         by = (F * (3 * K - 1) + 2 * F + 1) * 8
         tf = timeit(lambda: TR.rqs_forward(phi, x, bound=1.1))
         out["K3_rqs_forward_F10_K35_f64_256k"] = {"points_per_s": B / tf, "GBps": by * B / tf / 1e9, "frac_hbm": by * B / tf / 1e9 / hbm_peak}
-        del phi, x
+        # the same parameters through the zuko-shaped Transform API: MonotonicRQSTransform(widths, heights, derivatives) on the
+        # three split views of one hyper-network output (rows [B*F, 1, 3K-1], packed without a copy), y and log|dy/dx|
+        wv, hv, dv = phi.split((K, K, K - 1), dim=-1)
+        tt = timeit(lambda: TR.MonotonicRQSTransform(wv, hv, dv, bound=1.1).call_and_ladj(x))
+        out["K3_transform_api_rows_F1_K35_f64_2.6M"] = {"rows_per_s": B * F / tt, "points_per_s": B / tt, "GBps": by * B / tt / 1e9,
+                                                         "frac_hbm": by * B / tt / 1e9 / hbm_peak}
+        del phi, x, wv, hv, dv
         torch.cuda.empty_cache()
         # BASELINE config 5 shape on this GPU: tt-bar-H + 1 jet (n=4), production flow F=10, K=40, T=6
         from memflow_b200 import estimator as ES
@@ -353,6 +359,37 @@ def extras(torch, dev, hbm_peak):
         out["chain_config5_shape_n4_F10_K40_T6_512k"] = {
             "points_per_s": N5 / (ta + tb), "flow_sample_GBps": by5 * N5 / ta / 1e9, "frac_hbm": by5 * N5 / ta / 1e9 / hbm_peak,
             "algorithmic_bytes_per_event": by5, "ms_flow_sample": ta * 1e3, "ms_phase_space_and_reduce": tb * 1e3}
+        del phi5, u5, lq5
+        torch.cuda.empty_cache()
+        # K5 alone: weight + estimator accumulation over resident (target, jac, log q), 24 B/event
+        N6 = 1 << 26
+        jac6 = torch.rand(N6, dtype=torch.float64, device=dev)
+        lq6 = torch.randn(N6, dtype=torch.float64, device=dev)
+        tg6 = torch.rand(N6, dtype=torch.float64, device=dev)
+        acc6 = ES.new_accumulator(dev)
+        t6 = timeit(lambda: ES.accumulate_weights(tg6, jac6, lq6, acc6))
+        out["K5_is_reduce_64M"] = {"points_per_s": N6 / t6, "GBps": 24 * N6 / t6 / 1e9, "frac_hbm": 24 * N6 / t6 / 1e9 / hbm_peak}
+        del jac6, lq6, tg6
+        torch.cuda.empty_cache()
+        # the sampling branch of the training loss (unfolding_flow_withDecay_v2.py:376-417) through the fused entry: one
+        # forward and one backward launch; bytes = ps + 5 angle pairs in, partons + boost + saved K1 outputs + propagators out
+        from memflow_b200.unfolding_flow import utils as UU
+        N7 = 1 << 20
+        ps4 = PhaseSpace(E_CM, [21, 21], [25, 6, -6, 21], final_masses=torch.tensor([125.25, 172.5, 172.5, 1e-5], dtype=torch.float64), dev=dev)
+        u7 = torch.rand(N7, 10, dtype=torch.float64, device=dev).clamp_(1e-6, 1 - 1e-6).requires_grad_(True)
+        ang7 = [torch.stack((torch.randn(N7, device=dev, dtype=torch.float64),
+                             (torch.rand(N7, device=dev, dtype=torch.float64) * 2 - 1) * 3.1), 1) for _ in range(5)]
+        kw7 = dict(log_mean_parton_lab=[0.0] * 3, log_std_parton_lab=[1.0] * 3, log_mean_boost=[0.0] * 2, log_std_boost=[1.0] * 2,
+                   log_mean_parton_Hthadtlep=[0.0] * 3, log_std_parton_Hthadtlep=[1.0] * 3)
+        tf7 = timeit(lambda: UU.sampled_decayPartons_from_ps(ps4, u7.detach(), *ang7, **kw7))
+        o7, b7, *_ = UU.sampled_decayPartons_from_ps(ps4, u7, *ang7, **kw7)
+        go7 = torch.ones_like(o7)
+        def bwd7():
+            u7.grad = None
+            torch.autograd.backward([o7, b7], [go7, torch.ones_like(b7)], retain_graph=True)
+        tb7 = timeit(bwd7)
+        out["sampling_branch_n4_1M"] = {"forward_events_per_s": N7 / tf7, "backward_events_per_s": N7 / tb7,
+                                        "forward_GBps": 848 * N7 / tf7 / 1e9, "launches_forward": 1, "launches_backward": 1}
         out["note"] = "wrapper-level timings (include the output allocations of the Python API)"
     except Exception as e:  # extras must never break the headline line
         out["error"] = repr(e)

@@ -66,4 +66,25 @@ if what in ("chain64", "chain64k35"):   # float64 flow stage of the chain at the
     for i in range(3):
         smp.run_chunk(phi, event_offset=i * N, acc=acc)
     torch.cuda.synchronize()
+if what == "sampling":   # fused sampling branch of the training loss (csrc/sampling.cu), forward + backward, n = 4
+    from memflow_b200.unfolding_flow import utils as UU
+    N = 1 << 20
+    ps4 = PhaseSpace(E, [21, 21], [25, 6, -6, 21], final_masses=torch.tensor([125.25, 172.5, 172.5, 1e-5], dtype=torch.float64), dev=dev)
+    u = torch.rand(N, 10, dtype=torch.float64, device=dev).clamp_(1e-6, 1 - 1e-6).requires_grad_(True)
+    ang = [torch.stack((torch.randn(N, device=dev, dtype=torch.float64), (torch.rand(N, device=dev, dtype=torch.float64) * 2 - 1) * 3.1), 1).requires_grad_(True)
+           for _ in range(5)]
+    z3, o3, z2, o2 = [0.0] * 3, [1.0] * 3, [0.0] * 2, [1.0] * 2
+    for i in range(3):
+        out, bs, *_ = UU.sampled_decayPartons_from_ps(ps4, u, *ang, log_mean_parton_lab=z3, log_std_parton_lab=o3, log_mean_boost=z2,
+                                                      log_std_boost=o2, log_mean_parton_Hthadtlep=z3, log_std_parton_Hthadtlep=o3)
+        (out.nan_to_num().sum() + bs.sum()).backward()
+    torch.cuda.synchronize()
+if what == "k5":   # weight + estimator reduction alone (csrc/is_reduce.cu)
+    N = 1 << 26
+    jac = torch.rand(N, dtype=torch.float64, device=dev); lq = torch.randn(N, dtype=torch.float64, device=dev)
+    tg = torch.rand(N, dtype=torch.float64, device=dev)
+    acc = ES.new_accumulator(dev)
+    for i in range(3):
+        ES.accumulate_weights(tg, jac, lq, acc)
+    torch.cuda.synchronize()
 print("done")
