@@ -362,8 +362,8 @@ __device__ __noinline__ void rambo_is_redo(const RamboParams<double, NF>& P, con
 #ifndef MF_CHAINB_MINB
 #define MF_CHAINB_MINB 3
 #endif
-template <int NF>
-__global__ void __launch_bounds__(256, MF_CHAINB_MINB)
+template <int NF, int THREADS>
+__global__ void __launch_bounds__(THREADS, MF_CHAINB_MINB * 256 / THREADS)
 rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, int64_t N,
                 const __grid_constant__ RamboParams<double, NF> P, double inv_2s, double* __restrict__ acc,
                 void* workspace, double* __restrict__ momenta, double* __restrict__ weight, double* __restrict__ x1o,
@@ -400,7 +400,7 @@ rambo_is_kernel(const double* __restrict__ u, const double* __restrict__ logq, i
         if (x1o) x1o[ev] = x1;
         if (x2o) x2o[ev] = x2;
     }
-    grid_accumulate<256>(k1.value(), k2.value(), cnt, acc, workspace);
+    grid_accumulate<THREADS>(k1.value(), k2.value(), cnt, acc, workspace);
 }
 
 struct ChainGeom { int E, bulk_ok, sms, smem_max; };
@@ -595,6 +595,8 @@ static int flow_sample_launch(const float* phi, int64_t N, int F, int T, int K, 
             int ctas = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 256, smem);
             if (ctas < 1) ctas = 1;
+            static const int ctas_env = env_int("MF_CHAINA_CTAS", 0);   // fewer resident CTAs: room for launch B of the previous chunk
+            if (ctas_env > 0 && ctas_env < ctas) ctas = ctas_env;
             int64_t grid = (int64_t)g.sms * ctas;
             if (grid > num_tiles) grid = num_tiles;
             kern<<<(unsigned)grid, 256, smem, stream>>>(phi, N, F, T, C, g.E, g.bulk_ok, seed, event_offset, u, logq);
@@ -620,16 +622,26 @@ static int rambo_is_launch(const double* u, const double* logq, int64_t N, const
                            double* x2, cudaStream_t stream) {
     const RamboParams<double, NF> P = make_forward_params<double, NF>(masses, e_collider, nullptr, flags & ~MF_FLAG_CUTS);
     const double inv_2s = 1.0 / (2.0 * e_collider * e_collider);
-    int dev = 0, sms = 148, ctas = 1;
+    int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, rambo_is_kernel<NF>, 256, 0);
-    if (ctas < 1) ctas = 1;
-    int64_t grid = (int64_t)sms * ctas;
-    const int64_t want = (N + 255) / 256;
-    if (grid > want) grid = want;
-    if (grid > kReduceMaxBlocks) grid = kReduceMaxBlocks;
-    rambo_is_kernel<NF><<<(unsigned)grid, 256, 0, stream>>>(u, logq, N, P, inv_2s, acc, workspace, momenta, weight, x1, x2);
+    // MF_CHAINB_THREADS=128 with MF_CHAINB_CTAS=<CTAs per SM>: a small-footprint launch that can share the SMs with launch A of
+    // the next chunk (scripts/overlap_ab.py); default: 256 threads, as many CTAs as fit
+    static const int thr = env_int("MF_CHAINB_THREADS", 256);
+    static const int ctas_env = env_int("MF_CHAINB_CTAS", 0);
+    auto go = [&](auto kern, int threads) {
+        int ctas = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, threads, 0);
+        if (ctas < 1) ctas = 1;
+        if (ctas_env > 0 && ctas_env < ctas) ctas = ctas_env;
+        int64_t grid = (int64_t)sms * ctas;
+        const int64_t want = (N + threads - 1) / threads;
+        if (grid > want) grid = want;
+        if (grid > kReduceMaxBlocks) grid = kReduceMaxBlocks;
+        kern<<<(unsigned)grid, threads, 0, stream>>>(u, logq, N, P, inv_2s, acc, workspace, momenta, weight, x1, x2);
+    };
+    if (thr == 128) go(rambo_is_kernel<NF, 128>, 128);
+    else go(rambo_is_kernel<NF, 256>, 256);
     return launch_status();
 }
 

@@ -13,21 +13,35 @@ from ..phasespace.rambo_generator import MF_ST_NOT_CM
 
 M_HIGGS = 125.25
 M_TOP = 172.5
-M_GLUON = 1e-5
+M_GLUON = 1e-3   # memflow/read_data/Dataset_Parton_Level.py:19 (the phase-space module's own default is 1e-5)
 
 
-def phasespace_products(momenta_HttISR, boost, on_shell=True, E_CM=13000, masses=None, pdgs=(25, 6, -6, 21)):
+def intermediateParticles_cartesian_onShell(momenta_HttISR, masses=None):
+    """`get_intermediateParticles_cartesian_onShell` (:400-408): energies recomputed from the 3-momenta and the nominal
+    masses (H, t, tbar, ISR); the cached tensor `H_thad_tlep_ISR_cartesian_onShell`. Elementwise torch (offline path)."""
+    if masses is None:
+        masses = torch.tensor([M_HIGGS, M_TOP, M_TOP, M_GLUON], dtype=torch.float64)
+    m = torch.as_tensor(masses, dtype=momenta_HttISR.dtype, device=momenta_HttISR.device)
+    out = momenta_HttISR.clone()
+    out[:, :, 0] = torch.sqrt(out[:, :, 1] ** 2 + out[:, :, 2] ** 2 + out[:, :, 3] ** 2 + m ** 2)
+    return out
+
+
+def phasespace_products(momenta_HttISR, boost, on_shell=True, E_CM=13000, masses=None, pdgs=(25, 6, -6, 21),
+                        ref_fp32_quirks=False):
     """momenta_HttISR [N, 4, 4] (H, t, tbar, ISR; CM frame, E,px,py,pz), boost [N, 1, 4] or [N, 4] -> dict.
 
     on_shell=True  (:410-446): minimal-energy fix of the boost (:418-420), x1/x2 clamped to [0,1], plus
                    logit(ps, eps=5e-5), its nan-mean / 5*nan-std scaling and the scaled logits.
     on_shell=False (:448-463): plain x1/x2, ps and det-jacobian only.
+    ref_fp32_quirks=True reproduces the float32 weight chain of the literal reference in the det-jacobian (relative 1e-7;
+    DESIGN.md section 2); the default is clean float64.
     """
     dev = momenta_HttISR.device
     if masses is None:
         masses = torch.tensor([M_HIGGS, M_TOP, M_TOP, M_GLUON], dtype=torch.float64)
     masses = torch.as_tensor(masses, dtype=torch.float64)
-    ps_gen = PhaseSpace(E_CM, [21, 21], list(pdgs), final_masses=masses, dev=dev)
+    ps_gen = PhaseSpace(E_CM, [21, 21], list(pdgs), final_masses=masses, dev=dev, ref_fp32_quirks=ref_fp32_quirks)
     b = boost.reshape(boost.shape[0], -1, 4)[:, 0, :].to(torch.float64).clone()
     suffix = "_onShell" if on_shell else ""
     if on_shell:

@@ -357,11 +357,80 @@ def make_sampling_pipeline():
     print("sampling pipeline written; |g_ps| columns:", np.abs(ps.grad.numpy()).max(0))
 
 
+def make_dataset_products():
+    """dataset_products.npz: the tensors MEMFlow caches per dataset, memflow/read_data/Dataset_Parton_Level.py:400-463
+    (get_intermediateParticles_cartesian_onShell, get_PS_intermediateParticles_onShell, get_PS_intermediateParticles).
+    The module itself cannot be imported here (awkward / numba / hist are not installed), so the three methods are lifted
+    UNMODIFIED from the reference's source with `ast` and run on a stub `self` that holds the three data tensors and
+    collects what the methods `torch.save`. torch default dtype float64, like every other fixture of this directory."""
+    import ast
+    phasespace, _, _ = import_reference()
+    src_path = os.path.join(REF, "memflow", "read_data", "Dataset_Parton_Level.py")
+    tree = ast.parse(open(src_path).read())
+    ns = {"torch": torch, "np": np, "PhaseSpace": phasespace.PhaseSpace}
+    for node in tree.body:   # module-level constants M_HIGGS, M_TOP, M_GLUON
+        if isinstance(node, ast.Assign) and all(isinstance(t, ast.Name) and t.id.startswith("M_") for t in node.targets):
+            exec(compile(ast.Module([node], []), src_path, "exec"), ns)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "Dataset_PartonLevel")
+    wanted = ("get_intermediateParticles_cartesian_onShell", "get_PS_intermediateParticles_onShell", "get_PS_intermediateParticles")
+    for node in cls.body:
+        if isinstance(node, ast.FunctionDef) and node.name in wanted:
+            exec(compile(ast.Module([node], []), src_path, "exec"), ns)
+    saved = {}
+    real_save = torch.save
+    N, E_CM = 2000, 13000.0
+    masses = torch.tensor([ns["M_HIGGS"], ns["M_TOP"], ns["M_TOP"], ns["M_GLUON"]], dtype=torch.float64)
+    gen = torch.Generator().manual_seed(2025)
+    u = torch.rand(N, 10, generator=gen, dtype=torch.float64) * 0.98 + 0.01
+    with contextlib.redirect_stdout(io.StringIO()):
+        rambo = phasespace.PhaseSpace(E_CM, [21, 21], [25, 6, -6, 21], final_masses=masses, dev="cpu")
+        mom, _, x1, x2 = rambo.get_momenta_from_ps(u)
+    data = mom[:, 2:].clone()
+    # the dataset's propagators are off shell (event-by-event masses): energies moved by 1e-4 relative
+    data[:, :, 0] *= 1.0 + 1e-4 * torch.randn(N, 4, generator=gen, dtype=torch.float64)
+    boost = torch.stack((E_CM * (x1 + x2) / 2, torch.zeros(N), torch.zeros(N), E_CM * (x1 - x2) / 2), dim=1).unsqueeze(1)
+    boost[:50, 0, 0] = boost[:50, 0, 3].abs() + 100.0   # a few events below the minimal energy (:418-420)
+
+    class Stub:
+        pass
+    stub = Stub()
+    stub.data_higgs_t_tbar_ISR_cartesian = data.clone()
+    stub.data_boost = boost.clone()
+    stub.processed_file_names = lambda name: name
+    torch.save = lambda obj, name: saved.__setitem__(name, obj)
+    out = {"data": data.numpy(), "boost": boost.numpy(), "masses": masses.numpy(), "e_cm": np.float64(E_CM)}
+    try:
+        # literal reference first, then "fp64-clean" (its two float32 casts neutralised, see the module docstring): the
+        # det-jacobians differ at 1e-7 relative, everything else is identical
+        for tag, ctx in (("", contextlib.nullcontext()), ("__clean", fp64_clean())):
+            saved.clear()
+            stub.data_boost = boost.clone()
+            with contextlib.redirect_stdout(io.StringIO()), ctx:
+                ns["get_intermediateParticles_cartesian_onShell"](stub)
+                stub.data_higgs_t_tbar_ISR_cartesian_onShell = saved["H_thad_tlep_ISR_cartesian_onShell"]
+                ns["get_PS_intermediateParticles"](stub)                 # uses data_boost as is
+                ns["get_PS_intermediateParticles_onShell"](stub)         # modifies data_boost in place (:418-420)
+            for k, v in saved.items():
+                if tag and "detjacobian" not in k:
+                    continue
+                if isinstance(v, tuple):
+                    out[k + "__mean"], out[k + "__scale"] = v[0].numpy(), v[1].numpy()
+                else:
+                    out[k + tag] = v.numpy()
+    finally:
+        torch.save = real_save
+    np.savez_compressed(os.path.join(HERE, "dataset_products.npz"), **out)
+    print("dataset products written:", sorted(saved), "; nan rows on shell:",
+          int(np.isnan(out["phasespace_intermediateParticles_onShell"]).any(axis=1).sum()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "decay_partons":
         make_decay_partons()
     elif len(sys.argv) > 1 and sys.argv[1] == "sampling_pipeline":
         make_sampling_pipeline()
+    elif len(sys.argv) > 1 and sys.argv[1] == "dataset_products":
+        make_dataset_products()
     else:
         main()
         make_decay_partons()

@@ -422,6 +422,59 @@ def test_dataset_products(oracle):
     assert set(plain) == {"phasespace_intermediateParticles", "phasespace_rambo_detjacobian"}
 
 
+def test_dataset_products_vs_reference_golden(golden_dir):
+    """The same products against what the UNMODIFIED reference methods computed (Dataset_Parton_Level.py:400-463, lifted
+    with `ast` and run on CPU by tests/golden/make_golden.py dataset_products): every cached tensor by its on-disk name,
+    default masses of that file (M_GLUON = 1e-3), off-shell dataset momenta, events below the minimal energy."""
+    from memflow_b200.read_data import phasespace_products
+    from memflow_b200.read_data.products import intermediateParticles_cartesian_onShell
+    g = np.load(os.path.join(golden_dir, "dataset_products.npz"))
+    data, boost = torch.from_numpy(g["data"]).cuda(), torch.from_numpy(g["boost"]).cuda()
+    on = intermediateParticles_cartesian_onShell(data)
+    ref_on = g["H_thad_tlep_ISR_cartesian_onShell"]
+    assert np.max(np.abs(on.cpu().numpy() - ref_on) / np.abs(ref_on).max()) < 1e-15
+    out = phasespace_products(torch.from_numpy(ref_on).cuda(), boost, on_shell=True)
+    out.update(phasespace_products(data, boost, on_shell=False))
+    quirk = phasespace_products(torch.from_numpy(ref_on).cuda(), boost, on_shell=True, ref_fp32_quirks=True)
+    quirk.update(phasespace_products(data, boost, on_shell=False, ref_fp32_quirks=True))
+
+    def close(name, tol, kappa=None):
+        a, r = out[name].cpu().numpy(), g[name]
+        assert np.array_equal(np.isnan(a), np.isnan(r)), name
+        err = np.abs(a - r) / (1.0 + np.abs(r))
+        if kappa is not None:
+            err = err / kappa
+        q = np.nanquantile(err, 0.99)
+        print("%-60s max %.2e q99 %.2e" % (name, np.nanmax(err), q))
+        assert np.nanmax(err) < tol and q < 1e-12, (name, np.nanmax(err), q)
+
+    # conditioning of an event (tests/parity.py): gamma^2 of its intermediate systems and the mass-variable / threshold factors;
+    # the ISR gluon of mass 1e-3 next to TeV-scale momenta makes the last decay ill-conditioned
+    for sfx, mom in (("_onShell", ref_on), ("", g["data"])):
+        ps_ref = g["phasespace_intermediateParticles" + sfx]
+        full = np.concatenate((np.zeros((mom.shape[0], 2, 4)), mom), axis=1)
+        kappa = parity.conditioning(np.clip(np.nan_to_num(ps_ref, nan=0.5), 1e-12, 1 - 1e-12), full, 4, list(g["masses"]))
+        close("phasespace_intermediateParticles" + sfx, 1e-12, kappa[:, None])
+        # det-jacobian: clean float64 by default; the literal reference's float32 weight chain with ref_fp32_quirks=True
+        for variant, res in (("__clean", out), ("", quirk)):
+            a, r = res["phasespace_rambo_detjacobian" + sfx].cpu().numpy(), g["phasespace_rambo_detjacobian" + sfx + variant]
+            ok = np.isfinite(r) & (r > 0)
+            assert np.array_equal(np.isfinite(a), np.isfinite(r))
+            dl = np.abs(np.log(a[ok]) - np.log(r[ok])) / kappa[ok]
+            print("ln detjac%s%s: max/kappa %.2e q99 %.2e" % (sfx, variant, dl.max(), np.quantile(dl, 0.99)))
+            assert dl.max() < (1e-12 if variant else 1e-6)   # literal: a few float32 ulps (6e-8 each) of the in-place chain
+    lk = 1.0 / np.minimum(np.clip(g["phasespace_intermediateParticles_onShell"], 5e-5, 1 - 5e-5),
+                          1 - np.clip(g["phasespace_intermediateParticles_onShell"], 5e-5, 1 - 5e-5))   # d logit / d ps
+    full = np.concatenate((np.zeros((ref_on.shape[0], 2, 4)), ref_on), axis=1)
+    kappa = parity.conditioning(np.clip(np.nan_to_num(g["phasespace_intermediateParticles_onShell"], nan=0.5), 1e-12, 1 - 1e-12),
+                                full, 4, list(g["masses"]))[:, None] * lk
+    close("phasespace_intermediateParticles_onShell_logit", 1e-12, kappa)
+    close("phasespace_intermediateParticles_onShell_logit_scaled", 1e-12, kappa)
+    mean, scale = out["mean_std_phasespace_intermediateParticles_onShell_logit"]
+    assert np.max(np.abs(mean.cpu().numpy() - g["mean_std_phasespace_intermediateParticles_onShell_logit__mean"])) < 1e-10
+    assert np.max(np.abs(scale.cpu().numpy() / g["mean_std_phasespace_intermediateParticles_onShell_logit__scale"] - 1)) < 1e-10
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_random_masses_and_energies(oracle, seed):
     """Sweep over multiplicity, mass spectra (incl. exactly massless bodies) and collider energies."""
