@@ -175,6 +175,10 @@ class HostPipeline:
         self.t1 = [torch.cuda.Event(enable_timing=True) for _ in range(self.n_copy)]
         self.bytes = 0
         self._i = 0
+        # scratch of the chain's two launches (u, log q), owned here: no stream-ordered allocation per chunk
+        F = self.shape[2]
+        self._u = torch.empty((self.shape[1], F), dtype=torch.float64, device=self.device)
+        self._lq = torch.empty(self.shape[1], dtype=torch.float64, device=self.device)
 
     def pinned_chunk(self):
         """A pinned host staging tensor of the chunk shape (allocate after bind_to_gpu_cpus)."""
@@ -221,7 +225,9 @@ class HostPipeline:
                 self.t1[s].record(cs)
             main.wait_event(self.copied[b][s])
         self.bytes += host_phi.numel() * host_phi.element_size()
-        self.sampler.run_chunk(dst if n == self.shape[1] else dst.contiguous(), event_offset=event_offset, acc=acc)
+        phi = dst if n == self.shape[1] else dst.contiguous()
+        u, lq = self.sampler.sample_flow(phi, event_offset=event_offset, u=self._u[:n], logq=self._lq[:n])
+        self.sampler.weigh(u, lq, acc=acc)
         self.consumed[b].record(main)
         self._i += 1
         return acc
