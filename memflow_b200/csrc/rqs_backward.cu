@@ -545,6 +545,338 @@ static int rqs_bwd_coop_launch(const T* phi, const T* vin, const T* g_out, const
     return launch_status();
 }
 
+// ---------------------------------------------------------------------------------------------
+// float64 with the soft clip, register-chunk form (round 2): EVERY PARAMETER IS EXPONENTIATED ONCE.
+// The cooperative kernel above re-derives 2^q from the stored q wherever the exponential is needed again (S2 search, S3
+// knots, S5 gradients: ~3.4 exp2 of 14 FP64 instructions per parameter, ~52 FP64-pipe instructions per parameter in all).
+// Here thread (row, chunk) owns CH consecutive bins of BOTH softmax arrays: one pass computes q, e = 2^q and the
+// gradient factor p = e (1 - k1|q|)^2 = d exp(clip(a)) / da, keeps p in REGISTERS (2 CH doubles) and stores the chunk's
+// RUNNING SUM of e in place -- the search (count of chunk totals below the target + count inside one chunk) and the four
+// knots around the bin then cost a handful of shared-memory loads (as in rqs_f64.cu), and the last pass is one
+// multiplication and one select per parameter: ~25 FP64-pipe instructions per parameter.
+//   S1   all threads: q, e, p; running sums in place; chunk totals -> tot[]
+//   S3a  evaluator thread of the row (chunk LANES-1): exclusive prefixes of the chunk totals (back into tot[]), bin
+//   S3b  four threads of the row, one task each: knots of the widths, knots of the heights, exp of the bin's left /
+//        right derivative parameter -> pub[]   (one thread doing all of it was 35 % of the tile's critical path)
+//   S4   seven local adjoints split over the row's threads (rq_adjoints, NT = ceil(7 / LANES) tangents each) -> adj[]
+//   S5   all threads: gradients of their chunk from the registers, in place; the tile leaves by TMA bulk store
+// Two tile buffers: the next tile's bulk copy is issued after S1 (once the bulk store of the tile before has finished
+// reading that buffer) and lands while S3-S5 run.
+// Odd K (even row pitch): one bulk copy per row into 16-byte aligned rows of pitch 2 (mod 4) doubles, as rqs_f64.cu.
+// ---------------------------------------------------------------------------------------------
+struct Rqs64BwdArgs {
+    const double *phi, *vin, *g_out, *g_ladj;
+    double *g_phi, *g_v;
+    int64_t rows;
+    RqsConst<double> C;
+    int K, pitch, bulk_ok, chw;
+};
+
+// published per row: cwl cwh chl chh | iSw iSh | d0 d1 f0 f1 | v go gl | bin | Sw Sh | oc
+constexpr int kBwdPub = 17;
+
+template <bool INV, int LANES, int CH>
+__global__ void __launch_bounds__(256, 3)
+rqs64_backward_kernel(const __grid_constant__ Rqs64BwdArgs A) {
+    constexpr int RPT = 256 / LANES;
+    constexpr int NT = (7 + LANES - 1) / LANES;
+    constexpr double kNaN = __builtin_nan("");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int K = A.K, PW = 3 * K - 1, PWP = A.pitch, chw = A.chw;
+    const RqsConst<double>& C = A.C;
+    const size_t buf_bytes = ((size_t)RPT * PWP * sizeof(double) + 127) / 128 * 128;
+    double* const tot = reinterpret_cast<double*>(smem_raw + 2 * buf_bytes);   // [2 LANES][RPT]
+    double* const pub = tot + (size_t)2 * LANES * RPT;    // [kBwdPub][RPT]
+    double* const adjs = pub + (size_t)kBwdPub * RPT;     // [7][RPT]
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(adjs + (size_t)7 * RPT);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int chunk = wid % LANES, rr = (wid / LANES) * 32 + lane;
+    const bool evaluator = chunk == LANES - 1;
+    const int k0 = min(K, chunk * chw), k1 = min(K, k0 + chw);
+    const double Bd = C.bound, half_over_B = 0.5 / Bd;
+    const int64_t num_tiles = (A.rows + RPT - 1) / RPT;
+    const int64_t full_tiles = A.bulk_ok ? A.rows / RPT : 0;
+    const uint32_t tile_bytes = (uint32_t)((size_t)RPT * PW * sizeof(double));
+    constexpr int PER = (RPT + 7) / 8;                    // padded rows: rows copied by each warp (one per lane)
+    const int myrow = wid * PER + lane;                   // the row this thread copies in / out when rows are padded
+    const bool copier = lane < PER && myrow < RPT;
+    auto buf = [&](int b) { return reinterpret_cast<double*>(smem_raw + (size_t)b * buf_bytes); };
+
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    __syncthreads();
+    // copy of a full tile: one bulk copy when the shared-memory rows are packed, one per row when they are padded. The
+    // thread that issues a copy into rows first waits until its own earlier bulk stores have finished reading them.
+    auto issue = [&](int64_t tile, int b) {
+        const double* src = A.phi + (size_t)tile * RPT * PW;
+        if (PWP == PW) {
+            if (tid == 0) {
+                bulk_store_wait_read();
+                mbar_expect_tx(&bars[b], tile_bytes);
+                bulk_g2s(buf(b), src, tile_bytes, &bars[b]);
+            }
+        } else {
+            if (tid == 0) mbar_expect_tx(&bars[b], tile_bytes);
+            if (copier) {
+                bulk_store_wait_read();
+                bulk_g2s(buf(b) + (size_t)myrow * PWP, src + (size_t)myrow * PW, (uint32_t)(PW * sizeof(double)), &bars[b]);
+            }
+        }
+    };
+    uint32_t parity0 = 0u, parity1 = 0u;
+    int64_t tile = blockIdx.x;
+    if (tile < full_tiles) issue(tile, 0);
+    for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        double* const sm = buf(b);
+        double* const r = sm + (size_t)rr * PWP;
+        const bool bulk = tile < full_tiles;
+        const int64_t row0 = tile * RPT;
+        const int nrows = (int)((A.rows - row0) < RPT ? (A.rows - row0) : RPT);
+        const bool valid = rr < nrows;
+        const int64_t row = row0 + rr;
+        double v = 0.0, go = 0.0, gl = 0.0;
+        if (evaluator && valid) {   // requested before the tile wait
+            v = __ldg(A.vin + row);
+            go = A.g_out ? __ldg(A.g_out + row) : 0.0;
+            gl = A.g_ladj ? __ldg(A.g_ladj + row) : 0.0;
+        }
+        if (bulk) {
+            mbar_wait(&bars[b], b ? parity1 : parity0);
+            if (b) parity1 ^= 1u; else parity0 ^= 1u;
+        } else {   // ragged last tile or unaligned pointers: plain cooperative copy into the same (padded) rows
+            if (tid == 0 || (PWP != PW && copier)) bulk_store_wait_read();
+            __syncthreads();
+            for (int rw = wid; rw < nrows; rw += 8) {
+                const double* src = A.phi + (size_t)(row0 + rw) * PW;
+                for (int i = lane; i < PW; i += 32) sm[(size_t)rw * PWP + i] = __ldg(src + i);
+            }
+            __syncthreads();
+        }
+        // ---- S1: one exponential per parameter; gradient factors into registers, running sums in place ----
+        double pw[CH], ph[CH];
+        {
+            double cw = 0.0, chh = 0.0;
+            int hmax = 0;
+            double* const rw_ = r + k0;
+            double* const rh_ = r + K + k0;
+            auto one = [&](int j) {
+                const double aw = rw_[j], ah = rh_[j];
+                const double qw = clip_log2(aw, C.k1w, C.ln2, hmax), qh = clip_log2(ah, C.k1w, C.ln2, hmax);
+                const double ew = exp2_of_q(qw), eh = exp2_of_q(qh);
+                const double tw = fma(-C.k1w, fabs(qw), 1.0), th = fma(-C.k1w, fabs(qh), 1.0);
+                pw[j] = ew * (tw * tw);
+                ph[j] = eh * (th * th);
+                cw += ew;
+                chh += eh;
+                rw_[j] = cw;
+                rh_[j] = chh;
+            };
+            if (k1 - k0 == CH) {   // warp-uniform (chunk = warp index mod LANES): the usual case, no per-bin test
+#pragma unroll
+                for (int j = 0; j < CH; ++j) one(j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    pw[j] = 0.0; ph[j] = 0.0;
+                    if (k0 + j < k1) one(j);
+                }
+            }
+            if (hmax >= kHiAbsLimit) cw = chh = kNaN;   // outside the lean sequence's domain
+            tot[(size_t)chunk * RPT + rr] = cw;
+            tot[(size_t)(LANES + chunk) * RPT + rr] = chh;
+        }
+        __syncthreads();
+        {   // the other buffer: the store of the tile before has had S1 to finish reading it
+            const int64_t nt = tile + gridDim.x;
+            if (nt < full_tiles) issue(nt, b ^ 1);
+        }
+        double* const pb = pub + rr;
+        // ---- S3a (one thread per row): exclusive prefixes of the chunk totals, bin ----
+        if (evaluator && valid) {
+            double* const tw_ = tot + rr;
+            double* const th_ = tot + (size_t)LANES * RPT + rr;
+            double Sw = 0.0, Sh = 0.0;
+            int oc = 0;
+            double tws[LANES], ths[LANES];
+#pragma unroll
+            for (int c = 0; c < LANES; ++c) { tws[c] = tw_[(size_t)c * RPT]; ths[c] = th_[(size_t)c * RPT]; }
+#pragma unroll
+            for (int c = 0; c < LANES; ++c) {   // inclusive running sums; the exclusive ones go back to shared memory
+                tw_[(size_t)c * RPT] = Sw;
+                th_[(size_t)c * RPT] = Sh;
+                Sw += tws[c];
+                Sh += ths[c];
+                tws[c] = Sw;
+                ths[c] = Sh;
+            }
+            const double target = fma(v, half_over_B, 0.5) * (INV ? Sh : Sw);   // v in units of the searched running sum
+#pragma unroll
+            for (int c = 0; c + 1 < LANES; ++c) oc += ((INV ? ths[c] : tws[c]) < target) ? 1 : 0;   // monotone: first chunk whose sum reaches the target
+            const double off = (INV ? th_ : tw_)[(size_t)oc * RPT];
+            const int sb = INV ? K : 0;
+            const int c0 = min(K, oc * chw), len = min(K, c0 + chw) - c0;
+            const double tloc = target - off;
+            int lo = 0;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) lo += (j < len && r[sb + c0 + j] < tloc) ? 1 : 0;
+            int bin = c0 + lo - ((-Bd < v) ? 0 : 1);   // searchsorted(knots, v) - 1 with X_0 = -B
+            if (!(Sw == Sw) || !(Sh == Sh)) {
+                bin = -2;                          // NaN gradients for the whole row
+                A.g_v[row] = kNaN;
+            } else if (bin < 0 || bin >= K) {
+                bin = -1;                          // identity tails: out = v, ladj = 0
+                A.g_v[row] = go;
+            }
+            pb[10 * RPT] = v; pb[11 * RPT] = go; pb[12 * RPT] = gl;
+            pb[13 * RPT] = (double)bin;
+            pb[14 * RPT] = Sw; pb[15 * RPT] = Sh;
+            pb[16 * RPT] = (double)oc;
+        }
+        __syncthreads();
+        const int bin = valid ? (int)pb[13 * RPT] : -1;
+        // ---- S3b: knots and the bin's derivative parameters, one task per thread of the row ----
+        if (bin >= 0) {
+            // (a valid bin lies in chunk oc; bin - 1 in the same chunk or the one before)
+            auto knots = [&](int base, const double* ex, double S, int slot) {
+                const int oc = (int)pb[16 * RPT];
+                const double iS = rcp_fast(S);
+                const int jm = max(bin - 1, 0);
+                const int cm = (jm >= oc * chw) ? oc : oc - 1;
+                const double lo_ = bin > 0 ? (ex[(size_t)max(cm, 0) * RPT] + r[base + jm]) * iS : 0.0;
+                const double hi_ = (ex[(size_t)oc * RPT] + r[base + bin]) * iS;
+                pb[slot * RPT] = lo_; pb[(slot + 1) * RPT] = hi_; pb[(4 + slot / 2) * RPT] = iS;
+            };
+            auto deriv = [&](bool has, int idx, int slot) {
+                double d = 1.0, f = 0.0;   // D_0 = D_K = exp(0): constants
+                if (has) lean_deriv<true>(r[2 * K + idx], C, d, f);
+                pb[slot * RPT] = d; pb[(slot + 2) * RPT] = f;
+            };
+            if constexpr (LANES >= 4) {
+                if (chunk == 0) knots(0, tot + rr, pb[14 * RPT], 0);
+                else if (chunk == 1) knots(K, tot + (size_t)LANES * RPT + rr, pb[15 * RPT], 2);
+                else if (chunk == 2) deriv(bin > 0, bin - 1, 6);
+                else if (chunk == 3) deriv(bin < K - 1, bin, 7);
+            } else {
+                if (chunk == 0) { knots(0, tot + rr, pb[14 * RPT], 0); deriv(bin > 0, bin - 1, 6); }
+                else { knots(K, tot + (size_t)LANES * RPT + rr, pb[15 * RPT], 2); deriv(bin < K - 1, bin, 7); }
+            }
+        }
+        __syncthreads();
+        // ---- S4: seven local adjoints, NT per thread ----
+        if (bin >= 0 && chunk * NT < 7) {
+            const double cwl = pb[0], cwh = pb[RPT], chl = pb[2 * RPT], chh = pb[3 * RPT];
+            double part[NT];
+            rq_adjoints<double, INV, NT>(chunk * NT, Bd * fma(2.0, cwl, -1.0), Bd * fma(2.0, cwh, -1.0), Bd * fma(2.0, chl, -1.0),
+                                         Bd * fma(2.0, chh, -1.0), pb[6 * RPT], pb[7 * RPT], pb[10 * RPT], pb[11 * RPT],
+                                         pb[12 * RPT], part);
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+                if (chunk * NT + j < 7) adjs[(size_t)(chunk * NT + j) * RPT + rr] = part[j];
+        }
+        __syncthreads();
+        // ---- S5: gradients of this chunk from the registers, in place ----
+        if (valid) {
+            double* const rw_ = r + k0;
+            double* const rh_ = r + K + k0;
+            double* const rd_ = r + 2 * K + k0;
+            const int nd = min(k1, K - 1) - k0;   // derivative parameters of this chunk
+            if (bin >= 0) {
+                const double* const ad = adjs + rr;
+                const double cwl = pb[0], cwh = pb[RPT], chl = pb[2 * RPT], chh = pb[3 * RPT];
+                const double a0 = ad[0], a1 = ad[RPT], a2 = ad[2 * RPT], a3 = ad[3 * RPT];
+                const double sw2 = (2.0 * Bd) * pb[4 * RPT], sh2 = (2.0 * Bd) * pb[5 * RPT];
+                // (the bracket takes three values per array: i < bin, i == bin, i > bin)
+                const double uw = a1 * (1.0 - cwh), lw = a0 * cwl, uh = a3 * (1.0 - chh), lh = a2 * chl;
+                const double gw_lt = sw2 * (uw + a0 * (1.0 - cwl)), gw_eq = sw2 * (uw - lw), gw_gt = -sw2 * (a1 * cwh + lw);
+                const double gh_lt = sh2 * (uh + a2 * (1.0 - chl)), gh_eq = sh2 * (uh - lh), gh_gt = -sh2 * (a3 * chh + lh);
+                const double gd0 = ad[4 * RPT] * pb[8 * RPT], gd1 = ad[5 * RPT] * pb[9 * RPT];
+                const int jb = bin - k0;   // the bin's place in this chunk (may lie outside it)
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    if (k0 + j < k1) {
+                        rw_[j] = pw[j] * (j < jb ? gw_lt : (j == jb ? gw_eq : gw_gt));
+                        rh_[j] = ph[j] * (j < jb ? gh_lt : (j == jb ? gh_eq : gh_gt));
+                    }
+                    if (j < nd) rd_[j] = (j == jb - 1) ? gd0 : ((j == jb) ? gd1 : 0.0);
+                }
+                if (evaluator) A.g_v[row] = ad[6 * RPT];
+            } else {
+                const double fill = bin == -2 ? kNaN : 0.0;
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    if (k0 + j < k1) { rw_[j] = fill; rh_[j] = fill; }
+                    if (j < nd) rd_[j] = fill;
+                }
+            }
+        }
+        fence_proxy_async();   // generic writes of the gradients -> visible to the bulk store
+        __syncthreads();
+        double* const dst = A.g_phi + (size_t)row0 * PW;
+        if (bulk) {
+            if (PWP == PW) {
+                if (tid == 0) bulk_s2g(dst, sm, tile_bytes);
+            } else if (copier) {
+                bulk_s2g(dst + (size_t)myrow * PW, sm + (size_t)myrow * PWP, (uint32_t)(PW * sizeof(double)));
+            }
+        } else {
+            for (int rw = wid; rw < nrows; rw += 8)
+                for (int i = lane; i < PW; i += 32) dst[(size_t)rw * PW + i] = sm[(size_t)rw * PWP + i];
+            __syncthreads();
+        }
+    }
+    bulk_store_wait_read();
+}
+
+// MF_E_SHAPE when the shape is outside this kernel: the caller then takes rqs_backward_coop_kernel.
+template <bool INV>
+static int rqs64_bwd_launch(const double* phi, const double* vin, const double* g_out, const double* g_ladj, int64_t rows,
+                            int K, const RqsConst<double>& C, double* g_phi, double* g_v, cudaStream_t stream) {
+    static const bool enabled = [] { const char* e = getenv("MF_RQS64_BWD"); return !(e && e[0] == '0'); }();
+    static const int forced = [] { const char* e = getenv("MF_RQS64_BWD_LANES"); return e ? atoi(e) : 0; }();
+    if (!enabled || K < 6 || K > 64) return MF_E_SHAPE;
+    // fewest threads per row whose chunk fits the register budget (5 bins; 8 for long rows)
+    int lanes = forced ? forced : (K <= 10 ? 2 : (K <= 20 ? 4 : 8));
+    if (lanes != 2 && lanes != 4 && lanes != 8) return MF_E_SHAPE;
+    const int chw = (K + lanes - 1) / lanes;
+    if (chw > 8) return MF_E_SHAPE;
+    const int PW = 3 * K - 1;
+    const bool pair = (K & 1) != 0;   // odd K: even row pitch -> padded, 16-byte aligned rows
+    const int pitch = pair ? (((PW / 2) & 1) ? PW : PW + 2) : PW;
+    const int rpt = 256 / lanes;
+    const size_t smem = 2 * (((size_t)rpt * pitch * sizeof(double) + 127) / 128 * 128) +
+                        (size_t)(2 * lanes + kBwdPub + 7) * rpt * sizeof(double) + 16;
+    int dev = 0, sms = 148, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > (size_t)smem_max) return MF_E_SHAPE;
+    Rqs64BwdArgs A{};
+    A.phi = phi; A.vin = vin; A.g_out = g_out; A.g_ladj = g_ladj; A.g_phi = g_phi; A.g_v = g_v;
+    A.rows = rows; A.C = C; A.K = K; A.pitch = pitch; A.chw = chw;
+    // packed rows: tile = rpt * PW * 8 bytes, a multiple of 128; padded rows: PW even, every row is a multiple of 16 bytes
+    A.bulk_ok = (aligned(phi, 16) && aligned(g_phi, 16)) ? 1 : 0;
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int ctas = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 256, smem);
+        if (ctas < 1) ctas = 1;
+        const int64_t tiles = (rows + rpt - 1) / rpt;
+        int64_t grid = (int64_t)sms * ctas;
+        if (grid > tiles) grid = tiles;
+        kern<<<(unsigned)grid, 256, smem, stream>>>(A);
+        return launch_status();
+    };
+    if (chw <= 5) {
+        if (lanes == 2) return go(rqs64_backward_kernel<INV, 2, 5>);
+        if (lanes == 4) return go(rqs64_backward_kernel<INV, 4, 5>);
+        return go(rqs64_backward_kernel<INV, 8, 5>);
+    }
+    if (lanes == 2) return go(rqs64_backward_kernel<INV, 2, 8>);
+    if (lanes == 4) return go(rqs64_backward_kernel<INV, 4, 8>);
+    return go(rqs64_backward_kernel<INV, 8, 8>);
+}
+
 template <typename T, bool INV>
 static int rqs_bwd_launch(const T* phi, const T* vin, const T* g_out, const T* g_ladj, int64_t B, int F, int K, T bound,
                           T slope, T* g_phi, T* g_v, cudaStream_t stream) {
@@ -557,6 +889,12 @@ static int rqs_bwd_launch(const T* phi, const T* vin, const T* g_out, const T* g
     // float64 with the soft clip: the lean exp2 sequence (MF_RQS64=0 keeps the library path, for A/B timing)
     static const bool lean_on = [] { const char* e = getenv("MF_RQS64"); return !(e && e[0] == '0'); }();
     const bool lean = sizeof(T) == 8 && lean_on && C.clip && (double)C.k1w < 1048576.0;
+    if constexpr (sizeof(T) == 8) {   // register-chunk kernel: one exponential per parameter
+        if (lean) {
+            const int rc = rqs64_bwd_launch<INV>(phi, vin, g_out, g_ladj, rows, K, C, g_phi, g_v, stream);
+            if (rc != MF_E_SHAPE) return rc;
+        }
+    }
     {   // long rows: several threads per row. Thresholds from scripts/rqs_bwd_time.py sweeps on B200 (row bytes decide:
         // they set how many one-thread-per-row warps fit in shared memory). MF_RQS_BWD_LANES = 1/2/4/8 forces a variant.
         static const int forced = [] { const char* e = getenv("MF_RQS_BWD_LANES"); return e ? atoi(e) : 0; }();

@@ -261,9 +261,12 @@ def test_ragged_and_unaligned(oracle):
             assert torch.equal(grads[0], grads[1]) and bool(torch.isfinite(grads[0]).all())
 
 
-# K < 12: one thread per row; 12..23 / 24..47 / >= 48: 2 / 4 / 8 threads per row (rqs_backward_coop_kernel)
+# fp64 with the soft clip, K = 6..64: rqs64_backward_kernel (2 / 4 / 8 threads per row for K <= 10 / 20 / 64, odd K in
+# padded rows); otherwise K < 12: one thread per row; 12..23 / 24..47 / >= 48: 2 / 4 / 8 threads per row (rqs_backward_coop_kernel)
 @pytest.mark.parametrize("F,K,bound,slope", [(7, 10, 1.0, 1e-3), (4, 33, 1.1, 1e-3), (3, 8, 5.0, None), (5, 16, 1.0, 1e-3),
-                                             (3, 64, 1.1, 1e-3), (2, 50, 2.0, None), (3, 13, 1.0, None)])
+                                             (3, 64, 1.1, 1e-3), (2, 50, 2.0, None), (3, 13, 1.0, None), (10, 40, 1.1, 1e-3),
+                                             (6, 35, 1.1, 1e-3), (2, 20, 1.0, 1e-3), (3, 6, 1.0, 1e-3), (3, 45, 2.0, 1e-3),
+                                             (2, 7, 1.0, 1e-3), (2, 19, 1.0, 1e-3), (3, 5, 1.0, 1e-3)])
 def test_spline_autograd_vs_torch_restatement(F, K, bound, slope):
     """SURVEY 8f-4 for K3/K4: gradients w.r.t. the parameters and the input == torch autograd through the op-for-op
     restatement of zuko (oracle/rqs_torch.py), both directions, cotangents on the output AND on the log-det."""
@@ -309,6 +312,53 @@ def test_spline_autograd_vs_torch_restatement(F, K, bound, slope):
     y32, l32, _ = TR.rqs_forward(p32, x32, bound=bound, slope=slope)
     (y32 * gy.float().cuda()).sum().backward()
     assert torch.isfinite(p32.grad).all()
+
+
+@pytest.mark.parametrize("F,K", [(10, 40), (10, 35), (7, 10), (8, 16)])
+def test_fp64_backward_many_tiles_and_bad_rows(F, K):
+    """rqs64_backward_kernel with more tiles than resident CTAs (every CTA loops: bulk store of tile i, then the bulk copy of
+    tile i + grid into the same rows), against torch autograd of the restatement; a row with a non-finite parameter gets
+    NaN gradients and leaves every other row untouched; inputs in the identity tails get zero parameter gradients."""
+    from memflow_b200 import transforms as TR
+    from oracle import rqs_torch
+    B = 6007
+    g = torch.Generator().manual_seed(5)
+    phi0 = torch.randn(B, F, 3 * K - 1, generator=g, dtype=torch.float64)
+    x0 = (torch.rand(B, F, generator=g, dtype=torch.float64) * 2.4 - 1.2) * 1.1
+    gy = torch.randn(B, F, generator=g, dtype=torch.float64)
+    gl = torch.randn(B, F, generator=g, dtype=torch.float64)
+    for inverse in (False, True):
+        phi_r, x_r = phi0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        t = rqs_torch.MonotonicRQSTransform(phi_r[..., :K], phi_r[..., K:2 * K], phi_r[..., 2 * K:], bound=1.1)
+        if not inverse:
+            y_r, l_r = t.call_and_ladj(x_r)
+        else:
+            y_r = t._inverse(x_r)
+            l_r = t.call_and_ladj(y_r)[1]
+        ((y_r * gy).sum() + (l_r * gl).sum()).backward()
+        phi_k, x_k = phi0.clone().cuda().requires_grad_(True), x0.clone().cuda().requires_grad_(True)
+        y_k, l_k, _ = (TR.rqs_inverse if inverse else TR.rqs_forward)(phi_k, x_k, bound=1.1)
+        ((y_k * gy.cuda()).sum() + (l_k * gl.cuda()).sum()).backward()
+        for got, ref, name in ((phi_k.grad, phi_r.grad, "phi"), (x_k.grad, x_r.grad, "x")):
+            got, ref = got.cpu().numpy().reshape(B, -1), ref.numpy().reshape(B, -1)
+            rel = np.abs(got - ref) / (np.abs(ref).max(axis=1, keepdims=True) + 1e-300)
+            print("many tiles K=%d inv=%s %s: max rel %.2e median %.2e" % (K, inverse, name, rel.max(), np.median(rel)))
+            assert np.median(rel) < 1e-12 and np.quantile(rel, 0.999) < 1e-8 and rel.max() < 1e-6
+        tails = (x0.abs() >= 1.1)
+        assert tails.any() and float(phi_k.grad.cpu()[tails].abs().max()) == 0.0
+        # poisoned rows
+        bad = phi0.clone()
+        bad[17, 1, 3] = float("inf")
+        bad[4000, F - 1, K + 2] = float("nan")
+        bad[5000, 0, 0] = 1e300
+        pb = bad.cuda().requires_grad_(True)
+        yb, lb, _ = (TR.rqs_inverse if inverse else TR.rqs_forward)(pb, x0.cuda(), bound=1.1)
+        ((yb * gy.cuda()).sum() + (lb * gl.cuda()).sum()).backward()
+        gb = pb.grad.cpu()
+        badrow = torch.zeros(B, F, dtype=torch.bool)
+        badrow[17, 1] = badrow[4000, F - 1] = badrow[5000, 0] = True
+        assert bool(torch.isnan(gb[badrow]).all())
+        assert torch.equal(gb[~badrow], phi_k.grad.cpu()[~badrow])
 
 
 @pytest.mark.parametrize("dt,F,K", [(torch.float64, 10, 40), (torch.float64, 6, 35), (torch.float32, 10, 40), (torch.float32, 7, 10), (torch.float64, 7, 10)])
