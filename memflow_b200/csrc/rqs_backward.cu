@@ -774,40 +774,47 @@ rqs64_backward_kernel(const __grid_constant__ Rqs64BwdArgs A) {
                 if (chunk * NT + j < 7) adjs[(size_t)(chunk * NT + j) * RPT + rr] = part[j];
         }
         __syncthreads();
-        // ---- S5: gradients of this chunk from the registers, in place ----
+        // ---- S5: gradients of this chunk from the registers, in place. One path for every row: identity tails take zero
+        //      multipliers, poisoned rows NaN ones (whatever their unwritten pub / adj slots hold is discarded by the selects) ----
         if (valid) {
             double* const rw_ = r + k0;
             double* const rh_ = r + K + k0;
             double* const rd_ = r + 2 * K + k0;
             const int nd = min(k1, K - 1) - k0;   // derivative parameters of this chunk
-            if (bin >= 0) {
-                const double* const ad = adjs + rr;
-                const double cwl = pb[0], cwh = pb[RPT], chl = pb[2 * RPT], chh = pb[3 * RPT];
-                const double a0 = ad[0], a1 = ad[RPT], a2 = ad[2 * RPT], a3 = ad[3 * RPT];
-                const double sw2 = (2.0 * Bd) * pb[4 * RPT], sh2 = (2.0 * Bd) * pb[5 * RPT];
-                // (the bracket takes three values per array: i < bin, i == bin, i > bin)
-                const double uw = a1 * (1.0 - cwh), lw = a0 * cwl, uh = a3 * (1.0 - chh), lh = a2 * chl;
-                const double gw_lt = sw2 * (uw + a0 * (1.0 - cwl)), gw_eq = sw2 * (uw - lw), gw_gt = -sw2 * (a1 * cwh + lw);
-                const double gh_lt = sh2 * (uh + a2 * (1.0 - chl)), gh_eq = sh2 * (uh - lh), gh_gt = -sh2 * (a3 * chh + lh);
-                const double gd0 = ad[4 * RPT] * pb[8 * RPT], gd1 = ad[5 * RPT] * pb[9 * RPT];
-                const int jb = bin - k0;   // the bin's place in this chunk (may lie outside it)
+            const double* const ad = adjs + rr;
+            const bool in = bin >= 0;
+            const double fill = bin == -2 ? kNaN : 0.0;
+            const double cwl = pb[0], cwh = pb[RPT], chl = pb[2 * RPT], chh = pb[3 * RPT];
+            const double a0 = ad[0], a1 = ad[RPT], a2 = ad[2 * RPT], a3 = ad[3 * RPT];
+            const double sw2 = (2.0 * Bd) * pb[4 * RPT], sh2 = (2.0 * Bd) * pb[5 * RPT];
+            // (the bracket takes three values per array: i < bin, i == bin, i > bin)
+            const double uw = a1 * (1.0 - cwh), lw = a0 * cwl, uh = a3 * (1.0 - chh), lh = a2 * chl;
+            const double gw_lt = in ? sw2 * (uw + a0 * (1.0 - cwl)) : fill, gw_eq = in ? sw2 * (uw - lw) : fill;
+            const double gw_gt = in ? -sw2 * (a1 * cwh + lw) : fill;
+            const double gh_lt = in ? sh2 * (uh + a2 * (1.0 - chl)) : fill, gh_eq = in ? sh2 * (uh - lh) : fill;
+            const double gh_gt = in ? -sh2 * (a3 * chh + lh) : fill;
+            const double gd0 = in ? ad[4 * RPT] * pb[8 * RPT] : fill, gd1 = in ? ad[5 * RPT] * pb[9 * RPT] : fill;
+            const int jb = in ? bin - k0 : -16;   // the bin's place in this chunk (may lie outside it)
+            auto grad = [&](int j) {
+                rw_[j] = pw[j] * (j < jb ? gw_lt : (j == jb ? gw_eq : gw_gt));
+                rh_[j] = ph[j] * (j < jb ? gh_lt : (j == jb ? gh_eq : gh_gt));
+            };
+            auto dgrad = [&](int j) { rd_[j] = (j == jb - 1) ? gd0 : ((j == jb) ? gd1 : fill); };
+            if (k1 - k0 == CH) {   // warp-uniform: the usual case, no per-bin test (a full chunk has CH or CH - 1 derivative slots)
 #pragma unroll
                 for (int j = 0; j < CH; ++j) {
-                    if (k0 + j < k1) {
-                        rw_[j] = pw[j] * (j < jb ? gw_lt : (j == jb ? gw_eq : gw_gt));
-                        rh_[j] = ph[j] * (j < jb ? gh_lt : (j == jb ? gh_eq : gh_gt));
-                    }
-                    if (j < nd) rd_[j] = (j == jb - 1) ? gd0 : ((j == jb) ? gd1 : 0.0);
+                    grad(j);
+                    if (j < CH - 1) dgrad(j);
                 }
-                if (evaluator) A.g_v[row] = ad[6 * RPT];
+                if (nd == CH) dgrad(CH - 1);
             } else {
-                const double fill = bin == -2 ? kNaN : 0.0;
 #pragma unroll
                 for (int j = 0; j < CH; ++j) {
-                    if (k0 + j < k1) { rw_[j] = fill; rh_[j] = fill; }
-                    if (j < nd) rd_[j] = fill;
+                    if (k0 + j < k1) grad(j);
+                    if (j < nd) dgrad(j);
                 }
             }
+            if (evaluator && in) A.g_v[row] = ad[6 * RPT];
         }
         fence_proxy_async();   // generic writes of the gradients -> visible to the bulk store
         __syncthreads();

@@ -93,6 +93,7 @@ struct Rqs64Args {
     int rows_per_tile;      // whole events (a multiple of F: per-event sums in the kernel) or any even count <= 256 / LANES
     int whole_events;
     int pitch /*shared-memory row pitch in elements*/, bulk_ok, chw /*chunk length*/, nsteps /*binary search*/;
+    int stages;             // tile buffers: 2 = the next (tile, transform) is copied while this one is processed
 };
 
 template <bool INV, int LANES, bool PAIR, bool CHAIN>
@@ -104,10 +105,12 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = A.K, PW = 3 * K - 1, PWP = A.pitch, F = A.F, T = A.T;
     const RqsConst<double>& C = A.C;
-    double* const sm = reinterpret_cast<double*>(smem_raw);
-    double* const tot = reinterpret_cast<double*>(smem_raw + ((size_t)RPT * PWP * sizeof(double) + 127) / 128 * 128);  // [NS][RPT]
+    const size_t buf_bytes = ((size_t)RPT * PWP * sizeof(double) + 127) / 128 * 128;
+    const int stages = A.stages;
+    double* const tot = reinterpret_cast<double*>(smem_raw + (size_t)stages * buf_bytes);  // [NS][RPT]
     double* const lad = tot + (size_t)NS * RPT;   // [RPT] per-row log-det (sums over the event's features)
-    uint64_t* const bar = reinterpret_cast<uint64_t*>(lad + RPT);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(lad + RPT);
+    auto buf = [&](int st) { return reinterpret_cast<double*>(smem_raw + (size_t)st * buf_bytes); };
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int chunk = wid % LANES, group = wid / LANES, rr = group * 32 + lane;
     const bool evaluator = chunk == (group % LANES);   // the thread of the row that searches and evaluates (spread over the schedulers)
@@ -118,14 +121,15 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
     const size_t tile_elems = (size_t)rows_per_tile * PW;
     const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(double));
     const double Bd = C.bound, half_over_B = 0.5 / Bd;
-    double* const r = sm + (size_t)rr * PWP;
     const bool want_sum = A.ladj_sum != nullptr && A.whole_events;
 
-    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
     __syncthreads();
     // bulk copy of (tile, transform): one copy when the shared-memory rows are packed, one per row when they are padded
-    auto issue = [&](int64_t tile, int t) {
+    auto issue = [&](int64_t tile, int t, int st) {
         const double* src = A.phi + (size_t)t * A.transform_pitch + (size_t)tile * tile_elems;
+        double* const sm = buf(st);
+        uint64_t* const bar = &bars[st];
         if (PWP == PW) {
             if (tid == 0) {
                 mbar_expect_tx(bar, tile_bytes);
@@ -141,9 +145,10 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
                 bulk_g2s(sm + (size_t)row * PWP, src + (size_t)row * PW, (uint32_t)(PW * sizeof(double)), bar);
         }
     };
-    uint32_t parity = 0u;
+    uint32_t parity0 = 0u, parity1 = 0u;
+    int step = 0;   // (tile, transform) steps done by this CTA: step & 1 is the buffer of a two-stage run
     int64_t tile = blockIdx.x;
-    if (tile < full_tiles) issue(tile, T - 1);
+    if (tile < full_tiles) issue(tile, T - 1, 0);
     for (; tile < num_tiles; tile += gridDim.x) {
         const bool bulk = tile < full_tiles;
         const int64_t row0 = tile * rows_per_tile;
@@ -171,11 +176,17 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
             const int64_t g = row0 + row, e = g / F;
             return base + (size_t)e * A.event_stride + (size_t)(g - e * F) * PW;
         };
-        for (int t = T - 1; t >= 0; --t) {   // sampling applies the transforms in reverse order (T = 1 for K3 / K4)
+        for (int t = T - 1; t >= 0; --t, ++step) {   // sampling applies the transforms in reverse order (T = 1 for K3 / K4)
             const double* tbase = A.phi + (size_t)t * A.transform_pitch;
+            const int st = stages == 2 ? (step & 1) : 0;
+            double* const sm = buf(st);
+            double* const r = sm + (size_t)rr * PWP;
+            // two stages: the other buffer was released by the second barrier of the step before, refill it now
+            const int64_t nt = t > 0 ? tile : tile + gridDim.x;
+            if (stages == 2 && nt < full_tiles) issue(nt, t > 0 ? t - 1 : T - 1, st ^ 1);
             if (bulk) {
-                mbar_wait(bar, parity);
-                parity ^= 1u;
+                mbar_wait(&bars[st], st ? parity1 : parity0);
+                if (st) parity1 ^= 1u; else parity0 ^= 1u;
             } else {  // ragged last tile or unaligned phi: plain cooperative copy into the same (padded) rows
                 for (int row = wid; row < nrows; row += 8) {
                     const double* src = row_src(tbase, row);
@@ -250,10 +261,8 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
             }
             fence_proxy_async();  // in-place generic writes to the tile happen-before the next TMA refill
             __syncthreads();
-            {   // refill the (single) stage: next transform of this tile, else the next tile's first
-                const int64_t nt = t > 0 ? tile : tile + gridDim.x;
-                if (nt < full_tiles) issue(nt, t > 0 ? t - 1 : T - 1);
-            }
+            // single stage: refill it with the next transform of this tile, else the next tile's first
+            if (stages == 1 && nt < full_tiles) issue(nt, t > 0 ? t - 1 : T - 1, 0);
             // ---- S3b: the rational quadratic on the bin's four knots, registers only, while the next copy is in flight ----
             if (evaluator && valid) {
                 double out = v, ladj = 0.0;
@@ -376,15 +385,23 @@ int rqs64_launch(bool inverse, bool chain, const double* phi, const double* vin,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const size_t row_bytes = (size_t)pitch * sizeof(double);
-    auto need = [&](int lanes) {
+    auto need = [&](int lanes, int stages) {
         const int rpt = 256 / lanes, ns = lanes >= 2 ? lanes : 2;
-        return ((size_t)rpt * row_bytes + 127) / 128 * 128 + (size_t)(ns + 1) * rpt * sizeof(double) + 16;
+        return (((size_t)rpt * row_bytes + 127) / 128 * 128) * stages + (size_t)(ns + 1) * rpt * sizeof(double) + 16;
     };
+    // MF_RQS64_STAGES=2: two tile buffers (the next (tile, transform) is copied while this one is processed). Measured on
+    // B200 (scripts/rqs64_ab.py) and NOT the default: two 61 KB buffers leave one CTA per SM at 4 threads per row, and 8
+    // threads per row (32-row tiles, three CTAs) put the per-row evaluation of 32 rows on one warp: F=10 K=40 0.270 ms
+    // single stage / 4 threads per row, 0.364 ms two stages / 8, 0.374 ms single stage / 8.
+    static const int stages_env = [] { const char* e = getenv("MF_RQS64_STAGES"); return e ? atoi(e) : 0; }();
     const int pref = forced ? forced : (row_bytes < 420 ? 1 : (row_bytes < 700 ? 2 : (row_bytes < 2000 ? 4 : 8)));
-    int lanes = 0;
-    for (int pass = 0; pass < 2 && !lanes; ++pass)   // first aim at 3 CTAs per SM, then at anything that fits
+    int lanes = 0, stages = 1;
+    if (stages_env == 2)
         for (int l = pref; l <= 8 && !lanes; l *= 2)
-            if (need(l) <= (size_t)smem_max / (pass == 0 ? 3 : 1)) lanes = l;
+            if (need(l, 2) <= (size_t)smem_max) { lanes = l; stages = 2; }
+    for (int pass = 0; pass < 2 && !lanes; ++pass)   // single stage: first aim at 3 CTAs per SM, then at anything that fits
+        for (int l = pref; l <= 8 && !lanes; l *= 2)
+            if (need(l, 1) <= (size_t)smem_max / (pass == 0 ? 3 : 1)) lanes = l;
     if (!lanes) return MF_E_SHAPE;
     const int rpt = 256 / lanes, hc = lanes >= 2 ? lanes / 2 : 1;
     // Tiles of whole events keep the per-event log-det sum in the kernel; when the events pack a tile badly (F = 20 in
@@ -418,9 +435,10 @@ int rqs64_launch(bool inverse, bool chain, const double* phi, const double* vin,
     A.B = B; A.seed = seed; A.event_offset = event_offset;
     A.F = F; A.K = K; A.T = T; A.rows_per_tile = rows_per_tile; A.whole_events = whole ? 1 : 0; A.pitch = pitch; A.bulk_ok = bulk_ok;
     A.chw = (K + hc - 1) / hc;
+    A.stages = stages;
     A.nsteps = 0;
     while ((1 << A.nsteps) < A.chw + 1) ++A.nsteps;
-    const size_t smem = need(lanes);
+    const size_t smem = need(lanes, stages);
     int rc;
     if (chain) rc = rqs64_pick<true, true>(A, lanes, pair, smem, sms, stream);
     else rc = inverse ? rqs64_pick<true, false>(A, lanes, pair, smem, sms, stream)
