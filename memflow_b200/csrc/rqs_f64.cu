@@ -96,10 +96,12 @@ struct Rqs64Args {
     int stages;             // tile buffers: 2 = the next (tile, transform) is copied while this one is processed
 };
 
-template <bool INV, int LANES, bool PAIR, bool CHAIN>
-__global__ void __launch_bounds__(256, 3)
+// NW = warps per CTA: 8 (three CTAs per SM) or 4 (six CTAs of half the rows: the same 24 warps per SM in twice as many
+// independent tile pipelines and barriers that span four warps instead of eight)
+template <bool INV, int LANES, bool PAIR, bool CHAIN, int NW>
+__global__ void __launch_bounds__(NW * 32, 24 / NW)
 rqs64_kernel(const __grid_constant__ Rqs64Args A) {
-    constexpr int RPT = 256 / LANES;              // rows per tile (capacity)
+    constexpr int RPT = NW * 32 / LANES;          // rows per tile (capacity)
     constexpr int HC = LANES >= 2 ? LANES / 2 : 1;  // chunks per softmax array
     constexpr int NS = 2 * HC;                    // segments per row
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -139,7 +141,7 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
             // (a bulk copy is issued from uniform registers: the lanes of a warp take turns, so the rows are spread over
             //  all 8 warps; complete_tx may overtake thread 0's expect_tx, the pending arrival keeps the phase open)
             if (tid == 0) mbar_expect_tx(bar, tile_bytes);
-            const int per = (rows_per_tile + 7) >> 3;
+            const int per = (rows_per_tile + NW - 1) / NW;
             const int row = wid * per + lane;
             if (lane < per && row < rows_per_tile)
                 bulk_g2s(sm + (size_t)row * PWP, src + (size_t)row * PW, (uint32_t)(PW * sizeof(double)), bar);
@@ -188,7 +190,7 @@ rqs64_kernel(const __grid_constant__ Rqs64Args A) {
                 mbar_wait(&bars[st], st ? parity1 : parity0);
                 if (st) parity1 ^= 1u; else parity0 ^= 1u;
             } else {  // ragged last tile or unaligned phi: plain cooperative copy into the same (padded) rows
-                for (int row = wid; row < nrows; row += 8) {
+                for (int row = wid; row < nrows; row += NW) {
                     const double* src = row_src(tbase, row);
                     for (int i = lane; i < PW; i += 32) sm[(size_t)row * PWP + i] = __ldg(src + i);
                 }
@@ -337,30 +339,36 @@ __global__ void __launch_bounds__(256) rqs64_event_sum_kernel(const double* __re
     out[ev] = s;
 }
 
-template <bool INV, int LANES, bool PAIR, bool CHAIN>
+template <bool INV, int LANES, bool PAIR, bool CHAIN, int NW>
 static int rqs64_go(Rqs64Args& A, size_t smem, int sms, cudaStream_t stream) {
-    auto kern = rqs64_kernel<INV, LANES, PAIR, CHAIN>;
+    auto kern = rqs64_kernel<INV, LANES, PAIR, CHAIN, NW>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int ctas = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 256, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, NW * 32, smem);
     if (ctas < 1) ctas = 1;
     const int64_t total_rows = A.B * (int64_t)A.F;
     const int64_t num_tiles = (total_rows + A.rows_per_tile - 1) / A.rows_per_tile;
     int64_t grid = (int64_t)sms * ctas;
     if (grid > num_tiles) grid = num_tiles;
-    kern<<<(unsigned)grid, 256, smem, stream>>>(A);
+    kern<<<(unsigned)grid, NW * 32, smem, stream>>>(A);
     return launch_status();
 }
 
 template <bool INV, bool CHAIN>
-static int rqs64_pick(Rqs64Args& A, int lanes, bool pair, size_t smem, int sms, cudaStream_t stream) {
-#define MF_GO(L) (pair ? rqs64_go<INV, L, true, CHAIN>(A, smem, sms, stream) : rqs64_go<INV, L, false, CHAIN>(A, smem, sms, stream))
+static int rqs64_pick(Rqs64Args& A, int lanes, bool pair, int nw, size_t smem, int sms, cudaStream_t stream) {
+#define MF_GO(L, W) (pair ? rqs64_go<INV, L, true, CHAIN, W>(A, smem, sms, stream) : rqs64_go<INV, L, false, CHAIN, W>(A, smem, sms, stream))
+    if (nw == 4) {
+        switch (lanes) {
+        case 2: return MF_GO(2, 4);
+        default: return MF_GO(4, 4);
+        }
+    }
     switch (lanes) {
-    case 1: return MF_GO(1);
-    case 2: return MF_GO(2);
-    case 4: return MF_GO(4);
-    default: return MF_GO(8);
+    case 1: return MF_GO(1, 8);
+    case 2: return MF_GO(2, 8);
+    case 4: return MF_GO(4, 8);
+    default: return MF_GO(8, 8);
     }
 #undef MF_GO
 }
@@ -385,8 +393,11 @@ int rqs64_launch(bool inverse, bool chain, const double* phi, const double* vin,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const size_t row_bytes = (size_t)pitch * sizeof(double);
+    // MF_RQS64_WARPS = 4 / 8 forces 128- / 256-thread CTAs (128: 2 or 4 threads per row only)
+    static const int warps_env = [] { const char* e = getenv("MF_RQS64_WARPS"); return e ? atoi(e) : 0; }();
+    int nw = 8;
     auto need = [&](int lanes, int stages) {
-        const int rpt = 256 / lanes, ns = lanes >= 2 ? lanes : 2;
+        const int rpt = nw * 32 / lanes, ns = lanes >= 2 ? lanes : 2;
         return (((size_t)rpt * row_bytes + 127) / 128 * 128) * stages + (size_t)(ns + 1) * rpt * sizeof(double) + 16;
     };
     // MF_RQS64_STAGES=2: two tile buffers (the next (tile, transform) is copied while this one is processed). Measured on
@@ -395,15 +406,19 @@ int rqs64_launch(bool inverse, bool chain, const double* phi, const double* vin,
     // single stage / 4 threads per row, 0.364 ms two stages / 8, 0.374 ms single stage / 8.
     static const int stages_env = [] { const char* e = getenv("MF_RQS64_STAGES"); return e ? atoi(e) : 0; }();
     const int pref = forced ? forced : (row_bytes < 420 ? 1 : (row_bytes < 700 ? 2 : (row_bytes < 2000 ? 4 : 8)));
+    // odd K (one bulk copy per row) gains 3-5 % from the smaller CTAs (scripts/rqs64_ab.py: F=10 K=35 0.298 -> 0.290 ms, the
+    // chain's flow stage 1.489 -> 1.418 ms), even K loses 0-4 %
+    if ((warps_env == 4 || (warps_env == 0 && pair)) && (pref == 2 || pref == 4)) nw = 4;
     int lanes = 0, stages = 1;
     if (stages_env == 2)
         for (int l = pref; l <= 8 && !lanes; l *= 2)
             if (need(l, 2) <= (size_t)smem_max) { lanes = l; stages = 2; }
     for (int pass = 0; pass < 2 && !lanes; ++pass)   // single stage: first aim at 3 CTAs per SM, then at anything that fits
         for (int l = pref; l <= 8 && !lanes; l *= 2)
-            if (need(l, 1) <= (size_t)smem_max / (pass == 0 ? 3 : 1)) lanes = l;
+            if (need(l, 1) <= (size_t)smem_max / (pass == 0 ? 24 / nw : 1)) lanes = l;
     if (!lanes) return MF_E_SHAPE;
-    const int rpt = 256 / lanes, hc = lanes >= 2 ? lanes / 2 : 1;
+    if (nw == 4 && lanes != 2 && lanes != 4) nw = 8;
+    const int rpt = nw * 32 / lanes, hc = lanes >= 2 ? lanes / 2 : 1;
     // Tiles of whole events keep the per-event log-det sum in the kernel; when the events pack a tile badly (F = 20 in
     // 32 rows: 37 % of the lanes idle) or no sum is asked for, tiles are plain runs of rows and the sum is a second,
     // tiny launch over 8 B per row.
@@ -440,9 +455,9 @@ int rqs64_launch(bool inverse, bool chain, const double* phi, const double* vin,
     while ((1 << A.nsteps) < A.chw + 1) ++A.nsteps;
     const size_t smem = need(lanes, stages);
     int rc;
-    if (chain) rc = rqs64_pick<true, true>(A, lanes, pair, smem, sms, stream);
-    else rc = inverse ? rqs64_pick<true, false>(A, lanes, pair, smem, sms, stream)
-                      : rqs64_pick<false, false>(A, lanes, pair, smem, sms, stream);
+    if (chain) rc = rqs64_pick<true, true>(A, lanes, pair, nw, smem, sms, stream);
+    else rc = inverse ? rqs64_pick<true, false>(A, lanes, pair, nw, smem, sms, stream)
+                      : rqs64_pick<false, false>(A, lanes, pair, nw, smem, sms, stream);
     if (rc == MF_OK && want_sum && !whole) {
         rqs64_event_sum_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(ladj_rows, B, F, ladj_sum);
         rc = launch_status();

@@ -1,9 +1,8 @@
 """Same-box A/B of the float64 spline forward / inverse (csrc/rqs_f64.cu) and of the float64 flow stage of the chain under
 environment knobs (read once per process, so every variant runs in its own process).
-usage: rqs64_ab.py [F:K ...]      variants: MF_RQS64_STAGES = 1 / 2, MF_RQS64_LANES"""
+usage: rqs64_ab.py [F:K ...]      variants: MF_RQS64_WARPS = 8 / 4 (threads per CTA 256 / 128); MF_RQS64_STAGES, MF_RQS64_LANES from the environment"""
 import os, sys, subprocess, json
-VARIANTS = [("stages1", {"MF_RQS64_STAGES": "1"}), ("auto", {}), ("stages2_L4", {"MF_RQS64_STAGES": "2", "MF_RQS64_LANES": "4"}),
-            ("stages1_L8", {"MF_RQS64_STAGES": "1", "MF_RQS64_LANES": "8"})]
+VARIANTS = [("8 warps", {}), ("4 warps", {"MF_RQS64_WARPS": "4"})]
 if os.environ.get("_AB_CHILD"):
     import torch
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
