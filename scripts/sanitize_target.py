@@ -20,6 +20,16 @@ for (dt, F, K) in ((torch.float32, 20, 64), (torch.float32, 10, 40), (torch.floa
     phi = torch.randn(1003, F, 3 * K - 1, device=dev, dtype=dt)
     x = (torch.rand(1003, F, device=dev, dtype=dt) * 2.6 - 1.3)
     TR.rqs_forward(phi, x, bound=1.0); TR.rqs_inverse(phi, x, bound=1.0)
+for (F, K) in ((10, 40), (6, 35), (7, 10), (5, 16), (3, 64), (2, 5)):   # spline backward, float64 (rqs64_backward_kernel and the cooperative one) and float32
+    for dt in (torch.float64, torch.float32):
+        phi = torch.randn(1531, F, 3 * K - 1, device=dev, dtype=dt, requires_grad=True)
+        x = (torch.rand(1531, F, device=dev, dtype=dt) * 2.6 - 1.3)
+        for fn in (TR.rqs_forward, TR.rqs_inverse):
+            y, l, ls = fn(phi, x, bound=1.0)
+            (y.sum() + ls.sum()).backward()
+smp4 = ES.ImportanceSampler([125.25, 172.5, 172.5, 1e-5], E, seed=3, device=dev)
+for K in (40, 35):   # float64 flow stage of the chain
+    smp4.run_chunk(torch.randn(3, 1201, 10, 3 * K - 1, device=dev, dtype=torch.float64))
 smp = ES.ImportanceSampler([125.25, 172.5, 172.5], E, seed=1, device=dev)
 phi = torch.randn(2, 5003, 7, 29, device=dev, dtype=torch.float32)
 acc = smp.run_chunk(phi); acc, out = smp.run_chunk(phi, debug_outputs=True)
