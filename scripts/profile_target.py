@@ -45,6 +45,15 @@ if what in ("rqs64", "all"):   # the reference's configs run the flows in float6
         phi.grad = None
         ls.sum().backward()
     torch.cuda.synchronize()
+if what == "rqs64bk35":   # float64 backward at the most common bin count of the reference's configs (odd K: padded rows)
+    B, F, K = 1 << 18, 10, 35
+    phi = torch.randn(B, F, 3 * K - 1, device=dev, dtype=torch.float64, requires_grad=True)
+    x = (torch.rand(B, F, device=dev, dtype=torch.float64) * 2.6 - 1.3) * 1.1
+    for i in range(3):
+        y, l, ls = TR.rqs_forward(phi, x, bound=1.1)
+        phi.grad = None
+        ls.sum().backward()
+    torch.cuda.synchronize()
 if what in ("rqs64k40", "rqs64k35", "rqs64k33", "rqs64k64", "rqs64k10"):   # float64 forward / inverse alone (csrc/rqs_f64.cu)
     K = int(what[6:])
     F = {40: 10, 35: 10, 33: 10, 64: 20, 10: 7}[K]
