@@ -45,7 +45,7 @@ rambo_forward_kernel(const T* __restrict__ u, int64_t N, const __grid_constant__
     // dependency chains wait for are shared-memory reads instead of global loads issued one by one along the chain
     constexpr bool PREFETCH = !EPILOGUE && NF >= 6 && sizeof(T) == 8;  // n = 6: +15 %, n = 7, 8: +4-7 %, n = 5: neutral
     // row pitch in shared memory: W = 16 doubles (n = 6) would put every row of a warp in the same banks (32-way conflicts on
-    // each read); those rows come in by one bulk copy per row, 18 doubles apart
+    // each read); those rows are spaced 18 doubles apart and filled by 16-byte asynchronous copies
     constexpr int WP = (W % 16 == 0) ? W + 2 : W;
     __shared__ __align__(128) T su[PREFETCH ? 256 * WP : 1];
     __shared__ uint64_t bar;
@@ -55,17 +55,26 @@ rambo_forward_kernel(const T* __restrict__ u, int64_t N, const __grid_constant__
         const T* src = u + ev0 * W;
         const uint32_t bytes = (uint32_t)nrows * W * (uint32_t)sizeof(T);
         const bool bulk = (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (bytes & 15) == 0;
-        if (bulk) {
+        if (bulk && WP != W) {
+            // padded rows (n = 6): 16-byte asynchronous copies (LDGSTS), coalesced over the CTA's contiguous rows, each
+            // landing at its padded place. (One bulk copy per row, 256 per CTA, was what made n = 6 the slowest map per byte.)
+            constexpr int CPR = W * (int)sizeof(T) / 16;   // 16-byte chunks per row
+            for (int c = threadIdx.x; c < nrows * CPR; c += blockDim.x) {
+                const int row = c / CPR, ch = c - row * CPR;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(su + row * WP) + 16u * ch;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const char*>(src) + 16 * (size_t)c) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+        } else if (bulk) {
             if (threadIdx.x == 0) {
                 mbar_init(&bar, 1);
                 fence_mbar_init();
                 mbar_expect_tx(&bar, bytes);
-                if constexpr (WP == W) bulk_g2s(su, src, bytes, &bar);
+                bulk_g2s(su, src, bytes, &bar);
             }
             __syncthreads();
-            if constexpr (WP != W) {
-                if ((int)threadIdx.x < nrows) bulk_g2s(su + threadIdx.x * WP, src + threadIdx.x * W, W * (uint32_t)sizeof(T), &bar);
-            }
             mbar_wait(&bar, 0u);
         } else {
             for (int i = threadIdx.x; i < nrows * W; i += blockDim.x) su[(i / W) * WP + (i % W)] = src[i];
