@@ -640,7 +640,8 @@ static int rambo_is_launch(const double* u, const double* logq, int64_t N, const
         if (grid > kReduceMaxBlocks) grid = kReduceMaxBlocks;
         kern<<<(unsigned)grid, threads, 0, stream>>>(u, logq, N, P, inv_2s, acc, workspace, momenta, weight, x1, x2);
     };
-    if (thr == 128) go(rambo_is_kernel<NF, 128>, 128);
+    if (thr == 96) go(rambo_is_kernel<NF, 96>, 96);
+    else if (thr == 128) go(rambo_is_kernel<NF, 128>, 128);
     else go(rambo_is_kernel<NF, 256>, 256);
     return launch_status();
 }
