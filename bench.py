@@ -579,7 +579,21 @@ def main():
     h2d_gbps = torch.tensor([host.numel() * 4 * e2e_steps / te_med / 1e9], dtype=torch.float64, device=dev)
     e2e_value = world * e2e_steps * e2e_chunk / te_med
     e2e_passes = [world * e2e_steps * e2e_chunk / t for t in pass_s]
-    del pipe
+    # The ceiling of that leg on THIS box: the same pinned chunk copied host -> device by every rank at once, nothing else
+    # running. (On the pool's multi-GPU boxes GPUs can share a host link: 55 GB/s per GPU alone, 29 GB/s each when the
+    # ranks' GPUs sit in pairs behind one PCIe switch uplink -- scripts/h2d_ranks.py, scripts/e2e_probe.py.)
+    dplain = pipe.bufs[0]
+    dplain.copy_(host, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        dplain.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    tpl = torch.tensor([4 * host.numel() * 4 / (time.perf_counter() - t0) / 1e9], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tpl, op=dist.ReduceOp.MIN)
+    h2d_plain = float(tpl.item())
+    del pipe, dplain
 
     # ---- BASELINE configs[4] at its own shape on every N: n = 4 (H, t, tbar, j), production flow F = 10, K = 40, T = 6,
     #      float32 and float64 parameters, events sharded, max over ranks ----
@@ -608,10 +622,12 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": 24,
                 "steps": e2e_steps, "chunk_events": e2e_chunk, "api": "memflow_b200.distributed.HostPipeline.submit",
                 "h2d_GBps_per_rank": float(h2d_gbps.item()), "copy_streams": 2,
+                "h2d_plain_concurrent_GBps_per_rank_min": h2d_plain,
                 "passes": 5, "statistic": "median pass (each pass = max over ranks)", "passes_points_per_s": e2e_passes,
                 "cpu_binding": {"numa_node": numa[0], "cpus": numa[1]},
                 "note": "spline parameters start in pinned host memory (1624 B/event): PCIe-bound by construction; "
-                        "H2D double-buffered against the kernels on 2 copy streams"},
+                        "H2D double-buffered against the kernels on 2 copy streams; h2d_plain_concurrent = the bare pinned "
+                        "copy of the same chunk by all ranks at once (the leg's ceiling on this box: GPUs may share a host link)"},
         "config5": config5,
         "gpu_launches": 2 * K * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
