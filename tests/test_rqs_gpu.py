@@ -361,6 +361,27 @@ def test_fp64_backward_many_tiles_and_bad_rows(F, K):
         assert torch.equal(gb[~badrow], phi_k.grad.cpu()[~badrow])
 
 
+@pytest.mark.parametrize("F,K", [(10, 40), (6, 35), (7, 10), (3, 64)])
+def test_fp64_backward_unaligned_pointers_same_bits(F, K):
+    """Parameters (and therefore gradients) that are 8- but not 16-byte aligned cannot take the bulk copy / bulk store:
+    every tile then goes through the plain-copy path of rqs64_backward_kernel. Same arithmetic: bit-identical gradients."""
+    import memflow_b200.ops  # noqa: F401
+    B, PW = 2999, 3 * K - 1
+    g = torch.Generator().manual_seed(3)
+    phi = torch.randn(B, F, PW, generator=g, dtype=torch.float64).cuda()
+    x = ((torch.rand(B, F, generator=g, dtype=torch.float64) * 2.4 - 1.2) * 1.1).cuda()
+    gy = torch.randn(B, F, generator=g, dtype=torch.float64).cuda()
+    gl = torch.randn(B, F, generator=g, dtype=torch.float64).cuda()
+    flat = torch.empty(B * F * PW + 1, dtype=torch.float64, device="cuda")
+    phi_u = flat[1:].view(B, F, PW)
+    phi_u.copy_(phi)
+    assert phi_u.data_ptr() % 16 == 8 and phi.data_ptr() % 16 == 0
+    for inverse in (False, True):
+        ga, gva = torch.ops.memflow_b200.rqs_bwd(phi, x, gy, gl, 1.1, 1e-3, inverse)
+        gu, gvu = torch.ops.memflow_b200.rqs_bwd(phi_u, x, gy, gl, 1.1, 1e-3, inverse)
+        assert torch.equal(ga, gu) and torch.equal(gva, gvu) and bool(torch.isfinite(ga).all())
+
+
 @pytest.mark.parametrize("dt,F,K", [(torch.float64, 10, 40), (torch.float64, 6, 35), (torch.float32, 10, 40), (torch.float32, 7, 10), (torch.float64, 7, 10)])
 def test_feature_subset_reads_rows_in_place(dt, F, K):
     """Autoregressive sampling: pass j of zuko's MaskedAutoregressiveTransform inverse determines feature j only, so it
