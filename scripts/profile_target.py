@@ -45,6 +45,15 @@ if what in ("rqs64", "all"):   # the reference's configs run the flows in float6
         phi.grad = None
         ls.sum().backward()
     torch.cuda.synchronize()
+if what == "k1n6":   # n = 6: padded input rows filled by 16-byte asynchronous copies
+    m6 = [4.7, 4.7, 80.4, 172.5, 0.0, 1e-5]
+    ps = PhaseSpace(E, [21, 21], list(range(6)), final_masses=torch.tensor(m6, dtype=torch.float64), dev=dev)
+    u = torch.rand(1 << 22, 16, dtype=torch.float64, device=dev).clamp_(1e-10, 1 - 1e-10)
+    for i in range(3):
+        mom, w, x1, x2 = ps.get_momenta_from_ps(u)
+    for i in range(3):
+        ps.generator.getPSpoint_batch(mom[:, 2:], x1, x2, order=list(range(6)))
+    torch.cuda.synchronize()
 if what == "rqs64bk35":   # float64 backward at the most common bin count of the reference's configs (odd K: padded rows)
     B, F, K = 1 << 18, 10, 35
     phi = torch.randn(B, F, 3 * K - 1, device=dev, dtype=torch.float64, requires_grad=True)
