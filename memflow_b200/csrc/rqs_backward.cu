@@ -597,9 +597,12 @@ rqs64_backward_kernel(const __grid_constant__ Rqs64BwdArgs A) {
     const int64_t num_tiles = (A.rows + RPT - 1) / RPT;
     const int64_t full_tiles = A.bulk_ok ? A.rows / RPT : 0;
     const uint32_t tile_bytes = (uint32_t)((size_t)RPT * PW * sizeof(double));
-    constexpr int PER = (RPT + 7) / 8;                    // padded rows: rows copied by each warp (one per lane)
-    const int myrow = wid * PER + lane;                   // the row this thread copies in / out when rows are padded
-    const bool copier = lane < PER && myrow < RPT;
+    // padded rows: one bulk copy / bulk store per row, one row per lane, issued by the warps that do NOT evaluate (the
+    // evaluating warp is the tile's critical path between the first two barriers)
+    constexpr int NCW = 8 - 8 / LANES;                    // copier warps
+    constexpr int PER = (RPT + NCW - 1) / NCW;            // rows per copier warp
+    const int myrow = (wid - wid / LANES) * PER + lane;   // the row this thread copies in / out
+    const bool copier = !evaluator && lane < PER && myrow < RPT;
     auto buf = [&](int b) { return reinterpret_cast<double*>(smem_raw + (size_t)b * buf_bytes); };
 
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
