@@ -249,7 +249,7 @@ flow_sample_kernel(const float* __restrict__ phi, int64_t N, int F, int T, int K
 // transforms of a tile: the new x goes back to the searching side through shared memory.
 // ---------------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, MF_REG2_MINB(K))
 flow_sample_reg2_kernel(const float* __restrict__ phi, int64_t N, int F, int T, RqsConst<float> C, int E, int bulk_ok,
                         uint64_t seed, uint64_t event_offset, double* __restrict__ u_out, double* __restrict__ logq_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -143,7 +143,7 @@ rqs_kernel(const T* __restrict__ phi, const T* __restrict__ vin, int64_t B, int 
 // TMA tile per CTA, several CTAs per SM overlap each other's copies.
 // ---------------------------------------------------------------------------------------------
 template <int K, bool INV>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, MF_REG2_MINB(K))
 rqs_reg2_kernel(const float* __restrict__ phi, const float* __restrict__ vin, int64_t B, int F, RqsConst<float> C, int ept,
                 int bulk_ok, float* __restrict__ vout, float* __restrict__ ladj_out, float* __restrict__ ladj_sum,
                 int32_t* __restrict__ bin_out, int64_t event_stride /*elements between events*/) {

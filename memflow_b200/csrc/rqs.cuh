@@ -38,6 +38,11 @@ template <> struct FastMath<double> {
     static MF_D double log(double x) { return ::log(x); }
 };
 
+// CTAs per SM asked of the two-sided register-row kernels (rqs_reg2_kernel, flow_sample_reg2_kernel; 128 threads): K <= 40
+// fits five (<= 102 registers), longer rows four
+#ifndef MF_REG2_MINB
+#define MF_REG2_MINB(K) ((K) <= 40 ? 5 : 4)
+#endif
 template <typename T> struct RqsConst {
     T bound;
     T two_over_L;  // 2 / log(slope)   (soft clip of widths/heights), 0 when clip disabled
