@@ -38,10 +38,13 @@ template <> struct FastMath<double> {
     static MF_D double log(double x) { return ::log(x); }
 };
 
-// CTAs per SM asked of the two-sided register-row kernels (rqs_reg2_kernel, flow_sample_reg2_kernel; 128 threads): K <= 40
-// fits five (<= 102 registers), longer rows four
+// CTAs per SM asked of the two-sided register-row kernels (rqs_reg2_kernel, flow_sample_reg2_kernel; 128 threads). Their
+// single-stage TMA tiles want as many tiles in flight per SM as fit: the compiler keeps K <= 48 within 80 registers (six
+// CTAs) and K <= 32 within 72 (seven) without spills; K = 64 is limited to four by its 46 KB tiles. Measured on B200
+// (profiles/r2/reg2_minb_ab.log): the chain's flow stage at the production shape (K = 40) 2.57 ms with four CTAs, 2.38 ms
+// with five, 2.26 ms with six (6.6 TB/s)
 #ifndef MF_REG2_MINB
-#define MF_REG2_MINB(K) ((K) <= 40 ? 5 : 4)
+#define MF_REG2_MINB(K) ((K) <= 32 ? 7 : ((K) <= 48 ? 6 : 4))
 #endif
 template <typename T> struct RqsConst {
     T bound;

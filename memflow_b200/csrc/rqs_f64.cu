@@ -96,10 +96,13 @@ struct Rqs64Args {
     int stages;             // tile buffers: 2 = the next (tile, transform) is copied while this one is processed
 };
 
+#ifndef MF_RQS64_MINB
+#define MF_RQS64_MINB(NW) (24 / (NW))   // (seven 128-thread CTAs: 72 registers with spills, measured 1-2 % slower than six)
+#endif
 // NW = warps per CTA: 8 (three CTAs per SM) or 4 (six CTAs of half the rows: the same 24 warps per SM in twice as many
 // independent tile pipelines and barriers that span four warps instead of eight)
 template <bool INV, int LANES, bool PAIR, bool CHAIN, int NW>
-__global__ void __launch_bounds__(NW * 32, 24 / NW)
+__global__ void __launch_bounds__(NW * 32, MF_RQS64_MINB(NW))
 rqs64_kernel(const __grid_constant__ Rqs64Args A) {
     constexpr int RPT = NW * 32 / LANES;          // rows per tile (capacity)
     constexpr int HC = LANES >= 2 ? LANES / 2 : 1;  // chunks per softmax array

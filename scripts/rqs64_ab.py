@@ -2,7 +2,10 @@
 environment knobs (read once per process, so every variant runs in its own process).
 usage: rqs64_ab.py [F:K ...]      variants: MF_RQS64_WARPS = 8 / 4 (threads per CTA 256 / 128); MF_RQS64_STAGES, MF_RQS64_LANES from the environment"""
 import os, sys, subprocess, json
-VARIANTS = [("8 warps", {}), ("4 warps", {"MF_RQS64_WARPS": "4"})]
+VARIANTS = [("default", {}), ("4 warps", {"MF_RQS64_WARPS": "4"}), ("8 warps", {"MF_RQS64_WARPS": "8"})]
+_PREV = os.environ.get("AB_PREV_LIB")   # another build of the library to compare with
+if _PREV:
+    VARIANTS.append(("prev build", {"MEMFLOW_B200_LIB": _PREV}))
 if os.environ.get("_AB_CHILD"):
     import torch
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
