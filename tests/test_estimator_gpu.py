@@ -32,7 +32,7 @@ def test_is_reduce_vs_oracle(oracle):
     assert acc.tolist() == [10.0, 10.0, 10.0]
 
 
-@pytest.mark.parametrize("n,T,K", [(3, 2, 10), (4, 3, 8), (3, 1, 16), (4, 2, 40), (3, 2, 64), (3, 2, 9)])
+@pytest.mark.parametrize("n,T,K", [(3, 2, 10), (4, 3, 8), (3, 1, 16), (4, 2, 40), (3, 2, 64), (3, 2, 9), (3, 2, 32), (4, 2, 48)])
 def test_chain_vs_oracle_composition(oracle, n, T, K):
     """Fused chain == Philox -> K4 x T -> affine -> K1 -> weight -> K5 done step by step with the oracle."""
     from memflow_b200 import estimator as ES

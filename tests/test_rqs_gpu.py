@@ -135,7 +135,7 @@ def test_kernels_vs_high_precision_known_answers(golden_dir):
         assert np.abs(y32.cpu().numpy()[:, 0] - ry)[~moved].max() < 1e-5 and np.abs(l32.cpu().numpy()[:, 0] - rl)[~moved].max() < 1e-4
 
 
-@pytest.mark.parametrize("F,K,bound", [(20, 64, 1.1), (7, 10, 1.0), (10, 40, 1.1)])
+@pytest.mark.parametrize("F,K,bound", [(20, 64, 1.1), (7, 10, 1.0), (10, 40, 1.1), (6, 32, 1.0), (5, 48, 1.1)])
 def test_fp32_forward_inverse(oracle, F, K, bound):
     from memflow_b200 import transforms as TR
     B = 20000
