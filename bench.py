@@ -446,7 +446,9 @@ def config5_block(torch, dist, dev, rank, world, hbm_peak, barrier):
                          "roofline": {"bound": "hbm", "achieved": by * N5 / ta / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                       "frac": by * N5 / ta / 1e9 / hbm_peak, "algorithmic_bytes_per_event": by,
                                       "kernel": "flow_sample_reg2_kernel<40>" if dt == torch.float32 else "rqs64_kernel<inverse, 4, chain>",
-                                      "kernel_ms": ta * 1e3, "rank": 0},
+                                      "kernel_ms": ta * 1e3, "rank": 0,
+                                      "note": "peak = the measured read + write COPY rate (MEASURED_PEAKS.json); a read-only "
+                                              "parameter stream can run a few per cent above it"},
                          "estimate": {"I": I, "sigma": sigma, "n_valid": nv}}
             del phi5, u5, lq5
             torch.cuda.empty_cache()
