@@ -877,6 +877,24 @@ static int rqs64_bwd_launch(const double* phi, const double* vin, const double* 
         kern<<<(unsigned)grid, 256, smem, stream>>>(A);
         return launch_status();
     };
+    // the register chunk is compiled for the exact chunk length: a chunk shorter than the template's takes the per-bin
+    // tests in every pass (K = 45 with chunks of 6 in an 8-bin template ran no faster than the cooperative kernel)
+    switch (lanes * 16 + chw) {
+    case 2 * 16 + 3: return go(rqs64_backward_kernel<INV, 2, 3>);
+    case 2 * 16 + 4: return go(rqs64_backward_kernel<INV, 2, 4>);
+    case 2 * 16 + 5: return go(rqs64_backward_kernel<INV, 2, 5>);
+    case 4 * 16 + 3: return go(rqs64_backward_kernel<INV, 4, 3>);
+    case 4 * 16 + 4: return go(rqs64_backward_kernel<INV, 4, 4>);
+    case 4 * 16 + 5: return go(rqs64_backward_kernel<INV, 4, 5>);
+    case 8 * 16 + 3: return go(rqs64_backward_kernel<INV, 8, 3>);
+    case 8 * 16 + 4: return go(rqs64_backward_kernel<INV, 8, 4>);
+    case 8 * 16 + 5: return go(rqs64_backward_kernel<INV, 8, 5>);
+    case 8 * 16 + 6: return go(rqs64_backward_kernel<INV, 8, 6>);
+    case 8 * 16 + 7: return go(rqs64_backward_kernel<INV, 8, 7>);
+    case 8 * 16 + 8: return go(rqs64_backward_kernel<INV, 8, 8>);
+    default: break;
+    }
+    // (a forced thread count outside the table: the nearest template that holds the chunk)
     if (chw <= 5) {
         if (lanes == 2) return go(rqs64_backward_kernel<INV, 2, 5>);
         if (lanes == 4) return go(rqs64_backward_kernel<INV, 4, 5>);
