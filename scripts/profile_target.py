@@ -45,6 +45,14 @@ if what in ("rqs64", "all"):   # the reference's configs run the flows in float6
         phi.grad = None
         ls.sum().backward()
     torch.cuda.synchronize()
+if what == "chain5":   # the chain's flow stage at the production shape (n=4: T=6, F=10, K=40), fp32 parameters
+    N, T, F, K = 1 << 18, 6, 10, 40
+    phi = torch.randn(T, N, F, 3 * K - 1, device=dev, dtype=torch.float32)
+    smp = ES.ImportanceSampler([125.25, 172.5, 172.5, 1e-5], E, seed=3, device=dev)
+    acc = ES.new_accumulator(dev)
+    for i in range(3):
+        smp.run_chunk(phi, event_offset=i * N, acc=acc)
+    torch.cuda.synchronize()
 if what == "k1n6":   # n = 6: padded input rows filled by 16-byte asynchronous copies
     m6 = [4.7, 4.7, 80.4, 172.5, 0.0, 1e-5]
     ps = PhaseSpace(E, [21, 21], list(range(6)), final_masses=torch.tensor(m6, dtype=torch.float64), dev=dev)
