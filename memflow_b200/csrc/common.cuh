@@ -1,5 +1,13 @@
 // common.cuh -- shared device helpers for the sm_100a kernels of memflow_b200.
 #pragma once
+// Build-time checks with a clear message: the kernels use 256-bit ld / st.global.v4.f64, 1-D
+// cp.async.bulk with mbarrier completion and __grid_constant__ parameters, and are tuned for 148 SMs / 227 KB of shared memory.
+#if defined(__CUDACC_VER_MAJOR__) && (__CUDACC_VER_MAJOR__ * 100 + __CUDACC_VER_MINOR__ < 1209)
+#error "memflow_b200 needs nvcc >= 12.9 (sm_100a, 256-bit global loads / stores); found an older CUDA toolkit"
+#endif
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "memflow_b200 is written for sm_100a (B200) only: compile with -gencode arch=compute_100a,code=sm_100a"
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 
