@@ -163,6 +163,22 @@ def needs_dispatcher(*tensors):
     return False
 
 
+def plain_eager(*tensors):
+    """True when every tensor is a plain torch.Tensor / Parameter and nothing is tracing (torch.compile, functorch
+    transforms, torch.func): such a call may use a directly-applied torch.autograd.Function instead of the dispatcher."""
+    if torch.compiler.is_compiling():
+        return False
+    try:
+        if torch._C._functorch.peek_interpreter_stack() is not None:   # inside vmap / grad / functionalize
+            return False
+    except Exception:
+        return False
+    for t in tensors:
+        if t is not None and type(t) is not torch.Tensor and type(t) is not torch.nn.Parameter:
+            return False
+    return True
+
+
 def host_array(values, ctype):
     vals = [float(v) for v in values] if ctype in (ctypes.c_double, ctypes.c_float) else [int(v) for v in values]
     return (ctype * len(vals))(*vals)

@@ -17,7 +17,7 @@ import torch
 from torch.distributions import Transform, constraints
 
 from . import ops
-from ._lib import check, device_guard, lib, MemflowB200Error, needs_dispatcher, ptr, require_cuda, stream_ptr
+from ._lib import check, device_guard, lib, MemflowB200Error, needs_dispatcher, plain_eager, ptr, require_cuda, stream_ptr
 
 
 def _run(direction, phi, v, bound, slope, want_ladj=True, want_sum=False, want_bin=False):
@@ -28,8 +28,14 @@ def _run(direction, phi, v, bound, slope, want_ladj=True, want_sum=False, want_b
     if phi.dtype not in (torch.float32, torch.float64):
         raise MemflowB200Error("spline kernels support float32 / float64, got %s" % phi.dtype)
     outputs = (ops.RQS_LADJ if want_ladj else 0) | (ops.RQS_SUM if want_sum else 0) | (ops.RQS_BINS if want_bin else 0)
-    # plain eager inference goes straight to the C ABI; autograd / torch.compile / fake tensors go through the dispatcher
-    call = torch.ops.memflow_b200.rqs if needs_dispatcher(phi, v) else ops.rqs_cuda
+    # plain eager inference goes straight to the C ABI; plain eager autograd through a directly-applied Function;
+    # torch.compile / fake tensors / functorch transforms through the dispatcher (the registered op)
+    if not needs_dispatcher(phi, v):
+        call = ops.rqs_cuda
+    elif plain_eager(phi, v):
+        call = ops.RqsEager.apply
+    else:
+        call = torch.ops.memflow_b200.rqs
     out, ladj, lsum, bins = call(phi, v, float(bound), float(slope) if slope is not None else 0.0, direction == "inverse", outputs)
     return out, (ladj if want_ladj else None), (lsum if want_sum else None), (bins if want_bin else None)
 
