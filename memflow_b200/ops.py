@@ -185,6 +185,23 @@ class RqsEager(torch.autograd.Function):
         return g_phi, g_v.to(vdt), None, None, None, None
 
 
+def _eager_function(name, impl, setup, backward, n_inputs):
+    """A torch.autograd.Function that applies `impl` / `backward` of a registered op directly (plain eager autograd: the
+    dispatcher round trip of the registered op costs ~55 us per recorded call, see RqsEager). `setup` and `backward` are
+    the functions given to torch.library.register_autograd: one formula, two ways in."""
+    def forward(ctx, *inputs):
+        out = impl(*(t.detach() if isinstance(t, torch.Tensor) else t for t in inputs))
+        setup(ctx, inputs, out)
+        ctx.mark_non_differentiable(*(o for o in out if isinstance(o, torch.Tensor) and not o.is_floating_point()))
+        return out
+
+    def bwd(ctx, *grads):
+        res = backward(ctx, *grads)
+        return tuple(res) + (None,) * (n_inputs - len(res))
+
+    return type(name, (torch.autograd.Function,), {"forward": staticmethod(forward), "backward": staticmethod(bwd)})
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # K1: RAMBO forward
 # ---------------------------------------------------------------------------------------------------------------------
@@ -262,6 +279,7 @@ def _k1_backward(ctx, g_mom, g_w, g_x1, g_x2, g_logw, _g_status):
 
 
 torch.library.register_autograd(_NS + "::rambo_forward", _k1_backward, setup_context=_k1_setup)
+RamboForwardEager = _eager_function("RamboForwardEager", lambda *a: _k1_cuda(*a), _k1_setup, _k1_backward, 6)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -347,6 +365,7 @@ def _k2_backward(ctx, g_ps, _g_prob, _g_logp, _g_status):
 
 
 torch.library.register_autograd(_NS + "::rambo_inverse", _k2_backward, setup_context=_k2_setup)
+RamboInverseEager = _eager_function("RamboInverseEager", lambda *a: _k2_cuda(*a), _k2_setup, _k2_backward, 9)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

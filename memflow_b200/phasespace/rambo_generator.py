@@ -20,7 +20,7 @@ import torch
 
 from .. import _lib
 from .. import ops  # noqa: F401  (registers torch.ops.memflow_b200.*)
-from .._lib import check, device_guard, host_array, lib, MemflowB200Error, needs_dispatcher, ptr, require_cuda, stream_ptr
+from .._lib import check, device_guard, host_array, lib, MemflowB200Error, needs_dispatcher, plain_eager, ptr, require_cuda, stream_ptr
 
 M_HIGGS = 125.25
 M_TOP = 172.5
@@ -215,7 +215,7 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         if cuts_on:   # the reference evaluates the cuts always; with the default -1 thresholds they cannot fire
             flags |= MF_FLAG_CUTS
         # ONE launch through the registered op (memflow_b200/ops.py): K1, its status word, autograd via the backward kernel
-        call = torch.ops.memflow_b200.rambo_forward if needs_dispatcher(u) else ops.rambo_forward_cuda
+        call = ops.rambo_forward_cuda if not needs_dispatcher(u) else (ops.RamboForwardEager.apply if plain_eager(u) else torch.ops.memflow_b200.rambo_forward)
         momenta, weight, x1, x2, logw, status = call(
             u, self._masses_host, float(self.collider_energy),
             [float(pT_mincut), float(delR_mincut), float(rap_maxcut)] if cuts_on else [], flags, bool(return_logweight))
@@ -267,7 +267,7 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
             flags |= MF_FLAG_NO_CM_CHECK
         # ONE launch through the registered op: a strided [N, n, 4] view (e.g. forward_output[:, 2:]) is read in place;
         # `ps` is differentiable w.r.t. the momenta and x1, x2 (backward kernel), `prob` carries no gradient
-        call = torch.ops.memflow_b200.rambo_inverse if needs_dispatcher(mom, x1, x2) else ops.rambo_inverse_cuda
+        call = ops.rambo_inverse_cuda if not needs_dispatcher(mom, x1, x2) else (ops.RamboInverseEager.apply if plain_eager(mom, x1, x2) else torch.ops.memflow_b200.rambo_inverse)
         ps, prob, logp, status = call(
             mom, x1 if needs_grad else x1.detach(), x2 if needs_grad else x2.detach(), order, self._masses_host, target_host,
             float(self.collider_energy), flags, bool(return_logprob))
