@@ -284,3 +284,24 @@ def test_world_size_2_gloo_allreduce(oracle):
     for _, acc in res:
         np.testing.assert_allclose(acc, ref, rtol=1e-13)
     assert res[0][1] == res[1][1]
+
+
+def test_call_path_selection():
+    """Which way a call takes into the kernels (memflow_b200/_lib.py): plain eager inference -> C ABI directly; plain eager
+    autograd -> the directly-applied autograd.Function; functorch transforms / tensor subclasses -> the registered op."""
+    import torch
+    from memflow_b200._lib import needs_dispatcher, plain_eager
+    t = torch.zeros(3)
+    assert plain_eager(t) and not needs_dispatcher(t)
+    g = torch.zeros(3, requires_grad=True)
+    assert needs_dispatcher(g) and plain_eager(g)
+    with torch.no_grad():
+        assert not needs_dispatcher(g)
+    seen = []
+
+    def f(x):
+        seen.append((needs_dispatcher(x), plain_eager(x)))
+        return (x * x).sum()
+
+    torch.func.grad(f)(torch.ones(3))
+    assert seen == [(True, False)]
