@@ -27,13 +27,8 @@ def timeit(fn, n=200):
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n * 1e6
 eager = timeit(step)
-s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
-with torch.cuda.stream(s):
-    for _ in range(3): step()
-torch.cuda.current_stream().wait_stream(s)
-g = torch.cuda.CUDAGraph()
-with torch.cuda.graph(g):
-    out = step()
-graph = timeit(g.replay)
+from memflow_b200.graphs import capture
+g = capture(step)
+graph = timeit(g)
 print("B=%d: K1 + K2 (n=4) + %d x (spline forward + backward, float64 F=%d K=%d): eager %.0f us / step, one graph replay %.0f us / step (%.1fx)"
       % (B, T, F, K, eager, graph, eager / graph))

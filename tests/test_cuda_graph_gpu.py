@@ -10,16 +10,9 @@ E = 13000.0
 
 
 def _capture(fn):
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        for _ in range(3):           # warm-up on a side stream (library loading, cudaFuncSetAttribute, allocator pools)
-            fn()
-    torch.cuda.current_stream().wait_stream(s)
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        out = fn()
-    return g, out
+    from memflow_b200.graphs import capture
+    step = capture(fn)
+    return step.graph, step.outputs
 
 
 def test_phase_space_maps_in_a_graph():
